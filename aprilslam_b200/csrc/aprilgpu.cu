@@ -1,0 +1,1004 @@
+// aprilgpu.cu -- host side of libaprilgpu.so: the C ABI declared in include/aprilgpu.h, workspace
+// management and the per-chunk kernel pipeline.  sm_100a only; no CPU fallback of any stage.
+//
+// Pipeline per chunk of frames (all on one stream):
+//   [H2D] -> image (k_pack / k_blur_pass / k_decimate_threshold) -> CC (k_cc_local, k_cc_boundary,
+//   k_cc_finalize) -> k_edges -> segmented radix sort (k_sort_hist/scan/scatter x passes) ->
+//   k_cluster_heads -> k_fit_quads (3 size tiers) -> k_decode_quads -> k_reconcile [-> k_pose] -> D2H
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aprilgpu.h"
+#include "common.cuh"
+#include "k_image.cuh"
+#include "k_cc.cuh"
+#include "k_cluster.cuh"
+#include "k_quad.cuh"
+#include "k_decode.cuh"
+#include "k_pose.cuh"
+
+#include "families_data.inc"
+
+static_assert(sizeof(DetRec) == sizeof(agpu_detection), "DetRec layout");
+static_assert(sizeof(PoseRec) == sizeof(agpu_pose_t), "PoseRec layout");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int TIER_CAP[3] = {2048, 8192, 16384};
+// counter block layout (ints)
+enum { CNT_SMALL = 0, CNT_LARGE = 1, CNT_OVERSIZE = 2, CNT_HEADS = 3, CNT_MID = 4, CNT_NQUADS = 5, CNT_FIXED = 8 };
+
+}  // namespace
+
+struct agpu_handle {
+    agpu_config cfg;
+    std::string families_str;
+    std::vector<const FamilyDef*> fams;
+    DevParams prm;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool profiling = false;
+    float stage_ms[AGPU_NUM_STAGES];
+    long long launches = 0;
+    long long counters[8];
+    std::vector<cudaEvent_t> events;
+
+    // device data
+    DevBuf d_fams, d_codes;
+    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes;
+    DevBuf d_keys[2], d_vals[2], d_hist, d_lfps, d_errs;
+    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk]
+    DevBuf d_clusters[3], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses, d_pose_in;
+    HostBuf h_out, h_counts, h_poses, h_counters;
+
+    // state of the last chunk (debug fetch)
+    Geom geom;
+    int last_chunk = 0, last_cap = 0, last_sorted = 0;
+    bool have_last = false;
+
+    void set_err(const std::string& s) { err = s; }
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            h->set_err(std::string(#call) + ": " + cudaGetErrorString(e__));                      \
+            return AGPU_E_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                                                         \
+    do {                                                                                           \
+        h->launches++;                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) {                                                                  \
+            h->set_err(std::string("launch ") + name + ": " + cudaGetErrorString(e__));           \
+            return AGPU_E_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+const FamilyDef* find_family(const std::string& name) {
+    for (const FamilyDef& f : k_builtin_families)
+        if (name == f.name) return &f;
+    return nullptr;
+}
+
+int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+Geom make_geom(int W, int H, int f) {
+    Geom g;
+    g.W = W; g.H = H;
+    g.wd = 1 + (W - 1) / f;
+    g.hd = 1 + (H - 1) / f;
+    g.wp = (g.wd + 15) & ~15;
+    g.plane = (size_t)g.wp * g.hd;
+    return g;
+}
+
+int gaussian_kernel_host(float sigma, uint8_t* k) {
+    int ksz = (int)(4 * sigma);
+    if ((ksz & 1) == 0) ksz++;
+    if (ksz <= 1) return 0;
+    if (ksz > 63) ksz = 63;
+    double dk[64], acc = 0;
+    for (int i = 0; i < ksz; i++) {
+        int x = -ksz / 2 + i;
+        dk[i] = std::exp(-.5 * (x / (double)sigma) * (x / (double)sigma));
+        acc += dk[i];
+    }
+    for (int i = 0; i < ksz; i++) k[i] = (uint8_t)(dk[i] / acc * 255.0);
+    return ksz;
+}
+
+struct StageTimer {
+    agpu_handle* h;
+    size_t next = 0;
+    explicit StageTimer(agpu_handle* hh) : h(hh) {}
+    void mark() {
+        if (!h->profiling) return;
+        if (next >= h->events.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            h->events.push_back(e);
+        }
+        cudaEventRecord(h->events[next++], h->stream);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// image + CC stages on `n` frames already on the device (shared by the pipeline and the stage hooks)
+// ------------------------------------------------------------------------------------------
+int run_image_stage(agpu_handle* h, const uint8_t* d_src, int channels, int W, int H, size_t stride,
+                    size_t frame_stride, int n, const Geom& g, const uint8_t** quad_im_out, size_t* q_pitch,
+                    size_t* q_frame, const uint8_t** gray_full, size_t* gray_pitch, size_t* gray_frame) {
+    const int f = h->prm.decim;
+    const float sigma = h->cfg.quad_sigma;
+    CK(h->d_thresh.ensure(g.plane * n));
+    const uint8_t* src = d_src;
+    size_t s_stride = stride, s_frame = frame_stride;
+    int srcW = W, srcH = H;
+    int F = f;
+    // full-resolution gray image for refine_edges / decode
+    if (channels == 3) {
+        Geom gf = make_geom(W, H, 1);
+        CK(h->d_gray.ensure(gf.plane * n));
+        size_t total = (size_t)n * gf.hd * (gf.wp >> 2);
+        k_pack<<<ceil_div(total, 256), 256, 0, h->stream>>>(d_src, W, H, stride, frame_stride, 3, 1,
+                                                            h->d_gray.as<uint8_t>(), gf, n);
+        LAUNCH_CHECK("k_pack(bgr)");
+        *gray_full = h->d_gray.as<uint8_t>();
+        *gray_pitch = gf.wp;
+        *gray_frame = gf.plane;
+        src = h->d_gray.as<uint8_t>();
+        s_stride = gf.wp;
+        s_frame = gf.plane;
+        channels = 1;
+    } else {
+        *gray_full = d_src;
+        *gray_pitch = stride;
+        *gray_frame = frame_stride;
+    }
+    const bool fast2 = (f == 1 || f == 2 || f == 4) && sigma == 0.0f;
+    uint8_t* quad_im = nullptr;
+    if (!fast2) {
+        // generic: decimate into quad_im, optional blur, then threshold the quad image with F = 1
+        CK(h->d_quad_im.ensure(g.plane * n));
+        quad_im = h->d_quad_im.as<uint8_t>();
+        size_t total = (size_t)n * g.hd * (g.wp >> 2);
+        k_pack<<<ceil_div(total, 256), 256, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, 1, f, quad_im, g, n);
+        LAUNCH_CHECK("k_pack");
+        if (sigma != 0.0f) {
+            BlurKernel bk;
+            memset(&bk, 0, sizeof(bk));
+            bk.ksz = gaussian_kernel_host(std::fabs(sigma), bk.k);
+            if (bk.ksz > 1) {
+                CK(h->d_blur_tmp.ensure(g.plane * n));
+                uint8_t* tmp = h->d_blur_tmp.as<uint8_t>();
+                if (sigma < 0) {
+                    CK(h->d_blur_orig.ensure(g.plane * n));
+                    CK(cudaMemcpyAsync(h->d_blur_orig.p, quad_im, g.plane * n, cudaMemcpyDeviceToDevice, h->stream));
+                }
+                size_t tot = (size_t)n * g.hd * g.wd;
+                k_blur_pass<<<ceil_div(tot, 256), 256, 0, h->stream>>>(quad_im, tmp, g, n, bk, 0);
+                LAUNCH_CHECK("k_blur_pass(rows)");
+                k_blur_pass<<<ceil_div(tot, 256), 256, 0, h->stream>>>(tmp, quad_im, g, n, bk, 1);
+                LAUNCH_CHECK("k_blur_pass(cols)");
+                if (sigma < 0) {
+                    k_unsharp<<<ceil_div(g.plane * n, 256), 256, 0, h->stream>>>(h->d_blur_orig.as<uint8_t>(), quad_im, g, n);
+                    LAUNCH_CHECK("k_unsharp");
+                }
+            }
+        }
+        src = quad_im;
+        s_stride = g.wp;
+        s_frame = g.plane;
+        srcW = g.wd;
+        srcH = g.hd;
+        F = 1;
+    }
+    uint8_t* quad_out = nullptr;
+    if (F > 1) {
+        CK(h->d_quad_im.ensure(g.plane * n));
+        quad_out = h->d_quad_im.as<uint8_t>();
+    }
+    if ((g.wd >> 2) == 0 || (g.hd >> 2) == 0) {
+        CK(cudaMemsetAsync(h->d_thresh.p, 127, g.plane * n, h->stream));
+    } else {
+        const int TPL = 4 / F;
+        const int strip_px = 30 * TPL * 4;
+        const int nstrips = ceil_div(g.wp, strip_px);
+        const int th = g.hd >> 2;
+        int seg_tiles = 8;
+        const int nsegs = ceil_div(th, seg_tiles);
+        const long long warps = (long long)n * nstrips * nsegs;
+        const int blocks = ceil_div(warps * 32, 256);
+        const int vec_ok = (s_stride % 16 == 0) && (s_frame % 16 == 0) && (((uintptr_t)src) % 16 == 0);
+        const int md = h->prm.min_white_black_diff;
+        uint8_t* th_out = h->d_thresh.as<uint8_t>();
+        if (F == 1)
+            k_decimate_threshold<1><<<blocks, 256, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
+                                                                   nstrips, nsegs, seg_tiles, n, md, vec_ok);
+        else if (F == 2)
+            k_decimate_threshold<2><<<blocks, 256, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
+                                                                   nstrips, nsegs, seg_tiles, n, md, vec_ok);
+        else
+            k_decimate_threshold<4><<<blocks, 256, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
+                                                                   nstrips, nsegs, seg_tiles, n, md, vec_ok);
+        LAUNCH_CHECK("k_decimate_threshold");
+    }
+    if (F > 1) {
+        *quad_im_out = quad_out; *q_pitch = g.wp; *q_frame = g.plane;
+    } else {
+        *quad_im_out = src; *q_pitch = s_stride; *q_frame = s_frame;
+    }
+    return AGPU_OK;
+}
+
+int run_cc_stage(agpu_handle* h, const uint8_t* d_thresh, int n, const Geom& g) {
+    CK(h->d_labels.ensure(g.plane * n * 4));
+    CK(h->d_sizes.ensure(g.plane * n * 4));
+    const int tx = ceil_div(g.wd, CC_TW), ty = ceil_div(g.hd, CC_TH);
+    dim3 grid(tx, ty, n);
+    k_cc_local<<<grid, CC_THREADS, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), h->d_sizes.as<uint32_t>(), g, tx, ty);
+    LAUNCH_CHECK("k_cc_local");
+    k_cc_boundary<<<grid, 128, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), g, tx, ty);
+    LAUNCH_CHECK("k_cc_boundary");
+    k_cc_finalize<<<grid, CC_THREADS, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), h->d_sizes.as<uint32_t>(), g);
+    LAUNCH_CHECK("k_cc_finalize");
+    return AGPU_OK;
+}
+
+struct PoseSpec {
+    bool enabled = false;
+    double K[9];
+    double dist[8];
+    int ndist = 0;
+    double tag_size = 0;
+};
+
+void fill_pose_args(PoseArgs& pa, const PoseSpec& ps, int method) {
+    pa.fx = ps.K[0]; pa.fy = ps.K[4]; pa.cx = ps.K[2]; pa.cy = ps.K[5];
+    for (int i = 0; i < 8; i++) pa.dist[i] = ps.dist[i];
+    pa.ndist = ps.ndist;
+    pa.half = (double)(float)(ps.tag_size / 2);
+    pa.method = method;
+}
+
+int parse_dist(agpu_handle* h, const double* dist, int ndist, PoseSpec& ps) {
+    for (int i = 0; i < 8; i++) ps.dist[i] = 0;
+    if (ndist < 0 || ndist > 8 || (ndist > 0 && !dist)) {
+        h->set_err("dist: expected 0, 4, 5 or 8 coefficients");
+        return AGPU_E_INVALID;
+    }
+    bool any = false;
+    for (int i = 0; i < ndist; i++) {
+        ps.dist[i] = dist[i];
+        any |= dist[i] != 0.0;
+    }
+    ps.ndist = any ? ndist : 0;
+    return AGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the pipeline
+// ------------------------------------------------------------------------------------------
+int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channels, int B, int W, int H, int stride,
+                void* cuda_stream, const PoseSpec& pose, agpu_detection* out, agpu_pose_t* poses, int cap_out,
+                int* counts) {
+    if (!h) return AGPU_E_INVALID;
+    if (!frames || !out || !counts || B <= 0 || W <= 0 || H <= 0 || cap_out <= 0 || (channels != 1 && channels != 3) ||
+        stride < W * channels) {
+        h->set_err("agpu_detect: invalid argument");
+        return AGPU_E_INVALID;
+    }
+    if (2 * W + 1 > 16383 || 2 * H + 1 > 16383) {
+        h->set_err("agpu_detect: frames larger than 8190 pixels per side are not supported");
+        return AGPU_E_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(h->device));
+    h->launches = 0;
+    for (int i = 0; i < AGPU_NUM_STAGES; i++) h->stage_ms[i] = 0;
+    for (int i = 0; i < 8; i++) h->counters[i] = 0;
+    const int f = h->prm.decim;
+    const Geom g = make_geom(W, H, f);
+    h->geom = g;
+    for (int b = 0; b < B; b++) counts[b] = 0;
+    if (g.wd < 8 || g.hd < 8) return AGPU_OK;  // nothing detectable (and the tile grid would be empty)
+
+    // chunking
+    int chunk = h->cfg.chunk_frames;
+    if (chunk <= 0) {
+        const size_t target_px = (size_t)48 << 20;  // ~48 Mpx of working image per pass
+        chunk = (int)std::max<size_t>(1, target_px / g.plane);
+        chunk = std::min(chunk, 256);
+    }
+    chunk = std::min(chunk, B);
+    int cap = h->cfg.max_points_per_frame;
+    if (cap <= 0) cap = (int)std::max<size_t>(65536, g.plane / 8);
+    cap = (cap + RS_TILE - 1) / RS_TILE * RS_TILE;
+    int maxcl = h->cfg.max_clusters_per_frame > 0 ? h->cfg.max_clusters_per_frame : std::max(4096, cap / 24);
+    int maxq = h->cfg.max_quads_per_frame > 0 ? h->cfg.max_quads_per_frame : 1024;
+    const int nblk_max = cap / RS_TILE;
+    const size_t frame_bytes = (size_t)H * stride;
+
+    // workspaces
+    if (!on_device) CK(h->d_in.ensure(frame_bytes * chunk));
+    for (int i = 0; i < 2; i++) {
+        CK(h->d_keys[i].ensure((size_t)chunk * cap * 8));
+        CK(h->d_vals[i].ensure((size_t)chunk * cap * 4));
+    }
+    CK(h->d_hist.ensure((size_t)chunk * RS_RADIX * nblk_max * 4));
+    CK(h->d_lfps.ensure((size_t)chunk * cap * 48));
+    CK(h->d_errs.ensure((size_t)chunk * cap * 8));
+    const size_t ncnt = CNT_FIXED + (size_t)4 * chunk;
+    CK(h->d_counters.ensure(ncnt * 4));
+    for (int t = 0; t < 3; t++) CK(h->d_clusters[t].ensure((size_t)chunk * maxcl * sizeof(ClusterRef)));
+    if (h->cfg.debug) {
+        CK(h->d_dbg_heads.ensure((size_t)chunk * cap / 4 * sizeof(ClusterRef)));
+        CK(h->d_refined.ensure((size_t)chunk * maxq * 32));
+    }
+    CK(h->d_quads.ensure((size_t)chunk * maxq * sizeof(QuadRec)));
+    CK(h->d_dets.ensure((size_t)chunk * REC_CAP * sizeof(DetRec)));
+    CK(h->d_out.ensure((size_t)chunk * cap_out * sizeof(DetRec)));
+    CK(h->h_out.ensure((size_t)chunk * cap_out * sizeof(DetRec)));
+    CK(h->h_counts.ensure(ncnt * 4));
+    if (pose.enabled) {
+        CK(h->d_poses.ensure((size_t)chunk * cap_out * sizeof(PoseRec)));
+        CK(h->h_poses.ensure((size_t)chunk * cap_out * sizeof(PoseRec)));
+    }
+    int* d_cnt = h->d_counters.as<int>();
+    int* d_npts = d_cnt + CNT_FIXED;
+    int* d_frame_quads = d_npts + chunk;
+    int* d_ndets = d_frame_quads + chunk;
+    int* d_out_counts = d_ndets + chunk;
+
+    cudaStream_t user_stream = (cudaStream_t)cuda_stream;
+    if (on_device) {
+        // order our stream after the producer's stream
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(ev, user_stream));
+        CK(cudaStreamWaitEvent(h->stream, ev, 0));
+        CK(cudaEventDestroy(ev));
+    }
+    int rc_final = AGPU_OK;
+    const int key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
+
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int n = std::min(chunk, B - b0);
+        StageTimer tm(h);
+        tm.mark();  // 0
+        const uint8_t* d_src;
+        if (on_device) {
+            d_src = frames + (size_t)b0 * frame_bytes;
+        } else {
+            CK(cudaMemcpyAsync(h->d_in.p, frames + (size_t)b0 * frame_bytes, frame_bytes * n, cudaMemcpyHostToDevice,
+                               h->stream));
+            d_src = h->d_in.as<uint8_t>();
+        }
+        CK(cudaMemsetAsync(d_cnt, 0, ncnt * 4, h->stream));
+        tm.mark();  // 1: after H2D
+        const uint8_t *quad_im, *gray_full;
+        size_t q_pitch, q_frame, gray_pitch, gray_frame;
+        int rc = run_image_stage(h, d_src, channels, W, H, stride, frame_bytes, n, g, &quad_im, &q_pitch, &q_frame,
+                                 &gray_full, &gray_pitch, &gray_frame);
+        if (rc) return rc;
+        tm.mark();  // 2: after image
+        rc = run_cc_stage(h, h->d_thresh.as<uint8_t>(), n, g);
+        if (rc) return rc;
+        tm.mark();  // 3: after CC
+        {
+            dim3 grid(ceil_div(g.wd, 32), ceil_div(g.hd - 1, 8), n);
+            k_edges<<<grid, 256, 0, h->stream>>>(h->d_thresh.as<uint8_t>(), h->d_labels.as<uint32_t>(),
+                                                 h->d_sizes.as<uint32_t>(), g, h->d_keys[0].as<unsigned long long>(),
+                                                 h->d_vals[0].as<uint32_t>(), d_npts, cap);
+            LAUNCH_CHECK("k_edges");
+        }
+        tm.mark();  // 4: after edges
+        int cur = 0;
+        {
+            std::vector<int> shifts;
+            for (int s = 0; s < key_bits; s += 8) shifts.push_back(s);
+            for (int s = 0; s < key_bits; s += 8) shifts.push_back(32 + s);
+            for (int shift : shifts) {
+                dim3 grid(nblk_max, n);
+                k_sort_hist<<<grid, RS_THREADS, 0, h->stream>>>(h->d_keys[cur].as<unsigned long long>(), d_npts, cap, shift,
+                                                                h->d_hist.as<uint32_t>(), nblk_max);
+                LAUNCH_CHECK("k_sort_hist");
+                k_sort_scan<<<n, 1024, 0, h->stream>>>(d_npts, cap, h->d_hist.as<uint32_t>(), nblk_max);
+                LAUNCH_CHECK("k_sort_scan");
+                k_sort_scatter<<<grid, RS_THREADS, 0, h->stream>>>(
+                    h->d_keys[cur].as<unsigned long long>(), h->d_vals[cur].as<uint32_t>(),
+                    h->d_keys[cur ^ 1].as<unsigned long long>(), h->d_vals[cur ^ 1].as<uint32_t>(), d_npts, cap, shift,
+                    h->d_hist.as<uint32_t>(), nblk_max);
+                LAUNCH_CHECK("k_sort_scatter");
+                cur ^= 1;
+            }
+        }
+        tm.mark();  // 5: after sort
+        const unsigned long long* skeys = h->d_keys[cur].as<unsigned long long>();
+        const uint32_t* svals = h->d_vals[cur].as<uint32_t>();
+        {
+            ClusterLists cl;
+            cl.small_list = h->d_clusters[0].as<ClusterRef>();
+            cl.mid_list = h->d_clusters[1].as<ClusterRef>();
+            cl.large_list = h->d_clusters[2].as<ClusterRef>();
+            cl.counters = d_cnt;
+            cl.cap_list = n * maxcl;
+            cl.dbg_heads = h->cfg.debug ? h->d_dbg_heads.as<ClusterRef>() : nullptr;
+            cl.cap_dbg = (int)(h->d_dbg_heads.bytes / sizeof(ClusterRef));
+            dim3 grid(ceil_div(cap, 256), n);
+            k_cluster_heads<<<grid, 256, 0, h->stream>>>(skeys, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24),
+                                                         TIER_CAP[0], TIER_CAP[1], TIER_CAP[2], cl);
+            LAUNCH_CHECK("k_cluster_heads");
+            QuadFitArgs qa;
+            qa.vals = svals; qa.keys = skeys; qa.cap = cap;
+            qa.quad_im = quad_im; qa.q_pitch = q_pitch; qa.q_frame = q_frame;
+            qa.g = g;
+            qa.lfps = h->d_lfps.as<double>();
+            qa.errs = h->d_errs.as<double>();
+            qa.list_cap = n * maxcl;
+            qa.quads = h->d_quads.as<QuadRec>();
+            qa.nquads = d_cnt + CNT_NQUADS;
+            qa.cap_quads = n * maxq;
+            qa.per_frame_quads = d_frame_quads;
+            const int cnt_idx[3] = {CNT_SMALL, CNT_MID, CNT_LARGE};
+            const int wpb[3] = {4, 1, 1};
+            const int grids[3] = {h->num_sms * 2, h->num_sms * 3, h->num_sms};
+            for (int t = 0; t < 3; t++) {
+                qa.list = h->d_clusters[t].as<ClusterRef>();
+                qa.list_count = d_cnt + cnt_idx[t];
+                size_t smem = (size_t)wpb[t] * ((size_t)TIER_CAP[t] * 8 + QF_PTAB_DOUBLES * 8 + 64);
+                k_fit_quads<<<grids[t], wpb[t] * 32, smem, h->stream>>>(qa, h->prm, TIER_CAP[t]);
+                LAUNCH_CHECK("k_fit_quads");
+            }
+        }
+        tm.mark();  // 6: after quads
+        {
+            DecodeArgs da;
+            da.im = gray_full; da.pitch = gray_pitch; da.frame_stride = gray_frame;
+            da.W = W; da.H = H;
+            da.quads = h->d_quads.as<QuadRec>();
+            da.nquads = d_cnt + CNT_NQUADS;
+            da.cap_quads = n * maxq;
+            da.fams = h->d_fams.as<DevFamily>();
+            da.codes = h->d_codes.as<unsigned long long>();
+            da.dets = h->d_dets.as<DetRec>();
+            da.ndets = d_ndets;
+            da.cap_dets = REC_CAP;
+            da.dbg_refined = h->cfg.debug ? h->d_refined.as<float>() : nullptr;
+            k_decode_quads<<<h->num_sms * 4, 128, 0, h->stream>>>(da, h->prm);
+            LAUNCH_CHECK("k_decode_quads");
+        }
+        tm.mark();  // 7: after decode
+        k_reconcile<<<ceil_div(n, 4), 128, 0, h->stream>>>(h->d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
+                                                          h->d_out.as<DetRec>(), d_out_counts, cap_out);
+        LAUNCH_CHECK("k_reconcile");
+        if (pose.enabled) {
+            PoseArgs pa;
+            fill_pose_args(pa, pose, 0);
+            pa.corners = reinterpret_cast<const double*>(h->d_out.as<char>() + offsetof(DetRec, p));
+            pa.corner_stride = (int)(sizeof(DetRec) / 8);
+            pa.counts = d_out_counts;
+            pa.per_frame = cap_out;
+            pa.M = n * cap_out;
+            pa.out = h->d_poses.as<PoseRec>();
+            k_pose<<<ceil_div((long long)pa.M * 4, 128), 128, 0, h->stream>>>(pa);
+            LAUNCH_CHECK("k_pose");
+        }
+        tm.mark();  // 8: after reconcile/pose
+        CK(cudaMemcpyAsync(h->h_counts.p, d_cnt, ncnt * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_out.p, h->d_out.p, (size_t)n * cap_out * sizeof(DetRec), cudaMemcpyDeviceToHost, h->stream));
+        if (pose.enabled)
+            CK(cudaMemcpyAsync(h->h_poses.p, h->d_poses.p, (size_t)n * cap_out * sizeof(PoseRec), cudaMemcpyDeviceToHost,
+                               h->stream));
+        tm.mark();  // 9: after D2H
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->profiling) {
+            for (int s = 0; s < AGPU_NUM_STAGES; s++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, h->events[s], h->events[s + 1]);
+                h->stage_ms[s] += ms;
+            }
+        }
+        // gather
+        const int* hc = h->h_counts.as<int>();
+        const int* h_npts = hc + CNT_FIXED;
+        const int* h_fq = h_npts + chunk;
+        const int* h_nd = h_fq + chunk;
+        const int* h_oc = h_nd + chunk;
+        const DetRec* ho = h->h_out.as<DetRec>();
+        for (int i = 0; i < n; i++) {
+            const int c = h_oc[i];
+            counts[b0 + i] = c;
+            const int m = std::min(c, cap_out);
+            memcpy(out + (size_t)(b0 + i) * cap_out, ho + (size_t)i * cap_out, (size_t)m * sizeof(DetRec));
+            if (pose.enabled && poses)
+                memcpy(poses + (size_t)(b0 + i) * cap_out, h->h_poses.as<PoseRec>() + (size_t)i * cap_out,
+                       (size_t)m * sizeof(PoseRec));
+            if (c > cap_out && rc_final == AGPU_OK) rc_final = AGPU_E_TRUNCATED;
+            h->counters[0] += h_npts[i];
+            h->counters[3] += h_nd[i];
+            if (h_npts[i] > cap) {
+                h->set_err("edge-point list overflow: raise agpu_config.max_points_per_frame");
+                rc_final = AGPU_E_WORKSPACE;
+            }
+            if (h_nd[i] > REC_CAP) {
+                h->set_err("more than 256 raw detections in one frame");
+                rc_final = AGPU_E_WORKSPACE;
+            }
+        }
+        h->counters[1] += hc[CNT_SMALL] + hc[CNT_MID] + hc[CNT_LARGE];
+        h->counters[2] += hc[CNT_NQUADS];
+        h->counters[4] += hc[CNT_OVERSIZE];
+        if (hc[CNT_SMALL] > n * maxcl || hc[CNT_MID] > n * maxcl || hc[CNT_LARGE] > n * maxcl) {
+            h->set_err("cluster list overflow: raise agpu_config.max_clusters_per_frame");
+            rc_final = AGPU_E_WORKSPACE;
+        }
+        if (hc[CNT_NQUADS] > n * maxq) {
+            h->set_err("quad list overflow: raise agpu_config.max_quads_per_frame");
+            rc_final = AGPU_E_WORKSPACE;
+        }
+        h->last_chunk = n;
+        h->last_cap = cap;
+        h->last_sorted = cur;
+        h->have_last = true;
+    }
+    return rc_final;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int agpu_version(void) { return AGPU_VERSION; }
+
+void agpu_default_config(agpu_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->families = "tag36h11";
+    cfg->threads = 1;
+    cfg->maxhamming = 1;
+    cfg->quad_decimate = 2.0f;
+    cfg->quad_sigma = 0.0f;
+    cfg->refine_edges = 1;
+    cfg->decode_sharpening = 0.25;
+    cfg->debug = 0;
+    cfg->device = 0;
+}
+
+const char* agpu_last_error(const agpu_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int agpu_create(const agpu_config* cfg, agpu_handle** out) {
+    if (!cfg || !out || !cfg->families) {
+        g_create_error = "agpu_create: NULL argument";
+        return AGPU_E_INVALID;
+    }
+    *out = nullptr;
+    agpu_handle* h = new agpu_handle();
+    h->cfg = *cfg;
+    h->families_str = cfg->families;
+    h->cfg.families = h->families_str.c_str();
+    auto fail = [&](int rc, const std::string& msg) {
+        g_create_error = msg;
+        delete h;
+        return rc;
+    };
+    // families
+    {
+        std::string s = h->families_str, tok;
+        size_t pos = 0;
+        while (pos <= s.size()) {
+            size_t e = s.find_first_of(" ,", pos);
+            if (e == std::string::npos) e = s.size();
+            tok = s.substr(pos, e - pos);
+            pos = e + 1;
+            if (tok.empty()) continue;
+            const FamilyDef* f = find_family(tok);
+            if (!f) return fail(AGPU_E_INVALID, "Unrecognized tag family name: " + tok);
+            h->fams.push_back(f);
+        }
+        if (h->fams.empty()) return fail(AGPU_E_INVALID, "no tag family given");
+        if ((int)h->fams.size() > AGPU_MAX_FAMILIES) return fail(AGPU_E_INVALID, "too many families");
+    }
+    if (!(cfg->quad_decimate >= 1.0f) || cfg->quad_decimate != std::floor(cfg->quad_decimate) || cfg->quad_decimate > 16)
+        return fail(AGPU_E_UNSUPPORTED, "quad_decimate must be an integer factor in [1, 16]");
+    if (cfg->maxhamming < 0 || cfg->maxhamming > 2) return fail(AGPU_E_INVALID, "maxhamming must be 0, 1 or 2");
+    for (const FamilyDef* f : h->fams)
+        if (2 * cfg->maxhamming >= f->h)
+            return fail(AGPU_E_INVALID, std::string("maxhamming too large for family ") + f->name);
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(AGPU_E_CUDA, std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "count = 0"));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(AGPU_E_INVALID, "device ordinal out of range");
+    h->device = cfg->device;
+    if ((ce = cudaSetDevice(h->device)) != cudaSuccess) return fail(AGPU_E_CUDA, cudaGetErrorString(ce));
+    cudaDeviceProp prop;
+    if ((ce = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return fail(AGPU_E_CUDA, cudaGetErrorString(ce));
+    if (prop.major != 10)
+        return fail(AGPU_E_CUDA, "libaprilgpu is built for sm_100a (B200) only; device is sm_" +
+                                     std::to_string(prop.major) + std::to_string(prop.minor));
+    h->num_sms = prop.multiProcessorCount;
+    if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail(AGPU_E_CUDA, cudaGetErrorString(ce));
+
+    // parameters
+    DevParams& P = h->prm;
+    memset(&P, 0, sizeof(P));
+    P.quad_decimate = cfg->quad_decimate;
+    P.decim = (int)cfg->quad_decimate;
+    P.refine_edges = cfg->refine_edges ? 1 : 0;
+    P.decode_sharpening = cfg->decode_sharpening;
+    P.maxhamming = cfg->maxhamming;
+    P.min_cluster_pixels = 5;
+    P.max_nmaxima = 10;
+    P.cos_critical_rad = (float)std::cos(10.0 * M_PI / 180.0);
+    P.max_line_fit_mse = 10.0f;
+    P.min_white_black_diff = 5;
+    int min_w = 1000000;
+    for (const FamilyDef* f : h->fams) {
+        min_w = std::min(min_w, f->width_at_border);
+        if (f->reversed_border) P.reversed_border = 1; else P.normal_border = 1;
+    }
+    min_w = (int)(min_w / cfg->quad_decimate);
+    P.min_tag_width = std::max(3, min_w);
+    P.nfamilies = (int)h->fams.size();
+    for (int i = 0; i < 7; i++) {
+        int j = i - 3;
+        P.smooth_f[i] = (float)std::exp(-j * j / (2 * 1.0 * 1.0));
+    }
+    for (int r = 0; r < 4; r++) {
+        double theta = r * M_PI / 2.0;
+        P.rot_c[r] = std::cos(theta);
+        P.rot_s[r] = std::sin(theta);
+    }
+    // family tables
+    {
+        std::vector<DevFamily> df(h->fams.size());
+        std::vector<unsigned long long> codes;
+        for (size_t i = 0; i < h->fams.size(); i++) {
+            const FamilyDef* f = h->fams[i];
+            memset(&df[i], 0, sizeof(DevFamily));
+            df[i].nbits = f->nbits; df[i].ncodes = f->ncodes; df[i].width_at_border = f->width_at_border;
+            df[i].total_width = f->total_width; df[i].reversed_border = f->reversed_border;
+            df[i].code_offset = (int)codes.size();
+            for (int b = 0; b < f->nbits; b++) { df[i].bit_x[b] = f->bit_x[b]; df[i].bit_y[b] = f->bit_y[b]; }
+            codes.insert(codes.end(), f->codes, f->codes + f->ncodes);
+        }
+        if (h->d_fams.ensure(df.size() * sizeof(DevFamily)) != cudaSuccess || h->d_codes.ensure(codes.size() * 8) != cudaSuccess)
+            return fail(AGPU_E_CUDA, "cudaMalloc(family tables) failed");
+        cudaMemcpy(h->d_fams.p, df.data(), df.size() * sizeof(DevFamily), cudaMemcpyHostToDevice);
+        cudaMemcpy(h->d_codes.p, codes.data(), codes.size() * 8, cudaMemcpyHostToDevice);
+    }
+    // the large quad-fit tiers need more than 48 KB of dynamic shared memory
+    ce = cudaFuncSetAttribute(k_fit_quads, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)((size_t)TIER_CAP[2] * 8 + QF_PTAB_DOUBLES * 8 + 64));
+    if (ce != cudaSuccess) return fail(AGPU_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+    *out = h;
+    return AGPU_OK;
+}
+
+int agpu_destroy(agpu_handle* h) {
+    if (!h) return AGPU_E_INVALID;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->d_fams, &h->d_codes, &h->d_in, &h->d_gray, &h->d_quad_im, &h->d_blur_tmp, &h->d_blur_orig,
+                      &h->d_thresh, &h->d_labels, &h->d_sizes, &h->d_keys[0], &h->d_keys[1], &h->d_vals[0], &h->d_vals[1],
+                      &h->d_hist, &h->d_lfps, &h->d_errs, &h->d_counters, &h->d_clusters[0], &h->d_clusters[1],
+                      &h->d_clusters[2], &h->d_dbg_heads, &h->d_quads, &h->d_refined, &h->d_dets, &h->d_out, &h->d_poses,
+                      &h->d_pose_in};
+    for (DevBuf* b : bufs) b->release();
+    h->h_out.release(); h->h_counts.release(); h->h_poses.release(); h->h_counters.release();
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return AGPU_OK;
+}
+
+int agpu_detect(agpu_handle* h, const uint8_t* frames, int on_device, int B, int W, int H, int stride, void* cuda_stream,
+                agpu_detection* out, int cap_per_frame, int* counts) {
+    PoseSpec ps;
+    return detect_impl(h, frames, on_device, 1, B, W, H, stride, cuda_stream, ps, out, nullptr, cap_per_frame, counts);
+}
+
+int agpu_detect_bgr(agpu_handle* h, const uint8_t* frames, int on_device, int B, int W, int H, int stride,
+                    void* cuda_stream, agpu_detection* out, int cap_per_frame, int* counts) {
+    PoseSpec ps;
+    return detect_impl(h, frames, on_device, 3, B, W, H, stride, cuda_stream, ps, out, nullptr, cap_per_frame, counts);
+}
+
+int agpu_detect_pose(agpu_handle* h, const uint8_t* frames, int on_device, int channels, int B, int W, int H, int stride,
+                     void* cuda_stream, const double K[9], const double* dist, int ndist, double tag_size,
+                     agpu_detection* out, agpu_pose_t* poses, int cap_per_frame, int* counts) {
+    if (!h) return AGPU_E_INVALID;
+    if (!K || !poses) {
+        h->set_err("agpu_detect_pose: NULL K or poses");
+        return AGPU_E_INVALID;
+    }
+    PoseSpec ps;
+    ps.enabled = true;
+    for (int i = 0; i < 9; i++) ps.K[i] = K[i];
+    ps.tag_size = tag_size;
+    int rc = parse_dist(h, dist, ndist, ps);
+    if (rc) return rc;
+    return detect_impl(h, frames, on_device, channels, B, W, H, stride, cuda_stream, ps, out, poses, cap_per_frame, counts);
+}
+
+int agpu_pose(agpu_handle* h, const double* corners, int M, const double K[9], const double* dist, int ndist,
+              double tag_size, int method, agpu_pose_t* poses) {
+    if (!h) return AGPU_E_INVALID;
+    if (!corners || !K || !poses || M < 0 || (method != 0 && method != 1)) {
+        h->set_err("agpu_pose: invalid argument");
+        return AGPU_E_INVALID;
+    }
+    if (M == 0) return AGPU_OK;
+    CK(cudaSetDevice(h->device));
+    h->launches = 0;
+    PoseSpec ps;
+    ps.enabled = true;
+    for (int i = 0; i < 9; i++) ps.K[i] = K[i];
+    ps.tag_size = tag_size;
+    int rc = parse_dist(h, dist, ndist, ps);
+    if (rc) return rc;
+    CK(h->d_pose_in.ensure((size_t)M * 64));
+    CK(h->d_poses.ensure((size_t)M * sizeof(PoseRec)));
+    CK(cudaMemcpyAsync(h->d_pose_in.p, corners, (size_t)M * 64, cudaMemcpyHostToDevice, h->stream));
+    PoseArgs pa;
+    fill_pose_args(pa, ps, method);
+    pa.corners = h->d_pose_in.as<double>();
+    pa.corner_stride = 8;
+    pa.counts = nullptr;
+    pa.per_frame = 0;
+    pa.M = M;
+    pa.out = h->d_poses.as<PoseRec>();
+    k_pose<<<ceil_div((long long)M * 4, 128), 128, 0, h->stream>>>(pa);
+    LAUNCH_CHECK("k_pose");
+    CK(cudaMemcpyAsync(poses, h->d_poses.p, (size_t)M * sizeof(PoseRec), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AGPU_OK;
+}
+
+int agpu_set_profiling(agpu_handle* h, int on) {
+    if (!h) return AGPU_E_INVALID;
+    h->profiling = on != 0;
+    if (h->profiling) {
+        cudaSetDevice(h->device);
+        while (h->events.size() < AGPU_NUM_STAGES + 1) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return AGPU_E_CUDA;
+            h->events.push_back(e);
+        }
+    }
+    return AGPU_OK;
+}
+
+int agpu_get_stage_ms(agpu_handle* h, float* ms) {
+    if (!h || !ms) return AGPU_E_INVALID;
+    for (int i = 0; i < AGPU_NUM_STAGES; i++) ms[i] = h->stage_ms[i];
+    return AGPU_OK;
+}
+
+int agpu_get_launch_count(agpu_handle* h, long long* launches) {
+    if (!h || !launches) return AGPU_E_INVALID;
+    *launches = h->launches;
+    return AGPU_OK;
+}
+
+int agpu_get_counters(agpu_handle* h, long long* counters) {
+    if (!h || !counters) return AGPU_E_INVALID;
+    for (int i = 0; i < 8; i++) counters[i] = h->counters[i];
+    return AGPU_OK;
+}
+
+int agpu_debug_dims(agpu_handle* h, int* wd, int* hd) {
+    if (!h || !h->have_last) return AGPU_E_INVALID;
+    if (wd) *wd = h->geom.wd;
+    if (hd) *hd = h->geom.hd;
+    return AGPU_OK;
+}
+
+long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* host_out, long long cap_bytes) {
+    if (!h || !what || !host_out) return AGPU_E_INVALID;
+    if (!h->have_last || !h->cfg.debug || frame < 0 || frame >= h->last_chunk) {
+        h->set_err("agpu_debug_fetch: no debug state (cfg.debug = 1 and a previous agpu_detect are required)");
+        return AGPU_E_INVALID;
+    }
+    cudaSetDevice(h->device);
+    const Geom& g = h->geom;
+    const std::string w = what;
+    const size_t npx = (size_t)g.wd * g.hd;
+    auto unpitch = [&](uint32_t id) { return (uint32_t)((id / g.wp) * g.wd + (id % g.wp)); };
+    auto unpitch_key = [&](unsigned long long k) {
+        return ((unsigned long long)unpitch((uint32_t)(k >> 32)) << 32) | unpitch((uint32_t)k);
+    };
+    if (w == "quad_im" || w == "thresh") {
+        const uint8_t* src = (w == "thresh") ? h->d_thresh.as<uint8_t>() : h->d_quad_im.as<uint8_t>();
+        if (!src) { h->set_err("agpu_debug_fetch: buffer not materialised (decimate = 1 keeps no quad_im copy)"); return AGPU_E_INVALID; }
+        if ((size_t)cap_bytes < npx) return (long long)npx;
+        if (cudaMemcpy2D(host_out, g.wd, src + (size_t)frame * g.plane, g.wp, g.wd, g.hd, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return AGPU_E_CUDA;
+        return (long long)npx;
+    }
+    if (w == "labels" || w == "sizes") {
+        if ((size_t)cap_bytes < npx * 4) return (long long)npx;
+        std::vector<uint32_t> tmp(g.plane), lab;
+        const uint32_t* src = (w == "labels" ? h->d_labels.as<uint32_t>() : h->d_sizes.as<uint32_t>()) + (size_t)frame * g.plane;
+        if (cudaMemcpy(tmp.data(), src, g.plane * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
+        uint32_t* o = (uint32_t*)host_out;
+        if (w == "labels") {
+            for (int y = 0; y < g.hd; y++)
+                for (int x = 0; x < g.wd; x++) o[(size_t)y * g.wd + x] = unpitch(tmp[(size_t)y * g.wp + x]);
+        } else {
+            lab.resize(g.plane);
+            std::vector<uint8_t> th(g.plane);
+            cudaMemcpy(lab.data(), h->d_labels.as<uint32_t>() + (size_t)frame * g.plane, g.plane * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(th.data(), h->d_thresh.as<uint8_t>() + (size_t)frame * g.plane, g.plane, cudaMemcpyDeviceToHost);
+            for (int y = 0; y < g.hd; y++)
+                for (int x = 0; x < g.wd; x++) {
+                    size_t id = (size_t)y * g.wp + x;
+                    // sizes are defined at representatives; 127-pixels are singletons that the device never counts
+                    uint32_t v = 0;
+                    if (lab[id] == id) v = (th[id] == 127) ? 1u : tmp[id];
+                    o[(size_t)y * g.wd + x] = v;
+                }
+        }
+        return (long long)npx;
+    }
+    if (w == "cluster_keys" || w == "cluster_sizes") {
+        std::vector<int> cnt(CNT_FIXED);
+        if (cudaMemcpy(cnt.data(), h->d_counters.p, CNT_FIXED * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
+        int nh = std::min<long long>(cnt[CNT_HEADS], (long long)(h->d_dbg_heads.bytes / sizeof(ClusterRef)));
+        std::vector<ClusterRef> heads(nh);
+        if (nh) cudaMemcpy(heads.data(), h->d_dbg_heads.p, (size_t)nh * sizeof(ClusterRef), cudaMemcpyDeviceToHost);
+        std::vector<unsigned long long> keys((size_t)h->last_cap);
+        cudaMemcpy(keys.data(), h->d_keys[h->last_sorted].as<unsigned long long>() + (size_t)frame * h->last_cap,
+                   (size_t)h->last_cap * 8, cudaMemcpyDeviceToHost);
+        std::vector<std::pair<unsigned long long, int>> v;
+        for (const ClusterRef& r : heads)
+            if (r.frame == frame) v.push_back({unpitch_key(keys[r.start]), r.size});
+        std::sort(v.begin(), v.end());
+        long long n = (long long)v.size();
+        if (w == "cluster_keys") {
+            if (cap_bytes >= n * 8) for (long long i = 0; i < n; i++) ((unsigned long long*)host_out)[i] = v[i].first;
+        } else {
+            if (cap_bytes >= n * 4) for (long long i = 0; i < n; i++) ((int*)host_out)[i] = v[i].second;
+        }
+        return n;
+    }
+    if (w == "quads" || w == "quad_keys" || w == "quads_refined") {
+        std::vector<int> cnt(CNT_FIXED);
+        if (cudaMemcpy(cnt.data(), h->d_counters.p, CNT_FIXED * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
+        int nq = std::min<long long>(cnt[CNT_NQUADS], (long long)(h->d_quads.bytes / sizeof(QuadRec)));
+        std::vector<QuadRec> q(nq);
+        std::vector<float> ref((size_t)nq * 8);
+        if (nq) {
+            cudaMemcpy(q.data(), h->d_quads.p, (size_t)nq * sizeof(QuadRec), cudaMemcpyDeviceToHost);
+            cudaMemcpy(ref.data(), h->d_refined.p, (size_t)nq * 32, cudaMemcpyDeviceToHost);
+        }
+        std::vector<int> idx;
+        for (int i = 0; i < nq; i++)
+            if (q[i].frame == frame) idx.push_back(i);
+        std::sort(idx.begin(), idx.end(), [&](int a, int b) { return unpitch_key(q[a].key) < unpitch_key(q[b].key); });
+        long long n = (long long)idx.size();
+        if (w == "quads") {
+            if (cap_bytes >= n * 36)
+                for (long long i = 0; i < n; i++) {
+                    float* o = (float*)host_out + i * 9;
+                    memcpy(o, q[idx[i]].p, 32);
+                    o[8] = (float)q[idx[i]].reversed_border;
+                }
+        } else if (w == "quads_refined") {
+            if (cap_bytes >= n * 32)
+                for (long long i = 0; i < n; i++) memcpy((float*)host_out + i * 8, &ref[(size_t)idx[i] * 8], 32);
+        } else {
+            if (cap_bytes >= n * 8)
+                for (long long i = 0; i < n; i++) ((unsigned long long*)host_out)[i] = unpitch_key(q[idx[i]].key);
+        }
+        return n;
+    }
+    h->set_err("agpu_debug_fetch: unknown buffer name");
+    return AGPU_E_INVALID;
+}
+
+int agpu_stage_threshold(agpu_handle* h, const uint8_t* im, int W, int H, uint8_t* quad_im_out, uint8_t* thresh_out) {
+    if (!h || !im || !thresh_out || W <= 0 || H <= 0) return AGPU_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const Geom g = make_geom(W, H, h->prm.decim);
+    CK(h->d_in.ensure((size_t)W * H));
+    CK(cudaMemcpyAsync(h->d_in.p, im, (size_t)W * H, cudaMemcpyHostToDevice, h->stream));
+    const uint8_t *quad_im, *gray_full;
+    size_t q_pitch, q_frame, gp, gf;
+    int rc = run_image_stage(h, h->d_in.as<uint8_t>(), 1, W, H, W, (size_t)W * H, 1, g, &quad_im, &q_pitch, &q_frame,
+                             &gray_full, &gp, &gf);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(thresh_out, g.wd, h->d_thresh.p, g.wp, g.wd, g.hd, cudaMemcpyDeviceToHost, h->stream));
+    if (quad_im_out)
+        CK(cudaMemcpy2DAsync(quad_im_out, g.wd, quad_im, q_pitch, g.wd, g.hd, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AGPU_OK;
+}
+
+int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint32_t* labels_out, uint32_t* sizes_out) {
+    if (!h || !thresh || !labels_out || W <= 0 || H <= 0) return AGPU_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const Geom g = make_geom(W, H, 1);
+    CK(h->d_thresh.ensure(g.plane));
+    CK(cudaMemsetAsync(h->d_thresh.p, 127, g.plane, h->stream));
+    CK(cudaMemcpy2DAsync(h->d_thresh.p, g.wp, thresh, W, W, H, cudaMemcpyHostToDevice, h->stream));
+    int rc = run_cc_stage(h, h->d_thresh.as<uint8_t>(), 1, g);
+    if (rc) return rc;
+    std::vector<uint32_t> lab(g.plane), sz(g.plane);
+    CK(cudaMemcpyAsync(lab.data(), h->d_labels.p, g.plane * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sz.data(), h->d_sizes.p, g.plane * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            size_t id = (size_t)y * g.wp + x;
+            uint32_t l = lab[id];
+            labels_out[(size_t)y * W + x] = (l / g.wp) * W + (l % g.wp);
+            if (sizes_out) {
+                uint32_t v = 0;
+                if (l == id) v = (thresh[(size_t)y * W + x] == 127) ? 1u : sz[id];
+                sizes_out[(size_t)y * W + x] = v;
+            }
+        }
+    return AGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,253 @@
+// k_cluster.cuh -- gradient-edge clusters (upstream stage U5; part of the native call
+// at /root/reference/src/detection/tag_detector.py:26).
+//
+//   k_edges          one thread per pixel: emits up to four edge points keyed by the unordered pair
+//                    of component representatives, (max(rep0,rep1) << 32) | min(rep0,rep1); points go
+//                    to the frame's own segment of the point list (warp-aggregated atomics).
+//   k_sort_hist / k_sort_scan / k_sort_scatter
+//                    hand-written SEGMENTED least-significant-digit radix sort (8-bit digits, stable):
+//                    every frame's segment is sorted independently, grid = (blocks, frames).
+//   k_cluster_heads  run heads of equal keys -> cluster work lists (binary search for the run end).
+#pragma once
+#include "common.cuh"
+
+__global__ void __launch_bounds__(256)
+k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes,
+        Geom g, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ npts, int cap) {
+    const int frame = blockIdx.z;
+    const uint8_t* ft = thresh + (size_t)frame * g.plane;
+    const uint32_t* fl = labels + (size_t)frame * g.plane;
+    const uint32_t* fs = sizes + (size_t)frame * g.plane;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+
+    int cnt = 0;
+    unsigned long long k[4];
+    uint32_t v[4];
+    if (x >= 1 && x <= g.wd - 2 && y <= g.hd - 2) {
+        const size_t id = (size_t)y * g.wp + x;
+        const int v0 = ft[id];
+        if (v0 != 127) {
+            const int dxs[4] = {1, 0, -1, 1}, dys[4] = {0, 1, 1, 1};
+            uint32_t rep0 = 0;
+            bool have0 = false, ok0 = false;
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                const size_t id1 = id + (size_t)dys[d] * g.wp + dxs[d];
+                const int v1 = ft[id1];
+                if (v0 + v1 != 255) continue;
+                if (!have0) {
+                    rep0 = fl[id];
+                    ok0 = fs[rep0] >= 25u;
+                    have0 = true;
+                }
+                if (!ok0) break;
+                const uint32_t rep1 = fl[id1];
+                if (fs[rep1] < 25u) continue;
+                const uint32_t hi = max(rep0, rep1), lo = min(rep0, rep1);
+                k[cnt] = ((unsigned long long)hi << 32) | lo;
+                v[cnt] = pack_point(2 * x + dxs[d], 2 * y + dys[d], d, v1 > v0);
+                cnt++;
+            }
+        }
+    }
+    // warp-aggregated append
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int n = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= off) incl += n;
+    }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(&npts[frame], total);
+    base = __shfl_sync(FULL_MASK, base, 31);
+    int pos = base + incl - cnt;
+    unsigned long long* fk = keys + (size_t)frame * cap;
+    uint32_t* fv = vals + (size_t)frame * cap;
+    for (int i = 0; i < cnt; i++, pos++)
+        if (pos < cap) {
+            fk[pos] = k[i];
+            fv[pos] = v[i];
+        }
+}
+
+// ---- segmented LSD radix sort ---------------------------------------------------------------
+#define RS_THREADS 256
+#define RS_ITEMS 8
+#define RS_TILE (RS_THREADS * RS_ITEMS)  // 2048 keys per block
+#define RS_RADIX 256
+
+// hist[frame][digit * nblk_f + block]  (nblk_f = ceil(n_f / RS_TILE); frame stride = RS_RADIX * nblk_max)
+__global__ void __launch_bounds__(RS_THREADS)
+k_sort_hist(const unsigned long long* __restrict__ keys, const int* __restrict__ npts, int cap, int shift,
+            uint32_t* __restrict__ hist, int nblk_max) {
+    __shared__ uint32_t h[RS_RADIX];
+    const int frame = blockIdx.y, b = blockIdx.x;
+    const int n = min(npts[frame], cap);
+    const int nblk = (n + RS_TILE - 1) / RS_TILE;
+    if (b >= nblk) return;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long* fk = keys + (size_t)frame * cap;
+    const int base = b * RS_TILE;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i = base + (threadIdx.x >> 5) * (32 * RS_ITEMS) + r * 32 + (threadIdx.x & 31);
+        if (i < n) atomicAdd(&h[(uint32_t)(fk[i] >> shift) & (RS_RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)frame * RS_RADIX * nblk_max + (size_t)threadIdx.x * nblk + b] = h[threadIdx.x];
+}
+
+// exclusive scan of a frame's RS_RADIX*nblk_f counters (digit-major), one CTA per frame
+__global__ void __launch_bounds__(1024)
+k_sort_scan(const int* __restrict__ npts, int cap, uint32_t* __restrict__ hist, int nblk_max) {
+    __shared__ uint32_t warp_tot[32];
+    const int frame = blockIdx.x;
+    const int n = min(npts[frame], cap);
+    const int nblk = (n + RS_TILE - 1) / RS_TILE;
+    const int E = RS_RADIX * nblk;
+    if (E == 0) return;
+    uint32_t* fh = hist + (size_t)frame * RS_RADIX * nblk_max;
+    const int chunk = (E + 1023) / 1024;
+    const int lo = threadIdx.x * chunk, hi = min(lo + chunk, E);
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; i++) sum += fh[i];
+    // block exclusive scan of `sum`
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t u = __shfl_up_sync(FULL_MASK, ti, off);
+            if (lane >= off) ti += u;
+        }
+        warp_tot[lane] = ti - t;
+    }
+    __syncthreads();
+    uint32_t run = warp_tot[w] + incl - sum;
+    for (int i = lo; i < hi; i++) {
+        uint32_t c = fh[i];
+        fh[i] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+               unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+               const int* __restrict__ npts, int cap, int shift, const uint32_t* __restrict__ hist, int nblk_max) {
+    __shared__ uint32_t wcnt[RS_THREADS / 32][RS_RADIX];
+    const int frame = blockIdx.y, b = blockIdx.x;
+    const int n = min(npts[frame], cap);
+    const int nblk = (n + RS_TILE - 1) / RS_TILE;
+    if (b >= nblk) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (RS_THREADS / 32) * RS_RADIX; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    const size_t seg = (size_t)frame * cap;
+    const int base = b * RS_TILE + w * (32 * RS_ITEMS);
+    unsigned long long key[RS_ITEMS];
+    uint32_t val[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const int i = base + r * 32 + lane;
+        const bool valid = i < n;
+        key[r] = valid ? keys_in[seg + i] : 0xffffffffffffffffull;
+        val[r] = valid ? vals_in[seg + i] : 0u;
+        const uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & (RS_RADIX - 1)) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(FULL_MASK, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t before = 0;
+        if (valid && lane == leader) {
+            before = wcnt[w][d];
+            wcnt[w][d] = before + __popc(peers);
+        }
+        before = __shfl_sync(FULL_MASK, before, leader);
+        rank[r] = before + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit d = threadIdx.x: turn per-warp counts into global start offsets
+        const uint32_t d = threadIdx.x;
+        uint32_t run = hist[(size_t)frame * RS_RADIX * nblk_max + (size_t)d * nblk + b];
+#pragma unroll
+        for (int ww = 0; ww < RS_THREADS / 32; ww++) {
+            uint32_t c = wcnt[ww][d];
+            wcnt[ww][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const int i = base + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (uint32_t)(key[r] >> shift) & (RS_RADIX - 1);
+            const uint32_t pos = wcnt[w][d] + rank[r];
+            keys_out[seg + pos] = key[r];
+            vals_out[seg + pos] = val[r];
+        }
+    }
+}
+
+// cluster work lists, by size tier (the tier decides how much shared memory the fitting warp gets)
+struct ClusterLists {
+    ClusterRef* small_list;
+    ClusterRef* mid_list;
+    ClusterRef* large_list;
+    int* counters;   // [0] small, [1] large, [2] oversize (skipped), [3] all heads (debug), [4] mid
+    int cap_list;
+    ClusterRef* dbg_heads;  // all run heads (debug only, may be null)
+    int cap_dbg;
+};
+
+__global__ void __launch_bounds__(256)
+k_cluster_heads(const unsigned long long* __restrict__ keys, const int* __restrict__ npts, int cap, Geom g,
+                int min_size, int cap0, int cap1, int cap2, ClusterLists cl) {
+    const int frame = blockIdx.y;
+    const int n = min(npts[frame], cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long* fk = keys + (size_t)frame * cap;
+    const unsigned long long k = fk[i];
+    if (i > 0 && fk[i - 1] == k) return;
+    int lo = i + 1, hi = n;  // first index in (i, n] whose key differs
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (fk[mid] == k) lo = mid + 1; else hi = mid;
+    }
+    const int size = lo - i;
+    ClusterRef ref;
+    ref.frame = frame; ref.start = i; ref.size = size; ref.pad = 0;
+    if (cl.dbg_heads) {
+        int s = atomicAdd(&cl.counters[3], 1);
+        if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
+    }
+    const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);
+    if (size < min_size || size > max_cluster) return;
+    if (size <= cap0) {
+        int s = atomicAdd(&cl.counters[0], 1);
+        if (s < cl.cap_list) cl.small_list[s] = ref;
+    } else if (size <= cap1) {
+        int s = atomicAdd(&cl.counters[4], 1);
+        if (s < cl.cap_list) cl.mid_list[s] = ref;
+    } else if (size <= cap2) {
+        int s = atomicAdd(&cl.counters[1], 1);
+        if (s < cl.cap_list) cl.large_list[s] = ref;
+    } else {
+        atomicAdd(&cl.counters[2], 1);
+    }
+}

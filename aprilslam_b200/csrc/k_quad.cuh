@@ -1,0 +1,453 @@
+// k_quad.cuh -- quad fitting, one warp per cluster (upstream stage U6 fit_quad /
+// quad_segment_maxima / fit_line; part of the native call at
+// /root/reference/src/detection/tag_detector.py:26).
+//
+// Per cluster: bounding box + border polarity (exact integer sums) -> slope keys -> bitonic sort in
+// shared memory on (slope, y, x) -> de-duplication -> prefix line-fit moments (warp scans, stored in
+// an L2-resident scratch) -> windowed line-fit error, 7-tap smoothing, local maxima, top-10 selection
+// -> exhaustive 4-corner search over a pre-computed table of pairwise line fits -> corners + gates.
+#pragma once
+#include "common.cuh"
+
+struct QuadFitArgs {
+    const uint32_t* vals;       // sorted packed points, per-frame segments of `cap`
+    const unsigned long long* keys;
+    int cap;
+    const uint8_t* quad_im;     // decimated gray image (may alias the source frames)
+    size_t q_pitch, q_frame;    // bytes per row / per frame of quad_im
+    Geom g;
+    double* lfps;               // [nframes*cap][6] prefix moments
+    double* errs;               // [nframes*cap]   smoothed line-fit errors
+    const ClusterRef* list;
+    const int* list_count;
+    int list_cap;
+    QuadRec* quads;
+    int* nquads;
+    int cap_quads;              // per chunk
+    int* per_frame_quads;       // [nframes] count per frame (limit check / debug)
+};
+
+struct LineFit {
+    double Ex, Ey, nx, ny, err, mse;
+};
+
+__device__ __forceinline__ void ld_lfp(const double* lf, int i, double (&m)[6]) {
+    const double2* p = reinterpret_cast<const double2*>(lf + (size_t)i * 6);
+    double2 a = __ldcg(p), b = __ldcg(p + 1), c = __ldcg(p + 2);
+    m[0] = a.x; m[1] = a.y; m[2] = b.x; m[3] = b.y; m[4] = c.x; m[5] = c.y;
+}
+
+// same arithmetic as the oracle's fit_line (apriltag_oracle.cpp), moments by prefix differences
+__device__ void fit_line_dev(const double* lf, int sz, int i0, int i1, LineFit& out, bool want_params) {
+    double M[6], T[6];
+    int N;
+    if (i0 < i1) {
+        N = i1 - i0 + 1;
+        ld_lfp(lf, i1, M);
+        if (i0 > 0) {
+            ld_lfp(lf, i0 - 1, T);
+#pragma unroll
+            for (int k = 0; k < 6; k++) M[k] -= T[k];
+        }
+    } else {
+        double A[6];
+        ld_lfp(lf, sz - 1, A);
+        ld_lfp(lf, i0 - 1, T);
+        ld_lfp(lf, i1, M);
+#pragma unroll
+        for (int k = 0; k < 6; k++) M[k] = (A[k] - T[k]) + M[k];
+        N = sz - i0 + i1 + 1;
+    }
+    const double Mx = M[0], My = M[1], Mxx = M[2], Mxy = M[3], Myy = M[4], W = M[5];
+    double Ex = Mx / W, Ey = My / W;
+    double Cxx = Mxx / W - Ex * Ex;
+    double Cxy = Mxy / W - Ex * Ey;
+    double Cyy = Myy / W - Ey * Ey;
+    float disc = sqrtf((float)((Cxx - Cyy) * (Cxx - Cyy) + 4 * Cxy * Cxy));
+    double eig_small = 0.5 * (Cxx + Cyy - disc);
+    if (want_params) {
+        out.Ex = Ex;
+        out.Ey = Ey;
+        double eig = 0.5 * (Cxx + Cyy + disc);
+        double nx1 = Cxx - eig, ny1 = Cxy, M1 = nx1 * nx1 + ny1 * ny1;
+        double nx2 = Cxy, ny2 = Cyy - eig, M2 = nx2 * nx2 + ny2 * ny2;
+        double nx, ny, MM;
+        if (M1 > M2) { nx = nx1; ny = ny1; MM = M1; } else { nx = nx2; ny = ny2; MM = M2; }
+        double length = sqrtf((float)MM);
+        if (fabs(length) < 1e-12) { out.nx = 0; out.ny = 0; }
+        else { out.nx = nx / length; out.ny = ny / length; }
+    }
+    out.err = N * eig_small;
+    out.mse = eig_small;
+}
+
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long* s, int n2, bool descending) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < n2; i += 32) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = s[i], b = s[ixj];
+                    bool up = ((i & k) == 0) != descending;
+                    if ((a > b) == up) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+#define QF_PTAB_DOUBLES (100 * 6)
+
+// Returns true and fills q when the cluster yields a quad.
+__device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const ClusterRef ref,
+                                 unsigned long long* sbuf, double* ptab, int* sidx, QuadRec& q) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const size_t seg = (size_t)ref.frame * a.cap + ref.start;
+    const uint32_t* pv = a.vals + seg;
+    int sz = ref.size;
+
+    // ---- bounding box and polarity sums
+    int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
+    long long Sxgx = 0, Sygy = 0;
+    int Sgx = 0, Sgy = 0;
+    for (int i = lane; i < sz; i += 32) {
+        uint32_t v = pv[i];
+        int px = v & 0x3fff, py = (v >> 14) & 0x3fff, dir = (v >> 28) & 3;
+        int s = ((v >> 30) & 1) ? 255 : -255;
+        int dx = (dir == 0 || dir == 3) ? 1 : (dir == 2 ? -1 : 0);
+        int dy = dir == 0 ? 0 : 1;
+        int gx = dx * s, gy = dy * s;
+        xmin = min(xmin, px); xmax = max(xmax, px);
+        ymin = min(ymin, py); ymax = max(ymax, py);
+        Sxgx += (long long)px * gx; Sgx += gx;
+        Sygy += (long long)py * gy; Sgy += gy;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(FULL_MASK, xmin, off));
+        xmax = max(xmax, __shfl_xor_sync(FULL_MASK, xmax, off));
+        ymin = min(ymin, __shfl_xor_sync(FULL_MASK, ymin, off));
+        ymax = max(ymax, __shfl_xor_sync(FULL_MASK, ymax, off));
+        Sxgx += __shfl_xor_sync(FULL_MASK, Sxgx, off);
+        Sygy += __shfl_xor_sync(FULL_MASK, Sygy, off);
+        Sgx += __shfl_xor_sync(FULL_MASK, Sgx, off);
+        Sgy += __shfl_xor_sync(FULL_MASK, Sgy, off);
+    }
+    if ((xmax - xmin) * (ymax - ymin) < P.min_tag_width) return false;
+    const float cx = (xmin + xmax) * 0.5f + 0.05118f;
+    const float cy = (ymin + ymax) * 0.5f - 0.028581f;
+    const double dot = ((double)Sxgx - (double)cx * (double)Sgx) + ((double)Sygy - (double)cy * (double)Sgy);
+    const int reversed = dot < 0;
+    if (!P.reversed_border && reversed) return false;
+    if (!P.normal_border && !reversed) return false;
+
+    // ---- slope keys
+    int n2 = 32;
+    while (n2 < sz) n2 <<= 1;
+    for (int i = lane; i < n2; i += 32) {
+        unsigned long long key = ~0ull;
+        if (i < sz) {
+            uint32_t v = pv[i];
+            int px = v & 0x3fff, py = (v >> 14) & 0x3fff;
+            float dx = (float)px - cx, dy = (float)py - cy;
+            float qd;
+            if (dy > 0) qd = (dx > 0) ? 65536.0f : 131072.0f;
+            else qd = (dx > 0) ? 0.0f : -65536.0f;
+            if (dy < 0) { dy = -dy; dx = -dx; }
+            if (dx < 0) { float t = dx; dx = dy; dy = -t; }
+            float slope = qd + dy / dx;
+            key = ((unsigned long long)float_orderable(slope) << 32) | (uint32_t)((py << 16) | px);
+        }
+        sbuf[i] = key;
+    }
+    __syncwarp();
+    warp_bitonic_sort(sbuf, n2, false);
+
+    // ---- remove consecutive duplicates (same x, y)
+    {
+        int outn = 0;
+        uint32_t prev_xy = 0xffffffffu;
+        for (int base = 0; base < sz; base += 32) {
+            int i = base + lane;
+            unsigned long long kk = i < sz ? sbuf[i] : 0ull;
+            uint32_t xy = (uint32_t)kk;
+            uint32_t pxy = __shfl_up_sync(FULL_MASK, xy, 1);
+            if (lane == 0) pxy = prev_xy;
+            bool keep = i < sz && xy != pxy;
+            uint32_t m = __ballot_sync(FULL_MASK, keep);
+            prev_xy = __shfl_sync(FULL_MASK, xy, 31);
+            __syncwarp();
+            if (keep) sbuf[outn + __popc(m & lt_mask)] = kk;
+            outn += __popc(m);
+            __syncwarp();
+        }
+        sz = outn;
+    }
+    if (sz < 24) return false;
+
+    // ---- prefix moments (inclusive), written to the scratch at the cluster's own offset
+    double* lf = a.lfps + seg * 6;
+    {
+        const uint8_t* im = a.quad_im + (size_t)ref.frame * a.q_frame;
+        double carry[6] = {0, 0, 0, 0, 0, 0};
+        for (int base = 0; base < sz; base += 32) {
+            int i = base + lane;
+            double t[6] = {0, 0, 0, 0, 0, 0};
+            if (i < sz) {
+                uint32_t xy = (uint32_t)sbuf[i];
+                int px = xy & 0xffff, py = xy >> 16;
+                double x = px * .5 + 0.5, y = py * .5 + 0.5;
+                int ix = (int)x, iy = (int)y;
+                double W = 1;
+                if (ix > 0 && ix + 1 < a.g.wd && iy > 0 && iy + 1 < a.g.hd) {
+                    int grad_x = (int)im[(size_t)iy * a.q_pitch + ix + 1] - (int)im[(size_t)iy * a.q_pitch + ix - 1];
+                    int grad_y = (int)im[(size_t)(iy + 1) * a.q_pitch + ix] - (int)im[(size_t)(iy - 1) * a.q_pitch + ix];
+                    W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
+                }
+                t[0] = W * x;
+                t[1] = W * y;
+                t[2] = W * x * x;
+                t[3] = W * x * y;
+                t[4] = W * y * y;
+                t[5] = W;
+            }
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    double n = __shfl_up_sync(FULL_MASK, t[k], off);
+                    if (lane >= off) t[k] += n;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) t[k] = carry[k] + t[k];
+            if (i < sz) {
+                double2* p = reinterpret_cast<double2*>(lf + (size_t)i * 6);
+                __stcg(p, make_double2(t[0], t[1]));
+                __stcg(p + 1, make_double2(t[2], t[3]));
+                __stcg(p + 2, make_double2(t[4], t[5]));
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) carry[k] = __shfl_sync(FULL_MASK, t[k], 31);
+        }
+    }
+    __syncwarp();
+
+    // ---- windowed line-fit error -> sbuf (as doubles), smoothed -> scratch
+    const int ksz = min(20, sz / 12);
+    if (ksz < 2) return false;
+    double* sraw = reinterpret_cast<double*>(sbuf);
+    for (int i = lane; i < sz; i += 32) {
+        LineFit f;
+        fit_line_dev(lf, sz, (i + sz - ksz) % sz, (i + ksz) % sz, f, false);
+        sraw[i] = f.err;
+    }
+    __syncwarp();
+    double* es = a.errs + seg;
+    for (int i = lane; i < sz; i += 32) {
+        double acc = 0;
+#pragma unroll
+        for (int j = 0; j < 7; j++) acc += sraw[(i + j - 3 + sz) % sz] * P.smooth_f[j];
+        __stcg(es + i, acc);
+    }
+    __syncwarp();
+
+    // ---- local maxima, in index order
+    const int half = n2 >> 1;
+    unsigned long long* mvals = sbuf;                       // [half]
+    int* midx = reinterpret_cast<int*>(sbuf + half);        // [<= half]
+    int nmax = 0;
+    for (int base = 0; base < sz; base += 32) {
+        int i = base + lane;
+        bool ismax = false;
+        double e = 0;
+        if (i < sz) {
+            e = __ldcg(es + i);
+            double en = __ldcg(es + (i + 1) % sz), ep = __ldcg(es + (i + sz - 1) % sz);
+            ismax = e > en && e > ep;
+        }
+        uint32_t m = __ballot_sync(FULL_MASK, ismax);
+        if (ismax) {
+            int pos = nmax + __popc(m & lt_mask);
+            midx[pos] = i;
+            mvals[pos] = double_orderable(e);
+        }
+        nmax += __popc(m);
+    }
+    __syncwarp();
+    if (nmax < 4) return false;
+    if (nmax > P.max_nmaxima) {
+        int p2 = 32;
+        while (p2 < nmax) p2 <<= 1;
+        for (int i = nmax + lane; i < p2; i += 32) mvals[i] = 0ull;
+        __syncwarp();
+        warp_bitonic_sort(mvals, p2, true);
+        const unsigned long long thr = mvals[P.max_nmaxima];
+        __syncwarp();
+        int outn = 0;
+        for (int base = 0; base < nmax; base += 32) {
+            int i = base + lane;
+            int id = 0;
+            bool keep = false;
+            if (i < nmax) {
+                id = midx[i];
+                keep = double_orderable(__ldcg(es + id)) > thr;
+            }
+            uint32_t m = __ballot_sync(FULL_MASK, keep);
+            __syncwarp();
+            if (keep) midx[outn + __popc(m & lt_mask)] = id;
+            outn += __popc(m);
+            __syncwarp();
+        }
+        nmax = outn;
+        if (nmax < 4) return false;   // (ties at the threshold can drop below 4: no 4-subset exists)
+    }
+    if (lane < nmax) sidx[lane] = midx[lane];
+    __syncwarp();
+
+    // ---- table of pairwise line fits between maxima
+    for (int t = lane; t < nmax * nmax; t += 32) {
+        int ia = t / nmax, ib = t - ia * nmax;
+        if (ia == ib) continue;
+        LineFit f;
+        fit_line_dev(lf, sz, sidx[ia], sidx[ib], f, true);
+        double* e = ptab + (ia * 10 + ib) * 6;
+        e[0] = f.Ex; e[1] = f.Ey; e[2] = f.nx; e[3] = f.ny; e[4] = f.err; e[5] = f.mse;
+    }
+    __syncwarp();
+
+    // ---- exhaustive search over 4-subsets (lexicographic order; first minimum wins)
+    double best = HUGE_VALF;
+    int best_c = 0x7fffffff, best_pack = 0;
+    {
+        const double max_mse = P.max_line_fit_mse, max_dot = P.cos_critical_rad;
+        int c = 0;
+        for (int m0 = 0; m0 < nmax - 3; m0++)
+            for (int m1 = m0 + 1; m1 < nmax - 2; m1++)
+                for (int m2 = m1 + 1; m2 < nmax - 1; m2++)
+                    for (int m3 = m2 + 1; m3 < nmax; m3++, c++) {
+                        if ((c & 31) != lane) continue;
+                        const double* e01 = ptab + (m0 * 10 + m1) * 6;
+                        const double* e12 = ptab + (m1 * 10 + m2) * 6;
+                        const double* e23 = ptab + (m2 * 10 + m3) * 6;
+                        const double* e30 = ptab + (m3 * 10 + m0) * 6;
+                        if (e01[5] > max_mse) continue;
+                        if (e12[5] > max_mse) continue;
+                        double d = e01[2] * e12[2] + e01[3] * e12[3];
+                        if (fabs(d) > max_dot) continue;
+                        if (e23[5] > max_mse) continue;
+                        if (e30[5] > max_mse) continue;
+                        double err = e01[4] + e12[4] + e23[4] + e30[4];
+                        if (err < best) {
+                            best = err;
+                            best_c = c;
+                            best_pack = m0 | (m1 << 4) | (m2 << 8) | (m3 << 12);
+                        }
+                    }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ob = __shfl_xor_sync(FULL_MASK, best, off);
+        int oc = __shfl_xor_sync(FULL_MASK, best_c, off);
+        int op = __shfl_xor_sync(FULL_MASK, best_pack, off);
+        if (ob < best || (ob == best && oc < best_c)) { best = ob; best_c = oc; best_pack = op; }
+    }
+    if (best_c == 0x7fffffff) return false;
+    if (!(best / sz < P.max_line_fit_mse)) return false;
+
+    // ---- corners and gates (every lane computes the same values)
+    int mi[4] = {best_pack & 15, (best_pack >> 4) & 15, (best_pack >> 8) & 15, (best_pack >> 12) & 15};
+    double lines[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double* e = ptab + (mi[i] * 10 + mi[(i + 1) & 3]) * 6;
+        if (e[5] > P.max_line_fit_mse) return false;
+        lines[i][0] = e[0]; lines[i][1] = e[1]; lines[i][2] = e[2]; lines[i][3] = e[3];
+    }
+    float p[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
+        double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
+        double B0 = -lines[i][0] + lines[(i + 1) & 3][0];
+        double B1 = -lines[i][1] + lines[(i + 1) & 3][1];
+        double det = A00 * A11 - A10 * A01;
+        if (fabs(det) < 0.001) return false;
+        double W00 = A11 / det, W01 = -A01 / det;
+        double L0 = W00 * B0 + W01 * B1;
+        p[i][0] = (float)(lines[i][0] + L0 * A00);
+        p[i][1] = (float)(lines[i][1] + L0 * A10);
+    }
+    {
+        double area = 0, length[3], pp;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            int ia = i, ib = (i + 1) % 3;
+            double ddx = p[ib][0] - p[ia][0], ddy = p[ib][1] - p[ia][1];
+            length[i] = sqrt(ddx * ddx + ddy * ddy);
+        }
+        pp = (length[0] + length[1] + length[2]) / 2;
+        area += sqrt(pp * (pp - length[0]) * (pp - length[1]) * (pp - length[2]));
+        const int idxs[4] = {2, 3, 0, 2};
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            int ia = idxs[i], ib = idxs[i + 1];
+            double ddx = p[ib][0] - p[ia][0], ddy = p[ib][1] - p[ia][1];
+            length[i] = sqrt(ddx * ddx + ddy * ddy);
+        }
+        pp = (length[0] + length[1] + length[2]) / 2;
+        area += sqrt(pp * (pp - length[0]) * (pp - length[1]) * (pp - length[2]));
+        if (area < 0.95 * P.min_tag_width * P.min_tag_width) return false;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
+        double dx1 = p[i1][0] - p[i0][0], dy1 = p[i1][1] - p[i0][1];
+        double dx2 = p[i2][0] - p[i1][0], dy2 = p[i2][1] - p[i1][1];
+        double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
+        if ((cos_dtheta > P.cos_critical_rad || cos_dtheta < -P.cos_critical_rad) || dx1 * dy2 < dy1 * dx2) return false;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (P.quad_decimate > 1) {
+            q.p[i][0] = (p[i][0] - 0.5f) * P.quad_decimate + 0.5f;
+            q.p[i][1] = (p[i][1] - 0.5f) * P.quad_decimate + 0.5f;
+        } else {
+            q.p[i][0] = p[i][0];
+            q.p[i][1] = p[i][1];
+        }
+    }
+    q.frame = ref.frame;
+    q.reversed_border = reversed;
+    q.key = a.keys[seg];
+    return true;
+}
+
+// Persistent warps: warp w takes clusters w, w + nwarps, ...  Dynamic shared memory per warp:
+// wcap u64 (sort buffer) + 600 doubles (pair table) + 16 ints.
+__global__ void k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wpb = blockDim.x >> 5;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = (size_t)wcap * 8 + QF_PTAB_DOUBLES * 8 + 64;
+    unsigned char* base = smem_raw + per_warp * w;
+    unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(base);
+    double* ptab = reinterpret_cast<double*>(base + (size_t)wcap * 8);
+    int* sidx = reinterpret_cast<int*>(base + (size_t)wcap * 8 + QF_PTAB_DOUBLES * 8);
+    const int n = min(*a.list_count, a.list_cap);
+    const int nwarps = gridDim.x * wpb;
+    for (int ci = blockIdx.x * wpb + w; ci < n; ci += nwarps) {
+        const ClusterRef ref = a.list[ci];
+        QuadRec q;
+        bool ok = fit_cluster_warp(a, P, ref, sbuf, ptab, sidx, q);
+        if (ok && lane == 0) {
+            int s = atomicAdd(a.nquads, 1);
+            atomicAdd(&a.per_frame_quads[ref.frame], 1);
+            if (s < a.cap_quads) a.quads[s] = q;
+        }
+        __syncwarp();
+    }
+}

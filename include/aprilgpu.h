@@ -1,0 +1,150 @@
+/* aprilgpu.h -- C ABI of libaprilgpu.so, the B200 (sm_100a) AprilTag detect + per-tag pose library.
+ *
+ * This is the drop-in boundary for the one hot path of mikostrzewa/AprilSLAM.  Each entry point
+ * names the reference interface it replaces (paths relative to /root/reference):
+ *
+ *   agpu_create        <-  apriltag(tag_type)                     src/detection/tag_detector.py:18
+ *                          (upstream apriltag_pywrap.c ctor kwargs: family, threads, maxhamming,
+ *                           decimate, blur, refine_edges, debug)
+ *   agpu_detect        <-  self.detector.detect(gray)             src/detection/tag_detector.py:26
+ *   agpu_detect_bgr    <-  cv2.cvtColor(image, BGR2GRAY) + detect src/detection/tag_detector.py:25-26
+ *   agpu_pose          <-  cv2.solvePnP(obj, corners, K, dist)    src/detection/tag_detector.py:41
+ *                          + cv2.Rodrigues(rvec) -> 4x4 T         src/detection/tag_detector.py:45-52
+ *   agpu_detect_pose   <-  the caller loop  detect(); for d in detections: get_pose(d)
+ *                          src/core/slam.py:21-32, src/simulation/simulation_engine.py:219-223
+ *
+ * Plain C: pointers and sizes only.  Nothing crosses this boundary as a C++ or torch type, and
+ * no exception leaves the library.  Every function returns AGPU_OK (0) or a negative agpu_status;
+ * agpu_last_error() gives the message.  There is no CPU fallback: if no CUDA device is usable,
+ * agpu_create fails with AGPU_E_CUDA.
+ *
+ * Threading: a handle is bound to one CUDA device and one internal stream set; it is not
+ * thread-safe.  Distinct handles are independent (one per GPU / per host thread).
+ */
+#ifndef APRILGPU_H
+#define APRILGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGPU_VERSION 100
+
+typedef enum agpu_status {
+    AGPU_OK = 0,
+    AGPU_E_INVALID = -1,    /* bad argument (NULL, non-positive size, unknown family, ...) */
+    AGPU_E_CUDA = -2,       /* CUDA runtime error or no device */
+    AGPU_E_TRUNCATED = -3,  /* more detections than cap_per_frame in at least one frame; counts[] hold the true numbers */
+    AGPU_E_WORKSPACE = -4,  /* an internal per-frame work list overflowed (edge points / clusters / quads); raise the agpu_config limits */
+    AGPU_E_UNSUPPORTED = -5
+} agpu_status;
+
+typedef struct agpu_handle agpu_handle;
+
+/* Constructor arguments.  The first block mirrors upstream's Python ctor exactly (defaults in
+ * parentheses are what AprilSLAM gets, because it passes only the family name). */
+typedef struct agpu_config {
+    const char* families;     /* space separated: tag36h11 tag25h9 tag16h5 tagStandard41h12 */
+    int threads;              /* (1)  accepted for API compatibility, ignored */
+    int maxhamming;           /* (1)  0..2 */
+    float quad_decimate;      /* (2.0) integer factors >= 1 */
+    float quad_sigma;         /* (0.0) "blur": >0 Gaussian blur, <0 unsharp */
+    int refine_edges;         /* (1) */
+    double decode_sharpening; /* (0.25) */
+    int debug;                /* (0)  1: keep stage buffers of the last chunk for agpu_debug_fetch */
+    /* B200 side */
+    int device;               /* CUDA device ordinal */
+    int chunk_frames;         /* frames processed per pipeline pass (0 = auto) */
+    int max_points_per_frame; /* edge-point list capacity per frame (0 = auto: decimated pixels / 4, >= 65536) */
+    int max_clusters_per_frame; /* (0 = auto) */
+    int max_quads_per_frame;  /* (0 = auto: 1024) */
+} agpu_config;
+
+/* One detection.  Field meaning follows upstream's apriltag_detection_t; the Python layer turns it
+ * into the dict the reference indexes ('id', 'lb-rb-rt-lt', ...; tag_detector.py:27,32). */
+typedef struct agpu_detection {
+    int32_t family;    /* index into the configured family list */
+    int32_t id;
+    int32_t hamming;
+    float margin;      /* decision_margin */
+    double c[2];       /* center */
+    double p[4][2];    /* corners: lb, rb, rt, lt (image y down) */
+    double H[9];       /* homography, row major: tag (+-1) -> pixels */
+} agpu_detection;
+
+/* One pose, as returned by TagDetector.get_pose (tag_detector.py:43): retval, rvec, tvec (+R of T). */
+typedef struct agpu_pose_t {
+    double rvec[3];
+    double tvec[3];
+    double R[9];       /* Rodrigues(rvec), row major: T = [R t; 0 1] (tag_detector.py:45-52) */
+    double err;        /* final RMS reprojection error in pixels */
+    int32_t ok;        /* solvePnP's retval */
+    int32_t iters;
+} agpu_pose_t;
+
+int agpu_version(void);
+void agpu_default_config(agpu_config* cfg);
+int agpu_create(const agpu_config* cfg, agpu_handle** out);
+int agpu_destroy(agpu_handle* h);
+const char* agpu_last_error(const agpu_handle* h);  /* h may be NULL: error of the last failed agpu_create */
+
+/* Detect on B gray frames of W x H, `stride` bytes between rows, frames contiguous
+ * (frame b starts at frames + b*H*stride).  on_device: 0 = host memory (copied H2D inside the
+ * call), 1 = device memory on cfg.device.  cuda_stream: a cudaStream_t the input is ready on
+ * (NULL = default stream); the call returns after results are in host memory.
+ * out: host array [B][cap_per_frame]; counts: host int[B] (true number found per frame). */
+int agpu_detect(agpu_handle* h, const uint8_t* frames, int on_device, int B, int W, int H, int stride,
+                void* cuda_stream, agpu_detection* out, int cap_per_frame, int* counts);
+
+/* Same, on interleaved BGR frames [B][H][W][3] (stride = bytes per row, >= 3*W); gray conversion
+ * is cv2.cvtColor(BGR2GRAY)'s fixed-point formula, fused into the front end. */
+int agpu_detect_bgr(agpu_handle* h, const uint8_t* frames, int on_device, int B, int W, int H, int stride,
+                    void* cuda_stream, agpu_detection* out, int cap_per_frame, int* counts);
+
+/* Detect + per-tag pose in one pass (poses[b][i] belongs to out[b][i]).
+ * K: 3x3 row major camera matrix; dist: ndist (0,4,5,8) OpenCV distortion coefficients or NULL. */
+int agpu_detect_pose(agpu_handle* h, const uint8_t* frames, int on_device, int channels, int B, int W, int H,
+                     int stride, void* cuda_stream, const double K[9], const double* dist, int ndist,
+                     double tag_size, agpu_detection* out, agpu_pose_t* poses, int cap_per_frame, int* counts);
+
+/* Pose only: M tags, corners [M][4][2] (lb, rb, rt, lt) in host memory.
+ * method 0: homography decomposition + Levenberg-Marquardt on the pixel reprojection error
+ *           (lands on cv2.solvePnP(SOLVEPNP_ITERATIVE)'s minimiser -- the reference's path);
+ * method 1: homography decomposition + orthogonal iteration (object-space error). */
+int agpu_pose(agpu_handle* h, const double* corners, int M, const double K[9], const double* dist, int ndist,
+              double tag_size, int method, agpu_pose_t* poses);
+
+/* ---- instrumentation -------------------------------------------------------------------- */
+
+enum { AGPU_STAGE_H2D = 0, AGPU_STAGE_IMAGE, AGPU_STAGE_CC, AGPU_STAGE_EDGES, AGPU_STAGE_SORT,
+       AGPU_STAGE_QUADS, AGPU_STAGE_DECODE, AGPU_STAGE_RECONCILE_POSE, AGPU_STAGE_D2H, AGPU_NUM_STAGES };
+
+/* CUDA-event timing of the stages of the last agpu_detect* call (milliseconds summed over its
+ * chunks, measured on the library's own stream).  on != 0 enables it (adds event records only). */
+int agpu_set_profiling(agpu_handle* h, int on);
+int agpu_get_stage_ms(agpu_handle* h, float* ms /* [AGPU_NUM_STAGES] */);
+/* Kernel launches issued by the last agpu_detect* / agpu_pose call. */
+int agpu_get_launch_count(agpu_handle* h, long long* launches);
+/* Work counters of the last call, summed over frames: [0] edge points, [1] clusters fitted,
+ * [2] quads, [3] detections before reconcile, [4] oversize clusters skipped. */
+int agpu_get_counters(agpu_handle* h, long long* counters /* [8] */);
+
+/* Stage dumps for parity tests (cfg.debug = 1): buffers of frame `frame` of the LAST chunk.
+ * what: "quad_im" u8[hd*wd], "thresh" u8[hd*wd], "labels" u32[hd*wd] (min-index representative),
+ * "sizes" u32[hd*wd] (valid at representatives), "cluster_keys" u64[n], "cluster_sizes" i32[n],
+ * "quads" f32[n*9] (8 corner coords + reversed flag), "quad_keys" u64[n].
+ * Returns the number of ELEMENTS available (copying at most cap_bytes), or a negative status. */
+long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* host_out, long long cap_bytes);
+int agpu_debug_dims(agpu_handle* h, int* wd, int* hd);
+
+/* Stand-alone image stages on host buffers (stage-level parity tests; each runs the same kernels
+ * the pipeline uses). */
+int agpu_stage_threshold(agpu_handle* h, const uint8_t* im, int W, int H, uint8_t* quad_im_out, uint8_t* thresh_out);
+int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint32_t* labels_out, uint32_t* sizes_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APRILGPU_H */
