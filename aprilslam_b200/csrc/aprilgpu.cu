@@ -99,6 +99,9 @@ struct agpu_handle {
     DevBuf d_clusters[3], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses, d_pose_in;
     HostBuf h_out, h_counts, h_poses, h_counters;
 
+    // growable per-frame list capacities (0 = not chosen yet)
+    int cap_points = 0, cap_clusters = 0, cap_quads = 0;
+
     // state of the last chunk (debug fetch)
     Geom geom;
     int last_chunk = 0, last_cap = 0, last_sorted = 0;
@@ -364,44 +367,55 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
         chunk = std::min(chunk, 256);
     }
     chunk = std::min(chunk, B);
-    int cap = h->cfg.max_points_per_frame;
-    if (cap <= 0) cap = (int)std::max<size_t>(65536, g.plane / 8);
+    // per-frame list capacities: user limits are hard; automatic ones grow (the chunk is re-run) on overflow
+    const bool auto_pts = h->cfg.max_points_per_frame <= 0, auto_cl = h->cfg.max_clusters_per_frame <= 0,
+               auto_q = h->cfg.max_quads_per_frame <= 0;
+    int cap = auto_pts ? std::max(h->cap_points, (int)std::max<size_t>(262144, g.plane / 4)) : h->cfg.max_points_per_frame;
     cap = (cap + RS_TILE - 1) / RS_TILE * RS_TILE;
-    int maxcl = h->cfg.max_clusters_per_frame > 0 ? h->cfg.max_clusters_per_frame : std::max(4096, cap / 24);
-    int maxq = h->cfg.max_quads_per_frame > 0 ? h->cfg.max_quads_per_frame : 1024;
-    const int nblk_max = cap / RS_TILE;
+    int maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
+    int maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
     const size_t frame_bytes = (size_t)H * stride;
-
-    // workspaces
-    if (!on_device) CK(h->d_in.ensure(frame_bytes * chunk));
-    for (int i = 0; i < 2; i++) {
-        CK(h->d_keys[i].ensure((size_t)chunk * cap * 8));
-        CK(h->d_vals[i].ensure((size_t)chunk * cap * 4));
-    }
-    CK(h->d_hist.ensure((size_t)chunk * RS_RADIX * nblk_max * 4));
-    CK(h->d_lfps.ensure((size_t)chunk * cap * 48));
-    CK(h->d_errs.ensure((size_t)chunk * cap * 8));
     const size_t ncnt = CNT_FIXED + (size_t)4 * chunk;
-    CK(h->d_counters.ensure(ncnt * 4));
-    for (int t = 0; t < 3; t++) CK(h->d_clusters[t].ensure((size_t)chunk * maxcl * sizeof(ClusterRef)));
-    if (h->cfg.debug) {
-        CK(h->d_dbg_heads.ensure((size_t)chunk * cap / 4 * sizeof(ClusterRef)));
-        CK(h->d_refined.ensure((size_t)chunk * maxq * 32));
+    int nblk_max = 0;
+    int *d_cnt = nullptr, *d_npts = nullptr, *d_frame_quads = nullptr, *d_ndets = nullptr, *d_out_counts = nullptr;
+
+    auto alloc_workspace = [&]() -> int {
+        nblk_max = cap / RS_TILE;
+        if (!on_device) CK(h->d_in.ensure(frame_bytes * chunk));
+        for (int i = 0; i < 2; i++) {
+            CK(h->d_keys[i].ensure((size_t)chunk * cap * 8));
+            CK(h->d_vals[i].ensure((size_t)chunk * cap * 4));
+        }
+        CK(h->d_hist.ensure((size_t)chunk * RS_RADIX * nblk_max * 4));
+        CK(h->d_lfps.ensure((size_t)chunk * cap * 48));
+        CK(h->d_errs.ensure((size_t)chunk * cap * 8));
+        CK(h->d_counters.ensure(ncnt * 4));
+        for (int t = 0; t < 3; t++) CK(h->d_clusters[t].ensure((size_t)chunk * maxcl * sizeof(ClusterRef)));
+        if (h->cfg.debug) {
+            CK(h->d_dbg_heads.ensure((size_t)chunk * cap / 4 * sizeof(ClusterRef)));
+            CK(h->d_refined.ensure((size_t)chunk * maxq * 32));
+        }
+        CK(h->d_quads.ensure((size_t)chunk * maxq * sizeof(QuadRec)));
+        CK(h->d_dets.ensure((size_t)chunk * REC_CAP * sizeof(DetRec)));
+        CK(h->d_out.ensure((size_t)chunk * cap_out * sizeof(DetRec)));
+        CK(h->h_out.ensure((size_t)chunk * cap_out * sizeof(DetRec)));
+        CK(h->h_counts.ensure(ncnt * 4));
+        if (pose.enabled) {
+            CK(h->d_poses.ensure((size_t)chunk * cap_out * sizeof(PoseRec)));
+            CK(h->h_poses.ensure((size_t)chunk * cap_out * sizeof(PoseRec)));
+        }
+        d_cnt = h->d_counters.as<int>();
+        d_npts = d_cnt + CNT_FIXED;
+        d_frame_quads = d_npts + chunk;
+        d_ndets = d_frame_quads + chunk;
+        d_out_counts = d_ndets + chunk;
+        h->cap_points = cap; h->cap_clusters = maxcl; h->cap_quads = maxq;
+        return AGPU_OK;
+    };
+    {
+        int rc = alloc_workspace();
+        if (rc) return rc;
     }
-    CK(h->d_quads.ensure((size_t)chunk * maxq * sizeof(QuadRec)));
-    CK(h->d_dets.ensure((size_t)chunk * REC_CAP * sizeof(DetRec)));
-    CK(h->d_out.ensure((size_t)chunk * cap_out * sizeof(DetRec)));
-    CK(h->h_out.ensure((size_t)chunk * cap_out * sizeof(DetRec)));
-    CK(h->h_counts.ensure(ncnt * 4));
-    if (pose.enabled) {
-        CK(h->d_poses.ensure((size_t)chunk * cap_out * sizeof(PoseRec)));
-        CK(h->h_poses.ensure((size_t)chunk * cap_out * sizeof(PoseRec)));
-    }
-    int* d_cnt = h->d_counters.as<int>();
-    int* d_npts = d_cnt + CNT_FIXED;
-    int* d_frame_quads = d_npts + chunk;
-    int* d_ndets = d_frame_quads + chunk;
-    int* d_out_counts = d_ndets + chunk;
 
     cudaStream_t user_stream = (cudaStream_t)cuda_stream;
     if (on_device) {
@@ -415,7 +429,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     int rc_final = AGPU_OK;
     const int key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
-    for (int b0 = 0; b0 < B; b0 += chunk) {
+    for (int b0 = 0; b0 < B;) {
         const int n = std::min(chunk, B - b0);
         StageTimer tm(h);
         tm.mark();  // 0
@@ -552,12 +566,39 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
                 h->stage_ms[s] += ms;
             }
         }
-        // gather
         const int* hc = h->h_counts.as<int>();
         const int* h_npts = hc + CNT_FIXED;
         const int* h_fq = h_npts + chunk;
         const int* h_nd = h_fq + chunk;
         const int* h_oc = h_nd + chunk;
+        (void)h_fq;
+        // overflow of a work list: grow it and run the chunk again (automatic limits), or report it
+        {
+            int max_pts = 0;
+            for (int i = 0; i < n; i++) max_pts = std::max(max_pts, h_npts[i]);
+            const int max_cl = std::max(hc[CNT_SMALL], std::max(hc[CNT_MID], hc[CNT_LARGE]));
+            bool regrow = false;
+            if (max_pts > cap) {
+                if (!auto_pts) { h->set_err("edge-point list overflow: raise agpu_config.max_points_per_frame"); return AGPU_E_WORKSPACE; }
+                cap = (max_pts + max_pts / 4 + RS_TILE - 1) / RS_TILE * RS_TILE;
+                regrow = true;
+            }
+            if (max_cl > n * maxcl) {
+                if (!auto_cl) { h->set_err("cluster list overflow: raise agpu_config.max_clusters_per_frame"); return AGPU_E_WORKSPACE; }
+                maxcl = (max_cl + n - 1) / n * 2;
+                regrow = true;
+            }
+            if (hc[CNT_NQUADS] > n * maxq) {
+                if (!auto_q) { h->set_err("quad list overflow: raise agpu_config.max_quads_per_frame"); return AGPU_E_WORKSPACE; }
+                maxq = (hc[CNT_NQUADS] + n - 1) / n * 2;
+                regrow = true;
+            }
+            if (regrow) {
+                int rc2 = alloc_workspace();
+                if (rc2) return rc2;
+                continue;  // same b0
+            }
+        }
         const DetRec* ho = h->h_out.as<DetRec>();
         for (int i = 0; i < n; i++) {
             const int c = h_oc[i];
@@ -567,13 +608,12 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
             if (pose.enabled && poses)
                 memcpy(poses + (size_t)(b0 + i) * cap_out, h->h_poses.as<PoseRec>() + (size_t)i * cap_out,
                        (size_t)m * sizeof(PoseRec));
-            if (c > cap_out && rc_final == AGPU_OK) rc_final = AGPU_E_TRUNCATED;
+            if (c > cap_out && rc_final == AGPU_OK) {
+                h->set_err("more detections than cap_per_frame; counts[] hold the true numbers");
+                rc_final = AGPU_E_TRUNCATED;
+            }
             h->counters[0] += h_npts[i];
             h->counters[3] += h_nd[i];
-            if (h_npts[i] > cap) {
-                h->set_err("edge-point list overflow: raise agpu_config.max_points_per_frame");
-                rc_final = AGPU_E_WORKSPACE;
-            }
             if (h_nd[i] > REC_CAP) {
                 h->set_err("more than 256 raw detections in one frame");
                 rc_final = AGPU_E_WORKSPACE;
@@ -582,18 +622,11 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
         h->counters[1] += hc[CNT_SMALL] + hc[CNT_MID] + hc[CNT_LARGE];
         h->counters[2] += hc[CNT_NQUADS];
         h->counters[4] += hc[CNT_OVERSIZE];
-        if (hc[CNT_SMALL] > n * maxcl || hc[CNT_MID] > n * maxcl || hc[CNT_LARGE] > n * maxcl) {
-            h->set_err("cluster list overflow: raise agpu_config.max_clusters_per_frame");
-            rc_final = AGPU_E_WORKSPACE;
-        }
-        if (hc[CNT_NQUADS] > n * maxq) {
-            h->set_err("quad list overflow: raise agpu_config.max_quads_per_frame");
-            rc_final = AGPU_E_WORKSPACE;
-        }
         h->last_chunk = n;
         h->last_cap = cap;
         h->last_sorted = cur;
         h->have_last = true;
+        b0 += n;
     }
     return rc_final;
 }

@@ -1,0 +1,300 @@
+"""GPU parity tests (B200): every call goes through the C ABI (ctypes -> libaprilgpu.so) and is compared with
+the CPU oracle on the same seeded inputs, with the committed golden fixtures, and -- at BASELINE.json's full
+frame size -- through size-independent properties.
+
+Bars (BASELINE.json north_star): threshold images and canonical component labels bit-exact; ids, Hamming
+distances and the detection set bit-exact; corners within 0.05 px; pose within 1e-4 rad / 1e-4 units of the
+reference's cv2.solvePnP path.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from aprilslam_b200 import synth  # noqa: E402
+from aprilslam_b200.detector import Detector, TagDetector, apriltag  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CORNER_TOL_PX = 0.05
+POSE_TOL = 1e-4
+
+CASES = {
+    "sim1000_41h12_d2": ("tagStandard41h12", 2.0), "sim640_41h12_d2": ("tagStandard41h12", 2.0),
+    "sim640_36h11_d2": ("tag36h11", 2.0), "grid720_36h11_d2": ("tag36h11", 2.0),
+    "grid1080_36h11_d1": ("tag36h11", 1.0), "grid1080_mixed_d1": ("tag25h9 tagStandard41h12", 1.0),
+    "grid481_16h5_d1": ("tag16h5", 1.0),
+}
+
+
+@pytest.fixture(scope="module")
+def det_gold():
+    return np.load(os.path.join(GOLD, "detect_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def ob():
+    from oracle import binding
+    return binding
+
+
+def geodesic(Ra, Rb):
+    return float(np.arccos(np.clip((np.trace(Ra @ Rb.T) - 1) / 2, -1, 1)))
+
+
+def assert_same_detections(recs, ref, tol=CORNER_TOL_PX):
+    assert len(recs) == len(ref)
+    assert recs["id"].tolist() == ref["id"].tolist()
+    assert recs["hamming"].tolist() == ref["hamming"].tolist()
+    assert recs["family"].tolist() == ref["family"].tolist()
+    if len(ref):
+        assert np.abs(recs["p"] - ref["p"]).max() <= tol
+        assert np.abs(recs["c"] - ref["c"]).max() <= tol
+        assert np.abs(recs["margin"] - ref["margin"]).max() <= 1e-2
+
+
+# ---- stage level: bit-exact -----------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H,d", [(640, 480, 1), (640, 480, 2), (643, 481, 1), (1000, 1000, 2), (1001, 997, 4),
+                                   (1920, 1080, 1), (333, 77, 1), (64, 64, 2), (97, 131, 3), (16, 16, 1), (35, 9, 1)])
+def test_threshold_and_labels_bit_exact(ob, W, H, d):
+    rng = np.random.default_rng(W * 7 + H + d)
+    det = Detector("tag36h11", decimate=float(d))
+    images = [rng.integers(0, 256, (H, W), dtype=np.uint8),
+              (np.kron(rng.integers(0, 2, (H // 5 + 1, W // 5 + 1), dtype=np.uint8) * 180 + 30,
+                       np.ones((5, 5), np.uint8))[:H, :W] + rng.integers(0, 7, (H, W), dtype=np.uint8)).astype(np.uint8),
+              np.full((H, W), 93, np.uint8)]
+    for im in images:
+        im = np.ascontiguousarray(im)
+        q, t = det.stage_threshold(im)
+        q_ref = np.ascontiguousarray(im[::d, ::d])
+        t_ref = ob.stage_threshold(q_ref)
+        assert np.array_equal(q, q_ref)
+        assert np.array_equal(t, t_ref)
+        lab, sz = det.stage_labels(t_ref)
+        lab_ref, sz_ref = ob.stage_labels(t_ref)
+        assert np.array_equal(lab, lab_ref)
+        assert np.array_equal(sz, sz_ref)
+    det.close()
+
+
+@pytest.mark.parametrize("sigma", [0.8, 1.5, -0.8])
+def test_blur_front_end_bit_exact(ob, sigma):
+    rng = np.random.default_rng(5)
+    im = rng.integers(0, 256, (241, 323), dtype=np.uint8)
+    det = Detector("tag36h11", decimate=2.0, blur=sigma)
+    q, t = det.stage_threshold(im)
+    q_ref = ob.stage_blur(np.ascontiguousarray(im[::2, ::2]), sigma)
+    assert np.array_equal(q, q_ref)
+    assert np.array_equal(t, ob.stage_threshold(q_ref))
+    det.close()
+
+
+# ---- whole pipeline vs oracle and vs the committed fixtures ------------------------------------------------
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_pipeline_matches_oracle_and_golden(ob, det_gold, name):
+    fams, d = CASES[name]
+    img = det_gold[name + "_frame"]
+    g = Detector(fams, decimate=d, debug=True)
+    recs = g.detect_batch(img, cap_per_frame=256)[0]
+    ref, dbg = ob.OracleDetector(fams, decimate=d).detect_records(img, debug=True)
+    # stage dumps: bit-exact integer stages, exact cluster and quad sets
+    assert np.array_equal(g.debug_fetch("thresh"), dbg["thresh"])
+    assert np.array_equal(g.debug_fetch("labels"), dbg["labels"])
+    assert np.array_equal(g.debug_fetch("sizes"), dbg["sizes"])
+    assert np.array_equal(g.debug_fetch("cluster_keys"), dbg["cluster_keys"])
+    assert np.array_equal(g.debug_fetch("cluster_sizes"), dbg["cluster_sizes"])
+    assert np.array_equal(g.debug_fetch("quad_keys"), dbg["quad_keys"])
+    if len(dbg["quads"]):
+        assert np.abs(g.debug_fetch("quads") - dbg["quads"]).max() <= 1e-3
+        assert np.abs(g.debug_fetch("quads_refined") - dbg["quads_refined"]).max() <= 1e-2
+    assert g.counters()["edge_points"] == dbg["npoints"]
+    assert_same_detections(recs, ref)
+    # committed fixture (generated through the reference's TagDetector.detect, tools/make_golden.py)
+    assert recs["id"].tolist() == det_gold[name + "_id"].tolist()
+    assert recs["hamming"].tolist() == det_gold[name + "_hamming"].tolist()
+    assert np.abs(recs["p"] - det_gold[name + "_corners"]).max() <= CORNER_TOL_PX
+    g.close()
+
+
+def test_bgr_front_end_and_tagdetector_drop_in(ob, det_gold):
+    """TagDetector.detect(BGR) / get_pose(detection) keep the reference's shapes (tag_detector.py:23-43)."""
+    import cv2
+    name = "grid720_36h11_d2"
+    gray = det_gold[name + "_frame"]
+    rng = np.random.default_rng(2)
+    bgr = np.repeat(gray[..., None], 3, axis=2).astype(np.int16)
+    bgr[..., 0] += rng.integers(-3, 4, gray.shape)   # colour noise: gray conversion must follow cv2's rounding
+    bgr[..., 2] -= rng.integers(-3, 4, gray.shape)
+    bgr = np.clip(bgr, 0, 255).astype(np.uint8)
+    K = det_gold[name + "_K"]
+    td = TagDetector({"camera_matrix": K, "dist_coeffs": np.zeros((4, 1))}, "tag36h11", 0.15)
+    dets = td.detect(bgr)
+    ref = ob.OracleDetector("tag36h11", decimate=2.0).detect_records(cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    assert [x["id"] for x in dets] == ref["id"].tolist() == sorted(ref["id"].tolist())
+    assert len(dets) >= 8
+    for x, r in zip(dets, ref):
+        assert set(("hamming", "margin", "id", "center", "lb-rb-rt-lt", "tag_family", "tag_id", "decision_margin",
+                    "corners", "homography")) <= set(x)
+        assert x["lb-rb-rt-lt"].shape == (4, 2) and x["lb-rb-rt-lt"].dtype == np.float64
+        assert np.abs(x["lb-rb-rt-lt"] - r["p"]).max() <= CORNER_TOL_PX
+        retval, rvec, tvec, T = td.get_pose(x)
+        ok, rv, tv, TT = ob.reference_pose(x["lb-rb-rt-lt"], K, np.zeros((4, 1)), 0.15)
+        assert retval is True and rvec.shape == (3, 1) and tvec.shape == (3, 1) and T.shape == (4, 4)
+        assert np.abs(tvec - tv).max() < POSE_TOL and geodesic(T[:3, :3], TT[:3, :3]) < POSE_TOL
+        assert np.allclose(td.transformation(rvec, tvec), T, atol=1e-9)
+
+
+def test_apriltag_shim_matches_upstream_wrapper_contract(ob, det_gold):
+    img = det_gold["sim1000_41h12_d2_frame"]
+    d = apriltag("tagStandard41h12")                       # the exact call at tag_detector.py:18
+    out = d.detect(img)                                    # tag_detector.py:26
+    assert isinstance(out, tuple) and [x["id"] for x in out] == [0, 1, 2]
+    ref = ob.OracleDetector("tagStandard41h12").detect(img)
+    for a, b in zip(out, ref):
+        assert a["hamming"] == b["hamming"] and np.abs(a["lb-rb-rt-lt"] - b["lb-rb-rt-lt"]).max() <= CORNER_TOL_PX
+    with pytest.raises(RuntimeError):
+        d.detect(np.zeros((10, 10, 3), np.uint8))
+    with pytest.raises(RuntimeError):
+        d.detect(np.zeros((10, 10), np.float32))
+    assert d.detect(np.zeros((100, 100), np.uint8)) == ()   # scripts/verify_installation.py:45-51 smoke input
+
+
+# ---- pose -----------------------------------------------------------------------------------------------------
+def test_pose_matches_reference_fixture():
+    P = np.load(os.path.join(GOLD, "pose_golden.npz"))
+    g = Detector("tag36h11")
+    for s in ("sim", "webcam"):
+        poses = g.estimate_pose(P[s + "_corners"], P[s + "_K"], P[s + "_dist"], float(P[s + "_size"]))
+        assert poses["ok"].all() == P[s + "_ok"].all()
+        scale = max(1.0, float(P[s + "_size"]))
+        for p, tv, T in zip(poses, P[s + "_tvec"], P[s + "_T"]):
+            assert np.abs(p["tvec"] - tv).max() < POSE_TOL * scale
+            assert geodesic(p["R"].reshape(3, 3), T[:3, :3]) < POSE_TOL
+    g.close()
+
+
+def test_pose_orthogonal_iteration_is_close_to_the_reprojection_minimiser():
+    P = np.load(os.path.join(GOLD, "pose_golden.npz"))
+    g = Detector("tag36h11")
+    p1 = g.estimate_pose(P["sim_corners"], P["sim_K"], P["sim_dist"], float(P["sim_size"]), method=1)
+    ang = np.array([geodesic(p["R"].reshape(3, 3), T[:3, :3]) for p, T in zip(p1, P["sim_T"])])
+    assert np.median(ang) < 2e-3 and p1["ok"].all()
+    g.close()
+
+
+# ---- batches, device tensors, edge cases ---------------------------------------------------------------------------
+def test_batch_on_device_equals_per_frame_and_oracle(ob, det_gold):
+    import torch
+    frames = np.stack([synth.render(synth.grid_scene(1280, 720, s, (5, 2), px_range=(60, 110))) for s in range(6)])
+    frames[3] = 0                                          # an empty frame inside the batch
+    frames[4] = frames[1]                                  # a repeated frame
+    K = synth.intrinsics(1280, 720, 45.0)
+    g = Detector("tag36h11", decimate=2.0, chunk_frames=4)  # 6 frames -> two chunks (ragged last chunk)
+    dets_dev, poses_dev = g.detect_pose_batch(torch.from_numpy(frames).cuda(), K, None, 0.2)
+    dets_host = g.detect_batch(frames)
+    o = ob.OracleDetector("tag36h11", decimate=2.0)
+    for b in range(len(frames)):
+        ref = o.detect_records(frames[b])
+        assert_same_detections(dets_dev[b], ref)
+        assert np.array_equal(dets_dev[b], dets_host[b])   # same kernels, same inputs: identical records
+        for r, p in zip(dets_dev[b], poses_dev[b]):
+            ok, rv, tv, T = ob.reference_pose(r["p"], K, np.zeros((4, 1)), 0.2)
+            assert p["ok"] == 1 and np.abs(p["tvec"] - tv.ravel()).max() < POSE_TOL
+            assert geodesic(p["R"].reshape(3, 3), T[:3, :3]) < POSE_TOL
+    assert len(dets_dev[3]) == 0
+    assert np.array_equal(dets_dev[4], dets_dev[1])
+    g.close()
+
+
+def test_truncation_reports_true_counts(det_gold):
+    import ctypes as C
+    from aprilslam_b200 import _lib
+    img = np.ascontiguousarray(det_gold["grid720_36h11_d2_frame"])
+    g = Detector("tag36h11", decimate=2.0)
+    out = np.zeros((1, 4), _lib.DET_DTYPE)
+    counts = np.zeros(1, np.int32)
+    rc = g._L.agpu_detect(g._h, img.ctypes.data, 0, 1, img.shape[1], img.shape[0], img.shape[1], None,
+                          out.ctypes.data, 4, counts.ctypes.data)
+    assert rc == _lib.AGPU_E_TRUNCATED and counts[0] == 10
+    assert out["id"].tolist()[0] == sorted(det_gold["grid720_36h11_d2_id"].tolist())[:4]
+    rc = g._L.agpu_detect(g._h, None, 0, 1, 10, 10, 10, None, out.ctypes.data, 4, counts.ctypes.data)
+    assert rc == _lib.AGPU_E_INVALID
+    g.close()
+
+
+def test_tiny_and_ragged_frames():
+    g = Detector("tag36h11", decimate=2.0)
+    for shape in ((5, 7), (15, 15), (16, 16), (17, 33), (100, 100)):
+        assert len(g.detect_batch(np.zeros(shape, np.uint8))[0]) == 0
+    rng = np.random.default_rng(0)
+    assert len(g.detect_batch(rng.integers(0, 256, (3, 240, 321), dtype=np.uint8))[0]) == 0
+    g.close()
+
+
+def test_unknown_family_and_bad_config():
+    with pytest.raises(RuntimeError, match="Unrecognized tag family"):
+        Detector("tag99h99")
+    with pytest.raises(RuntimeError):
+        Detector("tag36h11", decimate=1.5)
+    with pytest.raises(RuntimeError):
+        Detector("tag16h5", maxhamming=3)
+
+
+def test_full_size_properties_1080p(ob):
+    """BASELINE configs[2] frame size, a 24-frame batch: every visible ground-truth tag is reported with
+    Hamming 0, corners near the analytic ground truth, results independent of batch position (idempotence),
+    and a detect -> pose -> reproject round trip lands on the detected corners."""
+    import torch
+    scenes = [synth.grid_scene(1920, 1080, s, (10, 5)) for s in range(8)]
+    frames = np.stack([synth.render(sc) for sc in scenes])
+    batch = np.concatenate([frames, frames[::-1], frames])      # 24 frames, each scene three times
+    K = scenes[0].K
+    g = Detector("tag36h11", decimate=1.0)
+    dets, poses = g.detect_pose_batch(torch.from_numpy(batch).cuda(), K, None, 1.0)
+    order = list(range(8)) + list(range(7, -1, -1)) + list(range(8))
+    first = {}
+    for b, s in enumerate(order):
+        if s in first:
+            assert np.array_equal(dets[b], dets[first[s]]) and np.array_equal(poses[b]["tvec"], poses[first[s]]["tvec"])
+        else:
+            first[s] = b
+    for s, sc in enumerate(scenes):
+        d = dets[first[s]]
+        p = poses[first[s]]
+        gt = {t.tag_id: synth.gt_corners(sc, t) for t in sc.tags}
+        assert sorted(d["id"].tolist()) == sorted(gt)            # all 50 found, nothing else
+        assert (d["hamming"] == 0).all() and list(d["id"]) == sorted(d["id"])
+        for r, q in zip(d, p):
+            assert np.abs(r["p"] - gt[int(r["id"])]).max() < 0.75      # aliased rasterisation: < 1 px
+            R, t = q["R"].reshape(3, 3), q["tvec"]
+            obj = np.array([[-.5, -.5, 0], [.5, -.5, 0], [.5, .5, 0], [-.5, .5, 0]])
+            cam = obj @ R.T + t
+            uv = cam[:, :2] / cam[:, 2:3] * np.array([K[0, 0], K[1, 1]]) + np.array([K[0, 2], K[1, 2]])
+            assert np.abs(uv - r["p"]).max() < 0.5 and q["err"] < 0.5
+            Rg, tg = synth.gt_pose([x for x in sc.tags if x.tag_id == int(r["id"])][0])
+            assert np.linalg.norm(t - tg) / np.linalg.norm(tg) < 0.02
+    # the oracle on two of the frames (seconds on the CPU)
+    o = ob.OracleDetector("tag36h11", decimate=1.0)
+    for s in (0, 5):
+        assert_same_detections(dets[first[s]], o.detect_records(frames[s]))
+    g.close()
+
+
+def test_instrumentation_counts_launches_and_stages():
+    img = synth.render(synth.grid_scene(640, 480, 11, (3, 2), px_range=(50, 90)))
+    g = Detector("tag36h11", decimate=2.0)
+    g.set_profiling(True)
+    g.detect_batch(img)
+    assert g.launch_count() >= 15
+    ms = g.stage_ms()
+    assert set(ms) == {"h2d", "image", "cc", "edges", "sort", "quads", "decode", "reconcile_pose", "d2h"}
+    assert all(v >= 0 for v in ms.values()) and sum(ms.values()) > 0
+    c = g.counters()
+    assert c["edge_points"] > 0 and c["quads"] >= 6 and c["oversize_clusters"] == 0
+    g.close()
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()

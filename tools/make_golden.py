@@ -45,6 +45,7 @@ def import_reference_tag_detector(**oracle_kwargs):
     if REF not in sys.path:
         sys.path.insert(0, REF)
     import importlib
+    sys.modules.pop("src.detection.tag_detector", None)   # re-import so that it binds THIS stub's class
     mod = importlib.import_module("src.detection.tag_detector")
     return mod
 
