@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,9 +71,12 @@ struct HostBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-constexpr int TIER_CAP[3] = {2048, 8192, 16384};
-// counter block layout (ints)
-enum { CNT_SMALL = 0, CNT_LARGE = 1, CNT_OVERSIZE = 2, CNT_HEADS = 3, CNT_MID = 4, CNT_NQUADS = 5, CNT_FIXED = 8 };
+// cluster size tiers of the quad-fit kernel: {largest cluster, warps per CTA, CTAs per SM}
+constexpr int TIER_CAP[AGPU_NTIERS] = {256, 1024, 2048, 16384};
+constexpr int TIER_WPB[AGPU_NTIERS] = {8, 8, 4, 1};
+constexpr int TIER_CTAS_PER_SM[AGPU_NTIERS] = {3, 3, 3, 1};
+// counter block layout (ints): [0..3] clusters per tier
+enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_FIXED = 8 };
 
 }  // namespace
 
@@ -84,6 +88,8 @@ struct agpu_handle {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};   // side streams: the quad-fit tiers run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
     std::string err;
     bool profiling = false;
     float stage_ms[AGPU_NUM_STAGES];
@@ -96,7 +102,7 @@ struct agpu_handle {
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes;
     DevBuf d_keys[2], d_vals[2], d_hist, d_lfps, d_errs;
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk]
-    DevBuf d_clusters[3], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses, d_pose_in;
+    DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses, d_pose_in;
     HostBuf h_out, h_counts, h_poses, h_counters;
 
     // growable per-frame list capacities (0 = not chosen yet)
@@ -263,20 +269,21 @@ int run_image_stage(agpu_handle* h, const uint8_t* d_src, int channels, int W, i
         const int nstrips = ceil_div(g.wp, strip_px);
         const int th = g.hd >> 2;
         int seg_tiles = 8;
+        if (const char* e = getenv("AGPU_SEG_TILES")) seg_tiles = std::max(1, atoi(e));
         const int nsegs = ceil_div(th, seg_tiles);
         const long long warps = (long long)n * nstrips * nsegs;
-        const int blocks = ceil_div(warps * 32, 256);
+        const int blocks = ceil_div(warps * 32, 128);
         const int vec_ok = (s_stride % 16 == 0) && (s_frame % 16 == 0) && (((uintptr_t)src) % 16 == 0);
         const int md = h->prm.min_white_black_diff;
         uint8_t* th_out = h->d_thresh.as<uint8_t>();
         if (F == 1)
-            k_decimate_threshold<1><<<blocks, 256, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
+            k_decimate_threshold<1><<<blocks, 128, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
                                                                    nstrips, nsegs, seg_tiles, n, md, vec_ok);
         else if (F == 2)
-            k_decimate_threshold<2><<<blocks, 256, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
+            k_decimate_threshold<2><<<blocks, 128, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
                                                                    nstrips, nsegs, seg_tiles, n, md, vec_ok);
         else
-            k_decimate_threshold<4><<<blocks, 256, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
+            k_decimate_threshold<4><<<blocks, 128, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
                                                                    nstrips, nsegs, seg_tiles, n, md, vec_ok);
         LAUNCH_CHECK("k_decimate_threshold");
     }
@@ -295,9 +302,10 @@ int run_cc_stage(agpu_handle* h, const uint8_t* d_thresh, int n, const Geom& g) 
     dim3 grid(tx, ty, n);
     k_cc_local<<<grid, CC_THREADS, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), h->d_sizes.as<uint32_t>(), g, tx, ty);
     LAUNCH_CHECK("k_cc_local");
-    k_cc_boundary<<<grid, 128, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), g, tx, ty);
+    k_cc_boundary<<<grid, 160, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), g, tx, ty);
     LAUNCH_CHECK("k_cc_boundary");
-    k_cc_finalize<<<grid, CC_THREADS, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), h->d_sizes.as<uint32_t>(), g);
+    dim3 gridf(ceil_div(g.wd, CCF_TW), ceil_div(g.hd, CCF_TH), n);
+    k_cc_finalize<<<gridf, CC_THREADS, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), h->d_sizes.as<uint32_t>(), g);
     LAUNCH_CHECK("k_cc_finalize");
     return AGPU_OK;
 }
@@ -390,7 +398,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
         CK(h->d_lfps.ensure((size_t)chunk * cap * 48));
         CK(h->d_errs.ensure((size_t)chunk * cap * 8));
         CK(h->d_counters.ensure(ncnt * 4));
-        for (int t = 0; t < 3; t++) CK(h->d_clusters[t].ensure((size_t)chunk * maxcl * sizeof(ClusterRef)));
+        for (int t = 0; t < AGPU_NTIERS; t++) CK(h->d_clusters[t].ensure((size_t)chunk * maxcl * sizeof(ClusterRef)));
         if (h->cfg.debug) {
             CK(h->d_dbg_heads.ensure((size_t)chunk * cap / 4 * sizeof(ClusterRef)));
             CK(h->d_refined.ensure((size_t)chunk * maxq * 32));
@@ -453,7 +461,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
         if (rc) return rc;
         tm.mark();  // 3: after CC
         {
-            dim3 grid(ceil_div(g.wd, 32), ceil_div(g.hd - 1, 8), n);
+            dim3 grid(ceil_div(g.wp >> 2, 32), ceil_div(g.hd - 1, 8), n);
             k_edges<<<grid, 256, 0, h->stream>>>(h->d_thresh.as<uint8_t>(), h->d_labels.as<uint32_t>(),
                                                  h->d_sizes.as<uint32_t>(), g, h->d_keys[0].as<unsigned long long>(),
                                                  h->d_vals[0].as<uint32_t>(), d_npts, cap);
@@ -485,16 +493,16 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
         const uint32_t* svals = h->d_vals[cur].as<uint32_t>();
         {
             ClusterLists cl;
-            cl.small_list = h->d_clusters[0].as<ClusterRef>();
-            cl.mid_list = h->d_clusters[1].as<ClusterRef>();
-            cl.large_list = h->d_clusters[2].as<ClusterRef>();
+            for (int t = 0; t < AGPU_NTIERS; t++) {
+                cl.list[t] = h->d_clusters[t].as<ClusterRef>();
+                cl.cap[t] = TIER_CAP[t];
+            }
             cl.counters = d_cnt;
             cl.cap_list = n * maxcl;
             cl.dbg_heads = h->cfg.debug ? h->d_dbg_heads.as<ClusterRef>() : nullptr;
             cl.cap_dbg = (int)(h->d_dbg_heads.bytes / sizeof(ClusterRef));
             dim3 grid(ceil_div(cap, 256), n);
-            k_cluster_heads<<<grid, 256, 0, h->stream>>>(skeys, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24),
-                                                         TIER_CAP[0], TIER_CAP[1], TIER_CAP[2], cl);
+            k_cluster_heads<<<grid, 256, 0, h->stream>>>(skeys, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
             LAUNCH_CHECK("k_cluster_heads");
             QuadFitArgs qa;
             qa.vals = svals; qa.keys = skeys; qa.cap = cap;
@@ -507,15 +515,21 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
             qa.nquads = d_cnt + CNT_NQUADS;
             qa.cap_quads = n * maxq;
             qa.per_frame_quads = d_frame_quads;
-            const int cnt_idx[3] = {CNT_SMALL, CNT_MID, CNT_LARGE};
-            const int wpb[3] = {4, 1, 1};
-            const int grids[3] = {h->num_sms * 2, h->num_sms * 3, h->num_sms};
-            for (int t = 0; t < 3; t++) {
+            // the tiers are independent (own work list, atomic appends to the quad list): fork them over side
+            // streams so that the latency-bound big-cluster warps overlap with the many small clusters
+            CK(cudaEventRecord(h->ev_fork, h->stream));
+            for (int t = AGPU_NTIERS - 1; t >= 0; t--) {
+                cudaStream_t st = t == 0 ? h->stream : h->aux[t - 1];
+                if (t > 0) CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
                 qa.list = h->d_clusters[t].as<ClusterRef>();
-                qa.list_count = d_cnt + cnt_idx[t];
-                size_t smem = (size_t)wpb[t] * ((size_t)TIER_CAP[t] * 8 + QF_PTAB_DOUBLES * 8 + 64);
-                k_fit_quads<<<grids[t], wpb[t] * 32, smem, h->stream>>>(qa, h->prm, TIER_CAP[t]);
+                qa.list_count = d_cnt + CNT_TIER0 + t;
+                const size_t smem = (size_t)TIER_WPB[t] * qf_smem_per_warp(TIER_CAP[t]);
+                k_fit_quads<<<h->num_sms * TIER_CTAS_PER_SM[t], TIER_WPB[t] * 32, smem, st>>>(qa, h->prm, TIER_CAP[t]);
                 LAUNCH_CHECK("k_fit_quads");
+                if (t > 0) {
+                    CK(cudaEventRecord(h->ev_join[t - 1], st));
+                    CK(cudaStreamWaitEvent(h->stream, h->ev_join[t - 1], 0));
+                }
             }
         }
         tm.mark();  // 6: after quads
@@ -576,7 +590,8 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
         {
             int max_pts = 0;
             for (int i = 0; i < n; i++) max_pts = std::max(max_pts, h_npts[i]);
-            const int max_cl = std::max(hc[CNT_SMALL], std::max(hc[CNT_MID], hc[CNT_LARGE]));
+            int max_cl = 0;
+            for (int t = 0; t < AGPU_NTIERS; t++) max_cl = std::max(max_cl, hc[CNT_TIER0 + t]);
             bool regrow = false;
             if (max_pts > cap) {
                 if (!auto_pts) { h->set_err("edge-point list overflow: raise agpu_config.max_points_per_frame"); return AGPU_E_WORKSPACE; }
@@ -619,7 +634,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
                 rc_final = AGPU_E_WORKSPACE;
             }
         }
-        h->counters[1] += hc[CNT_SMALL] + hc[CNT_MID] + hc[CNT_LARGE];
+        for (int t = 0; t < AGPU_NTIERS; t++) h->counters[1] += hc[CNT_TIER0 + t];
         h->counters[2] += hc[CNT_NQUADS];
         h->counters[4] += hc[CNT_OVERSIZE];
         h->last_chunk = n;
@@ -710,6 +725,13 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     h->num_sms = prop.multiProcessorCount;
     if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail(AGPU_E_CUDA, cudaGetErrorString(ce));
+    for (int t = 0; t < AGPU_NTIERS - 1; t++) {
+        if ((ce = cudaStreamCreateWithFlags(&h->aux[t], cudaStreamNonBlocking)) != cudaSuccess ||
+            (ce = cudaEventCreateWithFlags(&h->ev_join[t], cudaEventDisableTiming)) != cudaSuccess)
+            return fail(AGPU_E_CUDA, cudaGetErrorString(ce));
+    }
+    if ((ce = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess)
+        return fail(AGPU_E_CUDA, cudaGetErrorString(ce));
 
     // parameters
     DevParams& P = h->prm;
@@ -761,7 +783,7 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     }
     // the large quad-fit tiers need more than 48 KB of dynamic shared memory
     ce = cudaFuncSetAttribute(k_fit_quads, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)((size_t)TIER_CAP[2] * 8 + QF_PTAB_DOUBLES * 8 + 64));
+                              (int)qf_smem_per_warp(TIER_CAP[AGPU_NTIERS - 1]));
     if (ce != cudaSuccess) return fail(AGPU_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
     *out = h;
     return AGPU_OK;
@@ -779,6 +801,11 @@ int agpu_destroy(agpu_handle* h) {
     for (DevBuf* b : bufs) b->release();
     h->h_out.release(); h->h_counts.release(); h->h_poses.release(); h->h_counters.release();
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    for (int t = 0; t < AGPU_NTIERS - 1; t++) {
+        if (h->aux[t]) cudaStreamDestroy(h->aux[t]);
+        if (h->ev_join[t]) cudaEventDestroy(h->ev_join[t]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return AGPU_OK;

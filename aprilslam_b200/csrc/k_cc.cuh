@@ -6,9 +6,9 @@
 // pixels additionally link up-left and up-right.  Columns 0 and w-1 never initiate links.
 //
 // Three kernels (block-local union-find + boundary merge + canonical relabel):
-//   k_cc_local    64x32-pixel tile per CTA, union-find in shared memory (atomicMin hooks: the root
-//                 of a set is always its smallest pixel id), labels written as global pixel ids;
-//                 sizes[] zeroed at tile-local roots.
+//   k_cc_local    32x64-pixel tile per CTA, warp-ballot row runs + union-find in shared memory (atomicMin
+//                 hooks: the root of a set is always its smallest pixel id), labels written as global
+//                 pixel ids; sizes[] zeroed at tile-local roots.
 //   k_cc_boundary one thread per tile-border pixel, lock-free unions across tile edges in global memory.
 //   k_cc_finalize pointer jumping to the global root (= smallest pixel id of the component, so the
 //                 labelling is canonical by construction) + component sizes, aggregated per tile in
@@ -16,10 +16,15 @@
 #pragma once
 #include "common.cuh"
 
-#define CC_TW 64
-#define CC_TH 32
+// tile of the local pass: one warp row = 32 pixels, 64 rows, 8 warps x 8 rows
+#define CC_TW 32
+#define CC_TH 64
 #define CC_THREADS 256
-#define CC_RUN 8  // pixels per thread (one horizontal run)
+#define CC_ROWS_PER_WARP 8
+// tile of the finalize pass (8-pixel runs per thread)
+#define CCF_TW 64
+#define CCF_TH 32
+#define CC_RUN 8
 
 __device__ __forceinline__ uint32_t sfind(volatile uint32_t* L, uint32_t a) {
     uint32_t p = L[a];
@@ -63,6 +68,10 @@ __device__ __forceinline__ void gunion(uint32_t* L, uint32_t a, uint32_t b) {
     }
 }
 
+// Local pass.  Lane = column: a warp ballot finds the horizontal runs of a row (a pixel's first label is the
+// start of its run -- no atomics), then only the first column of every vertical / diagonal contact between
+// runs of adjacent rows issues a union, so the number of shared-memory atomics follows the number of runs,
+// not the number of pixels.
 __global__ void __launch_bounds__(CC_THREADS)
 k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, Geom g,
            int tiles_x, int tiles_y) {
@@ -73,82 +82,68 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
     const uint8_t* ft = thresh + (size_t)frame * g.plane;
     uint32_t* fl = labels + (size_t)frame * g.plane;
     uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const int t = threadIdx.x;
-    const int ry = t >> 3, rx = (t & 7) * CC_RUN;  // run start inside the tile
-    const int gy = y0 + ry, gx = x0 + rx;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int x = x0 + lane;
+    const bool col_init = x >= 1 && x <= g.wd - 2;   // columns 0 and w-1 never initiate links
 
-    // load 8 threshold bytes (rows are 16-byte aligned, gx % 8 == 0)
-    uint8_t v[CC_RUN];
-    if (gy < g.hd && gx < g.wp) {
-        uint2 raw = *reinterpret_cast<const uint2*>(ft + (size_t)gy * g.wp + gx);
+    uint32_t v[CC_ROWS_PER_WARP], starts[CC_ROWS_PER_WARP];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            v[k] = (raw.x >> (8 * k)) & 0xff;
-            v[4 + k] = (raw.y >> (8 * k)) & 0xff;
-        }
-#pragma unroll
-        for (int k = 0; k < CC_RUN; k++)
-            if (gx + k >= g.wd) v[k] = 127;  // outside the image: never linked
-    } else {
-#pragma unroll
-        for (int k = 0; k < CC_RUN; k++) v[k] = 127;
-    }
-    // run initialisation: a pixel linked to its left neighbour inside the run takes that label
-    uint32_t lab = 0;
-#pragma unroll
-    for (int k = 0; k < CC_RUN; k++) {
-        const int x = gx + k;
-        const uint32_t li = (uint32_t)(ry * CC_TW + rx + k);
-        bool link = k > 0 && v[k] != 127 && v[k] == v[k - 1] && x >= 1 && x <= g.wd - 2;
-        if (!link) lab = li;
-        L[li] = lab;
-        sv[ry][rx + k] = v[k];
+    for (int k = 0; k < CC_ROWS_PER_WARP; k++) {
+        const int ry = w * CC_ROWS_PER_WARP + k, gy = y0 + ry;
+        uint32_t c = 127;
+        if (gy < g.hd && x < g.wd) c = ft[(size_t)gy * g.wp + x];
+        const uint32_t cl = __shfl_up_sync(FULL_MASK, c, 1);
+        const bool link = lane > 0 && c != 127 && c == cl && col_init;
+        const uint32_t st = __ballot_sync(FULL_MASK, !link);
+        const int rs = 31 - __clz(st & (0xffffffffu >> (31 - lane)));
+        L[ry * CC_TW + lane] = (uint32_t)(ry * CC_TW + rs);
+        sv[ry][lane] = (uint8_t)c;
+        v[k] = c;
+        starts[k] = st;
     }
     __syncthreads();
-    // links to other runs / other rows inside the tile
 #pragma unroll
-    for (int k = 0; k < CC_RUN; k++) {
-        const int x = gx + k;
-        const uint8_t c = v[k];
-        if (c == 127 || x < 1 || x > g.wd - 2 || gy >= g.hd) continue;
-        const uint32_t li = (uint32_t)(ry * CC_TW + rx + k);
-        if (k == 0 && rx > 0 && sv[ry][rx - 1] == c) sunion(L, li, li - 1);
-        if (ry > 0 && gy >= 1) {
-            const uint8_t up = sv[ry - 1][rx + k];
-            if (up == c) {
-                // the union is implied when the left pixel and the pixel above it are already chained
-                bool implied = k > 0 && v[k - 1] == c && sv[ry - 1][rx + k - 1] == c && x - 1 >= 1;
-                if (!implied) sunion(L, li, li - CC_TW);
-            }
-            if (c == 255) {
-                // up == c implies both diagonals through (x, y-1)'s own left link and the left link
-                // initiated by (x+1, y-1) -- the latter only exists when x+1 <= w-2
-                if (rx + k > 0 && sv[ry - 1][rx + k - 1] == c && up != c) sunion(L, li, li - CC_TW - 1);
-                if (rx + k + 1 < CC_TW && sv[ry - 1][rx + k + 1] == c && (up != c || x + 1 > g.wd - 2))
-                    sunion(L, li, li - CC_TW + 1);
-            }
+    for (int k = 0; k < CC_ROWS_PER_WARP; k++) {
+        const int ry = w * CC_ROWS_PER_WARP + k, gy = y0 + ry;
+        const uint32_t c = v[k];
+        if (ry == 0 || gy < 1 || gy >= g.hd) continue;           // warp-uniform
+        const uint32_t up = sv[ry - 1][lane];
+        const uint32_t upl = __shfl_up_sync(FULL_MASK, up, 1), upr = __shfl_down_sync(FULL_MASK, up, 1);
+        const uint32_t cl = __shfl_up_sync(FULL_MASK, c, 1);
+        if (c == 127 || !col_init) continue;
+        const uint32_t li = (uint32_t)(ry * CC_TW + lane);
+        if (up == c) {
+            // implied when the left pixel is chained to this one, to the pixel above it, and that one to `up`
+            const bool implied = lane > 0 && cl == c && upl == c && x - 1 >= 1;
+            if (!implied) sunion(L, li, li - CC_TW);
+        }
+        if (c == 255) {
+            // up == c implies the diagonals through (x, y-1)'s left link and the left link initiated by
+            // (x+1, y-1); the latter only exists when x+1 <= w-2
+            if (lane > 0 && upl == 255 && up != 255) sunion(L, li, li - CC_TW - 1);
+            if (lane < 31 && upr == 255 && (up != 255 || x + 1 > g.wd - 2)) sunion(L, li, li - CC_TW + 1);
         }
     }
     __syncthreads();
-    // flatten and write global ids; zero the size counters at tile-local roots
-    if (gy < g.hd && gx < g.wp) {
-        uint32_t out[CC_RUN];
 #pragma unroll
-        for (int k = 0; k < CC_RUN; k++) {
-            const uint32_t li = (uint32_t)(ry * CC_TW + rx + k);
-            uint32_t r = sfind(L, li);
-            uint32_t gid = (uint32_t)((y0 + (int)(r / CC_TW)) * g.wp + x0 + (int)(r % CC_TW));
-            out[k] = gid;
-            if (r == li && v[k] != 127) fs[gid] = 0;
+    for (int k = 0; k < CC_ROWS_PER_WARP; k++) {
+        const int ry = w * CC_ROWS_PER_WARP + k, gy = y0 + ry;
+        const uint32_t st = starts[k];
+        const int rs = 31 - __clz(st & (0xffffffffu >> (31 - lane)));
+        const uint32_t li = (uint32_t)(ry * CC_TW + lane);
+        uint32_t r = 0;
+        if ((st >> lane) & 1u) r = sfind(L, li);
+        r = __shfl_sync(FULL_MASK, r, rs);
+        if (gy < g.hd && x < g.wp) {
+            const uint32_t gid = (uint32_t)((y0 + (int)(r / CC_TW)) * g.wp + x0 + (int)(r % CC_TW));
+            fl[(size_t)gy * g.wp + x] = gid;
+            if (r == li && v[k] != 127) fs[gid] = 0;   // size counters start at zero at every tile-local root
         }
-        uint4* dst = reinterpret_cast<uint4*>(fl + (size_t)gy * g.wp + gx);
-        dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-        dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
     }
 }
 
-// One thread per tile-border pixel: top row (64) + left column (32) + right column (32) = 128 per tile.
-__global__ void __launch_bounds__(128)
+// One thread per tile-border pixel: top row (32) + left column (64) + right column (64).
+__global__ void __launch_bounds__(160)
 k_cc_boundary(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, Geom g, int tiles_x, int tiles_y) {
     const int frame = blockIdx.z;
     const int x0 = blockIdx.x * CC_TW, y0 = blockIdx.y * CC_TH;
@@ -156,9 +151,9 @@ k_cc_boundary(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels,
     uint32_t* fl = labels + (size_t)frame * g.plane;
     const int t = threadIdx.x;
     int x, y;
-    if (t < 64) { x = x0 + t; y = y0; }
-    else if (t < 96) { x = x0; y = y0 + (t - 64); if (t == 64) return; }       // corner handled by the top row
-    else { x = x0 + CC_TW - 1; y = y0 + (t - 96); if (t == 96) return; }
+    if (t < CC_TW) { x = x0 + t; y = y0; }
+    else if (t < CC_TW + CC_TH) { x = x0; y = y0 + (t - CC_TW); if (t == CC_TW) return; }   // corner: top row's job
+    else { x = x0 + CC_TW - 1; y = y0 + (t - CC_TW - CC_TH); if (t == CC_TW + CC_TH) return; }
     if (x < 1 || x > g.wd - 2 || y >= g.hd) return;
     const uint8_t c = ft[(size_t)y * g.wp + x];
     if (c == 127) return;
@@ -181,7 +176,7 @@ k_cc_finalize(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels,
     __shared__ uint32_t hkey[CC_HASH];
     __shared__ uint32_t hcnt[CC_HASH];
     const int frame = blockIdx.z;
-    const int x0 = blockIdx.x * CC_TW, y0 = blockIdx.y * CC_TH;
+    const int x0 = blockIdx.x * CCF_TW, y0 = blockIdx.y * CCF_TH;
     const uint8_t* ft = thresh + (size_t)frame * g.plane;
     uint32_t* fl = labels + (size_t)frame * g.plane;
     uint32_t* fs = sizes + (size_t)frame * g.plane;

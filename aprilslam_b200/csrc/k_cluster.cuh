@@ -11,6 +11,42 @@
 #pragma once
 #include "common.cuh"
 
+// Four pixels (one 32-bit word of the threshold image) per thread.  An edge between v0 and v1 means
+// v0 ^ v1 == 0xff (values are 0 / 127 / 255), tested for all four pixels and one direction at a time with
+// three word operations; the vast majority of threads see no edge and leave after five word loads.
+template <bool WRITE>
+__device__ __forceinline__ int edges_emit(const uint32_t (&m)[4], int x0, int y, const Geom& g, const uint32_t* fl,
+                                          const uint32_t* fs, uint32_t cur, uint32_t (&nb)[4],
+                                          unsigned long long* fk, uint32_t* fv, int pos, int cap) {
+    const int dxs[4] = {1, 0, -1, 1}, dys[4] = {0, 1, 1, 1};
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (!(((m[0] | m[1] | m[2] | m[3]) >> (8 * i)) & 1u)) continue;
+        const int x = x0 + i;
+        const size_t id = (size_t)y * g.wp + x;
+        const uint32_t rep0 = fl[id];
+        if (fs[rep0] < 25u) continue;
+        const int v0 = (cur >> (8 * i)) & 0xff;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            if (!((m[d] >> (8 * i)) & 1u)) continue;
+            const uint32_t rep1 = fl[id + (size_t)dys[d] * g.wp + dxs[d]];
+            if (fs[rep1] < 25u) continue;
+            if (WRITE) {
+                if (pos + cnt < cap) {
+                    const uint32_t hi = max(rep0, rep1), lo = min(rep0, rep1);
+                    const int v1 = (nb[d] >> (8 * i)) & 0xff;
+                    fk[pos + cnt] = ((unsigned long long)hi << 32) | lo;
+                    fv[pos + cnt] = pack_point(2 * x + dxs[d], 2 * y + dys[d], d, v1 > v0);
+                }
+            }
+            cnt++;
+        }
+    }
+    return cnt;
+}
+
 __global__ void __launch_bounds__(256)
 k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes,
         Geom g, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ npts, int cap) {
@@ -18,40 +54,40 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
     const uint8_t* ft = thresh + (size_t)frame * g.plane;
     const uint32_t* fl = labels + (size_t)frame * g.plane;
     const uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    const int kx = blockIdx.x * 32 + lane;          // word index in the row
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int wpr = g.wp >> 2;
+    const int x0 = kx * 4;
 
-    int cnt = 0;
-    unsigned long long k[4];
-    uint32_t v[4];
-    if (x >= 1 && x <= g.wd - 2 && y <= g.hd - 2) {
-        const size_t id = (size_t)y * g.wp + x;
-        const int v0 = ft[id];
-        if (v0 != 127) {
-            const int dxs[4] = {1, 0, -1, 1}, dys[4] = {0, 1, 1, 1};
-            uint32_t rep0 = 0;
-            bool have0 = false, ok0 = false;
+    uint32_t m[4] = {0, 0, 0, 0}, nb[4] = {0, 0, 0, 0}, cur = 0;
+    if (y <= g.hd - 2 && kx < wpr && x0 <= g.wd - 2) {
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(ft + (size_t)y * g.wp);
+        const uint32_t* r1 = r0 + wpr;
+        const uint32_t none = 0x7f7f7f7fu;
+        cur = r0[kx];
+        const uint32_t nxt = kx + 1 < wpr ? r0[kx + 1] : none;
+        const uint32_t prv1 = kx > 0 ? r1[kx - 1] : none;
+        const uint32_t cur1 = r1[kx];
+        const uint32_t nxt1 = kx + 1 < wpr ? r1[kx + 1] : none;
+        nb[0] = __funnelshift_r(cur, nxt, 8);       // (x+1, y)
+        nb[1] = cur1;                               // (x,   y+1)
+        nb[2] = __funnelshift_l(prv1, cur1, 8);     // (x-1, y+1)
+        nb[3] = __funnelshift_r(cur1, nxt1, 8);     // (x+1, y+1)
+        uint32_t xm = 0;                            // initiators: 1 <= x <= w-2
 #pragma unroll
-            for (int d = 0; d < 4; d++) {
-                const size_t id1 = id + (size_t)dys[d] * g.wp + dxs[d];
-                const int v1 = ft[id1];
-                if (v0 + v1 != 255) continue;
-                if (!have0) {
-                    rep0 = fl[id];
-                    ok0 = fs[rep0] >= 25u;
-                    have0 = true;
-                }
-                if (!ok0) break;
-                const uint32_t rep1 = fl[id1];
-                if (fs[rep1] < 25u) continue;
-                const uint32_t hi = max(rep0, rep1), lo = min(rep0, rep1);
-                k[cnt] = ((unsigned long long)hi << 32) | lo;
-                v[cnt] = pack_point(2 * x + dxs[d], 2 * y + dys[d], d, v1 > v0);
-                cnt++;
-            }
+        for (int i = 0; i < 4; i++)
+            if (x0 + i >= 1 && x0 + i <= g.wd - 2) xm |= 1u << (8 * i);
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const uint32_t e = cur ^ nb[d];
+            m[d] = (e >> 7) & e & xm;
         }
     }
+    unsigned long long* fk = keys + (size_t)frame * cap;
+    uint32_t* fv = vals + (size_t)frame * cap;
+    int cnt = 0;
+    if (m[0] | m[1] | m[2] | m[3]) cnt = edges_emit<false>(m, x0, y, g, fl, fs, cur, nb, fk, fv, 0, cap);
     // warp-aggregated append
     int incl = cnt;
 #pragma unroll
@@ -64,14 +100,7 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
     int base = 0;
     if (lane == 31) base = atomicAdd(&npts[frame], total);
     base = __shfl_sync(FULL_MASK, base, 31);
-    int pos = base + incl - cnt;
-    unsigned long long* fk = keys + (size_t)frame * cap;
-    uint32_t* fv = vals + (size_t)frame * cap;
-    for (int i = 0; i < cnt; i++, pos++)
-        if (pos < cap) {
-            fk[pos] = k[i];
-            fv[pos] = v[i];
-        }
+    if (cnt) edges_emit<true>(m, x0, y, g, fl, fs, cur, nb, fk, fv, base + incl - cnt, cap);
 }
 
 // ---- segmented LSD radix sort ---------------------------------------------------------------
@@ -204,19 +233,19 @@ k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* _
 }
 
 // cluster work lists, by size tier (the tier decides how much shared memory the fitting warp gets)
+#define AGPU_NTIERS 4
 struct ClusterLists {
-    ClusterRef* small_list;
-    ClusterRef* mid_list;
-    ClusterRef* large_list;
-    int* counters;   // [0] small, [1] large, [2] oversize (skipped), [3] all heads (debug), [4] mid
+    ClusterRef* list[AGPU_NTIERS];
+    int cap[AGPU_NTIERS];    // largest cluster size of the tier
+    int* counters;           // [0..3] tier counts, [4] oversize (skipped), [5] all heads (debug)
     int cap_list;
-    ClusterRef* dbg_heads;  // all run heads (debug only, may be null)
+    ClusterRef* dbg_heads;   // all run heads (debug only, may be null)
     int cap_dbg;
 };
 
 __global__ void __launch_bounds__(256)
 k_cluster_heads(const unsigned long long* __restrict__ keys, const int* __restrict__ npts, int cap, Geom g,
-                int min_size, int cap0, int cap1, int cap2, ClusterLists cl) {
+                int min_size, ClusterLists cl) {
     const int frame = blockIdx.y;
     const int n = min(npts[frame], cap);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,21 +262,17 @@ k_cluster_heads(const unsigned long long* __restrict__ keys, const int* __restri
     ClusterRef ref;
     ref.frame = frame; ref.start = i; ref.size = size; ref.pad = 0;
     if (cl.dbg_heads) {
-        int s = atomicAdd(&cl.counters[3], 1);
+        int s = atomicAdd(&cl.counters[5], 1);
         if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
     }
     const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);
     if (size < min_size || size > max_cluster) return;
-    if (size <= cap0) {
-        int s = atomicAdd(&cl.counters[0], 1);
-        if (s < cl.cap_list) cl.small_list[s] = ref;
-    } else if (size <= cap1) {
-        int s = atomicAdd(&cl.counters[4], 1);
-        if (s < cl.cap_list) cl.mid_list[s] = ref;
-    } else if (size <= cap2) {
-        int s = atomicAdd(&cl.counters[1], 1);
-        if (s < cl.cap_list) cl.large_list[s] = ref;
-    } else {
-        atomicAdd(&cl.counters[2], 1);
-    }
+#pragma unroll
+    for (int t = 0; t < AGPU_NTIERS; t++)
+        if (size <= cl.cap[t]) {
+            int s = atomicAdd(&cl.counters[t], 1);
+            if (s < cl.cap_list) cl.list[t][s] = ref;
+            return;
+        }
+    atomicAdd(&cl.counters[4], 1);
 }

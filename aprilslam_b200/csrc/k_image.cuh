@@ -14,6 +14,7 @@
 // (their tiles are needed by the dilation of lanes 1 and 30 but are written by the neighbouring
 // strip).
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 template <int F>
@@ -29,41 +30,18 @@ __device__ __forceinline__ void unpack16(const uint4 v, uint32_t (&w)[4 / F]) {
     }
 }
 
-__device__ __forceinline__ uint32_t bytes_min(uint32_t w) {
-    uint32_t a = __vminu4(w, w >> 16);
-    a = __vminu4(a, a >> 8);
-    return a & 0xffu;
-}
-__device__ __forceinline__ uint32_t bytes_max(uint32_t w) {
-    uint32_t a = __vmaxu4(w, w >> 16);
-    a = __vmaxu4(a, a >> 8);
-    return a & 0xffu;
-}
-
-template <int TPL>
-__device__ __forceinline__ uint32_t nb_left(uint32_t own, uint32_t from_up) {
-    // byte j <- tile j-1 (byte 0 from the lane on the left)
-    uint32_t r = (own << 8) | ((from_up >> (8 * (TPL - 1))) & 0xffu);
-    if (TPL < 4) r &= (1u << (8 * (TPL & 3))) - 1u;
-    return r;
-}
-template <int TPL>
-__device__ __forceinline__ uint32_t nb_right(uint32_t own, uint32_t from_down) {
-    // byte j <- tile j+1 (last byte from the lane on the right)
-    uint32_t lowm = (TPL == 1) ? 0u : ((1u << (8 * ((TPL - 1) & 3))) - 1u);
-    return ((own >> 8) & lowm) | ((from_down & 0xffu) << (8 * (TPL - 1)));
-}
-
-// threshold of one word (4 pixels) against tile extrema (mn, mx)
-__device__ __forceinline__ uint32_t thresh_word(uint32_t px, uint32_t mn, uint32_t mx, int min_diff) {
-    int diff = (int)mx - (int)mn;
-    if (diff < min_diff) return 0x7f7f7f7fu;
-    uint32_t thr = mn + (uint32_t)(diff >> 1);
-    return __vcmpgtu4(px, thr * 0x01010101u);  // 0xff where v > thr
-}
+// Byte arithmetic on the packed-half pipe: a byte b becomes the half 0x6400 | b (= 1024 + b, exact), two per
+// register, so min / max / compare of pixel pairs are single HMNMX2 / HSET2 instructions (the byte-SIMD
+// __vminu4 family is emulated with ~10 LOP3/PRMT each on sm_100).
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 px_lo(uint32_t w) { return u2h(__byte_perm(w, 0x64646464u, 0x4140)); }
+__device__ __forceinline__ __half2 px_hi(uint32_t w) { return u2h(__byte_perm(w, 0x64646464u, 0x4342)); }
+#define H2_BIG 0x7bff7bffu   // 65504: neutral element of min
+#define H2_ZERO 0x00000000u  // 0 < 1024: neutral element of max
 
 template <int F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_stride, size_t src_frame_stride,
                      uint8_t* __restrict__ quad_im, uint8_t* __restrict__ thresh, Geom g, int nstrips, int nsegs,
                      int seg_tiles, int nframes, int min_diff, int vec_ok) {
@@ -83,71 +61,110 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
     const int px0 = tile0 * 4;
     const long sc0 = (long)px0 * F;
     const bool is_out = lane >= 1 && lane <= 30 && px0 < g.wd;
-    const bool vec = vec_ok && sc0 >= 0 && sc0 + 16 <= W;
+    const bool lane_in = sc0 + 16 > 0 && sc0 < W;           // the lane's column chunk overlaps the frame
+    const bool vec = vec_ok && sc0 >= 0 && sc0 + 16 <= W;   // ... and is a whole aligned 16-byte chunk
 
     auto load_row = [&](int gy, uint32_t(&w)[TPL]) {
 #pragma unroll
         for (int j = 0; j < TPL; j++) w[j] = 0;
-        if (gy >= g.hd) return;
+        if (gy >= g.hd || !lane_in) return;
         const uint8_t* row = fsrc + (size_t)gy * F * src_stride;
         if (vec) {
             uint4 v = __ldg(reinterpret_cast<const uint4*>(row + sc0));
             unpack16<F>(v, w);
         } else {
-#pragma unroll
             for (int k = 0; k < TPL * 4; k++) {
                 long sx = sc0 + (long)k * F;
                 if (sx >= 0 && sx < W) w[k >> 2] |= (uint32_t)row[sx] << (8 * (k & 3));
             }
         }
     };
-    // packed per-tile extrema of tile row T (neutral for tiles outside the tile grid), horizontally dilated
-    auto tile_extrema = [&](int T, const uint32_t(&px)[4][TPL], uint32_t& hmn, uint32_t& hmx) {
-        uint32_t mn = 0, mx = 0;
+    auto load_tile_row = [&](int T, uint32_t(&px)[4][TPL]) {
+        if (T >= 0 && T < th) {
 #pragma unroll
-        for (int j = 0; j < TPL; j++) {
-            uint32_t a = __vminu4(__vminu4(px[0][j], px[1][j]), __vminu4(px[2][j], px[3][j]));
-            uint32_t b = __vmaxu4(__vmaxu4(px[0][j], px[1][j]), __vmaxu4(px[2][j], px[3][j]));
-            uint32_t tmn = bytes_min(a), tmx = bytes_max(b);
-            int tx = tile0 + j;
-            if (tx < 0 || tx >= tw || T < 0 || T >= th) { tmn = 255u; tmx = 0u; }
-            mn |= tmn << (8 * j);
-            mx |= tmx << (8 * j);
-        }
-        uint32_t mn_up = __shfl_up_sync(FULL_MASK, mn, 1), mn_dn = __shfl_down_sync(FULL_MASK, mn, 1);
-        uint32_t mx_up = __shfl_up_sync(FULL_MASK, mx, 1), mx_dn = __shfl_down_sync(FULL_MASK, mx, 1);
-        if (lane == 0) { mn_up = 0xffffffffu; mx_up = 0u; }
-        if (lane == 31) { mn_dn = 0xffffffffu; mx_dn = 0u; }
-        hmn = __vminu4(__vminu4(nb_left<TPL>(mn, mn_up), mn), nb_right<TPL>(mn, mn_dn));
-        hmx = __vmaxu4(__vmaxu4(nb_left<TPL>(mx, mx_up), mx), nb_right<TPL>(mx, mx_dn));
-        if (TPL < 4) {  // keep unused bytes neutral
-            hmn |= ~((1u << (8 * (TPL & 3))) - 1u);
-            hmx &= (1u << (8 * (TPL & 3))) - 1u;
+            for (int r = 0; r < 4; r++) load_row(T * 4 + r, px[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int j = 0; j < TPL; j++) px[r][j] = 0;
         }
     };
-    auto store_row = [&](int gy, const uint32_t(&px)[TPL], uint32_t dmn, uint32_t dmx, uint32_t lmn, uint32_t lmx) {
-        uint32_t o[TPL];
+    // per-tile extrema of tile row T as replicated half2 (neutral outside the tile grid), horizontally dilated
+    auto tile_extrema = [&](int T, const uint32_t(&px)[4][TPL], uint32_t(&hmn)[TPL], uint32_t(&hmx)[TPL]) {
+        uint32_t mn[TPL], mx[TPL];
+        const bool rowv = T >= 0 && T < th;
 #pragma unroll
         for (int j = 0; j < TPL; j++) {
-            int tx = tile0 + j;
-            uint32_t mn = (dmn >> (8 * j)) & 0xffu, mx = (dmx >> (8 * j)) & 0xffu;
-            if (tx >= tw) {  // right leftover columns use the last tile column
-                mn = (lmn >> (8 * j)) & 0xffu;
-                mx = (lmx >> (8 * j)) & 0xffu;
+            __half2 a = px_lo(px[0][j]), b = px_hi(px[0][j]);
+            __half2 lo = __hmin2(a, b), hi = __hmax2(a, b);
+#pragma unroll
+            for (int r = 1; r < 4; r++) {
+                a = px_lo(px[r][j]);
+                b = px_hi(px[r][j]);
+                lo = __hmin2(lo, __hmin2(a, b));
+                hi = __hmax2(hi, __hmax2(a, b));
             }
-            o[j] = thresh_word(px[j], mn, mx, min_diff);
+            lo = __hmin2(lo, u2h(__byte_perm(h2u(lo), 0, 0x1032)));
+            hi = __hmax2(hi, u2h(__byte_perm(h2u(hi), 0, 0x1032)));
+            const int tx = tile0 + j;
+            const bool v = rowv && tx >= 0 && tx < tw;
+            mn[j] = v ? h2u(lo) : H2_BIG;
+            mx[j] = v ? h2u(hi) : H2_ZERO;
         }
-        if (!is_out || gy >= g.hd) return;
-        size_t off = (size_t)gy * g.wp + px0;
-        if (TPL == 4) {
-            *reinterpret_cast<uint4*>(fth + off) = make_uint4(o[0], o[1 % TPL], o[2 % TPL], o[3 % TPL]);
-            if (fq) *reinterpret_cast<uint4*>(fq + off) = make_uint4(px[0], px[1 % TPL], px[2 % TPL], px[3 % TPL]);
-        } else if (TPL == 2) {
-            *reinterpret_cast<uint2*>(fth + off) = make_uint2(o[0], o[1 % TPL]);
-            if (fq) *reinterpret_cast<uint2*>(fq + off) = make_uint2(px[0], px[1 % TPL]);
-        } else {
-            *reinterpret_cast<uint32_t*>(fth + off) = o[0];
-            if (fq) *reinterpret_cast<uint32_t*>(fq + off) = px[0];
+        uint32_t mn_l = __shfl_up_sync(FULL_MASK, mn[TPL - 1], 1), mn_r = __shfl_down_sync(FULL_MASK, mn[0], 1);
+        uint32_t mx_l = __shfl_up_sync(FULL_MASK, mx[TPL - 1], 1), mx_r = __shfl_down_sync(FULL_MASK, mx[0], 1);
+        if (lane == 0) { mn_l = H2_BIG; mx_l = H2_ZERO; }
+        if (lane == 31) { mn_r = H2_BIG; mx_r = H2_ZERO; }
+#pragma unroll
+        for (int j = 0; j < TPL; j++) {
+            const uint32_t l_mn = j == 0 ? mn_l : mn[(j + TPL - 1) % TPL], r_mn = j == TPL - 1 ? mn_r : mn[(j + 1) % TPL];
+            const uint32_t l_mx = j == 0 ? mx_l : mx[(j + TPL - 1) % TPL], r_mx = j == TPL - 1 ? mx_r : mx[(j + 1) % TPL];
+            hmn[j] = h2u(__hmin2(__hmin2(u2h(l_mn), u2h(mn[j])), u2h(r_mn)));
+            hmx[j] = h2u(__hmax2(__hmax2(u2h(l_mx), u2h(mx[j])), u2h(r_mx)));
+        }
+    };
+    // threshold + store the four rows of tile row T (or one leftover row) against dilated extrema d
+    auto store_rows = [&](int gy0, int nrows, const uint32_t(&px)[4][TPL], const uint32_t(&dmn)[TPL],
+                          const uint32_t(&dmx)[TPL]) {
+        // the tile column left of this lane's first tile: right leftover pixels (x >= 4*tw) use tile tw-1
+        const uint32_t lmn = __shfl_up_sync(FULL_MASK, dmn[TPL - 1], 1), lmx = __shfl_up_sync(FULL_MASK, dmx[TPL - 1], 1);
+        uint32_t thr2[TPL];
+        bool flat[TPL];
+#pragma unroll
+        for (int j = 0; j < TPL; j++) {
+            const int tx = tile0 + j;
+            uint32_t a = dmn[j], b = dmx[j];
+            if (tx >= tw) { a = j == 0 ? lmn : dmn[(j + TPL - 1) % TPL]; b = j == 0 ? lmx : dmx[(j + TPL - 1) % TPL]; }
+            const int imn = a & 0xff, imx = b & 0xff;
+            const int diff = imx - imn;
+            flat[j] = diff < min_diff;
+            const uint32_t thr = (uint32_t)(imn + (diff >> 1));
+            thr2[j] = 0x64006400u | thr | (thr << 16);
+        }
+        if (!is_out) return;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int gy = gy0 + r;
+            if (r >= nrows || gy >= g.hd) break;
+            uint32_t o[TPL];
+#pragma unroll
+            for (int j = 0; j < TPL; j++) {
+                const uint32_t m0 = __hgt2_mask(px_lo(px[r][j]), u2h(thr2[j]));
+                const uint32_t m1 = __hgt2_mask(px_hi(px[r][j]), u2h(thr2[j]));
+                o[j] = flat[j] ? 0x7f7f7f7fu : __byte_perm(m0, m1, 0x6420);
+            }
+            const size_t off = (size_t)gy * g.wp + px0;
+            if (TPL == 4) {
+                __stcs(reinterpret_cast<uint4*>(fth + off), make_uint4(o[0], o[1 % TPL], o[2 % TPL], o[3 % TPL]));
+                if (fq) *reinterpret_cast<uint4*>(fq + off) = make_uint4(px[r][0], px[r][1 % TPL], px[r][2 % TPL], px[r][3 % TPL]);
+            } else if (TPL == 2) {
+                *reinterpret_cast<uint2*>(fth + off) = make_uint2(o[0], o[1 % TPL]);
+                if (fq) *reinterpret_cast<uint2*>(fq + off) = make_uint2(px[r][0], px[r][1 % TPL]);
+            } else {
+                *reinterpret_cast<uint32_t*>(fth + off) = o[0];
+                if (fq) *reinterpret_cast<uint32_t*>(fq + off) = px[r][0];
+            }
         }
     };
 
@@ -155,48 +172,39 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
     const int T1 = min(T0 + seg_tiles, th);
     if (T0 >= th) return;
 
-    uint32_t cur[4][TPL], nxt[4][TPL];
-    uint32_t prevMn = 0xffffffffu, prevMx = 0u, curMn, curMx;
-    if (T0 > 0) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) load_row((T0 - 1) * 4 + r, cur[r]);
-        tile_extrema(T0 - 1, cur, prevMn, prevMx);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++) load_row(T0 * 4 + r, cur[r]);
+    // software pipeline, two tile rows deep: while tile row T is thresholded the loads of T+2 are in flight
+    uint32_t cur[4][TPL], nxt[4][TPL], nn[4][TPL];
+    uint32_t prevMn[TPL], prevMx[TPL], curMn[TPL], curMx[TPL], nextMn[TPL], nextMx[TPL];
+    load_tile_row(T0 - 1, nn);
+    load_tile_row(T0, cur);
+    load_tile_row(T0 + 1, nxt);
+    tile_extrema(T0 - 1, nn, prevMn, prevMx);
     tile_extrema(T0, cur, curMn, curMx);
-
     for (int T = T0; T < T1; T++) {
-        uint32_t nextMn = 0xffffffffu, nextMx = 0u;
-        if (T + 1 < th) {
+        load_tile_row(T + 2 < T1 + 1 ? T + 2 : th, nn);     // nothing beyond this segment's lower halo row
+        tile_extrema(T + 1, nxt, nextMn, nextMx);
+        uint32_t dmn[TPL], dmx[TPL];
 #pragma unroll
-            for (int r = 0; r < 4; r++) load_row((T + 1) * 4 + r, nxt[r]);
-        } else {
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-#pragma unroll
-                for (int j = 0; j < TPL; j++) nxt[r][j] = 0;
+        for (int j = 0; j < TPL; j++) {
+            dmn[j] = h2u(__hmin2(__hmin2(u2h(prevMn[j]), u2h(curMn[j])), u2h(nextMn[j])));
+            dmx[j] = h2u(__hmax2(__hmax2(u2h(prevMx[j]), u2h(curMx[j])), u2h(nextMx[j])));
         }
-        tile_extrema(T + 1, nxt, nextMn, nextMx);  // neutral when T+1 == th
-        uint32_t dmn = __vminu4(__vminu4(prevMn, curMn), nextMn);
-        uint32_t dmx = __vmaxu4(__vmaxu4(prevMx, curMx), nextMx);
-        uint32_t lmn = nb_left<TPL>(dmn, __shfl_up_sync(FULL_MASK, dmn, 1));
-        uint32_t lmx = nb_left<TPL>(dmx, __shfl_up_sync(FULL_MASK, dmx, 1));
-#pragma unroll
-        for (int r = 0; r < 4; r++) store_row(T * 4 + r, cur[r], dmn, dmx, lmn, lmx);
+        store_rows(T * 4, 4, cur, dmn, dmx);
         if (T == th - 1 && (g.hd & 3)) {  // bottom leftover rows use the last tile row
-            for (int gy = th * 4; gy < g.hd; gy++) {
-                uint32_t w[TPL];
-                load_row(gy, w);
-                store_row(gy, w, dmn, dmx, lmn, lmx);
-            }
+            uint32_t lr[4][TPL];
+#pragma unroll
+            for (int r = 0; r < 4; r++) load_row(th * 4 + r, lr[r]);
+            store_rows(th * 4, g.hd - th * 4, lr, dmn, dmx);
         }
-        prevMn = curMn; prevMx = curMx;
-        curMn = nextMn; curMx = nextMx;
+#pragma unroll
+        for (int j = 0; j < TPL; j++) {
+            prevMn[j] = curMn[j]; prevMx[j] = curMx[j];
+            curMn[j] = nextMn[j]; curMx[j] = nextMx[j];
+        }
 #pragma unroll
         for (int r = 0; r < 4; r++)
 #pragma unroll
-            for (int j = 0; j < TPL; j++) cur[r][j] = nxt[r][j];
+            for (int j = 0; j < TPL; j++) { cur[r][j] = nxt[r][j]; nxt[r][j] = nn[r][j]; }
     }
 }
 

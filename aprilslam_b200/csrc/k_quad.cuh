@@ -81,17 +81,20 @@ __device__ void fit_line_dev(const double* lf, int sz, int i0, int i1, LineFit& 
     out.mse = eig_small;
 }
 
+// Bitonic sort of n2 (power of two >= 64) 64-bit keys in shared memory by one warp: every lane owns
+// compare-exchange PAIRS (no idle half), four independent pairs per step for memory-level parallelism.
 __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* s, int n2, bool descending) {
     const int lane = threadIdx.x & 31;
+    const int npairs = n2 >> 1;
     for (int k = 2; k <= n2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < n2; i += 32) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = s[i], b = s[ixj];
-                    bool up = ((i & k) == 0) != descending;
-                    if ((a > b) == up) { s[i] = b; s[ixj] = a; }
-                }
+#pragma unroll 4
+            for (int t = lane; t < npairs; t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                unsigned long long a = s[i], b = s[ixj];
+                const bool up = ((i & k) == 0) != descending;
+                if ((a > b) == up) { s[i] = b; s[ixj] = a; }
             }
             __syncwarp();
         }
@@ -145,7 +148,7 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
     if (!P.normal_border && !reversed) return false;
 
     // ---- slope keys
-    int n2 = 32;
+    int n2 = 64;
     while (n2 < sz) n2 <<= 1;
     for (int i = lane; i < n2; i += 32) {
         unsigned long long key = ~0ull;
@@ -256,9 +259,9 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
     __syncwarp();
 
     // ---- local maxima, in index order
-    const int half = n2 >> 1;
+    const int half = max(n2 >> 1, 64);                      // room for the padded (>= 64) sort of the maxima values
     unsigned long long* mvals = sbuf;                       // [half]
-    int* midx = reinterpret_cast<int*>(sbuf + half);        // [<= half]
+    int* midx = reinterpret_cast<int*>(sbuf + half);        // [<= n2/2 ints]
     int nmax = 0;
     for (int base = 0; base < sz; base += 32) {
         int i = base + lane;
@@ -280,7 +283,7 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
     __syncwarp();
     if (nmax < 4) return false;
     if (nmax > P.max_nmaxima) {
-        int p2 = 32;
+        int p2 = 64;
         while (p2 < nmax) p2 <<= 1;
         for (int i = nmax + lane; i < p2; i += 32) mvals[i] = 0ull;
         __syncwarp();
@@ -426,17 +429,21 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
     return true;
 }
 
-// Persistent warps: warp w takes clusters w, w + nwarps, ...  Dynamic shared memory per warp:
-// wcap u64 (sort buffer) + 600 doubles (pair table) + 16 ints.
-__global__ void k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
+// Persistent warps: warp w takes clusters w, w + nwarps, ...  Dynamic shared memory per warp: `wcap` u64
+// (sort buffer; from 1024 keys on it also hosts the 600-double pair table once the sort is over) + 16 ints,
+// plus a separate pair table for the small tiers.
+__host__ __device__ inline size_t qf_smem_per_warp(int wcap) {
+    return (size_t)wcap * 8 + 64 + (wcap >= 1024 ? 0 : QF_PTAB_DOUBLES * 8);
+}
+
+__global__ void __launch_bounds__(256, 3) k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wpb = blockDim.x >> 5;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = (size_t)wcap * 8 + QF_PTAB_DOUBLES * 8 + 64;
-    unsigned char* base = smem_raw + per_warp * w;
+    unsigned char* base = smem_raw + qf_smem_per_warp(wcap) * w;
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(base);
-    double* ptab = reinterpret_cast<double*>(base + (size_t)wcap * 8);
-    int* sidx = reinterpret_cast<int*>(base + (size_t)wcap * 8 + QF_PTAB_DOUBLES * 8);
+    int* sidx = reinterpret_cast<int*>(base + (size_t)wcap * 8);
+    double* ptab = wcap >= 1024 ? reinterpret_cast<double*>(base) : reinterpret_cast<double*>(base + (size_t)wcap * 8 + 64);
     const int n = min(*a.list_count, a.list_cap);
     const int nwarps = gridDim.x * wpb;
     for (int ci = blockIdx.x * wpb + w; ci < n; ci += nwarps) {
