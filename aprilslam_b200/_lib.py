@@ -27,7 +27,7 @@ class AgpuConfig(C.Structure):
     _fields_ = [("families", C.c_char_p), ("threads", C.c_int), ("maxhamming", C.c_int),
                 ("quad_decimate", C.c_float), ("quad_sigma", C.c_float), ("refine_edges", C.c_int),
                 ("decode_sharpening", C.c_double), ("debug", C.c_int), ("device", C.c_int),
-                ("chunk_frames", C.c_int), ("max_points_per_frame", C.c_int),
+                ("chunk_frames", C.c_int), ("pipeline_slots", C.c_int), ("max_points_per_frame", C.c_int),
                 ("max_clusters_per_frame", C.c_int), ("max_quads_per_frame", C.c_int)]
 
 

@@ -80,6 +80,42 @@ enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_FIXED
 
 }  // namespace
 
+// One pipeline slot: the workspaces, streams and pinned result buffers of ONE chunk in flight.  Several
+// slots run concurrently (each on its own stream) so that the latency-bound stages of one chunk (quad
+// fitting, decode, reconcile, pose, the radix-sort scans) overlap the bandwidth-bound stages of another.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};   // side streams: quad-fit tiers run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> events;   // stage timing
+    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes;
+    DevBuf d_keys[2], d_vals[2], d_hist, d_lfps, d_errs;
+    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk]
+    DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
+    HostBuf h_out, h_counts, h_poses;
+    bool pending = false;
+    int b0 = 0, n = 0, sorted = 0;
+
+    void release() {
+        DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_labels, &d_sizes,
+                          &d_keys[0], &d_keys[1], &d_vals[0], &d_vals[1], &d_hist, &d_lfps, &d_errs, &d_counters,
+                          &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
+                          &d_refined, &d_dets, &d_out, &d_poses};
+        for (DevBuf* bb : bufs) bb->release();
+        h_out.release(); h_counts.release(); h_poses.release();
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        events.clear();
+        for (int t = 0; t < AGPU_NTIERS - 1; t++) {
+            if (aux[t]) cudaStreamDestroy(aux[t]);
+            if (ev_join[t]) cudaEventDestroy(ev_join[t]);
+            aux[t] = nullptr; ev_join[t] = nullptr;
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (stream) cudaStreamDestroy(stream);
+        ev_fork = nullptr; stream = nullptr;
+    }
+};
+
 struct agpu_handle {
     agpu_config cfg;
     std::string families_str;
@@ -87,30 +123,22 @@ struct agpu_handle {
     DevParams prm;
     int device = 0;
     int num_sms = 148;
-    cudaStream_t stream = nullptr;
-    cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};   // side streams: the quad-fit tiers run concurrently
-    cudaEvent_t ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
     std::string err;
     bool profiling = false;
     float stage_ms[AGPU_NUM_STAGES];
     long long launches = 0;
     long long counters[8];
-    std::vector<cudaEvent_t> events;
 
-    // device data
-    DevBuf d_fams, d_codes;
-    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes;
-    DevBuf d_keys[2], d_vals[2], d_hist, d_lfps, d_errs;
-    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk]
-    DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses, d_pose_in;
-    HostBuf h_out, h_counts, h_poses, h_counters;
+    DevBuf d_fams, d_codes, d_pose_in, d_pose_out;
+    std::vector<Slot> slots;
+    cudaEvent_t ev_user = nullptr;
 
     // growable per-frame list capacities (0 = not chosen yet)
     int cap_points = 0, cap_clusters = 0, cap_quads = 0;
 
-    // state of the last chunk (debug fetch)
+    // state of the last finished chunk (debug fetch)
     Geom geom;
-    int last_chunk = 0, last_cap = 0, last_sorted = 0;
+    int last_slot = 0, last_chunk = 0, last_cap = 0;
     bool have_last = false;
 
     void set_err(const std::string& s) { err = s; }
@@ -170,30 +198,42 @@ int gaussian_kernel_host(float sigma, uint8_t* k) {
     return ksz;
 }
 
+int init_slot(agpu_handle* h, Slot& s) {
+    if (s.stream) return AGPU_OK;
+    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (int t = 0; t < AGPU_NTIERS - 1; t++) {
+        CK(cudaStreamCreateWithFlags(&s.aux[t], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s.ev_join[t], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    return AGPU_OK;
+}
+
 struct StageTimer {
     agpu_handle* h;
+    Slot& s;
     size_t next = 0;
-    explicit StageTimer(agpu_handle* hh) : h(hh) {}
+    StageTimer(agpu_handle* hh, Slot& ss) : h(hh), s(ss) {}
     void mark() {
         if (!h->profiling) return;
-        if (next >= h->events.size()) {
+        if (next >= s.events.size()) {
             cudaEvent_t e;
             cudaEventCreate(&e);
-            h->events.push_back(e);
+            s.events.push_back(e);
         }
-        cudaEventRecord(h->events[next++], h->stream);
+        cudaEventRecord(s.events[next++], s.stream);
     }
 };
 
 // ------------------------------------------------------------------------------------------
 // image + CC stages on `n` frames already on the device (shared by the pipeline and the stage hooks)
 // ------------------------------------------------------------------------------------------
-int run_image_stage(agpu_handle* h, const uint8_t* d_src, int channels, int W, int H, size_t stride,
+int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels, int W, int H, size_t stride,
                     size_t frame_stride, int n, const Geom& g, const uint8_t** quad_im_out, size_t* q_pitch,
                     size_t* q_frame, const uint8_t** gray_full, size_t* gray_pitch, size_t* gray_frame) {
     const int f = h->prm.decim;
     const float sigma = h->cfg.quad_sigma;
-    CK(h->d_thresh.ensure(g.plane * n));
+    CK(sl.d_thresh.ensure(g.plane * n));
     const uint8_t* src = d_src;
     size_t s_stride = stride, s_frame = frame_stride;
     int srcW = W, srcH = H;
@@ -201,15 +241,15 @@ int run_image_stage(agpu_handle* h, const uint8_t* d_src, int channels, int W, i
     // full-resolution gray image for refine_edges / decode
     if (channels == 3) {
         Geom gf = make_geom(W, H, 1);
-        CK(h->d_gray.ensure(gf.plane * n));
+        CK(sl.d_gray.ensure(gf.plane * n));
         size_t total = (size_t)n * gf.hd * (gf.wp >> 2);
-        k_pack<<<ceil_div(total, 256), 256, 0, h->stream>>>(d_src, W, H, stride, frame_stride, 3, 1,
-                                                            h->d_gray.as<uint8_t>(), gf, n);
+        k_pack<<<ceil_div(total, 256), 256, 0, sl.stream>>>(d_src, W, H, stride, frame_stride, 3, 1,
+                                                            sl.d_gray.as<uint8_t>(), gf, n);
         LAUNCH_CHECK("k_pack(bgr)");
-        *gray_full = h->d_gray.as<uint8_t>();
+        *gray_full = sl.d_gray.as<uint8_t>();
         *gray_pitch = gf.wp;
         *gray_frame = gf.plane;
-        src = h->d_gray.as<uint8_t>();
+        src = sl.d_gray.as<uint8_t>();
         s_stride = gf.wp;
         s_frame = gf.plane;
         channels = 1;
@@ -218,33 +258,33 @@ int run_image_stage(agpu_handle* h, const uint8_t* d_src, int channels, int W, i
         *gray_pitch = stride;
         *gray_frame = frame_stride;
     }
-    const bool fast2 = (f == 1 || f == 2 || f == 4) && sigma == 0.0f;
+    const bool fast = (f == 1 || f == 2 || f == 4) && sigma == 0.0f;
     uint8_t* quad_im = nullptr;
-    if (!fast2) {
+    if (!fast) {
         // generic: decimate into quad_im, optional blur, then threshold the quad image with F = 1
-        CK(h->d_quad_im.ensure(g.plane * n));
-        quad_im = h->d_quad_im.as<uint8_t>();
+        CK(sl.d_quad_im.ensure(g.plane * n));
+        quad_im = sl.d_quad_im.as<uint8_t>();
         size_t total = (size_t)n * g.hd * (g.wp >> 2);
-        k_pack<<<ceil_div(total, 256), 256, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, 1, f, quad_im, g, n);
+        k_pack<<<ceil_div(total, 256), 256, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, 1, f, quad_im, g, n);
         LAUNCH_CHECK("k_pack");
         if (sigma != 0.0f) {
             BlurKernel bk;
             memset(&bk, 0, sizeof(bk));
             bk.ksz = gaussian_kernel_host(std::fabs(sigma), bk.k);
             if (bk.ksz > 1) {
-                CK(h->d_blur_tmp.ensure(g.plane * n));
-                uint8_t* tmp = h->d_blur_tmp.as<uint8_t>();
+                CK(sl.d_blur_tmp.ensure(g.plane * n));
+                uint8_t* tmp = sl.d_blur_tmp.as<uint8_t>();
                 if (sigma < 0) {
-                    CK(h->d_blur_orig.ensure(g.plane * n));
-                    CK(cudaMemcpyAsync(h->d_blur_orig.p, quad_im, g.plane * n, cudaMemcpyDeviceToDevice, h->stream));
+                    CK(sl.d_blur_orig.ensure(g.plane * n));
+                    CK(cudaMemcpyAsync(sl.d_blur_orig.p, quad_im, g.plane * n, cudaMemcpyDeviceToDevice, sl.stream));
                 }
                 size_t tot = (size_t)n * g.hd * g.wd;
-                k_blur_pass<<<ceil_div(tot, 256), 256, 0, h->stream>>>(quad_im, tmp, g, n, bk, 0);
+                k_blur_pass<<<ceil_div(tot, 256), 256, 0, sl.stream>>>(quad_im, tmp, g, n, bk, 0);
                 LAUNCH_CHECK("k_blur_pass(rows)");
-                k_blur_pass<<<ceil_div(tot, 256), 256, 0, h->stream>>>(tmp, quad_im, g, n, bk, 1);
+                k_blur_pass<<<ceil_div(tot, 256), 256, 0, sl.stream>>>(tmp, quad_im, g, n, bk, 1);
                 LAUNCH_CHECK("k_blur_pass(cols)");
                 if (sigma < 0) {
-                    k_unsharp<<<ceil_div(g.plane * n, 256), 256, 0, h->stream>>>(h->d_blur_orig.as<uint8_t>(), quad_im, g, n);
+                    k_unsharp<<<ceil_div(g.plane * n, 256), 256, 0, sl.stream>>>(sl.d_blur_orig.as<uint8_t>(), quad_im, g, n);
                     LAUNCH_CHECK("k_unsharp");
                 }
             }
@@ -258,11 +298,11 @@ int run_image_stage(agpu_handle* h, const uint8_t* d_src, int channels, int W, i
     }
     uint8_t* quad_out = nullptr;
     if (F > 1) {
-        CK(h->d_quad_im.ensure(g.plane * n));
-        quad_out = h->d_quad_im.as<uint8_t>();
+        CK(sl.d_quad_im.ensure(g.plane * n));
+        quad_out = sl.d_quad_im.as<uint8_t>();
     }
     if ((g.wd >> 2) == 0 || (g.hd >> 2) == 0) {
-        CK(cudaMemsetAsync(h->d_thresh.p, 127, g.plane * n, h->stream));
+        CK(cudaMemsetAsync(sl.d_thresh.p, 127, g.plane * n, sl.stream));
     } else {
         const int TPL = 4 / F;
         const int strip_px = 30 * TPL * 4;
@@ -275,15 +315,15 @@ int run_image_stage(agpu_handle* h, const uint8_t* d_src, int channels, int W, i
         const int blocks = ceil_div(warps * 32, 128);
         const int vec_ok = (s_stride % 16 == 0) && (s_frame % 16 == 0) && (((uintptr_t)src) % 16 == 0);
         const int md = h->prm.min_white_black_diff;
-        uint8_t* th_out = h->d_thresh.as<uint8_t>();
+        uint8_t* th_out = sl.d_thresh.as<uint8_t>();
         if (F == 1)
-            k_decimate_threshold<1><<<blocks, 128, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
+            k_decimate_threshold<1><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
                                                                    nstrips, nsegs, seg_tiles, n, md, vec_ok);
         else if (F == 2)
-            k_decimate_threshold<2><<<blocks, 128, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
+            k_decimate_threshold<2><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
                                                                    nstrips, nsegs, seg_tiles, n, md, vec_ok);
         else
-            k_decimate_threshold<4><<<blocks, 128, 0, h->stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
+            k_decimate_threshold<4><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
                                                                    nstrips, nsegs, seg_tiles, n, md, vec_ok);
         LAUNCH_CHECK("k_decimate_threshold");
     }
@@ -295,17 +335,17 @@ int run_image_stage(agpu_handle* h, const uint8_t* d_src, int channels, int W, i
     return AGPU_OK;
 }
 
-int run_cc_stage(agpu_handle* h, const uint8_t* d_thresh, int n, const Geom& g) {
-    CK(h->d_labels.ensure(g.plane * n * 4));
-    CK(h->d_sizes.ensure(g.plane * n * 4));
+int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const Geom& g) {
+    CK(sl.d_labels.ensure(g.plane * n * 4));
+    CK(sl.d_sizes.ensure(g.plane * n * 4));
     const int tx = ceil_div(g.wd, CC_TW), ty = ceil_div(g.hd, CC_TH);
     dim3 grid(tx, ty, n);
-    k_cc_local<<<grid, CC_THREADS, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), h->d_sizes.as<uint32_t>(), g, tx, ty);
+    k_cc_local<<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), g, tx, ty);
     LAUNCH_CHECK("k_cc_local");
-    k_cc_boundary<<<grid, 160, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), g, tx, ty);
+    k_cc_boundary<<<grid, 160, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), g, tx, ty);
     LAUNCH_CHECK("k_cc_boundary");
     dim3 gridf(ceil_div(g.wd, CCF_TW), ceil_div(g.hd, CCF_TH), n);
-    k_cc_finalize<<<gridf, CC_THREADS, 0, h->stream>>>(d_thresh, h->d_labels.as<uint32_t>(), h->d_sizes.as<uint32_t>(), g);
+    k_cc_finalize<<<gridf, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), g);
     LAUNCH_CHECK("k_cc_finalize");
     return AGPU_OK;
 }
@@ -344,6 +384,259 @@ int parse_dist(agpu_handle* h, const double* dist, int ndist, PoseSpec& ps) {
 // ------------------------------------------------------------------------------------------
 // the pipeline
 // ------------------------------------------------------------------------------------------
+struct CallCtx {   // constants of one agpu_detect* call
+    const uint8_t* frames;
+    int on_device, channels, B, W, H, stride;
+    size_t frame_bytes;
+    Geom g;
+    int chunk, cap, maxcl, maxq, cap_out, key_bits, nblk_max;
+    size_t ncnt;
+    const PoseSpec* pose;
+};
+
+int alloc_slot(agpu_handle* h, Slot& s, const CallCtx& c) {
+    int rc = init_slot(h, s);
+    if (rc) return rc;
+    const int chunk = c.chunk, cap = c.cap;
+    if (!c.on_device) CK(s.d_in.ensure(c.frame_bytes * chunk));
+    for (int i = 0; i < 2; i++) {
+        CK(s.d_keys[i].ensure((size_t)chunk * cap * 8));
+        CK(s.d_vals[i].ensure((size_t)chunk * cap * 4));
+    }
+    CK(s.d_hist.ensure((size_t)chunk * RS_RADIX * c.nblk_max * 4));
+    CK(s.d_lfps.ensure((size_t)chunk * cap * 48));
+    CK(s.d_errs.ensure((size_t)chunk * cap * 8));
+    CK(s.d_counters.ensure(c.ncnt * 4));
+    for (int t = 0; t < AGPU_NTIERS; t++) CK(s.d_clusters[t].ensure((size_t)chunk * c.maxcl * sizeof(ClusterRef)));
+    if (h->cfg.debug) {
+        CK(s.d_dbg_heads.ensure((size_t)chunk * cap / 4 * sizeof(ClusterRef)));
+        CK(s.d_refined.ensure((size_t)chunk * c.maxq * 32));
+    }
+    CK(s.d_quads.ensure((size_t)chunk * c.maxq * sizeof(QuadRec)));
+    CK(s.d_dets.ensure((size_t)chunk * REC_CAP * sizeof(DetRec)));
+    CK(s.d_out.ensure((size_t)chunk * c.cap_out * sizeof(DetRec)));
+    CK(s.h_out.ensure((size_t)chunk * c.cap_out * sizeof(DetRec)));
+    CK(s.h_counts.ensure(c.ncnt * 4));
+    if (c.pose->enabled) {
+        CK(s.d_poses.ensure((size_t)chunk * c.cap_out * sizeof(PoseRec)));
+        CK(s.h_poses.ensure((size_t)chunk * c.cap_out * sizeof(PoseRec)));
+    }
+    return AGPU_OK;
+}
+
+// enqueue the whole pipeline of frames [b0, b0+n) on the slot's stream (no host synchronisation)
+int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
+    const Geom& g = c.g;
+    const int chunk = c.chunk, cap = c.cap;
+    int* d_cnt = sl.d_counters.as<int>();
+    int* d_npts = d_cnt + CNT_FIXED;
+    int* d_frame_quads = d_npts + chunk;
+    int* d_ndets = d_frame_quads + chunk;
+    int* d_out_counts = d_ndets + chunk;
+    StageTimer tm(h, sl);
+    tm.mark();  // 0
+    const uint8_t* d_src;
+    if (c.on_device) {
+        d_src = c.frames + (size_t)b0 * c.frame_bytes;
+    } else {
+        CK(cudaMemcpyAsync(sl.d_in.p, c.frames + (size_t)b0 * c.frame_bytes, c.frame_bytes * n, cudaMemcpyHostToDevice,
+                           sl.stream));
+        d_src = sl.d_in.as<uint8_t>();
+    }
+    CK(cudaMemsetAsync(d_cnt, 0, c.ncnt * 4, sl.stream));
+    tm.mark();  // 1: after H2D
+    const uint8_t *quad_im, *gray_full;
+    size_t q_pitch, q_frame, gray_pitch, gray_frame;
+    int rc = run_image_stage(h, sl, d_src, c.channels, c.W, c.H, c.stride, c.frame_bytes, n, g, &quad_im, &q_pitch,
+                             &q_frame, &gray_full, &gray_pitch, &gray_frame);
+    if (rc) return rc;
+    tm.mark();  // 2: after image
+    rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), n, g);
+    if (rc) return rc;
+    tm.mark();  // 3: after CC
+    {
+        dim3 grid(ceil_div(g.wp >> 2, 32), ceil_div(g.hd - 1, 8), n);
+        k_edges<<<grid, 256, 0, sl.stream>>>(sl.d_thresh.as<uint8_t>(), sl.d_labels.as<uint32_t>(),
+                                             sl.d_sizes.as<uint32_t>(), g, sl.d_keys[0].as<unsigned long long>(),
+                                             sl.d_vals[0].as<uint32_t>(), d_npts, cap);
+        LAUNCH_CHECK("k_edges");
+    }
+    tm.mark();  // 4: after edges
+    int cur = 0;
+    {
+        int shifts[16], ns = 0;
+        for (int s = 0; s < c.key_bits; s += 8) shifts[ns++] = s;
+        for (int s = 0; s < c.key_bits; s += 8) shifts[ns++] = 32 + s;
+        for (int i = 0; i < ns; i++) {
+            const int shift = shifts[i];
+            dim3 grid(c.nblk_max, n);
+            k_sort_hist<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_keys[cur].as<unsigned long long>(), d_npts, cap, shift,
+                                                            sl.d_hist.as<uint32_t>(), c.nblk_max);
+            LAUNCH_CHECK("k_sort_hist");
+            k_sort_scan<<<n, 1024, 0, sl.stream>>>(d_npts, cap, sl.d_hist.as<uint32_t>(), c.nblk_max);
+            LAUNCH_CHECK("k_sort_scan");
+            k_sort_scatter<<<grid, RS_THREADS, 0, sl.stream>>>(
+                sl.d_keys[cur].as<unsigned long long>(), sl.d_vals[cur].as<uint32_t>(),
+                sl.d_keys[cur ^ 1].as<unsigned long long>(), sl.d_vals[cur ^ 1].as<uint32_t>(), d_npts, cap, shift,
+                sl.d_hist.as<uint32_t>(), c.nblk_max);
+            LAUNCH_CHECK("k_sort_scatter");
+            cur ^= 1;
+        }
+    }
+    tm.mark();  // 5: after sort
+    const unsigned long long* skeys = sl.d_keys[cur].as<unsigned long long>();
+    const uint32_t* svals = sl.d_vals[cur].as<uint32_t>();
+    {
+        ClusterLists cl;
+        for (int t = 0; t < AGPU_NTIERS; t++) {
+            cl.list[t] = sl.d_clusters[t].as<ClusterRef>();
+            cl.cap[t] = TIER_CAP[t];
+        }
+        cl.counters = d_cnt;
+        cl.cap_list = n * c.maxcl;
+        cl.dbg_heads = h->cfg.debug ? sl.d_dbg_heads.as<ClusterRef>() : nullptr;
+        cl.cap_dbg = (int)(sl.d_dbg_heads.bytes / sizeof(ClusterRef));
+        dim3 grid(ceil_div(cap, 256), n);
+        k_cluster_heads<<<grid, 256, 0, sl.stream>>>(skeys, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
+        LAUNCH_CHECK("k_cluster_heads");
+        QuadFitArgs qa;
+        qa.vals = svals; qa.keys = skeys; qa.cap = cap;
+        qa.quad_im = quad_im; qa.q_pitch = q_pitch; qa.q_frame = q_frame;
+        qa.g = g;
+        qa.lfps = sl.d_lfps.as<double>();
+        qa.errs = sl.d_errs.as<double>();
+        qa.list_cap = n * c.maxcl;
+        qa.quads = sl.d_quads.as<QuadRec>();
+        qa.nquads = d_cnt + CNT_NQUADS;
+        qa.cap_quads = n * c.maxq;
+        qa.per_frame_quads = d_frame_quads;
+        // the tiers are independent (own work list, atomic appends to the quad list): fork them over side
+        // streams so that the latency-bound big-cluster warps overlap with the many small clusters
+        CK(cudaEventRecord(sl.ev_fork, sl.stream));
+        for (int t = AGPU_NTIERS - 1; t >= 0; t--) {
+            cudaStream_t st = t == 0 ? sl.stream : sl.aux[t - 1];
+            if (t > 0) CK(cudaStreamWaitEvent(st, sl.ev_fork, 0));
+            qa.list = sl.d_clusters[t].as<ClusterRef>();
+            qa.list_count = d_cnt + CNT_TIER0 + t;
+            const size_t smem = (size_t)TIER_WPB[t] * qf_smem_per_warp(TIER_CAP[t]);
+            k_fit_quads<<<h->num_sms * TIER_CTAS_PER_SM[t], TIER_WPB[t] * 32, smem, st>>>(qa, h->prm, TIER_CAP[t]);
+            LAUNCH_CHECK("k_fit_quads");
+            if (t > 0) {
+                CK(cudaEventRecord(sl.ev_join[t - 1], st));
+                CK(cudaStreamWaitEvent(sl.stream, sl.ev_join[t - 1], 0));
+            }
+        }
+    }
+    tm.mark();  // 6: after quads
+    {
+        DecodeArgs da;
+        da.im = gray_full; da.pitch = gray_pitch; da.frame_stride = gray_frame;
+        da.W = c.W; da.H = c.H;
+        da.quads = sl.d_quads.as<QuadRec>();
+        da.nquads = d_cnt + CNT_NQUADS;
+        da.cap_quads = n * c.maxq;
+        da.fams = h->d_fams.as<DevFamily>();
+        da.codes = h->d_codes.as<unsigned long long>();
+        da.dets = sl.d_dets.as<DetRec>();
+        da.ndets = d_ndets;
+        da.cap_dets = REC_CAP;
+        da.dbg_refined = h->cfg.debug ? sl.d_refined.as<float>() : nullptr;
+        k_decode_quads<<<h->num_sms * 4, 128, 0, sl.stream>>>(da, h->prm);
+        LAUNCH_CHECK("k_decode_quads");
+    }
+    tm.mark();  // 7: after decode
+    k_reconcile<<<ceil_div(n, 4), 128, 0, sl.stream>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
+                                                      sl.d_out.as<DetRec>(), d_out_counts, c.cap_out);
+    LAUNCH_CHECK("k_reconcile");
+    if (c.pose->enabled) {
+        PoseArgs pa;
+        fill_pose_args(pa, *c.pose, 0);
+        pa.corners = reinterpret_cast<const double*>(sl.d_out.as<char>() + offsetof(DetRec, p));
+        pa.corner_stride = (int)(sizeof(DetRec) / 8);
+        pa.counts = d_out_counts;
+        pa.per_frame = c.cap_out;
+        pa.M = n * c.cap_out;
+        pa.out = sl.d_poses.as<PoseRec>();
+        k_pose<<<ceil_div((long long)pa.M * 4, 128), 128, 0, sl.stream>>>(pa);
+        LAUNCH_CHECK("k_pose");
+    }
+    tm.mark();  // 8: after reconcile/pose
+    CK(cudaMemcpyAsync(sl.h_counts.p, d_cnt, c.ncnt * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaMemcpyAsync(sl.h_out.p, sl.d_out.p, (size_t)n * c.cap_out * sizeof(DetRec), cudaMemcpyDeviceToHost, sl.stream));
+    if (c.pose->enabled)
+        CK(cudaMemcpyAsync(sl.h_poses.p, sl.d_poses.p, (size_t)n * c.cap_out * sizeof(PoseRec), cudaMemcpyDeviceToHost,
+                           sl.stream));
+    tm.mark();  // 9: after D2H
+    sl.pending = true;
+    sl.b0 = b0;
+    sl.n = n;
+    sl.sorted = cur;
+    return AGPU_OK;
+}
+
+struct Overflow {
+    int max_pts = 0, max_cl_per_frame = 0, max_q_per_frame = 0;
+    bool any = false;
+};
+
+// wait for the slot's chunk and move its results into the caller's arrays; 1 = a work list overflowed (redo)
+int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out, agpu_pose_t* poses, int* counts,
+                 Overflow& ov, int& rc_final) {
+    CK(cudaStreamSynchronize(sl.stream));
+    sl.pending = false;
+    const int n = sl.n, b0 = sl.b0, chunk = c.chunk;
+    if (h->profiling) {
+        for (int s = 0; s < AGPU_NUM_STAGES; s++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, sl.events[s], sl.events[s + 1]);
+            h->stage_ms[s] += ms;
+        }
+    }
+    const int* hc = sl.h_counts.as<int>();
+    const int* h_npts = hc + CNT_FIXED;
+    const int* h_nd = h_npts + 2 * chunk;
+    const int* h_oc = h_nd + chunk;
+    int max_pts = 0, max_cl = 0;
+    for (int i = 0; i < n; i++) max_pts = std::max(max_pts, h_npts[i]);
+    for (int t = 0; t < AGPU_NTIERS; t++) max_cl = std::max(max_cl, hc[CNT_TIER0 + t]);
+    bool redo = false;
+    if (max_pts > c.cap) { ov.max_pts = std::max(ov.max_pts, max_pts); redo = true; }
+    if (max_cl > n * c.maxcl) { ov.max_cl_per_frame = std::max(ov.max_cl_per_frame, (max_cl + n - 1) / n); redo = true; }
+    if (hc[CNT_NQUADS] > n * c.maxq) { ov.max_q_per_frame = std::max(ov.max_q_per_frame, (hc[CNT_NQUADS] + n - 1) / n); redo = true; }
+    if (redo) {
+        ov.any = true;
+        return 1;
+    }
+    const DetRec* ho = sl.h_out.as<DetRec>();
+    for (int i = 0; i < n; i++) {
+        const int cnt = h_oc[i];
+        counts[b0 + i] = cnt;
+        const int m = std::min(cnt, c.cap_out);
+        memcpy(out + (size_t)(b0 + i) * c.cap_out, ho + (size_t)i * c.cap_out, (size_t)m * sizeof(DetRec));
+        if (c.pose->enabled && poses)
+            memcpy(poses + (size_t)(b0 + i) * c.cap_out, sl.h_poses.as<PoseRec>() + (size_t)i * c.cap_out,
+                   (size_t)m * sizeof(PoseRec));
+        if (cnt > c.cap_out && rc_final == AGPU_OK) {
+            h->set_err("more detections than cap_per_frame; counts[] hold the true numbers");
+            rc_final = AGPU_E_TRUNCATED;
+        }
+        h->counters[0] += h_npts[i];
+        h->counters[3] += h_nd[i];
+        if (h_nd[i] > REC_CAP) {
+            h->set_err("more than 256 raw detections in one frame");
+            rc_final = AGPU_E_WORKSPACE;
+        }
+    }
+    for (int t = 0; t < AGPU_NTIERS; t++) h->counters[1] += hc[CNT_TIER0 + t];
+    h->counters[2] += hc[CNT_NQUADS];
+    h->counters[4] += hc[CNT_OVERSIZE];
+    h->last_slot = (int)(&sl - h->slots.data());
+    h->last_chunk = n;
+    h->last_cap = c.cap;
+    h->have_last = true;
+    return 0;
+}
+
 int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channels, int B, int W, int H, int stride,
                 void* cuda_stream, const PoseSpec& pose, agpu_detection* out, agpu_pose_t* poses, int cap_out,
                 int* counts) {
@@ -361,287 +654,94 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     h->launches = 0;
     for (int i = 0; i < AGPU_NUM_STAGES; i++) h->stage_ms[i] = 0;
     for (int i = 0; i < 8; i++) h->counters[i] = 0;
-    const int f = h->prm.decim;
-    const Geom g = make_geom(W, H, f);
+    CallCtx c;
+    c.frames = frames; c.on_device = on_device; c.channels = channels; c.B = B; c.W = W; c.H = H; c.stride = stride;
+    c.frame_bytes = (size_t)H * stride;
+    c.g = make_geom(W, H, h->prm.decim);
+    c.cap_out = cap_out;
+    c.pose = &pose;
+    const Geom& g = c.g;
     h->geom = g;
     for (int b = 0; b < B; b++) counts[b] = 0;
     if (g.wd < 8 || g.hd < 8) return AGPU_OK;  // nothing detectable (and the tile grid would be empty)
 
-    // chunking
+    // chunking: ~128 Mpx of working image per pass (61 frames of 1080p), several chunks in flight
     int chunk = h->cfg.chunk_frames;
     if (chunk <= 0) {
-        const size_t target_px = (size_t)48 << 20;  // ~48 Mpx of working image per pass
+        const size_t target_px = (size_t)128 << 20;
         chunk = (int)std::max<size_t>(1, target_px / g.plane);
         chunk = std::min(chunk, 256);
     }
     chunk = std::min(chunk, B);
-    // per-frame list capacities: user limits are hard; automatic ones grow (the chunk is re-run) on overflow
+    c.chunk = chunk;
+    int nslots = h->cfg.pipeline_slots > 0 ? h->cfg.pipeline_slots : 3;
+    if (const char* e = getenv("AGPU_SLOTS")) nslots = std::max(1, atoi(e));
+    nslots = std::min(nslots, 8);
+    nslots = std::min(nslots, ceil_div(B, chunk));
+    if ((int)h->slots.size() < nslots) h->slots.resize(nslots);   // (slots are only ever appended: buffers stay put)
+
+    // per-frame list capacities: user limits are hard; automatic ones grow (the chunks are re-run) on overflow
     const bool auto_pts = h->cfg.max_points_per_frame <= 0, auto_cl = h->cfg.max_clusters_per_frame <= 0,
                auto_q = h->cfg.max_quads_per_frame <= 0;
-    int cap = auto_pts ? std::max(h->cap_points, (int)std::max<size_t>(262144, g.plane / 4)) : h->cfg.max_points_per_frame;
-    cap = (cap + RS_TILE - 1) / RS_TILE * RS_TILE;
-    int maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
-    int maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
-    const size_t frame_bytes = (size_t)H * stride;
-    const size_t ncnt = CNT_FIXED + (size_t)4 * chunk;
-    int nblk_max = 0;
-    int *d_cnt = nullptr, *d_npts = nullptr, *d_frame_quads = nullptr, *d_ndets = nullptr, *d_out_counts = nullptr;
+    c.cap = auto_pts ? std::max(h->cap_points, (int)std::max<size_t>(262144, g.plane / 4)) : h->cfg.max_points_per_frame;
+    c.cap = (c.cap + RS_TILE - 1) / RS_TILE * RS_TILE;
+    c.maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
+    c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
+    c.ncnt = CNT_FIXED + (size_t)4 * chunk;
+    c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
-    auto alloc_workspace = [&]() -> int {
-        nblk_max = cap / RS_TILE;
-        if (!on_device) CK(h->d_in.ensure(frame_bytes * chunk));
-        for (int i = 0; i < 2; i++) {
-            CK(h->d_keys[i].ensure((size_t)chunk * cap * 8));
-            CK(h->d_vals[i].ensure((size_t)chunk * cap * 4));
-        }
-        CK(h->d_hist.ensure((size_t)chunk * RS_RADIX * nblk_max * 4));
-        CK(h->d_lfps.ensure((size_t)chunk * cap * 48));
-        CK(h->d_errs.ensure((size_t)chunk * cap * 8));
-        CK(h->d_counters.ensure(ncnt * 4));
-        for (int t = 0; t < AGPU_NTIERS; t++) CK(h->d_clusters[t].ensure((size_t)chunk * maxcl * sizeof(ClusterRef)));
-        if (h->cfg.debug) {
-            CK(h->d_dbg_heads.ensure((size_t)chunk * cap / 4 * sizeof(ClusterRef)));
-            CK(h->d_refined.ensure((size_t)chunk * maxq * 32));
-        }
-        CK(h->d_quads.ensure((size_t)chunk * maxq * sizeof(QuadRec)));
-        CK(h->d_dets.ensure((size_t)chunk * REC_CAP * sizeof(DetRec)));
-        CK(h->d_out.ensure((size_t)chunk * cap_out * sizeof(DetRec)));
-        CK(h->h_out.ensure((size_t)chunk * cap_out * sizeof(DetRec)));
-        CK(h->h_counts.ensure(ncnt * 4));
-        if (pose.enabled) {
-            CK(h->d_poses.ensure((size_t)chunk * cap_out * sizeof(PoseRec)));
-            CK(h->h_poses.ensure((size_t)chunk * cap_out * sizeof(PoseRec)));
-        }
-        d_cnt = h->d_counters.as<int>();
-        d_npts = d_cnt + CNT_FIXED;
-        d_frame_quads = d_npts + chunk;
-        d_ndets = d_frame_quads + chunk;
-        d_out_counts = d_ndets + chunk;
-        h->cap_points = cap; h->cap_clusters = maxcl; h->cap_quads = maxq;
-        return AGPU_OK;
-    };
-    {
-        int rc = alloc_workspace();
-        if (rc) return rc;
-    }
-
-    cudaStream_t user_stream = (cudaStream_t)cuda_stream;
-    if (on_device) {
-        // order our stream after the producer's stream
-        cudaEvent_t ev;
-        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        CK(cudaEventRecord(ev, user_stream));
-        CK(cudaStreamWaitEvent(h->stream, ev, 0));
-        CK(cudaEventDestroy(ev));
+    if (on_device) {   // order every slot stream after the producer's stream
+        if (!h->ev_user) CK(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
+        CK(cudaEventRecord(h->ev_user, (cudaStream_t)cuda_stream));
     }
     int rc_final = AGPU_OK;
-    const int key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
-
-    for (int b0 = 0; b0 < B;) {
-        const int n = std::min(chunk, B - b0);
-        StageTimer tm(h);
-        tm.mark();  // 0
-        const uint8_t* d_src;
-        if (on_device) {
-            d_src = frames + (size_t)b0 * frame_bytes;
-        } else {
-            CK(cudaMemcpyAsync(h->d_in.p, frames + (size_t)b0 * frame_bytes, frame_bytes * n, cudaMemcpyHostToDevice,
-                               h->stream));
-            d_src = h->d_in.as<uint8_t>();
+    std::vector<std::pair<int, int>> todo, redo;
+    for (int b0 = 0; b0 < B; b0 += chunk) todo.push_back({b0, std::min(chunk, B - b0)});
+    while (!todo.empty()) {
+        c.nblk_max = c.cap / RS_TILE;
+        for (int s = 0; s < nslots; s++) {
+            int rc = alloc_slot(h, h->slots[s], c);
+            if (rc) return rc;
+            if (on_device) CK(cudaStreamWaitEvent(h->slots[s].stream, h->ev_user, 0));
         }
-        CK(cudaMemsetAsync(d_cnt, 0, ncnt * 4, h->stream));
-        tm.mark();  // 1: after H2D
-        const uint8_t *quad_im, *gray_full;
-        size_t q_pitch, q_frame, gray_pitch, gray_frame;
-        int rc = run_image_stage(h, d_src, channels, W, H, stride, frame_bytes, n, g, &quad_im, &q_pitch, &q_frame,
-                                 &gray_full, &gray_pitch, &gray_frame);
-        if (rc) return rc;
-        tm.mark();  // 2: after image
-        rc = run_cc_stage(h, h->d_thresh.as<uint8_t>(), n, g);
-        if (rc) return rc;
-        tm.mark();  // 3: after CC
-        {
-            dim3 grid(ceil_div(g.wp >> 2, 32), ceil_div(g.hd - 1, 8), n);
-            k_edges<<<grid, 256, 0, h->stream>>>(h->d_thresh.as<uint8_t>(), h->d_labels.as<uint32_t>(),
-                                                 h->d_sizes.as<uint32_t>(), g, h->d_keys[0].as<unsigned long long>(),
-                                                 h->d_vals[0].as<uint32_t>(), d_npts, cap);
-            LAUNCH_CHECK("k_edges");
+        h->cap_points = c.cap; h->cap_clusters = c.maxcl; h->cap_quads = c.maxq;
+        Overflow ov;
+        redo.clear();
+        size_t next = 0;
+        int si = 0;
+        bool any_pending = true;
+        while (next < todo.size() || any_pending) {
+            Slot& sl = h->slots[si];
+            if (sl.pending) {
+                const std::pair<int, int> ch = {sl.b0, sl.n};
+                int rc = finish_chunk(h, sl, c, out, poses, counts, ov, rc_final);
+                if (rc < 0) return rc;
+                if (rc == 1) redo.push_back(ch);
+            }
+            if (next < todo.size()) {
+                int rc = launch_chunk(h, sl, c, todo[next].first, todo[next].second);
+                if (rc) return rc;
+                next++;
+            }
+            si = (si + 1) % nslots;
+            any_pending = false;
+            for (int s = 0; s < nslots; s++) any_pending |= h->slots[s].pending;
         }
-        tm.mark();  // 4: after edges
-        int cur = 0;
-        {
-            std::vector<int> shifts;
-            for (int s = 0; s < key_bits; s += 8) shifts.push_back(s);
-            for (int s = 0; s < key_bits; s += 8) shifts.push_back(32 + s);
-            for (int shift : shifts) {
-                dim3 grid(nblk_max, n);
-                k_sort_hist<<<grid, RS_THREADS, 0, h->stream>>>(h->d_keys[cur].as<unsigned long long>(), d_npts, cap, shift,
-                                                                h->d_hist.as<uint32_t>(), nblk_max);
-                LAUNCH_CHECK("k_sort_hist");
-                k_sort_scan<<<n, 1024, 0, h->stream>>>(d_npts, cap, h->d_hist.as<uint32_t>(), nblk_max);
-                LAUNCH_CHECK("k_sort_scan");
-                k_sort_scatter<<<grid, RS_THREADS, 0, h->stream>>>(
-                    h->d_keys[cur].as<unsigned long long>(), h->d_vals[cur].as<uint32_t>(),
-                    h->d_keys[cur ^ 1].as<unsigned long long>(), h->d_vals[cur ^ 1].as<uint32_t>(), d_npts, cap, shift,
-                    h->d_hist.as<uint32_t>(), nblk_max);
-                LAUNCH_CHECK("k_sort_scatter");
-                cur ^= 1;
-            }
+        if (redo.empty()) break;
+        // a work list overflowed somewhere: grow it (automatic limits) and run those chunks again
+        if (ov.max_pts > c.cap) {
+            if (!auto_pts) { h->set_err("edge-point list overflow: raise agpu_config.max_points_per_frame"); return AGPU_E_WORKSPACE; }
+            c.cap = (ov.max_pts + ov.max_pts / 4 + RS_TILE - 1) / RS_TILE * RS_TILE;
         }
-        tm.mark();  // 5: after sort
-        const unsigned long long* skeys = h->d_keys[cur].as<unsigned long long>();
-        const uint32_t* svals = h->d_vals[cur].as<uint32_t>();
-        {
-            ClusterLists cl;
-            for (int t = 0; t < AGPU_NTIERS; t++) {
-                cl.list[t] = h->d_clusters[t].as<ClusterRef>();
-                cl.cap[t] = TIER_CAP[t];
-            }
-            cl.counters = d_cnt;
-            cl.cap_list = n * maxcl;
-            cl.dbg_heads = h->cfg.debug ? h->d_dbg_heads.as<ClusterRef>() : nullptr;
-            cl.cap_dbg = (int)(h->d_dbg_heads.bytes / sizeof(ClusterRef));
-            dim3 grid(ceil_div(cap, 256), n);
-            k_cluster_heads<<<grid, 256, 0, h->stream>>>(skeys, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
-            LAUNCH_CHECK("k_cluster_heads");
-            QuadFitArgs qa;
-            qa.vals = svals; qa.keys = skeys; qa.cap = cap;
-            qa.quad_im = quad_im; qa.q_pitch = q_pitch; qa.q_frame = q_frame;
-            qa.g = g;
-            qa.lfps = h->d_lfps.as<double>();
-            qa.errs = h->d_errs.as<double>();
-            qa.list_cap = n * maxcl;
-            qa.quads = h->d_quads.as<QuadRec>();
-            qa.nquads = d_cnt + CNT_NQUADS;
-            qa.cap_quads = n * maxq;
-            qa.per_frame_quads = d_frame_quads;
-            // the tiers are independent (own work list, atomic appends to the quad list): fork them over side
-            // streams so that the latency-bound big-cluster warps overlap with the many small clusters
-            CK(cudaEventRecord(h->ev_fork, h->stream));
-            for (int t = AGPU_NTIERS - 1; t >= 0; t--) {
-                cudaStream_t st = t == 0 ? h->stream : h->aux[t - 1];
-                if (t > 0) CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
-                qa.list = h->d_clusters[t].as<ClusterRef>();
-                qa.list_count = d_cnt + CNT_TIER0 + t;
-                const size_t smem = (size_t)TIER_WPB[t] * qf_smem_per_warp(TIER_CAP[t]);
-                k_fit_quads<<<h->num_sms * TIER_CTAS_PER_SM[t], TIER_WPB[t] * 32, smem, st>>>(qa, h->prm, TIER_CAP[t]);
-                LAUNCH_CHECK("k_fit_quads");
-                if (t > 0) {
-                    CK(cudaEventRecord(h->ev_join[t - 1], st));
-                    CK(cudaStreamWaitEvent(h->stream, h->ev_join[t - 1], 0));
-                }
-            }
+        if (ov.max_cl_per_frame > c.maxcl) {
+            if (!auto_cl) { h->set_err("cluster list overflow: raise agpu_config.max_clusters_per_frame"); return AGPU_E_WORKSPACE; }
+            c.maxcl = ov.max_cl_per_frame * 2;
         }
-        tm.mark();  // 6: after quads
-        {
-            DecodeArgs da;
-            da.im = gray_full; da.pitch = gray_pitch; da.frame_stride = gray_frame;
-            da.W = W; da.H = H;
-            da.quads = h->d_quads.as<QuadRec>();
-            da.nquads = d_cnt + CNT_NQUADS;
-            da.cap_quads = n * maxq;
-            da.fams = h->d_fams.as<DevFamily>();
-            da.codes = h->d_codes.as<unsigned long long>();
-            da.dets = h->d_dets.as<DetRec>();
-            da.ndets = d_ndets;
-            da.cap_dets = REC_CAP;
-            da.dbg_refined = h->cfg.debug ? h->d_refined.as<float>() : nullptr;
-            k_decode_quads<<<h->num_sms * 4, 128, 0, h->stream>>>(da, h->prm);
-            LAUNCH_CHECK("k_decode_quads");
+        if (ov.max_q_per_frame > c.maxq) {
+            if (!auto_q) { h->set_err("quad list overflow: raise agpu_config.max_quads_per_frame"); return AGPU_E_WORKSPACE; }
+            c.maxq = ov.max_q_per_frame * 2;
         }
-        tm.mark();  // 7: after decode
-        k_reconcile<<<ceil_div(n, 4), 128, 0, h->stream>>>(h->d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
-                                                          h->d_out.as<DetRec>(), d_out_counts, cap_out);
-        LAUNCH_CHECK("k_reconcile");
-        if (pose.enabled) {
-            PoseArgs pa;
-            fill_pose_args(pa, pose, 0);
-            pa.corners = reinterpret_cast<const double*>(h->d_out.as<char>() + offsetof(DetRec, p));
-            pa.corner_stride = (int)(sizeof(DetRec) / 8);
-            pa.counts = d_out_counts;
-            pa.per_frame = cap_out;
-            pa.M = n * cap_out;
-            pa.out = h->d_poses.as<PoseRec>();
-            k_pose<<<ceil_div((long long)pa.M * 4, 128), 128, 0, h->stream>>>(pa);
-            LAUNCH_CHECK("k_pose");
-        }
-        tm.mark();  // 8: after reconcile/pose
-        CK(cudaMemcpyAsync(h->h_counts.p, d_cnt, ncnt * 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_out.p, h->d_out.p, (size_t)n * cap_out * sizeof(DetRec), cudaMemcpyDeviceToHost, h->stream));
-        if (pose.enabled)
-            CK(cudaMemcpyAsync(h->h_poses.p, h->d_poses.p, (size_t)n * cap_out * sizeof(PoseRec), cudaMemcpyDeviceToHost,
-                               h->stream));
-        tm.mark();  // 9: after D2H
-        CK(cudaStreamSynchronize(h->stream));
-        if (h->profiling) {
-            for (int s = 0; s < AGPU_NUM_STAGES; s++) {
-                float ms = 0;
-                cudaEventElapsedTime(&ms, h->events[s], h->events[s + 1]);
-                h->stage_ms[s] += ms;
-            }
-        }
-        const int* hc = h->h_counts.as<int>();
-        const int* h_npts = hc + CNT_FIXED;
-        const int* h_fq = h_npts + chunk;
-        const int* h_nd = h_fq + chunk;
-        const int* h_oc = h_nd + chunk;
-        (void)h_fq;
-        // overflow of a work list: grow it and run the chunk again (automatic limits), or report it
-        {
-            int max_pts = 0;
-            for (int i = 0; i < n; i++) max_pts = std::max(max_pts, h_npts[i]);
-            int max_cl = 0;
-            for (int t = 0; t < AGPU_NTIERS; t++) max_cl = std::max(max_cl, hc[CNT_TIER0 + t]);
-            bool regrow = false;
-            if (max_pts > cap) {
-                if (!auto_pts) { h->set_err("edge-point list overflow: raise agpu_config.max_points_per_frame"); return AGPU_E_WORKSPACE; }
-                cap = (max_pts + max_pts / 4 + RS_TILE - 1) / RS_TILE * RS_TILE;
-                regrow = true;
-            }
-            if (max_cl > n * maxcl) {
-                if (!auto_cl) { h->set_err("cluster list overflow: raise agpu_config.max_clusters_per_frame"); return AGPU_E_WORKSPACE; }
-                maxcl = (max_cl + n - 1) / n * 2;
-                regrow = true;
-            }
-            if (hc[CNT_NQUADS] > n * maxq) {
-                if (!auto_q) { h->set_err("quad list overflow: raise agpu_config.max_quads_per_frame"); return AGPU_E_WORKSPACE; }
-                maxq = (hc[CNT_NQUADS] + n - 1) / n * 2;
-                regrow = true;
-            }
-            if (regrow) {
-                int rc2 = alloc_workspace();
-                if (rc2) return rc2;
-                continue;  // same b0
-            }
-        }
-        const DetRec* ho = h->h_out.as<DetRec>();
-        for (int i = 0; i < n; i++) {
-            const int c = h_oc[i];
-            counts[b0 + i] = c;
-            const int m = std::min(c, cap_out);
-            memcpy(out + (size_t)(b0 + i) * cap_out, ho + (size_t)i * cap_out, (size_t)m * sizeof(DetRec));
-            if (pose.enabled && poses)
-                memcpy(poses + (size_t)(b0 + i) * cap_out, h->h_poses.as<PoseRec>() + (size_t)i * cap_out,
-                       (size_t)m * sizeof(PoseRec));
-            if (c > cap_out && rc_final == AGPU_OK) {
-                h->set_err("more detections than cap_per_frame; counts[] hold the true numbers");
-                rc_final = AGPU_E_TRUNCATED;
-            }
-            h->counters[0] += h_npts[i];
-            h->counters[3] += h_nd[i];
-            if (h_nd[i] > REC_CAP) {
-                h->set_err("more than 256 raw detections in one frame");
-                rc_final = AGPU_E_WORKSPACE;
-            }
-        }
-        for (int t = 0; t < AGPU_NTIERS; t++) h->counters[1] += hc[CNT_TIER0 + t];
-        h->counters[2] += hc[CNT_NQUADS];
-        h->counters[4] += hc[CNT_OVERSIZE];
-        h->last_chunk = n;
-        h->last_cap = cap;
-        h->last_sorted = cur;
-        h->have_last = true;
-        b0 += n;
+        todo = redo;
     }
     return rc_final;
 }
@@ -723,15 +823,9 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
         return fail(AGPU_E_CUDA, "libaprilgpu is built for sm_100a (B200) only; device is sm_" +
                                      std::to_string(prop.major) + std::to_string(prop.minor));
     h->num_sms = prop.multiProcessorCount;
-    if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
-        return fail(AGPU_E_CUDA, cudaGetErrorString(ce));
-    for (int t = 0; t < AGPU_NTIERS - 1; t++) {
-        if ((ce = cudaStreamCreateWithFlags(&h->aux[t], cudaStreamNonBlocking)) != cudaSuccess ||
-            (ce = cudaEventCreateWithFlags(&h->ev_join[t], cudaEventDisableTiming)) != cudaSuccess)
-            return fail(AGPU_E_CUDA, cudaGetErrorString(ce));
-    }
-    if ((ce = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess)
-        return fail(AGPU_E_CUDA, cudaGetErrorString(ce));
+    h->slots.reserve(8);
+    h->slots.resize(1);
+    if (init_slot(h, h->slots[0]) != AGPU_OK) return fail(AGPU_E_CUDA, h->err);
 
     // parameters
     DevParams& P = h->prm;
@@ -792,21 +886,12 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
 int agpu_destroy(agpu_handle* h) {
     if (!h) return AGPU_E_INVALID;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->d_fams, &h->d_codes, &h->d_in, &h->d_gray, &h->d_quad_im, &h->d_blur_tmp, &h->d_blur_orig,
-                      &h->d_thresh, &h->d_labels, &h->d_sizes, &h->d_keys[0], &h->d_keys[1], &h->d_vals[0], &h->d_vals[1],
-                      &h->d_hist, &h->d_lfps, &h->d_errs, &h->d_counters, &h->d_clusters[0], &h->d_clusters[1],
-                      &h->d_clusters[2], &h->d_dbg_heads, &h->d_quads, &h->d_refined, &h->d_dets, &h->d_out, &h->d_poses,
-                      &h->d_pose_in};
-    for (DevBuf* b : bufs) b->release();
-    h->h_out.release(); h->h_counts.release(); h->h_poses.release(); h->h_counters.release();
-    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
-    for (int t = 0; t < AGPU_NTIERS - 1; t++) {
-        if (h->aux[t]) cudaStreamDestroy(h->aux[t]);
-        if (h->ev_join[t]) cudaEventDestroy(h->ev_join[t]);
+    for (Slot& s : h->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        s.release();
     }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    h->d_fams.release(); h->d_codes.release(); h->d_pose_in.release(); h->d_pose_out.release();
+    if (h->ev_user) cudaEventDestroy(h->ev_user);
     delete h;
     return AGPU_OK;
 }
@@ -856,9 +941,10 @@ int agpu_pose(agpu_handle* h, const double* corners, int M, const double K[9], c
     ps.tag_size = tag_size;
     int rc = parse_dist(h, dist, ndist, ps);
     if (rc) return rc;
+    cudaStream_t stream = h->slots[0].stream;
     CK(h->d_pose_in.ensure((size_t)M * 64));
-    CK(h->d_poses.ensure((size_t)M * sizeof(PoseRec)));
-    CK(cudaMemcpyAsync(h->d_pose_in.p, corners, (size_t)M * 64, cudaMemcpyHostToDevice, h->stream));
+    CK(h->d_pose_out.ensure((size_t)M * sizeof(PoseRec)));
+    CK(cudaMemcpyAsync(h->d_pose_in.p, corners, (size_t)M * 64, cudaMemcpyHostToDevice, stream));
     PoseArgs pa;
     fill_pose_args(pa, ps, method);
     pa.corners = h->d_pose_in.as<double>();
@@ -866,25 +952,17 @@ int agpu_pose(agpu_handle* h, const double* corners, int M, const double K[9], c
     pa.counts = nullptr;
     pa.per_frame = 0;
     pa.M = M;
-    pa.out = h->d_poses.as<PoseRec>();
-    k_pose<<<ceil_div((long long)M * 4, 128), 128, 0, h->stream>>>(pa);
+    pa.out = h->d_pose_out.as<PoseRec>();
+    k_pose<<<ceil_div((long long)M * 4, 128), 128, 0, stream>>>(pa);
     LAUNCH_CHECK("k_pose");
-    CK(cudaMemcpyAsync(poses, h->d_poses.p, (size_t)M * sizeof(PoseRec), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(poses, h->d_pose_out.p, (size_t)M * sizeof(PoseRec), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
     return AGPU_OK;
 }
 
 int agpu_set_profiling(agpu_handle* h, int on) {
     if (!h) return AGPU_E_INVALID;
     h->profiling = on != 0;
-    if (h->profiling) {
-        cudaSetDevice(h->device);
-        while (h->events.size() < AGPU_NUM_STAGES + 1) {
-            cudaEvent_t e;
-            if (cudaEventCreate(&e) != cudaSuccess) return AGPU_E_CUDA;
-            h->events.push_back(e);
-        }
-    }
     return AGPU_OK;
 }
 
@@ -921,6 +999,7 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
     }
     cudaSetDevice(h->device);
     const Geom& g = h->geom;
+    Slot& sl = h->slots[h->last_slot];
     const std::string w = what;
     const size_t npx = (size_t)g.wd * g.hd;
     auto unpitch = [&](uint32_t id) { return (uint32_t)((id / g.wp) * g.wd + (id % g.wp)); };
@@ -928,7 +1007,7 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
         return ((unsigned long long)unpitch((uint32_t)(k >> 32)) << 32) | unpitch((uint32_t)k);
     };
     if (w == "quad_im" || w == "thresh") {
-        const uint8_t* src = (w == "thresh") ? h->d_thresh.as<uint8_t>() : h->d_quad_im.as<uint8_t>();
+        const uint8_t* src = (w == "thresh") ? sl.d_thresh.as<uint8_t>() : sl.d_quad_im.as<uint8_t>();
         if (!src) { h->set_err("agpu_debug_fetch: buffer not materialised (decimate = 1 keeps no quad_im copy)"); return AGPU_E_INVALID; }
         if ((size_t)cap_bytes < npx) return (long long)npx;
         if (cudaMemcpy2D(host_out, g.wd, src + (size_t)frame * g.plane, g.wp, g.wd, g.hd, cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -938,7 +1017,7 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
     if (w == "labels" || w == "sizes") {
         if ((size_t)cap_bytes < npx * 4) return (long long)npx;
         std::vector<uint32_t> tmp(g.plane), lab;
-        const uint32_t* src = (w == "labels" ? h->d_labels.as<uint32_t>() : h->d_sizes.as<uint32_t>()) + (size_t)frame * g.plane;
+        const uint32_t* src = (w == "labels" ? sl.d_labels.as<uint32_t>() : sl.d_sizes.as<uint32_t>()) + (size_t)frame * g.plane;
         if (cudaMemcpy(tmp.data(), src, g.plane * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
         uint32_t* o = (uint32_t*)host_out;
         if (w == "labels") {
@@ -947,8 +1026,8 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
         } else {
             lab.resize(g.plane);
             std::vector<uint8_t> th(g.plane);
-            cudaMemcpy(lab.data(), h->d_labels.as<uint32_t>() + (size_t)frame * g.plane, g.plane * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(th.data(), h->d_thresh.as<uint8_t>() + (size_t)frame * g.plane, g.plane, cudaMemcpyDeviceToHost);
+            cudaMemcpy(lab.data(), sl.d_labels.as<uint32_t>() + (size_t)frame * g.plane, g.plane * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(th.data(), sl.d_thresh.as<uint8_t>() + (size_t)frame * g.plane, g.plane, cudaMemcpyDeviceToHost);
             for (int y = 0; y < g.hd; y++)
                 for (int x = 0; x < g.wd; x++) {
                     size_t id = (size_t)y * g.wp + x;
@@ -962,12 +1041,12 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
     }
     if (w == "cluster_keys" || w == "cluster_sizes") {
         std::vector<int> cnt(CNT_FIXED);
-        if (cudaMemcpy(cnt.data(), h->d_counters.p, CNT_FIXED * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
-        int nh = std::min<long long>(cnt[CNT_HEADS], (long long)(h->d_dbg_heads.bytes / sizeof(ClusterRef)));
+        if (cudaMemcpy(cnt.data(), sl.d_counters.p, CNT_FIXED * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
+        int nh = std::min<long long>(cnt[CNT_HEADS], (long long)(sl.d_dbg_heads.bytes / sizeof(ClusterRef)));
         std::vector<ClusterRef> heads(nh);
-        if (nh) cudaMemcpy(heads.data(), h->d_dbg_heads.p, (size_t)nh * sizeof(ClusterRef), cudaMemcpyDeviceToHost);
+        if (nh) cudaMemcpy(heads.data(), sl.d_dbg_heads.p, (size_t)nh * sizeof(ClusterRef), cudaMemcpyDeviceToHost);
         std::vector<unsigned long long> keys((size_t)h->last_cap);
-        cudaMemcpy(keys.data(), h->d_keys[h->last_sorted].as<unsigned long long>() + (size_t)frame * h->last_cap,
+        cudaMemcpy(keys.data(), sl.d_keys[sl.sorted].as<unsigned long long>() + (size_t)frame * h->last_cap,
                    (size_t)h->last_cap * 8, cudaMemcpyDeviceToHost);
         std::vector<std::pair<unsigned long long, int>> v;
         for (const ClusterRef& r : heads)
@@ -983,13 +1062,13 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
     }
     if (w == "quads" || w == "quad_keys" || w == "quads_refined") {
         std::vector<int> cnt(CNT_FIXED);
-        if (cudaMemcpy(cnt.data(), h->d_counters.p, CNT_FIXED * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
-        int nq = std::min<long long>(cnt[CNT_NQUADS], (long long)(h->d_quads.bytes / sizeof(QuadRec)));
+        if (cudaMemcpy(cnt.data(), sl.d_counters.p, CNT_FIXED * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
+        int nq = std::min<long long>(cnt[CNT_NQUADS], (long long)(sl.d_quads.bytes / sizeof(QuadRec)));
         std::vector<QuadRec> q(nq);
         std::vector<float> ref((size_t)nq * 8);
         if (nq) {
-            cudaMemcpy(q.data(), h->d_quads.p, (size_t)nq * sizeof(QuadRec), cudaMemcpyDeviceToHost);
-            cudaMemcpy(ref.data(), h->d_refined.p, (size_t)nq * 32, cudaMemcpyDeviceToHost);
+            cudaMemcpy(q.data(), sl.d_quads.p, (size_t)nq * sizeof(QuadRec), cudaMemcpyDeviceToHost);
+            cudaMemcpy(ref.data(), sl.d_refined.p, (size_t)nq * 32, cudaMemcpyDeviceToHost);
         }
         std::vector<int> idx;
         for (int i = 0; i < nq; i++)
@@ -1020,17 +1099,18 @@ int agpu_stage_threshold(agpu_handle* h, const uint8_t* im, int W, int H, uint8_
     if (!h || !im || !thresh_out || W <= 0 || H <= 0) return AGPU_E_INVALID;
     CK(cudaSetDevice(h->device));
     const Geom g = make_geom(W, H, h->prm.decim);
-    CK(h->d_in.ensure((size_t)W * H));
-    CK(cudaMemcpyAsync(h->d_in.p, im, (size_t)W * H, cudaMemcpyHostToDevice, h->stream));
+    Slot& sl = h->slots[0];
+    CK(sl.d_in.ensure((size_t)W * H));
+    CK(cudaMemcpyAsync(sl.d_in.p, im, (size_t)W * H, cudaMemcpyHostToDevice, sl.stream));
     const uint8_t *quad_im, *gray_full;
     size_t q_pitch, q_frame, gp, gf;
-    int rc = run_image_stage(h, h->d_in.as<uint8_t>(), 1, W, H, W, (size_t)W * H, 1, g, &quad_im, &q_pitch, &q_frame,
+    int rc = run_image_stage(h, sl, sl.d_in.as<uint8_t>(), 1, W, H, W, (size_t)W * H, 1, g, &quad_im, &q_pitch, &q_frame,
                              &gray_full, &gp, &gf);
     if (rc) return rc;
-    CK(cudaMemcpy2DAsync(thresh_out, g.wd, h->d_thresh.p, g.wp, g.wd, g.hd, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(thresh_out, g.wd, sl.d_thresh.p, g.wp, g.wd, g.hd, cudaMemcpyDeviceToHost, sl.stream));
     if (quad_im_out)
-        CK(cudaMemcpy2DAsync(quad_im_out, g.wd, quad_im, q_pitch, g.wd, g.hd, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy2DAsync(quad_im_out, g.wd, quad_im, q_pitch, g.wd, g.hd, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaStreamSynchronize(sl.stream));
     return AGPU_OK;
 }
 
@@ -1038,15 +1118,16 @@ int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint3
     if (!h || !thresh || !labels_out || W <= 0 || H <= 0) return AGPU_E_INVALID;
     CK(cudaSetDevice(h->device));
     const Geom g = make_geom(W, H, 1);
-    CK(h->d_thresh.ensure(g.plane));
-    CK(cudaMemsetAsync(h->d_thresh.p, 127, g.plane, h->stream));
-    CK(cudaMemcpy2DAsync(h->d_thresh.p, g.wp, thresh, W, W, H, cudaMemcpyHostToDevice, h->stream));
-    int rc = run_cc_stage(h, h->d_thresh.as<uint8_t>(), 1, g);
+    Slot& sl = h->slots[0];
+    CK(sl.d_thresh.ensure(g.plane));
+    CK(cudaMemsetAsync(sl.d_thresh.p, 127, g.plane, sl.stream));
+    CK(cudaMemcpy2DAsync(sl.d_thresh.p, g.wp, thresh, W, W, H, cudaMemcpyHostToDevice, sl.stream));
+    int rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), 1, g);
     if (rc) return rc;
     std::vector<uint32_t> lab(g.plane), sz(g.plane);
-    CK(cudaMemcpyAsync(lab.data(), h->d_labels.p, g.plane * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(sz.data(), h->d_sizes.p, g.plane * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(lab.data(), sl.d_labels.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaMemcpyAsync(sz.data(), sl.d_sizes.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaStreamSynchronize(sl.stream));
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) {
             size_t id = (size_t)y * g.wp + x;

@@ -33,7 +33,7 @@ class Detector:
 
     def __init__(self, families: Sequence[str] | str = "tag36h11", threads: int = 1, maxhamming: int = 1,
                  decimate: float = 2.0, blur: float = 0.0, refine_edges: bool = True, debug: bool = False,
-                 decode_sharpening: float = 0.25, device: int = 0, chunk_frames: int = 0,
+                 decode_sharpening: float = 0.25, device: int = 0, chunk_frames: int = 0, pipeline_slots: int = 0,
                  max_points_per_frame: int = 0, max_clusters_per_frame: int = 0, max_quads_per_frame: int = 0):
         if not isinstance(families, str):
             families = " ".join(families)
@@ -53,6 +53,7 @@ class Detector:
         cfg.debug = int(bool(debug))
         cfg.device = int(device)
         cfg.chunk_frames = int(chunk_frames)
+        cfg.pipeline_slots = int(pipeline_slots)
         cfg.max_points_per_frame = int(max_points_per_frame)
         cfg.max_clusters_per_frame = int(max_clusters_per_frame)
         cfg.max_quads_per_frame = int(max_quads_per_frame)

@@ -197,8 +197,8 @@ def run_b200(args):
     t_gen = time.time() - t_gen
     pinned = torch.from_numpy(frames_host).pin_memory()
     frames_dev = pinned.to(dev, non_blocking=False)
-    det = Detector("tag36h11", decimate=1.0, refine_edges=True, device=local_rank, chunk_frames=args.chunk)
-    det.set_profiling(True)
+    det = Detector("tag36h11", decimate=1.0, refine_edges=True, device=local_rank, chunk_frames=args.chunk,
+                   pipeline_slots=args.slots)
 
     def step_dev():
         return det.detect_pose_batch(frames_dev, K, None, TAG_SIZE, cap_per_frame=CAP)
@@ -211,8 +211,9 @@ def run_b200(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, d=None):
         """-> (seconds for `steps` steps by CUDA events, launches, per-stage ms summed, last result)"""
+        d = d or det
         stage = {}
         launches = 0
         barrier()
@@ -221,8 +222,8 @@ def run_b200(args):
         res = None
         for _ in range(steps):
             res = fn()
-            launches += det.launch_count()
-            for k, v in det.stage_ms().items():
+            launches += d.launch_count()
+            for k, v in d.stage_ms().items():
                 stage[k] = stage.get(k, 0.0) + v
         e1.record()
         barrier()
@@ -238,7 +239,7 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    sec, launches, stage, res = timed(step_dev, args.steps)
+    sec, launches, _, res = timed(step_dev, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
     dets, poses = res
     tags_per_frame = float(np.mean([len(x) for x in dets]))
@@ -247,6 +248,19 @@ def run_b200(args):
     step_host()
     e2e_steps = max(1, min(args.steps, 3))
     sec_e2e, _, _, _ = timed(step_host, e2e_steps)
+    # per-stage times for the roofline: the same batch through a detector with ONE chunk in flight (no overlap of
+    # chunks, so every stage interval on the stream is that stage alone), CUDA events on the library's stream
+    det_prof = Detector("tag36h11", decimate=1.0, refine_edges=True, device=local_rank, chunk_frames=args.chunk,
+                        pipeline_slots=1)
+    det_prof.set_profiling(True)
+
+    def step_prof():
+        return det_prof.detect_pose_batch(frames_dev, K, None, TAG_SIZE, cap_per_frame=CAP)
+
+    step_prof()
+    prof_steps = max(1, min(args.steps, 2))
+    sec_prof, _, stage, _ = timed(step_prof, prof_steps, det_prof)
+    det_prof.close()
 
     if rank != 0:
         if distributed:
@@ -262,7 +276,7 @@ def run_b200(args):
     # algorithmic bytes per frame (decimate = 1): image stage R_src + N_d = 2N;
     # CC: read threshold N + write labels 4N = 5N; edges: threshold N + labels 4N = 5N; dense pipeline 12N
     alg = {"image": 2 * N, "cc": 5 * N, "edges": 5 * N}
-    nsteps = args.steps
+    nsteps = prof_steps
     stages = {}
     for k, ms in stage.items():
         per_frame_us = ms * 1e3 / (B * nsteps)
@@ -300,7 +314,10 @@ def run_b200(args):
                                "~50 tag36h11/frame, detect + per-tag pose" % B,
                    "batch_per_gpu": B, "distinct_frames": args.distinct, "tags_per_frame": tags_per_frame,
                    "pose_ok_fraction": pose_ok, "l2": "inputs (%.1f GB per GPU) larger than L2" % (B * N / 1e9),
-                   "chunk_frames": det_chunk(det, args), "parallelism": "frames sharded, %d rank(s), no collective" % world,
+                   "chunk_frames": det_chunk(det, args), "pipeline_slots": args.slots or 3,
+                   "stages_note": "stage times / roofline measured with pipeline_slots=1 (%.1f frames/s in that mode)" % (
+                       B * prof_steps / sec_prof),
+                   "parallelism": "frames sharded, %d rank(s), no collective" % world,
                    "frame_generation_s": t_gen},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(B * N),
                 "d2h_bytes_per_step": int(B * CAP * (168 + 136) + 4 * (8 + 4 * B)), "steps": e2e_steps},
@@ -325,7 +342,7 @@ def det_chunk(det, args):
     if args.chunk > 0:
         return args.chunk
     plane = ((W + 15) // 16 * 16) * H
-    return max(1, min(256, (48 << 20) // plane))
+    return max(1, min(256, (128 << 20) // plane))
 
 
 def main():
@@ -337,6 +354,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step (BASELINE config C3: 1024)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct rendered frames per rank")
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline pass (0 = library default)")
+    ap.add_argument("--slots", type=int, default=0, help="chunks in flight (0 = library default: 3)")
     ap.add_argument("--ref-frames", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
