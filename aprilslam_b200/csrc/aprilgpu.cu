@@ -89,7 +89,7 @@ struct Slot {
     cudaEvent_t ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;   // stage timing
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes;
-    DevBuf d_keys[2], d_vals[2], d_hist, d_lfps, d_errs;
+    DevBuf d_keys[2], d_vals[2], d_hist, d_dbase, d_lfps, d_errs;
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
@@ -98,7 +98,7 @@ struct Slot {
 
     void release() {
         DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_labels, &d_sizes,
-                          &d_keys[0], &d_keys[1], &d_vals[0], &d_vals[1], &d_hist, &d_lfps, &d_errs, &d_counters,
+                          &d_keys[0], &d_keys[1], &d_vals[0], &d_vals[1], &d_hist, &d_dbase, &d_lfps, &d_errs, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
         for (DevBuf* bb : bufs) bb->release();
@@ -404,6 +404,7 @@ int alloc_slot(agpu_handle* h, Slot& s, const CallCtx& c) {
         CK(s.d_vals[i].ensure((size_t)chunk * cap * 4));
     }
     CK(s.d_hist.ensure((size_t)chunk * RS_RADIX * c.nblk_max * 4));
+    CK(s.d_dbase.ensure((size_t)chunk * RS_RADIX * 4));
     CK(s.d_lfps.ensure((size_t)chunk * cap * 48));
     CK(s.d_errs.ensure((size_t)chunk * cap * 8));
     CK(s.d_counters.ensure(c.ncnt * 4));
@@ -465,20 +466,20 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int cur = 0;
     {
         int shifts[16], ns = 0;
-        for (int s = 0; s < c.key_bits; s += 8) shifts[ns++] = s;
-        for (int s = 0; s < c.key_bits; s += 8) shifts[ns++] = 32 + s;
+        for (int s = 0; s < c.key_bits; s += RS_BITS) shifts[ns++] = s;
+        for (int s = 0; s < c.key_bits; s += RS_BITS) shifts[ns++] = 32 + s;
         for (int i = 0; i < ns; i++) {
             const int shift = shifts[i];
             dim3 grid(c.nblk_max, n);
             k_sort_hist<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_keys[cur].as<unsigned long long>(), d_npts, cap, shift,
                                                             sl.d_hist.as<uint32_t>(), c.nblk_max);
             LAUNCH_CHECK("k_sort_hist");
-            k_sort_scan<<<n, 1024, 0, sl.stream>>>(d_npts, cap, sl.d_hist.as<uint32_t>(), c.nblk_max);
+            k_sort_scan<<<n, 1024, 0, sl.stream>>>(d_npts, cap, sl.d_hist.as<uint32_t>(), sl.d_dbase.as<uint32_t>(), c.nblk_max);
             LAUNCH_CHECK("k_sort_scan");
             k_sort_scatter<<<grid, RS_THREADS, 0, sl.stream>>>(
                 sl.d_keys[cur].as<unsigned long long>(), sl.d_vals[cur].as<uint32_t>(),
                 sl.d_keys[cur ^ 1].as<unsigned long long>(), sl.d_vals[cur ^ 1].as<uint32_t>(), d_npts, cap, shift,
-                sl.d_hist.as<uint32_t>(), c.nblk_max);
+                sl.d_hist.as<uint32_t>(), sl.d_dbase.as<uint32_t>(), c.nblk_max);
             LAUNCH_CHECK("k_sort_scatter");
             cur ^= 1;
         }
@@ -496,7 +497,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         cl.cap_list = n * c.maxcl;
         cl.dbg_heads = h->cfg.debug ? sl.d_dbg_heads.as<ClusterRef>() : nullptr;
         cl.cap_dbg = (int)(sl.d_dbg_heads.bytes / sizeof(ClusterRef));
-        dim3 grid(ceil_div(cap, 256), n);
+        dim3 grid(std::max(1, std::min(64, ceil_div(cap, 256))), n);   // grid-stride over the live points
         k_cluster_heads<<<grid, 256, 0, sl.stream>>>(skeys, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
         LAUNCH_CHECK("k_cluster_heads");
         QuadFitArgs qa;

@@ -13,54 +13,26 @@
 
 // Four pixels (one 32-bit word of the threshold image) per thread.  An edge between v0 and v1 means
 // v0 ^ v1 == 0xff (values are 0 / 127 / 255), tested for all four pixels and one direction at a time with
-// three word operations; the vast majority of threads see no edge and leave after five word loads.
-template <bool WRITE>
-__device__ __forceinline__ int edges_emit(const uint32_t (&m)[4], int x0, int y, const Geom& g, const uint32_t* fl,
-                                          const uint32_t* fs, uint32_t cur, uint32_t (&nb)[4],
-                                          unsigned long long* fk, uint32_t* fv, int pos, int cap) {
-    const int dxs[4] = {1, 0, -1, 1}, dys[4] = {0, 1, 1, 1};
-    int cnt = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        if (!(((m[0] | m[1] | m[2] | m[3]) >> (8 * i)) & 1u)) continue;
-        const int x = x0 + i;
-        const size_t id = (size_t)y * g.wp + x;
-        const uint32_t rep0 = fl[id];
-        if (fs[rep0] < 25u) continue;
-        const int v0 = (cur >> (8 * i)) & 0xff;
-#pragma unroll
-        for (int d = 0; d < 4; d++) {
-            if (!((m[d] >> (8 * i)) & 1u)) continue;
-            const uint32_t rep1 = fl[id + (size_t)dys[d] * g.wp + dxs[d]];
-            if (fs[rep1] < 25u) continue;
-            if (WRITE) {
-                if (pos + cnt < cap) {
-                    const uint32_t hi = max(rep0, rep1), lo = min(rep0, rep1);
-                    const int v1 = (nb[d] >> (8 * i)) & 0xff;
-                    fk[pos + cnt] = ((unsigned long long)hi << 32) | lo;
-                    fv[pos + cnt] = pack_point(2 * x + dxs[d], 2 * y + dys[d], d, v1 > v0);
-                }
-            }
-            cnt++;
-        }
-    }
-    return cnt;
-}
-
+// three word operations; the vast majority of warps see no edge and leave after five word loads.  The
+// (pixel, direction) candidates of a warp are compacted through shared memory and then handled ONE PER LANE
+// (label + size look-ups, ballot compaction, one atomic per 32 candidates), so the expensive part is not
+// serialised inside the few threads that sit on an edge.
+#define EDGE_CAND_PER_WARP 512   // 32 lanes x 4 pixels x 4 directions
 __global__ void __launch_bounds__(256)
 k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes,
         Geom g, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ npts, int cap) {
+    __shared__ uint16_t scand[8][EDGE_CAND_PER_WARP];
     const int frame = blockIdx.z;
     const uint8_t* ft = thresh + (size_t)frame * g.plane;
     const uint32_t* fl = labels + (size_t)frame * g.plane;
     const uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int kx = blockIdx.x * 32 + lane;          // word index in the row
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int y = blockIdx.y * 8 + w;
     const int wpr = g.wp >> 2;
     const int x0 = kx * 4;
 
-    uint32_t m[4] = {0, 0, 0, 0}, nb[4] = {0, 0, 0, 0}, cur = 0;
+    uint32_t m[4] = {0, 0, 0, 0}, cur = 0;
     if (y <= g.hd - 2 && kx < wpr && x0 <= g.wd - 2) {
         const uint32_t* r0 = reinterpret_cast<const uint32_t*>(ft + (size_t)y * g.wp);
         const uint32_t* r1 = r0 + wpr;
@@ -70,6 +42,7 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
         const uint32_t prv1 = kx > 0 ? r1[kx - 1] : none;
         const uint32_t cur1 = r1[kx];
         const uint32_t nxt1 = kx + 1 < wpr ? r1[kx + 1] : none;
+        uint32_t nb[4];
         nb[0] = __funnelshift_r(cur, nxt, 8);       // (x+1, y)
         nb[1] = cur1;                               // (x,   y+1)
         nb[2] = __funnelshift_l(prv1, cur1, 8);     // (x-1, y+1)
@@ -84,11 +57,7 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
             m[d] = (e >> 7) & e & xm;
         }
     }
-    unsigned long long* fk = keys + (size_t)frame * cap;
-    uint32_t* fv = vals + (size_t)frame * cap;
-    int cnt = 0;
-    if (m[0] | m[1] | m[2] | m[3]) cnt = edges_emit<false>(m, x0, y, g, fl, fs, cur, nb, fk, fv, 0, cap);
-    // warp-aggregated append
+    const int cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
     int incl = cnt;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -97,19 +66,63 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
     }
     const int total = __shfl_sync(FULL_MASK, incl, 31);
     if (total == 0) return;
-    int base = 0;
-    if (lane == 31) base = atomicAdd(&npts[frame], total);
-    base = __shfl_sync(FULL_MASK, base, 31);
-    if (cnt) edges_emit<true>(m, x0, y, g, fl, fs, cur, nb, fk, fv, base + incl - cnt, cap);
+    if (cnt) {
+        int o = incl - cnt;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t pos = ((cur >> (8 * i)) & 0xff) == 0 ? 1u : 0u;   // v1 > v0  <=>  v0 == 0
+#pragma unroll
+            for (int d = 0; d < 4; d++)
+                if ((m[d] >> (8 * i)) & 1u) scand[w][o++] = (uint16_t)((lane * 4 + i) | (d << 7) | (pos << 9));
+        }
+    }
+    __syncwarp();
+    unsigned long long* fk = keys + (size_t)frame * cap;
+    uint32_t* fv = vals + (size_t)frame * cap;
+    const int xbase = blockIdx.x * 128;
+    for (int b = 0; b < total; b += 32) {
+        bool ok = false;
+        unsigned long long key = 0;
+        uint32_t val = 0;
+        if (b + lane < total) {
+            const uint32_t c = scand[w][b + lane];
+            const int x = xbase + (int)(c & 127), d = (c >> 7) & 3, pos = (c >> 9) & 1;
+            const int dx = (d == 0 || d == 3) ? 1 : (d == 2 ? -1 : 0), dy = d == 0 ? 0 : 1;
+            const size_t id = (size_t)y * g.wp + x;
+            const uint32_t rep0 = fl[id];
+            if (fs[rep0] >= 25u) {
+                const uint32_t rep1 = fl[id + (size_t)dy * g.wp + dx];
+                if (fs[rep1] >= 25u) {
+                    ok = true;
+                    const uint32_t hi = max(rep0, rep1), lo = min(rep0, rep1);
+                    key = ((unsigned long long)hi << 32) | lo;
+                    val = pack_point(2 * x + dx, 2 * y + dy, d, pos);
+                }
+            }
+        }
+        const uint32_t okm = __ballot_sync(FULL_MASK, ok);
+        if (okm == 0) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&npts[frame], __popc(okm));
+        base = __shfl_sync(FULL_MASK, base, 0);
+        const int p = base + __popc(okm & ((1u << lane) - 1u));
+        if (ok && p < cap) {
+            fk[p] = key;
+            fv[p] = val;
+        }
+    }
 }
 
 // ---- segmented LSD radix sort ---------------------------------------------------------------
+// 11-bit digits (2048 bins): component ids of a 1080p frame have 21 bits, so each half of the
+// (rep_hi, rep_lo) key takes two passes -- four passes in all.
 #define RS_THREADS 256
 #define RS_ITEMS 8
 #define RS_TILE (RS_THREADS * RS_ITEMS)  // 2048 keys per block
-#define RS_RADIX 256
+#define RS_BITS 11
+#define RS_RADIX (1 << RS_BITS)
 
-// hist[frame][digit * nblk_f + block]  (nblk_f = ceil(n_f / RS_TILE); frame stride = RS_RADIX * nblk_max)
+// per frame: hist[block][digit] (block-major, frame stride RS_RADIX * nblk_max) and digit_base[digit]
 __global__ void __launch_bounds__(RS_THREADS)
 k_sort_hist(const unsigned long long* __restrict__ keys, const int* __restrict__ npts, int cap, int shift,
             uint32_t* __restrict__ hist, int nblk_max) {
@@ -118,34 +131,43 @@ k_sort_hist(const unsigned long long* __restrict__ keys, const int* __restrict__
     const int n = min(npts[frame], cap);
     const int nblk = (n + RS_TILE - 1) / RS_TILE;
     if (b >= nblk) return;
-    h[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < RS_RADIX; i += RS_THREADS) h[i] = 0;
     __syncthreads();
     const unsigned long long* fk = keys + (size_t)frame * cap;
     const int base = b * RS_TILE;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
-        int i = base + (threadIdx.x >> 5) * (32 * RS_ITEMS) + r * 32 + (threadIdx.x & 31);
+        int i = base + r * RS_THREADS + threadIdx.x;
         if (i < n) atomicAdd(&h[(uint32_t)(fk[i] >> shift) & (RS_RADIX - 1)], 1u);
     }
     __syncthreads();
-    hist[(size_t)frame * RS_RADIX * nblk_max + (size_t)threadIdx.x * nblk + b] = h[threadIdx.x];
+    uint32_t* out = hist + ((size_t)frame * nblk_max + b) * RS_RADIX;
+    for (int i = threadIdx.x; i < RS_RADIX; i += RS_THREADS) out[i] = h[i];
 }
 
-// exclusive scan of a frame's RS_RADIX*nblk_f counters (digit-major), one CTA per frame
+// one CTA per frame, thread t owns digits t and t + 1024: exclusive prefix over the blocks (in place) and the
+// exclusive prefix over the digit totals (digit_base)
 __global__ void __launch_bounds__(1024)
-k_sort_scan(const int* __restrict__ npts, int cap, uint32_t* __restrict__ hist, int nblk_max) {
+k_sort_scan(const int* __restrict__ npts, int cap, uint32_t* __restrict__ hist, uint32_t* __restrict__ digit_base,
+            int nblk_max) {
     __shared__ uint32_t warp_tot[32];
     const int frame = blockIdx.x;
     const int n = min(npts[frame], cap);
     const int nblk = (n + RS_TILE - 1) / RS_TILE;
-    const int E = RS_RADIX * nblk;
-    if (E == 0) return;
-    uint32_t* fh = hist + (size_t)frame * RS_RADIX * nblk_max;
-    const int chunk = (E + 1023) / 1024;
-    const int lo = threadIdx.x * chunk, hi = min(lo + chunk, E);
-    uint32_t sum = 0;
-    for (int i = lo; i < hi; i++) sum += fh[i];
-    // block exclusive scan of `sum`
+    if (nblk == 0) return;
+    uint32_t* fh = hist + (size_t)frame * nblk_max * RS_RADIX;
+    const int d0 = 2 * threadIdx.x;   // two adjacent digits per thread -> one 64-bit access per block row
+    uint32_t run0 = 0, run1 = 0;
+#pragma unroll 4
+    for (int b = 0; b < nblk; b++) {
+        uint2* p = reinterpret_cast<uint2*>(fh + (size_t)b * RS_RADIX + d0);
+        uint2 c = *p;
+        *p = make_uint2(run0, run1);
+        run0 += c.x;
+        run1 += c.y;
+    }
+    // block exclusive scan of the per-thread pair totals
+    const uint32_t sum = run0 + run1;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t incl = sum;
 #pragma unroll
@@ -165,25 +187,28 @@ k_sort_scan(const int* __restrict__ npts, int cap, uint32_t* __restrict__ hist, 
         warp_tot[lane] = ti - t;
     }
     __syncthreads();
-    uint32_t run = warp_tot[w] + incl - sum;
-    for (int i = lo; i < hi; i++) {
-        uint32_t c = fh[i];
-        fh[i] = run;
-        run += c;
-    }
+    const uint32_t excl = warp_tot[w] + incl - sum;
+    uint32_t* db = digit_base + (size_t)frame * RS_RADIX;
+    db[d0] = excl;
+    db[d0 + 1] = excl + run0;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
 k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-               const int* __restrict__ npts, int cap, int shift, const uint32_t* __restrict__ hist, int nblk_max) {
-    __shared__ uint32_t wcnt[RS_THREADS / 32][RS_RADIX];
+               const int* __restrict__ npts, int cap, int shift, const uint32_t* __restrict__ hist,
+               const uint32_t* __restrict__ digit_base, int nblk_max) {
+    __shared__ uint16_t wcnt[RS_THREADS / 32][RS_RADIX];   // per-warp digit counts (<= 256), then warp prefixes
+    __shared__ uint32_t dbase[RS_RADIX];                   // first output slot of digit d for this block
     const int frame = blockIdx.y, b = blockIdx.x;
     const int n = min(npts[frame], cap);
     const int nblk = (n + RS_TILE - 1) / RS_TILE;
     if (b >= nblk) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < (RS_THREADS / 32) * RS_RADIX; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(&wcnt[0][0]);
+        for (int i = threadIdx.x; i < (RS_THREADS / 32) * RS_RADIX / 2; i += RS_THREADS) z[i] = 0;
+    }
     __syncthreads();
     const size_t seg = (size_t)frame * cap;
     const int base = b * RS_TILE + w * (32 * RS_ITEMS);
@@ -196,27 +221,36 @@ k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* _
         const bool valid = i < n;
         key[r] = valid ? keys_in[seg + i] : 0xffffffffffffffffull;
         val[r] = valid ? vals_in[seg + i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const int i = base + r * 32 + lane;
+        const bool valid = i < n;
         const uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & (RS_RADIX - 1)) : 0xffffffffu;
         const uint32_t peers = __match_any_sync(FULL_MASK, d);
         const int leader = __ffs(peers) - 1;
         uint32_t before = 0;
         if (valid && lane == leader) {
             before = wcnt[w][d];
-            wcnt[w][d] = before + __popc(peers);
+            wcnt[w][d] = (uint16_t)(before + __popc(peers));
         }
         before = __shfl_sync(FULL_MASK, before, leader);
         rank[r] = before + __popc(peers & ((1u << lane) - 1u));
         __syncwarp();
     }
     __syncthreads();
-    {   // digit d = threadIdx.x: turn per-warp counts into global start offsets
-        const uint32_t d = threadIdx.x;
-        uint32_t run = hist[(size_t)frame * RS_RADIX * nblk_max + (size_t)d * nblk + b];
+    {   // turn per-warp counts into exclusive warp prefixes and the block's global digit offsets
+        const uint32_t* bh = hist + ((size_t)frame * nblk_max + b) * RS_RADIX;
+        const uint32_t* db = digit_base + (size_t)frame * RS_RADIX;
+        for (int d = threadIdx.x; d < RS_RADIX; d += RS_THREADS) {
+            uint32_t run = 0;
 #pragma unroll
-        for (int ww = 0; ww < RS_THREADS / 32; ww++) {
-            uint32_t c = wcnt[ww][d];
-            wcnt[ww][d] = run;
-            run += c;
+            for (int ww = 0; ww < RS_THREADS / 32; ww++) {
+                uint32_t c = wcnt[ww][d];
+                wcnt[ww][d] = (uint16_t)run;
+                run += c;
+            }
+            dbase[d] = db[d] + bh[d];
         }
     }
     __syncthreads();
@@ -225,7 +259,7 @@ k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* _
         const int i = base + r * 32 + lane;
         if (i < n) {
             const uint32_t d = (uint32_t)(key[r] >> shift) & (RS_RADIX - 1);
-            const uint32_t pos = wcnt[w][d] + rank[r];
+            const uint32_t pos = dbase[d] + wcnt[w][d] + rank[r];
             keys_out[seg + pos] = key[r];
             vals_out[seg + pos] = val[r];
         }
@@ -248,31 +282,32 @@ k_cluster_heads(const unsigned long long* __restrict__ keys, const int* __restri
                 int min_size, ClusterLists cl) {
     const int frame = blockIdx.y;
     const int n = min(npts[frame], cap);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     const unsigned long long* fk = keys + (size_t)frame * cap;
-    const unsigned long long k = fk[i];
-    if (i > 0 && fk[i - 1] == k) return;
-    int lo = i + 1, hi = n;  // first index in (i, n] whose key differs
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (fk[mid] == k) lo = mid + 1; else hi = mid;
-    }
-    const int size = lo - i;
-    ClusterRef ref;
-    ref.frame = frame; ref.start = i; ref.size = size; ref.pad = 0;
-    if (cl.dbg_heads) {
-        int s = atomicAdd(&cl.counters[5], 1);
-        if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
-    }
     const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);
-    if (size < min_size || size > max_cluster) return;
-#pragma unroll
-    for (int t = 0; t < AGPU_NTIERS; t++)
-        if (size <= cl.cap[t]) {
-            int s = atomicAdd(&cl.counters[t], 1);
-            if (s < cl.cap_list) cl.list[t][s] = ref;
-            return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = fk[i];
+        if (i > 0 && fk[i - 1] == k) continue;
+        int lo = i + 1, hi = n;  // first index in (i, n] whose key differs
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (fk[mid] == k) lo = mid + 1; else hi = mid;
         }
-    atomicAdd(&cl.counters[4], 1);
+        const int size = lo - i;
+        ClusterRef ref;
+        ref.frame = frame; ref.start = i; ref.size = size; ref.pad = 0;
+        if (cl.dbg_heads) {
+            int s = atomicAdd(&cl.counters[5], 1);
+            if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
+        }
+        if (size < min_size || size > max_cluster) continue;
+        bool placed = false;
+#pragma unroll
+        for (int t = 0; t < AGPU_NTIERS; t++)
+            if (!placed && size <= cl.cap[t]) {
+                int s = atomicAdd(&cl.counters[t], 1);
+                if (s < cl.cap_list) cl.list[t][s] = ref;
+                placed = true;
+            }
+        if (!placed) atomicAdd(&cl.counters[4], 1);
+    }
 }

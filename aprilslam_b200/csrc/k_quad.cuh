@@ -191,25 +191,40 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
     }
     if (sz < 24) return false;
 
+    // ---- gradient weights: squared gradient magnitude of the decimated image at every point, gathered in a
+    //      fully parallel pass (independent loads) and parked in the upper half of the sort slot (the slope bits
+    //      are dead after the sort), so that the sequential scan below never waits on global memory
+    {
+        const uint8_t* im = a.quad_im + (size_t)ref.frame * a.q_frame;
+#pragma unroll 4
+        for (int i = lane; i < sz; i += 32) {
+            const uint32_t xy = (uint32_t)sbuf[i];
+            const int px = xy & 0xffff, py = xy >> 16;
+            const double x = px * .5 + 0.5, y = py * .5 + 0.5;
+            const int ix = (int)x, iy = (int)y;
+            uint32_t g2 = 0;   // W = sqrt(g2) + 1 = 1 outside the interior, as upstream
+            if (ix > 0 && ix + 1 < a.g.wd && iy > 0 && iy + 1 < a.g.hd) {
+                int grad_x = (int)im[(size_t)iy * a.q_pitch + ix + 1] - (int)im[(size_t)iy * a.q_pitch + ix - 1];
+                int grad_y = (int)im[(size_t)(iy + 1) * a.q_pitch + ix] - (int)im[(size_t)(iy - 1) * a.q_pitch + ix];
+                g2 = (uint32_t)(grad_x * grad_x + grad_y * grad_y);
+            }
+            sbuf[i] = ((unsigned long long)g2 << 32) | xy;
+        }
+    }
+    __syncwarp();
     // ---- prefix moments (inclusive), written to the scratch at the cluster's own offset
     double* lf = a.lfps + seg * 6;
     {
-        const uint8_t* im = a.quad_im + (size_t)ref.frame * a.q_frame;
         double carry[6] = {0, 0, 0, 0, 0, 0};
         for (int base = 0; base < sz; base += 32) {
             int i = base + lane;
             double t[6] = {0, 0, 0, 0, 0, 0};
             if (i < sz) {
-                uint32_t xy = (uint32_t)sbuf[i];
+                const unsigned long long e = sbuf[i];
+                const uint32_t xy = (uint32_t)e;
                 int px = xy & 0xffff, py = xy >> 16;
                 double x = px * .5 + 0.5, y = py * .5 + 0.5;
-                int ix = (int)x, iy = (int)y;
-                double W = 1;
-                if (ix > 0 && ix + 1 < a.g.wd && iy > 0 && iy + 1 < a.g.hd) {
-                    int grad_x = (int)im[(size_t)iy * a.q_pitch + ix + 1] - (int)im[(size_t)iy * a.q_pitch + ix - 1];
-                    int grad_y = (int)im[(size_t)(iy + 1) * a.q_pitch + ix] - (int)im[(size_t)(iy - 1) * a.q_pitch + ix];
-                    W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
-                }
+                double W = sqrt((double)(uint32_t)(e >> 32)) + 1;
                 t[0] = W * x;
                 t[1] = W * y;
                 t[2] = W * x * x;
@@ -243,6 +258,7 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
     const int ksz = min(20, sz / 12);
     if (ksz < 2) return false;
     double* sraw = reinterpret_cast<double*>(sbuf);
+#pragma unroll 2
     for (int i = lane; i < sz; i += 32) {
         LineFit f;
         fit_line_dev(lf, sz, (i + sz - ksz) % sz, (i + ksz) % sz, f, false);
@@ -263,13 +279,16 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
     unsigned long long* mvals = sbuf;                       // [half]
     int* midx = reinterpret_cast<int*>(sbuf + half);        // [<= n2/2 ints]
     int nmax = 0;
+#pragma unroll 2
     for (int base = 0; base < sz; base += 32) {
         int i = base + lane;
         bool ismax = false;
-        double e = 0;
+        double e = i < sz ? __ldcg(es + i) : 0.0;
+        // neighbours from the adjacent lanes; only the tile ends (and the wrap-around) need their own loads
+        double en = __shfl_down_sync(FULL_MASK, e, 1), ep = __shfl_up_sync(FULL_MASK, e, 1);
         if (i < sz) {
-            e = __ldcg(es + i);
-            double en = __ldcg(es + (i + 1) % sz), ep = __ldcg(es + (i + sz - 1) % sz);
+            if (lane == 31 || i == sz - 1) en = __ldcg(es + (i + 1) % sz);
+            if (lane == 0) ep = __ldcg(es + (i + sz - 1) % sz);
             ismax = e > en && e > ep;
         }
         uint32_t m = __ballot_sync(FULL_MASK, ismax);
