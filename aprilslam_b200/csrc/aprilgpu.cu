@@ -88,16 +88,16 @@ struct Slot {
     cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};   // side streams: quad-fit tiers run concurrently
     cudaEvent_t ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;   // stage timing
-    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes;
+    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes, d_roots;
     DevBuf d_keys[2], d_vals[2], d_hist, d_dbase, d_lfps, d_errs;
-    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk]
+    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], nroots[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
     bool pending = false;
     int b0 = 0, n = 0, sorted = 0;
 
     void release() {
-        DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_labels, &d_sizes,
+        DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_labels, &d_sizes, &d_roots,
                           &d_keys[0], &d_keys[1], &d_vals[0], &d_vals[1], &d_hist, &d_dbase, &d_lfps, &d_errs, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
@@ -335,18 +335,27 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
     return AGPU_OK;
 }
 
-int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const Geom& g) {
+int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const Geom& g, int* d_nroots, bool flatten) {
     CK(sl.d_labels.ensure(g.plane * n * 4));
     CK(sl.d_sizes.ensure(g.plane * n * 4));
+    CK(sl.d_roots.ensure(g.plane * n * 4));
     const int tx = ceil_div(g.wd, CC_TW), ty = ceil_div(g.hd, CC_TH);
-    dim3 grid(tx, ty, n);
-    k_cc_local<<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), g, tx, ty);
+    dim3 grid(ceil_div(tx, CC_WARPS), ty, n);
+    k_cc_local<<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
+                                                   sl.d_roots.as<uint32_t>(), d_nroots, g);
     LAUNCH_CHECK("k_cc_local");
-    k_cc_boundary<<<grid, 160, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), g, tx, ty);
+    dim3 gridb(ceil_div((long long)tx * ty * CCB_ITEMS, 256), 1, n);
+    k_cc_boundary<<<gridb, 256, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), g, tx, ty);
     LAUNCH_CHECK("k_cc_boundary");
-    dim3 gridf(ceil_div(g.wd, CCF_TW), ceil_div(g.hd, CCF_TH), n);
-    k_cc_finalize<<<gridf, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), g);
-    LAUNCH_CHECK("k_cc_finalize");
+    dim3 grids(std::max(1, std::min(64, ceil_div(g.plane / 64, 256))), n);
+    k_cc_sizes<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
+                                             d_nroots, g);
+    LAUNCH_CHECK("k_cc_sizes");
+    if (flatten) {
+        dim3 gridf(ceil_div(g.wd, CCF_TW), ceil_div(g.hd, CCF_TH), n);
+        k_cc_flatten<<<gridf, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), g);
+        LAUNCH_CHECK("k_cc_flatten");
+    }
     return AGPU_OK;
 }
 
@@ -434,6 +443,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int* d_frame_quads = d_npts + chunk;
     int* d_ndets = d_frame_quads + chunk;
     int* d_out_counts = d_ndets + chunk;
+    int* d_nroots = d_out_counts + chunk;
     StageTimer tm(h, sl);
     tm.mark();  // 0
     const uint8_t* d_src;
@@ -452,7 +462,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
                              &q_frame, &gray_full, &gray_pitch, &gray_frame);
     if (rc) return rc;
     tm.mark();  // 2: after image
-    rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), n, g);
+    rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), n, g, d_nroots, h->cfg.debug != 0);
     if (rc) return rc;
     tm.mark();  // 3: after CC
     {
@@ -688,7 +698,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     c.cap = (c.cap + RS_TILE - 1) / RS_TILE * RS_TILE;
     c.maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
     c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
-    c.ncnt = CNT_FIXED + (size_t)4 * chunk;
+    c.ncnt = CNT_FIXED + (size_t)5 * chunk;
     c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
     if (on_device) {   // order every slot stream after the producer's stream
@@ -1123,7 +1133,9 @@ int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint3
     CK(sl.d_thresh.ensure(g.plane));
     CK(cudaMemsetAsync(sl.d_thresh.p, 127, g.plane, sl.stream));
     CK(cudaMemcpy2DAsync(sl.d_thresh.p, g.wp, thresh, W, W, H, cudaMemcpyHostToDevice, sl.stream));
-    int rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), 1, g);
+    CK(sl.d_counters.ensure(64));
+    CK(cudaMemsetAsync(sl.d_counters.p, 0, 64, sl.stream));
+    int rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), 1, g, sl.d_counters.as<int>(), true);
     if (rc) return rc;
     std::vector<uint32_t> lab(g.plane), sz(g.plane);
     CK(cudaMemcpyAsync(lab.data(), sl.d_labels.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));

@@ -5,47 +5,28 @@
 // links to its equal-valued neighbours left (x-1, y) and, for y >= 1, up (x, y-1); white (255)
 // pixels additionally link up-left and up-right.  Columns 0 and w-1 never initiate links.
 //
-// Three kernels (block-local union-find + boundary merge + canonical relabel):
-//   k_cc_local    32x64-pixel tile per CTA, warp-ballot row runs + union-find in shared memory (atomicMin
-//                 hooks: the root of a set is always its smallest pixel id), labels written as global
-//                 pixel ids; sizes[] zeroed at tile-local roots.
+// Kernels (block-local union-find + boundary merge + sizes [+ canonical relabel]):
+//   k_cc_local    32x32-pixel tile per warp, bit-parallel row runs + union-find over runs in shared memory
+//                 (atomicMin hooks: the root of a set is always its smallest pixel id); writes labels as
+//                 global pixel ids, the pixel count of every tile-local root, and the list of those roots.
 //   k_cc_boundary one thread per tile-border pixel, lock-free unions across tile edges in global memory.
-//   k_cc_finalize pointer jumping to the global root (= smallest pixel id of the component, so the
-//                 labelling is canonical by construction) + component sizes, aggregated per tile in
-//                 shared memory before the global atomics.
+//   k_cc_sizes    folds the counts of the tile-local roots into the final roots.
+//   k_cc_flatten  pointer jumping to the global root (= smallest pixel id of the component, so the
+//                 labelling is canonical by construction); only needed for the stage dumps, the
+//                 pipeline resolves representatives on the fly.
 #pragma once
 #include "common.cuh"
 
-// tile of the local pass: one warp row = 32 pixels, 64 rows, 8 warps x 8 rows
+// tile of the local pass: 32 x 32 pixels per warp (lane = ROW), 4 tiles side by side per CTA
 #define CC_TW 32
-#define CC_TH 64
-#define CC_THREADS 256
-#define CC_ROWS_PER_WARP 8
-// tile of the finalize pass (8-pixel runs per thread)
+#define CC_TH 32
+#define CC_WARPS 4
+#define CC_THREADS (CC_WARPS * 32)
+#define CC_PITCH 33   // run-start slots of row r live at r*33 + c: rows that touch the same column hit different banks
+// tile of the flatten pass (8-pixel runs per thread)
 #define CCF_TW 64
 #define CCF_TH 32
 #define CC_RUN 8
-
-__device__ __forceinline__ uint32_t sfind(volatile uint32_t* L, uint32_t a) {
-    uint32_t p = L[a];
-    while (p != a) {
-        a = p;
-        p = L[a];
-    }
-    return a;
-}
-
-__device__ __forceinline__ void sunion(uint32_t* L, uint32_t a, uint32_t b) {
-    for (;;) {
-        a = sfind(L, a);
-        b = sfind(L, b);
-        if (a == b) return;
-        if (a < b) { uint32_t t = a; a = b; b = t; }
-        uint32_t old = atomicMin(&L[a], b);  // hook the larger root under the smaller
-        if (old == a) return;
-        a = old;  // a was hooked elsewhere meanwhile; keep uniting its new parent with b
-    }
-}
 
 __device__ __forceinline__ uint32_t gfind(const uint32_t* L, uint32_t a) {
     uint32_t p = __ldcg(&L[a]);
@@ -62,182 +43,285 @@ __device__ __forceinline__ void gunion(uint32_t* L, uint32_t a, uint32_t b) {
         b = gfind(L, b);
         if (a == b) return;
         if (a < b) { uint32_t t = a; a = b; b = t; }
-        uint32_t old = atomicMin(&L[a], b);
+        uint32_t old = atomicMin(&L[a], b);  // hook the larger root under the smaller
+        if (old == a) return;
+        a = old;  // a was hooked elsewhere meanwhile; keep uniting its new parent with b
+    }
+}
+
+// logical run id r*32+c -> shared-memory slot
+__device__ __forceinline__ uint32_t cc_slot(uint32_t id) { return id + (id >> 5); }
+
+__device__ __forceinline__ uint32_t sfind(volatile uint32_t* L, uint32_t a) {
+    uint32_t p = L[cc_slot(a)];
+    while (p != a) {
+        a = p;
+        p = L[cc_slot(a)];
+    }
+    return a;
+}
+
+__device__ __forceinline__ void sunion(uint32_t* L, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = sfind(L, a);
+        b = sfind(L, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }
+        uint32_t old = atomicMin(&L[cc_slot(a)], b);
         if (old == a) return;
         a = old;
     }
 }
 
-// Local pass.  Lane = column: a warp ballot finds the horizontal runs of a row (a pixel's first label is the
-// start of its run -- no atomics), then only the first column of every vertical / diagonal contact between
-// runs of adjacent rows issues a union, so the number of shared-memory atomics follows the number of runs,
-// not the number of pixels.
+// 4 pixels (one word) -> 4 mask bits
+__device__ __forceinline__ uint32_t gather4(uint32_t t /* bytes of 0/1 */) { return (t * 0x01020408u) >> 24; }
+
+// bits s..e of the run that starts at s, given the row's continuation bits
+__device__ __forceinline__ uint32_t run_mask(uint32_t cont, int s) {
+    const uint32_t t = s == 31 ? 0u : (cont >> (s + 1));
+    const int e = s + __ffs(~t) - 1;            // trailing ones of t
+    const uint32_t hi = e >= 31 ? 0xffffffffu : ((2u << e) - 1u);
+    return hi & ~((1u << s) - 1u);
+}
+
+// Local pass, bit-parallel.  A lane owns one ROW of the 32x32 tile as two bit masks (white / black); the runs of
+// the row come from shifts and ANDs of the lane's own word, the contacts with the row above from the masks of
+// the lane above (one shuffle), and only runs -- not pixels -- take part in the shared-memory union-find.
+// Besides the labels the pass leaves, for every tile-local root: its pixel count in sizes[] and its id in the
+// frame's root list (k_cc_sizes folds the counts into the final roots after the boundary merges).
 __global__ void __launch_bounds__(CC_THREADS)
-k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, Geom g,
-           int tiles_x, int tiles_y) {
-    __shared__ uint8_t sv[CC_TH][CC_TW];
-    __shared__ uint32_t L[CC_TH * CC_TW];
+k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes,
+           uint32_t* __restrict__ roots, int* __restrict__ nroots, Geom g) {
+    __shared__ uint32_t sL[CC_WARPS][CC_TH * CC_PITCH];
+    __shared__ uint32_t sX[CC_WARPS][CC_TH * CC_PITCH];
     const int frame = blockIdx.z;
-    const int x0 = blockIdx.x * CC_TW, y0 = blockIdx.y * CC_TH;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = (blockIdx.x * CC_WARPS + w) * CC_TW, y0 = blockIdx.y * CC_TH;
+    if (x0 >= g.wd) return;   // (no block-level synchronisation anywhere below)
+    const int y = y0 + lane;
     const uint8_t* ft = thresh + (size_t)frame * g.plane;
     uint32_t* fl = labels + (size_t)frame * g.plane;
     uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int x = x0 + lane;
-    const bool col_init = x >= 1 && x <= g.wd - 2;   // columns 0 and w-1 never initiate links
+    uint32_t* L = sL[w];
+    uint32_t* X = sX[w];
+    const bool second = x0 + 32 <= g.wp;   // the row pitch is a multiple of 16, not of 32
 
-    uint32_t v[CC_ROWS_PER_WARP], starts[CC_ROWS_PER_WARP];
+    // ---- row masks
+    uint32_t Wm = 0, Bm = 0;
+    if (y < g.hd) {
+        const uint4* rp = reinterpret_cast<const uint4*>(ft + (size_t)y * g.wp + x0);
+        const uint4 a = __ldg(rp);
+        uint4 b = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+        if (second) b = __ldg(rp + 1);
+        const uint32_t wd8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int k = 0; k < CC_ROWS_PER_WARP; k++) {
-        const int ry = w * CC_ROWS_PER_WARP + k, gy = y0 + ry;
-        uint32_t c = 127;
-        if (gy < g.hd && x < g.wd) c = ft[(size_t)gy * g.wp + x];
-        const uint32_t cl = __shfl_up_sync(FULL_MASK, c, 1);
-        const bool link = lane > 0 && c != 127 && c == cl && col_init;
-        const uint32_t st = __ballot_sync(FULL_MASK, !link);
-        const int rs = 31 - __clz(st & (0xffffffffu >> (31 - lane)));
-        L[ry * CC_TW + lane] = (uint32_t)(ry * CC_TW + rs);
-        sv[ry][lane] = (uint8_t)c;
-        v[k] = c;
-        starts[k] = st;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < CC_ROWS_PER_WARP; k++) {
-        const int ry = w * CC_ROWS_PER_WARP + k, gy = y0 + ry;
-        const uint32_t c = v[k];
-        if (ry == 0 || gy < 1 || gy >= g.hd) continue;           // warp-uniform
-        const uint32_t up = sv[ry - 1][lane];
-        const uint32_t upl = __shfl_up_sync(FULL_MASK, up, 1), upr = __shfl_down_sync(FULL_MASK, up, 1);
-        const uint32_t cl = __shfl_up_sync(FULL_MASK, c, 1);
-        if (c == 127 || !col_init) continue;
-        const uint32_t li = (uint32_t)(ry * CC_TW + lane);
-        if (up == c) {
-            // implied when the left pixel is chained to this one, to the pixel above it, and that one to `up`
-            const bool implied = lane > 0 && cl == c && upl == c && x - 1 >= 1;
-            if (!implied) sunion(L, li, li - CC_TW);
-        }
-        if (c == 255) {
-            // up == c implies the diagonals through (x, y-1)'s left link and the left link initiated by
-            // (x+1, y-1); the latter only exists when x+1 <= w-2
-            if (lane > 0 && upl == 255 && up != 255) sunion(L, li, li - CC_TW - 1);
-            if (lane < 31 && upr == 255 && (up != 255 || x + 1 > g.wd - 2)) sunion(L, li, li - CC_TW + 1);
+        for (int k = 0; k < 8; k++) {
+            Wm |= gather4((wd8[k] >> 7) & 0x01010101u) << (4 * k);   // 255: bit 7 set
+            Bm |= gather4(~wd8[k] & 0x01010101u) << (4 * k);          // 0: bit 0 clear (127 and 255 have it set)
         }
     }
-    __syncthreads();
+    const int ncols = min(32, g.wd - x0);
+    const uint32_t V = ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u);
+    Wm &= V;
+    Bm &= V;
+    // initiator columns: 1 <= x <= w-2
+    uint32_t I = V;
+    if (x0 == 0) I &= ~1u;
+    if (g.wd - 1 - x0 < 32) I &= ~(1u << (g.wd - 1 - x0));
+    const uint32_t cw = Wm & (Wm << 1) & I, cb = Bm & (Bm << 1) & I;   // bit x: x continues the run of x-1
+    const uint32_t Sw = Wm & ~cw, Sb = Bm & ~cb;                       // run starts
+    const uint32_t S = Sw | Sb;
+    for (uint32_t m = S; m; m &= m - 1) {
+        const uint32_t id = (uint32_t)(lane * 32 + __ffs(m) - 1);
+        L[cc_slot(id)] = id;
+    }
+    __syncwarp();
+
+    // ---- contacts with the row above (lane 0's upper row belongs to another tile: k_cc_boundary)
+    {
+        uint32_t Wu = __shfl_up_sync(FULL_MASK, Wm, 1), Bu = __shfl_up_sync(FULL_MASK, Bm, 1);
+        uint32_t cwu = __shfl_up_sync(FULL_MASK, cw, 1), cbu = __shfl_up_sync(FULL_MASK, cb, 1);
+        uint32_t Swu = __shfl_up_sync(FULL_MASK, Sw, 1), Sbu = __shfl_up_sync(FULL_MASK, Sb, 1);
+        if (lane == 0) { Wu = Bu = 0; }
+        // white: 8-connected (up-left, up, up-right), black: 4-connected (up)
+        for (uint32_t m = Sw; m; m &= m - 1) {
+            const int s = __ffs(m) - 1;
+            const uint32_t rI = run_mask(cw, s) & I;
+            uint32_t touched = ((rI << 1) | rI | (rI >> 1)) & Wu;
+            while (touched) {
+                const int x = __ffs(touched) - 1;
+                const int su = 31 - __clz(Swu & (0xffffffffu >> (31 - x)));
+                sunion(L, (uint32_t)(lane * 32 + s), (uint32_t)((lane - 1) * 32 + su));
+                touched &= ~run_mask(cwu, su);
+            }
+        }
+        for (uint32_t m = Sb; m; m &= m - 1) {
+            const int s = __ffs(m) - 1;
+            uint32_t touched = run_mask(cb, s) & I & Bu;
+            while (touched) {
+                const int x = __ffs(touched) - 1;
+                const int su = 31 - __clz(Sbu & (0xffffffffu >> (31 - x)));
+                sunion(L, (uint32_t)(lane * 32 + s), (uint32_t)((lane - 1) * 32 + su));
+                touched &= ~run_mask(cbu, su);
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- root of every run, then pixel counts per tile-local root (L is reused as the counter array)
+    for (uint32_t m = S; m; m &= m - 1) {
+        const uint32_t id = (uint32_t)(lane * 32 + __ffs(m) - 1);
+        X[cc_slot(id)] = sfind(L, id);
+    }
+    __syncwarp();
+    int nroot = 0;
+    for (uint32_t m = S; m; m &= m - 1) {
+        const uint32_t id = (uint32_t)(lane * 32 + __ffs(m) - 1);
+        if (X[cc_slot(id)] == id) { L[cc_slot(id)] = 0; nroot++; }
+    }
+    __syncwarp();
+    for (uint32_t m = Sw; m; m &= m - 1) {
+        const int s = __ffs(m) - 1;
+        atomicAdd(&L[cc_slot(X[cc_slot((uint32_t)(lane * 32 + s))])], (uint32_t)__popc(run_mask(cw, s)));
+    }
+    for (uint32_t m = Sb; m; m &= m - 1) {
+        const int s = __ffs(m) - 1;
+        atomicAdd(&L[cc_slot(X[cc_slot((uint32_t)(lane * 32 + s))])], (uint32_t)__popc(run_mask(cb, s)));
+    }
+    __syncwarp();
+    // append the tile's roots to the frame's root list (one atomic per tile) and publish their counts
+    {
+        int incl = nroot;
 #pragma unroll
-    for (int k = 0; k < CC_ROWS_PER_WARP; k++) {
-        const int ry = w * CC_ROWS_PER_WARP + k, gy = y0 + ry;
-        const uint32_t st = starts[k];
-        const int rs = 31 - __clz(st & (0xffffffffu >> (31 - lane)));
-        const uint32_t li = (uint32_t)(ry * CC_TW + lane);
-        uint32_t r = 0;
-        if ((st >> lane) & 1u) r = sfind(L, li);
-        r = __shfl_sync(FULL_MASK, r, rs);
-        if (gy < g.hd && x < g.wp) {
-            const uint32_t gid = (uint32_t)((y0 + (int)(r / CC_TW)) * g.wp + x0 + (int)(r % CC_TW));
-            fl[(size_t)gy * g.wp + x] = gid;
-            if (r == li && v[k] != 127) fs[gid] = 0;   // size counters start at zero at every tile-local root
+        for (int off = 1; off < 32; off <<= 1) {
+            int n = __shfl_up_sync(FULL_MASK, incl, off);
+            if (lane >= off) incl += n;
+        }
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        int base = 0;
+        if (lane == 31 && total) base = atomicAdd(&nroots[frame], total);
+        base = __shfl_sync(FULL_MASK, base, 31);
+        int o = base + incl - nroot;
+        uint32_t* fr = roots + (size_t)frame * g.plane;
+        for (uint32_t m = S; m; m &= m - 1) {
+            const uint32_t id = (uint32_t)(lane * 32 + __ffs(m) - 1);
+            if (X[cc_slot(id)] == id) {
+                const uint32_t gid = (uint32_t)((y0 + (int)(id >> 5)) * g.wp + x0 + (int)(id & 31));
+                fs[gid] = L[cc_slot(id)];
+                fr[o++] = gid;
+            }
+        }
+    }
+    // ---- labels: every pixel of a run gets the global id of the run's root, everything else its own id
+    if (y < g.hd) {
+        const uint32_t own0 = (uint32_t)(y * g.wp + x0);
+        const uint32_t fg = Wm | Bm;
+        uint32_t cur = 0;
+        uint4* dst = reinterpret_cast<uint4*>(fl + (size_t)y * g.wp + x0);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint32_t o4[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = q * 4 + k;
+                if ((S >> c) & 1u) {
+                    const uint32_t r = X[cc_slot((uint32_t)(lane * 32 + c))];
+                    cur = (uint32_t)((y0 + (int)(r >> 5)) * g.wp + x0 + (int)(r & 31));
+                }
+                o4[k] = ((fg >> c) & 1u) ? cur : own0 + c;
+            }
+            if (q < 4 || second) dst[q] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
         }
     }
 }
 
-// One thread per tile-border pixel: top row (32) + left column (64) + right column (64).
-__global__ void __launch_bounds__(160)
+// One thread per tile-border pixel (top row, left column, right column of every 32x32 tile): lock-free unions
+// across tile borders.  As in the local pass only the first pixel of every contact issues a union.
+#define CCB_ITEMS (CC_TW + 2 * CC_TH)
+__global__ void __launch_bounds__(256)
 k_cc_boundary(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, Geom g, int tiles_x, int tiles_y) {
     const int frame = blockIdx.z;
-    const int x0 = blockIdx.x * CC_TW, y0 = blockIdx.y * CC_TH;
     const uint8_t* ft = thresh + (size_t)frame * g.plane;
     uint32_t* fl = labels + (size_t)frame * g.plane;
-    const int t = threadIdx.x;
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)tiles_x * tiles_y * CCB_ITEMS;
+    if (item >= total) return;
+    const int tile = (int)(item / CCB_ITEMS), t = (int)(item - (long long)tile * CCB_ITEMS);
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int x0 = tx * CC_TW, y0 = ty * CC_TH;
     int x, y;
     if (t < CC_TW) { x = x0 + t; y = y0; }
-    else if (t < CC_TW + CC_TH) { x = x0; y = y0 + (t - CC_TW); if (t == CC_TW) return; }   // corner: top row's job
+    else if (t < CC_TW + CC_TH) { x = x0; y = y0 + (t - CC_TW); if (t == CC_TW) return; }          // corner: top row's job
     else { x = x0 + CC_TW - 1; y = y0 + (t - CC_TW - CC_TH); if (t == CC_TW + CC_TH) return; }
     if (x < 1 || x > g.wd - 2 || y >= g.hd) return;
-    const uint8_t c = ft[(size_t)y * g.wp + x];
+    const uint8_t* row = ft + (size_t)y * g.wp;
+    const uint8_t c = row[x];
     if (c == 127) return;
     const uint32_t id = (uint32_t)(y * g.wp + x);
     const bool left_edge = (x == x0), top_edge = (y == y0), right_edge = (x == x0 + CC_TW - 1);
-    if (left_edge && ft[(size_t)y * g.wp + x - 1] == c) gunion(fl, id, id - 1);
+    const uint8_t* up = y >= 1 ? row - g.wp : nullptr;
+    if (left_edge && row[x - 1] == c) {
+        // implied when the row above carries the same contact and both pixels hang on it
+        const bool implied = !top_edge && y >= 1 && up[x] == c && up[x - 1] == c && x - 1 >= 1;
+        if (!implied) gunion(fl, id, id - 1);
+    }
     if (y >= 1) {
-        const uint8_t* up = ft + (size_t)(y - 1) * g.wp;
-        if (top_edge && up[x] == c) gunion(fl, id, id - g.wp);
+        const bool upsame = up[x] == c;
+        if (top_edge && upsame) {
+            const bool implied = x - 1 >= 1 && row[x - 1] == c && up[x - 1] == c;
+            if (!implied) gunion(fl, id, id - g.wp);
+        }
         if (c == 255) {
-            if ((top_edge || left_edge) && up[x - 1] == c) gunion(fl, id, id - g.wp - 1);
-            if ((top_edge || right_edge) && up[x + 1] == c) gunion(fl, id, id - g.wp + 1);
+            if ((top_edge || left_edge) && up[x - 1] == c && !upsame) gunion(fl, id, id - g.wp - 1);
+            if ((top_edge || right_edge) && up[x + 1] == c && (!upsame || x + 1 > g.wd - 2)) gunion(fl, id, id - g.wp + 1);
         }
     }
 }
 
-#define CC_HASH 128
-__global__ void __launch_bounds__(CC_THREADS)
-k_cc_finalize(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, Geom g) {
-    __shared__ uint32_t hkey[CC_HASH];
-    __shared__ uint32_t hcnt[CC_HASH];
+// Fold the pixel counts of the tile-local roots into the final roots (after the boundary merges).
+__global__ void __launch_bounds__(256)
+k_cc_sizes(const uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
+           const int* __restrict__ nroots, Geom g) {
+    const int frame = blockIdx.y;
+    const int n = nroots[frame];
+    const uint32_t* fl = labels + (size_t)frame * g.plane;
+    uint32_t* fs = sizes + (size_t)frame * g.plane;
+    const uint32_t* fr = roots + (size_t)frame * g.plane;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t a = fr[i];
+        const uint32_t r = gfind(fl, a);
+        if (r != a) atomicAdd(&fs[r], fs[a]);
+    }
+}
+
+// Pointer jumping to the global root (= smallest pixel id of the component): the canonical labelling.  The
+// pipeline itself resolves representatives on the fly (k_edges); this pass runs for the stage dumps.
+__global__ void __launch_bounds__(256)
+k_cc_flatten(uint32_t* __restrict__ labels, Geom g) {
     const int frame = blockIdx.z;
     const int x0 = blockIdx.x * CCF_TW, y0 = blockIdx.y * CCF_TH;
-    const uint8_t* ft = thresh + (size_t)frame * g.plane;
     uint32_t* fl = labels + (size_t)frame * g.plane;
-    uint32_t* fs = sizes + (size_t)frame * g.plane;
     const int t = threadIdx.x;
-    if (t < CC_HASH) { hkey[t] = 0xffffffffu; hcnt[t] = 0; }
-    __syncthreads();
     const int ry = t >> 3, rx = (t & 7) * CC_RUN;
     const int gy = y0 + ry, gx = x0 + rx;
     if (gy < g.hd && gx < g.wp) {
-        uint2 raw = *reinterpret_cast<const uint2*>(ft + (size_t)gy * g.wp + gx);
         uint4* lp = reinterpret_cast<uint4*>(fl + (size_t)gy * g.wp + gx);
         uint4 a = __ldcg(lp), b = __ldcg(lp + 1);
         uint32_t lab[CC_RUN] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         uint32_t root[CC_RUN];
-        uint32_t prev_lab = 0xffffffffu, prev_root = 0, run_root = 0xffffffffu, run_cnt = 0;
+        uint32_t prev_lab = 0xffffffffu, prev_root = 0;
         bool changed = false;
 #pragma unroll
         for (int k = 0; k < CC_RUN; k++) {
-            uint32_t v = ((k < 4 ? raw.x : raw.y) >> (8 * (k & 3))) & 0xff;
-            uint32_t r;
-            if (lab[k] == prev_lab) r = prev_root;
-            else r = gfind(fl, lab[k]);
+            uint32_t r = lab[k] == prev_lab ? prev_root : gfind(fl, lab[k]);
             prev_lab = lab[k];
             prev_root = r;
             root[k] = r;
             changed |= (r != lab[k]);
-            bool counted = (v != 127) && (gx + k < g.wd);
-            if (counted) {
-                if (r == run_root) run_cnt++;
-                else {
-                    if (run_cnt) {
-                        // flush the previous run into the tile hash (linear probing; overflow -> global)
-                        uint32_t hsh = (run_root * 2654435761u) >> 25;
-                        bool done = false;
-                        for (int probe = 0; probe < 8 && !done; probe++) {
-                            uint32_t s = (hsh + probe) & (CC_HASH - 1);
-                            uint32_t old = atomicCAS(&hkey[s], 0xffffffffu, run_root);
-                            if (old == 0xffffffffu || old == run_root) { atomicAdd(&hcnt[s], run_cnt); done = true; }
-                        }
-                        if (!done) atomicAdd(&fs[run_root], run_cnt);
-                    }
-                    run_root = r;
-                    run_cnt = 1;
-                }
-            }
-        }
-        if (run_cnt) {
-            uint32_t hsh = (run_root * 2654435761u) >> 25;
-            bool done = false;
-            for (int probe = 0; probe < 8 && !done; probe++) {
-                uint32_t s = (hsh + probe) & (CC_HASH - 1);
-                uint32_t old = atomicCAS(&hkey[s], 0xffffffffu, run_root);
-                if (old == 0xffffffffu || old == run_root) { atomicAdd(&hcnt[s], run_cnt); done = true; }
-            }
-            if (!done) atomicAdd(&fs[run_root], run_cnt);
         }
         if (changed) {
             lp[0] = make_uint4(root[0], root[1], root[2], root[3]);
             lp[1] = make_uint4(root[4], root[5], root[6], root[7]);
         }
     }
-    __syncthreads();
-    if (t < CC_HASH && hkey[t] != 0xffffffffu) atomicAdd(&fs[hkey[t]], hcnt[t]);
 }

@@ -10,6 +10,7 @@
 //   k_cluster_heads  run heads of equal keys -> cluster work lists (binary search for the run end).
 #pragma once
 #include "common.cuh"
+#include "k_cc.cuh"
 
 // Four pixels (one 32-bit word of the threshold image) per thread.  An edge between v0 and v1 means
 // v0 ^ v1 == 0xff (values are 0 / 127 / 255), tested for all four pixels and one direction at a time with
@@ -89,9 +90,9 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
             const int x = xbase + (int)(c & 127), d = (c >> 7) & 3, pos = (c >> 9) & 1;
             const int dx = (d == 0 || d == 3) ? 1 : (d == 2 ? -1 : 0), dy = d == 0 ? 0 : 1;
             const size_t id = (size_t)y * g.wp + x;
-            const uint32_t rep0 = fl[id];
+            const uint32_t rep0 = gfind(fl, (uint32_t)id);   // labels are parent links until k_cc_flatten (stage dumps only)
             if (fs[rep0] >= 25u) {
-                const uint32_t rep1 = fl[id + (size_t)dy * g.wp + dx];
+                const uint32_t rep1 = gfind(fl, (uint32_t)(id + (size_t)dy * g.wp + dx));
                 if (fs[rep1] >= 25u) {
                     ok = true;
                     const uint32_t hi = max(rep0, rep1), lo = min(rep0, rep1);
