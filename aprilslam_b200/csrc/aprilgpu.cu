@@ -73,8 +73,9 @@ struct HostBuf {
 
 // cluster size tiers of the quad-fit kernel: {largest cluster, warps per CTA, CTAs per SM}
 constexpr int TIER_CAP[AGPU_NTIERS] = {256, 1024, 2048, 16384};
-constexpr int TIER_WPB[AGPU_NTIERS] = {8, 8, 4, 1};
-constexpr int TIER_CTAS_PER_SM[AGPU_NTIERS] = {3, 3, 3, 1};
+// warps per cluster group (NW); tier 0 packs 8 one-warp groups into a CTA, the others use one CTA per cluster
+constexpr int TIER_NW[AGPU_NTIERS] = {1, 2, 4, 8};
+constexpr int TIER_CTAS_PER_SM[AGPU_NTIERS] = {3, 16, 8, 1};
 // counter block layout (ints): [0..3] clusters per tier
 enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_FIXED = 8 };
 
@@ -529,8 +530,17 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             if (t > 0) CK(cudaStreamWaitEvent(st, sl.ev_fork, 0));
             qa.list = sl.d_clusters[t].as<ClusterRef>();
             qa.list_count = d_cnt + CNT_TIER0 + t;
-            const size_t smem = (size_t)TIER_WPB[t] * qf_smem_per_warp(TIER_CAP[t]);
-            k_fit_quads<<<h->num_sms * TIER_CTAS_PER_SM[t], TIER_WPB[t] * 32, smem, st>>>(qa, h->prm, TIER_CAP[t]);
+            const int nblk = h->num_sms * TIER_CTAS_PER_SM[t];
+            if (t == 0) {
+                const size_t smem = 8 * qf_smem_per_group(TIER_CAP[t]);
+                k_fit_quads<1><<<nblk, 256, smem, st>>>(qa, h->prm, TIER_CAP[t]);
+            } else if (t == 1) {
+                k_fit_quads<2><<<nblk, 64, qf_smem_per_group(TIER_CAP[t]), st>>>(qa, h->prm, TIER_CAP[t]);
+            } else if (t == 2) {
+                k_fit_quads<4><<<nblk, 128, qf_smem_per_group(TIER_CAP[t]), st>>>(qa, h->prm, TIER_CAP[t]);
+            } else {
+                k_fit_quads<8><<<nblk, 256, qf_smem_per_group(TIER_CAP[t]), st>>>(qa, h->prm, TIER_CAP[t]);
+            }
             LAUNCH_CHECK("k_fit_quads");
             if (t > 0) {
                 CK(cudaEventRecord(sl.ev_join[t - 1], st));
@@ -887,8 +897,11 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
         cudaMemcpy(h->d_codes.p, codes.data(), codes.size() * 8, cudaMemcpyHostToDevice);
     }
     // the large quad-fit tiers need more than 48 KB of dynamic shared memory
-    ce = cudaFuncSetAttribute(k_fit_quads, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)qf_smem_per_warp(TIER_CAP[AGPU_NTIERS - 1]));
+    ce = cudaFuncSetAttribute(k_fit_quads<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)qf_smem_per_group(TIER_CAP[AGPU_NTIERS - 1]));
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(k_fit_quads<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(8 * qf_smem_per_group(TIER_CAP[0])));
     if (ce != cudaSuccess) return fail(AGPU_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
     *out = h;
     return AGPU_OK;

@@ -81,42 +81,97 @@ __device__ void fit_line_dev(const double* lf, int sz, int i0, int i1, LineFit& 
     out.mse = eig_small;
 }
 
-// Bitonic sort of n2 (power of two >= 64) 64-bit keys in shared memory by one warp: every lane owns
-// compare-exchange PAIRS (no idle half), four independent pairs per step for memory-level parallelism.
-__device__ __forceinline__ void warp_bitonic_sort(unsigned long long* s, int n2, bool descending) {
-    const int lane = threadIdx.x & 31;
+#define QF_PTAB_DOUBLES (100 * 6)
+
+// A cluster is fitted by a GROUP of NW warps.  NW == 1: the group is a warp (several clusters per CTA, warp
+// synchronisation); NW > 1: the group is the whole CTA (one cluster at a time, __syncthreads), which puts
+// NW times more warps on every shared-memory sort buffer -- the buffer, not the thread count, is what limits
+// how many clusters an SM can hold, so the latency-bound phases get NW times more warps to hide behind.
+template <int NW>
+struct QGroup {
+    static constexpr int T = NW * 32;
+    int tid, lane, w;
+    int* si;        // [NW + 4] ints of scratch
+    double* sd;     // [NW * 8] doubles of scratch
+    __device__ __forceinline__ void sync() const {
+        if (NW == 1) __syncwarp(); else __syncthreads();
+    }
+    // position of this thread's kept element among the kept elements of the group (thread order) and their number
+    __device__ __forceinline__ int compact_pos(bool keep, int& total) const {
+        const uint32_t m = __ballot_sync(FULL_MASK, keep);
+        const int below = __popc(m & ((1u << lane) - 1u));
+        if (NW == 1) { total = __popc(m); return below; }
+        if (lane == 0) si[w] = __popc(m);
+        __syncthreads();
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < NW; i++) { const int c = si[i]; if (i < w) off += c; tot += c; }
+        __syncthreads();
+        total = tot;
+        return off + below;
+    }
+    __device__ __forceinline__ int reduce_min(int v) const {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(FULL_MASK, v, off));
+        if (NW == 1) return v;
+        if (lane == 0) si[w] = v;
+        __syncthreads();
+        int r = si[0];
+#pragma unroll
+        for (int i = 1; i < NW; i++) r = min(r, si[i]);
+        __syncthreads();
+        return r;
+    }
+    __device__ __forceinline__ int reduce_max(int v) const { return -reduce_min(-v); }
+    __device__ __forceinline__ long long reduce_sum(long long v) const {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL_MASK, v, off);
+        if (NW == 1) return v;
+        long long* sl = reinterpret_cast<long long*>(sd);
+        if (lane == 0) sl[w] = v;
+        __syncthreads();
+        long long r = 0;
+#pragma unroll
+        for (int i = 0; i < NW; i++) r += sl[i];
+        __syncthreads();
+        return r;
+    }
+};
+
+// Bitonic sort of n2 (power of two >= 64) 64-bit keys in shared memory: every thread owns compare-exchange
+// PAIRS (no idle half), independent pairs per step for memory-level parallelism.
+template <int NW>
+__device__ __forceinline__ void group_bitonic_sort(const QGroup<NW>& G, unsigned long long* s, int n2, bool descending) {
     const int npairs = n2 >> 1;
     for (int k = 2; k <= n2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll 4
-            for (int t = lane; t < npairs; t += 32) {
+            for (int t = G.tid; t < npairs; t += QGroup<NW>::T) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int ixj = i | j;
                 unsigned long long a = s[i], b = s[ixj];
                 const bool up = ((i & k) == 0) != descending;
                 if ((a > b) == up) { s[i] = b; s[ixj] = a; }
             }
-            __syncwarp();
+            G.sync();
         }
     }
 }
 
-#define QF_PTAB_DOUBLES (100 * 6)
-
-// Returns true and fills q when the cluster yields a quad.
-__device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const ClusterRef ref,
-                                 unsigned long long* sbuf, double* ptab, int* sidx, QuadRec& q) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+// Returns true (uniformly over the group) and fills q when the cluster yields a quad.
+template <int NW>
+__device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, const DevParams& P, const ClusterRef ref,
+                                  unsigned long long* sbuf, double* ptab, int* sidx, QuadRec& q) {
+    constexpr int T = QGroup<NW>::T;
+    const int tid = G.tid, lane = G.lane;
     const size_t seg = (size_t)ref.frame * a.cap + ref.start;
     const uint32_t* pv = a.vals + seg;
     int sz = ref.size;
 
     // ---- bounding box and polarity sums
     int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
-    long long Sxgx = 0, Sygy = 0;
-    int Sgx = 0, Sgy = 0;
-    for (int i = lane; i < sz; i += 32) {
+    long long Sxgx = 0, Sygy = 0, Sgx = 0, Sgy = 0;
+    for (int i = tid; i < sz; i += T) {
         uint32_t v = pv[i];
         int px = v & 0x3fff, py = (v >> 14) & 0x3fff, dir = (v >> 28) & 3;
         int s = ((v >> 30) & 1) ? 255 : -255;
@@ -128,17 +183,10 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
         Sxgx += (long long)px * gx; Sgx += gx;
         Sygy += (long long)py * gy; Sgy += gy;
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        xmin = min(xmin, __shfl_xor_sync(FULL_MASK, xmin, off));
-        xmax = max(xmax, __shfl_xor_sync(FULL_MASK, xmax, off));
-        ymin = min(ymin, __shfl_xor_sync(FULL_MASK, ymin, off));
-        ymax = max(ymax, __shfl_xor_sync(FULL_MASK, ymax, off));
-        Sxgx += __shfl_xor_sync(FULL_MASK, Sxgx, off);
-        Sygy += __shfl_xor_sync(FULL_MASK, Sygy, off);
-        Sgx += __shfl_xor_sync(FULL_MASK, Sgx, off);
-        Sgy += __shfl_xor_sync(FULL_MASK, Sgy, off);
-    }
+    xmin = G.reduce_min(xmin); xmax = G.reduce_max(xmax);
+    ymin = G.reduce_min(ymin); ymax = G.reduce_max(ymax);
+    Sxgx = G.reduce_sum(Sxgx); Sygy = G.reduce_sum(Sygy);
+    Sgx = G.reduce_sum(Sgx); Sgy = G.reduce_sum(Sgy);
     if ((xmax - xmin) * (ymax - ymin) < P.min_tag_width) return false;
     const float cx = (xmin + xmax) * 0.5f + 0.05118f;
     const float cy = (ymin + ymax) * 0.5f - 0.028581f;
@@ -150,7 +198,7 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
     // ---- slope keys
     int n2 = 64;
     while (n2 < sz) n2 <<= 1;
-    for (int i = lane; i < n2; i += 32) {
+    for (int i = tid; i < n2; i += T) {
         unsigned long long key = ~0ull;
         if (i < sz) {
             uint32_t v = pv[i];
@@ -166,26 +214,28 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
         }
         sbuf[i] = key;
     }
-    __syncwarp();
-    warp_bitonic_sort(sbuf, n2, false);
+    G.sync();
+    group_bitonic_sort<NW>(G, sbuf, n2, false);
 
-    // ---- remove consecutive duplicates (same x, y)
+    // ---- remove consecutive duplicates (same x, y); in place: a tile is read completely before it is written,
+    //      and writes only go to positions at or below the ones read
     {
         int outn = 0;
-        uint32_t prev_xy = 0xffffffffu;
-        for (int base = 0; base < sz; base += 32) {
-            int i = base + lane;
-            unsigned long long kk = i < sz ? sbuf[i] : 0ull;
-            uint32_t xy = (uint32_t)kk;
-            uint32_t pxy = __shfl_up_sync(FULL_MASK, xy, 1);
-            if (lane == 0) pxy = prev_xy;
-            bool keep = i < sz && xy != pxy;
-            uint32_t m = __ballot_sync(FULL_MASK, keep);
-            prev_xy = __shfl_sync(FULL_MASK, xy, 31);
-            __syncwarp();
-            if (keep) sbuf[outn + __popc(m & lt_mask)] = kk;
-            outn += __popc(m);
-            __syncwarp();
+        for (int base = 0; base < sz; base += T) {
+            const int i = base + tid;
+            unsigned long long kk = 0ull;
+            bool keep = false;
+            if (i < sz) {
+                kk = sbuf[i];
+                const uint32_t pxy = i > 0 ? (uint32_t)sbuf[i - 1] : 0xffffffffu;
+                keep = (uint32_t)kk != pxy;
+            }
+            G.sync();
+            int total;
+            const int pos = G.compact_pos(keep, total);
+            if (keep) sbuf[outn + pos] = kk;
+            outn += total;
+            G.sync();
         }
         sz = outn;
     }
@@ -193,11 +243,11 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
 
     // ---- gradient weights: squared gradient magnitude of the decimated image at every point, gathered in a
     //      fully parallel pass (independent loads) and parked in the upper half of the sort slot (the slope bits
-    //      are dead after the sort), so that the sequential scan below never waits on global memory
+    //      are dead after the sort), so that the scan below never waits on global memory
     {
         const uint8_t* im = a.quad_im + (size_t)ref.frame * a.q_frame;
 #pragma unroll 4
-        for (int i = lane; i < sz; i += 32) {
+        for (int i = tid; i < sz; i += T) {
             const uint32_t xy = (uint32_t)sbuf[i];
             const int px = xy & 0xffff, py = xy >> 16;
             const double x = px * .5 + 0.5, y = py * .5 + 0.5;
@@ -211,13 +261,13 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
             sbuf[i] = ((unsigned long long)g2 << 32) | xy;
         }
     }
-    __syncwarp();
+    G.sync();
     // ---- prefix moments (inclusive), written to the scratch at the cluster's own offset
     double* lf = a.lfps + seg * 6;
     {
         double carry[6] = {0, 0, 0, 0, 0, 0};
-        for (int base = 0; base < sz; base += 32) {
-            int i = base + lane;
+        for (int base = 0; base < sz; base += T) {
+            const int i = base + tid;
             double t[6] = {0, 0, 0, 0, 0, 0};
             if (i < sz) {
                 const unsigned long long e = sbuf[i];
@@ -240,8 +290,27 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
                     if (lane >= off) t[k] += n;
                 }
             }
+            double add[6], tot[6];
 #pragma unroll
-            for (int k = 0; k < 6; k++) t[k] = carry[k] + t[k];
+            for (int k = 0; k < 6; k++) { add[k] = carry[k]; tot[k] = __shfl_sync(FULL_MASK, t[k], 31); }
+            if (NW > 1) {
+                if (lane == 31) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) G.sd[G.w * 8 + k] = t[k];
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    double below = 0, all = 0;
+#pragma unroll
+                    for (int ww = 0; ww < NW; ww++) { const double v = G.sd[ww * 8 + k]; if (ww < G.w) below += v; all += v; }
+                    add[k] = carry[k] + below;
+                    tot[k] = all;
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) t[k] = add[k] + t[k];
             if (i < sz) {
                 double2* p = reinterpret_cast<double2*>(lf + (size_t)i * 6);
                 __stcg(p, make_double2(t[0], t[1]));
@@ -249,89 +318,89 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
                 __stcg(p + 2, make_double2(t[4], t[5]));
             }
 #pragma unroll
-            for (int k = 0; k < 6; k++) carry[k] = __shfl_sync(FULL_MASK, t[k], 31);
+            for (int k = 0; k < 6; k++) carry[k] = carry[k] + tot[k];
         }
     }
-    __syncwarp();
+    __threadfence_block();
+    G.sync();
 
     // ---- windowed line-fit error -> sbuf (as doubles), smoothed -> scratch
     const int ksz = min(20, sz / 12);
     if (ksz < 2) return false;
     double* sraw = reinterpret_cast<double*>(sbuf);
 #pragma unroll 2
-    for (int i = lane; i < sz; i += 32) {
+    for (int i = tid; i < sz; i += T) {
         LineFit f;
         fit_line_dev(lf, sz, (i + sz - ksz) % sz, (i + ksz) % sz, f, false);
         sraw[i] = f.err;
     }
-    __syncwarp();
+    G.sync();
     double* es = a.errs + seg;
-    for (int i = lane; i < sz; i += 32) {
+    for (int i = tid; i < sz; i += T) {
         double acc = 0;
 #pragma unroll
         for (int j = 0; j < 7; j++) acc += sraw[(i + j - 3 + sz) % sz] * P.smooth_f[j];
         __stcg(es + i, acc);
     }
-    __syncwarp();
+    __threadfence_block();
+    G.sync();
 
     // ---- local maxima, in index order
     const int half = max(n2 >> 1, 64);                      // room for the padded (>= 64) sort of the maxima values
     unsigned long long* mvals = sbuf;                       // [half]
     int* midx = reinterpret_cast<int*>(sbuf + half);        // [<= n2/2 ints]
     int nmax = 0;
-#pragma unroll 2
-    for (int base = 0; base < sz; base += 32) {
-        int i = base + lane;
+    for (int base = 0; base < sz; base += T) {
+        const int i = base + tid;
         bool ismax = false;
-        double e = i < sz ? __ldcg(es + i) : 0.0;
-        // neighbours from the adjacent lanes; only the tile ends (and the wrap-around) need their own loads
-        double en = __shfl_down_sync(FULL_MASK, e, 1), ep = __shfl_up_sync(FULL_MASK, e, 1);
+        double e = 0;
         if (i < sz) {
-            if (lane == 31 || i == sz - 1) en = __ldcg(es + (i + 1) % sz);
-            if (lane == 0) ep = __ldcg(es + (i + sz - 1) % sz);
+            e = __ldcg(es + i);
+            const double en = __ldcg(es + (i + 1) % sz), ep = __ldcg(es + (i + sz - 1) % sz);
             ismax = e > en && e > ep;
         }
-        uint32_t m = __ballot_sync(FULL_MASK, ismax);
+        int total;
+        const int pos = G.compact_pos(ismax, total);
         if (ismax) {
-            int pos = nmax + __popc(m & lt_mask);
-            midx[pos] = i;
-            mvals[pos] = double_orderable(e);
+            midx[nmax + pos] = i;
+            mvals[nmax + pos] = double_orderable(e);
         }
-        nmax += __popc(m);
+        nmax += total;
     }
-    __syncwarp();
+    G.sync();
     if (nmax < 4) return false;
     if (nmax > P.max_nmaxima) {
         int p2 = 64;
         while (p2 < nmax) p2 <<= 1;
-        for (int i = nmax + lane; i < p2; i += 32) mvals[i] = 0ull;
-        __syncwarp();
-        warp_bitonic_sort(mvals, p2, true);
+        for (int i = nmax + tid; i < p2; i += T) mvals[i] = 0ull;
+        G.sync();
+        group_bitonic_sort<NW>(G, mvals, p2, true);
         const unsigned long long thr = mvals[P.max_nmaxima];
-        __syncwarp();
+        G.sync();
         int outn = 0;
-        for (int base = 0; base < nmax; base += 32) {
-            int i = base + lane;
+        for (int base = 0; base < nmax; base += T) {
+            const int i = base + tid;
             int id = 0;
             bool keep = false;
             if (i < nmax) {
                 id = midx[i];
                 keep = double_orderable(__ldcg(es + id)) > thr;
             }
-            uint32_t m = __ballot_sync(FULL_MASK, keep);
-            __syncwarp();
-            if (keep) midx[outn + __popc(m & lt_mask)] = id;
-            outn += __popc(m);
-            __syncwarp();
+            G.sync();
+            int total;
+            const int pos = G.compact_pos(keep, total);
+            if (keep) midx[outn + pos] = id;
+            outn += total;
+            G.sync();
         }
         nmax = outn;
         if (nmax < 4) return false;   // (ties at the threshold can drop below 4: no 4-subset exists)
     }
-    if (lane < nmax) sidx[lane] = midx[lane];
-    __syncwarp();
+    if (tid < nmax) sidx[tid] = midx[tid];
+    G.sync();
 
-    // ---- table of pairwise line fits between maxima
-    for (int t = lane; t < nmax * nmax; t += 32) {
+    // ---- table of pairwise line fits between maxima (the table may alias sbuf: everything in it is dead now)
+    for (int t = tid; t < nmax * nmax; t += T) {
         int ia = t / nmax, ib = t - ia * nmax;
         if (ia == ib) continue;
         LineFit f;
@@ -339,7 +408,7 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
         double* e = ptab + (ia * 10 + ib) * 6;
         e[0] = f.Ex; e[1] = f.Ey; e[2] = f.nx; e[3] = f.ny; e[4] = f.err; e[5] = f.mse;
     }
-    __syncwarp();
+    G.sync();
 
     // ---- exhaustive search over 4-subsets (lexicographic order; first minimum wins)
     double best = HUGE_VALF;
@@ -351,7 +420,7 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
             for (int m1 = m0 + 1; m1 < nmax - 2; m1++)
                 for (int m2 = m1 + 1; m2 < nmax - 1; m2++)
                     for (int m3 = m2 + 1; m3 < nmax; m3++, c++) {
-                        if ((c & 31) != lane) continue;
+                        if ((c % T) != tid) continue;
                         const double* e01 = ptab + (m0 * 10 + m1) * 6;
                         const double* e12 = ptab + (m1 * 10 + m2) * 6;
                         const double* e23 = ptab + (m2 * 10 + m3) * 6;
@@ -377,10 +446,22 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
         int op = __shfl_xor_sync(FULL_MASK, best_pack, off);
         if (ob < best || (ob == best && oc < best_c)) { best = ob; best_c = oc; best_pack = op; }
     }
+    if (NW > 1) {
+        if (lane == 0) { G.sd[G.w * 8] = best; G.si[G.w] = best_c; G.si[NW + 4 + G.w] = best_pack; }
+        __syncthreads();
+        best = G.sd[0]; best_c = G.si[0]; best_pack = G.si[NW + 4];
+#pragma unroll
+        for (int ww = 1; ww < NW; ww++) {
+            const double ob = G.sd[ww * 8];
+            const int oc = G.si[ww], op = G.si[NW + 4 + ww];
+            if (ob < best || (ob == best && oc < best_c)) { best = ob; best_c = oc; best_pack = op; }
+        }
+        __syncthreads();
+    }
     if (best_c == 0x7fffffff) return false;
     if (!(best / sz < P.max_line_fit_mse)) return false;
 
-    // ---- corners and gates (every lane computes the same values)
+    // ---- corners and gates (every thread computes the same values)
     int mi[4] = {best_pack & 15, (best_pack >> 4) & 15, (best_pack >> 8) & 15, (best_pack >> 12) & 15};
     double lines[4][4];
 #pragma unroll
@@ -448,32 +529,45 @@ __device__ bool fit_cluster_warp(const QuadFitArgs& a, const DevParams& P, const
     return true;
 }
 
-// Persistent warps: warp w takes clusters w, w + nwarps, ...  Dynamic shared memory per warp: `wcap` u64
-// (sort buffer; from 1024 keys on it also hosts the 600-double pair table once the sort is over) + 16 ints,
-// plus a separate pair table for the small tiers.
-__host__ __device__ inline size_t qf_smem_per_warp(int wcap) {
+// Dynamic shared memory per GROUP: `wcap` u64 (sort buffer; from 1024 keys on it also hosts the 600-double pair
+// table once the sort is over) + 16 ints, plus a separate pair table for the small tier.
+__host__ __device__ inline size_t qf_smem_per_group(int wcap) {
     return (size_t)wcap * 8 + 64 + (wcap >= 1024 ? 0 : QF_PTAB_DOUBLES * 8);
 }
 
-__global__ void __launch_bounds__(256, 3) k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
+// Persistent groups: group i takes clusters i, i + ngroups, ...   NW == 1: blockDim/32 warp groups per CTA;
+// NW > 1: the CTA (NW warps) is the group.
+template <int NW>
+__global__ void __launch_bounds__(NW == 1 ? 256 : NW * 32)
+k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int wpb = blockDim.x >> 5;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* base = smem_raw + qf_smem_per_warp(wcap) * w;
+    __shared__ int s_i[2 * NW + 8];
+    __shared__ double s_d[NW * 8];
+    __shared__ int s_ok;
+    QGroup<NW> G;
+    G.lane = threadIdx.x & 31;
+    G.w = NW == 1 ? 0 : (threadIdx.x >> 5);
+    G.tid = NW == 1 ? G.lane : threadIdx.x;
+    G.si = s_i;
+    G.sd = s_d;
+    const int groups_per_cta = NW == 1 ? (blockDim.x >> 5) : 1;
+    const int gi = NW == 1 ? (threadIdx.x >> 5) : 0;
+    unsigned char* base = smem_raw + qf_smem_per_group(wcap) * gi;
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(base);
     int* sidx = reinterpret_cast<int*>(base + (size_t)wcap * 8);
     double* ptab = wcap >= 1024 ? reinterpret_cast<double*>(base) : reinterpret_cast<double*>(base + (size_t)wcap * 8 + 64);
     const int n = min(*a.list_count, a.list_cap);
-    const int nwarps = gridDim.x * wpb;
-    for (int ci = blockIdx.x * wpb + w; ci < n; ci += nwarps) {
+    const int ngroups = gridDim.x * groups_per_cta;
+    for (int ci = blockIdx.x * groups_per_cta + gi; ci < n; ci += ngroups) {
         const ClusterRef ref = a.list[ci];
         QuadRec q;
-        bool ok = fit_cluster_warp(a, P, ref, sbuf, ptab, sidx, q);
-        if (ok && lane == 0) {
+        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sbuf, ptab, sidx, q);
+        if (ok && G.tid == 0) {
             int s = atomicAdd(a.nquads, 1);
             atomicAdd(&a.per_frame_quads[ref.frame], 1);
             if (s < a.cap_quads) a.quads[s] = q;
         }
-        __syncwarp();
+        (void)s_ok;
+        G.sync();
     }
 }
