@@ -89,9 +89,9 @@ struct Slot {
     cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};   // side streams: quad-fit tiers run concurrently
     cudaEvent_t ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;   // stage timing
-    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes, d_roots;
-    DevBuf d_keys[2], d_vals[2], d_hist, d_dbase, d_lfps, d_errs;
-    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], nroots[chunk]
+    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes, d_roots, d_dense, d_dense2rep;
+    DevBuf d_recs[2], d_hist, d_dtot, d_lfps, d_errs;
+    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], nroots[chunk], ndense[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
     bool pending = false;
@@ -99,7 +99,7 @@ struct Slot {
 
     void release() {
         DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_labels, &d_sizes, &d_roots,
-                          &d_keys[0], &d_keys[1], &d_vals[0], &d_vals[1], &d_hist, &d_dbase, &d_lfps, &d_errs, &d_counters,
+                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_hist, &d_dtot, &d_lfps, &d_errs, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
         for (DevBuf* bb : bufs) bb->release();
@@ -336,7 +336,8 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
     return AGPU_OK;
 }
 
-int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const Geom& g, int* d_nroots, bool flatten) {
+int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const Geom& g, int* d_nroots, int* d_ndense,
+                 bool flatten) {
     CK(sl.d_labels.ensure(g.plane * n * 4));
     CK(sl.d_sizes.ensure(g.plane * n * 4));
     CK(sl.d_roots.ensure(g.plane * n * 4));
@@ -352,6 +353,13 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
     k_cc_sizes<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
                                              d_nroots, g);
     LAUNCH_CHECK("k_cc_sizes");
+    if (d_ndense) {
+        CK(sl.d_dense.ensure(g.plane * n * 4));
+        CK(sl.d_dense2rep.ensure((size_t)n * AGPU_MAX_DENSE * 4));
+        k_cc_dense<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
+                                                 d_nroots, sl.d_dense.as<uint32_t>(), sl.d_dense2rep.as<uint32_t>(), d_ndense, g);
+        LAUNCH_CHECK("k_cc_dense");
+    }
     if (flatten) {
         dim3 gridf(ceil_div(g.wd, CCF_TW), ceil_div(g.hd, CCF_TH), n);
         k_cc_flatten<<<gridf, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), g);
@@ -409,12 +417,10 @@ int alloc_slot(agpu_handle* h, Slot& s, const CallCtx& c) {
     if (rc) return rc;
     const int chunk = c.chunk, cap = c.cap;
     if (!c.on_device) CK(s.d_in.ensure(c.frame_bytes * chunk));
-    for (int i = 0; i < 2; i++) {
-        CK(s.d_keys[i].ensure((size_t)chunk * cap * 8));
-        CK(s.d_vals[i].ensure((size_t)chunk * cap * 4));
-    }
+    for (int i = 0; i < 2; i++) CK(s.d_recs[i].ensure((size_t)chunk * cap * 8));
     CK(s.d_hist.ensure((size_t)chunk * RS_RADIX * c.nblk_max * 4));
-    CK(s.d_dbase.ensure((size_t)chunk * RS_RADIX * 4));
+    CK(s.d_dtot.ensure((size_t)chunk * RS_RADIX * 4));
+    CK(s.d_dense2rep.ensure((size_t)chunk * AGPU_MAX_DENSE * 4));
     CK(s.d_lfps.ensure((size_t)chunk * cap * 48));
     CK(s.d_errs.ensure((size_t)chunk * cap * 8));
     CK(s.d_counters.ensure(c.ncnt * 4));
@@ -445,6 +451,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int* d_ndets = d_frame_quads + chunk;
     int* d_out_counts = d_ndets + chunk;
     int* d_nroots = d_out_counts + chunk;
+    int* d_ndense = d_nroots + chunk;
     StageTimer tm(h, sl);
     tm.mark();  // 0
     const uint8_t* d_src;
@@ -463,41 +470,34 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
                              &q_frame, &gray_full, &gray_pitch, &gray_frame);
     if (rc) return rc;
     tm.mark();  // 2: after image
-    rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), n, g, d_nroots, h->cfg.debug != 0);
+    rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), n, g, d_nroots, d_ndense, h->cfg.debug != 0);
     if (rc) return rc;
     tm.mark();  // 3: after CC
     {
         dim3 grid(ceil_div(g.wp >> 2, 32), ceil_div(g.hd - 1, 8), n);
         k_edges<<<grid, 256, 0, sl.stream>>>(sl.d_thresh.as<uint8_t>(), sl.d_labels.as<uint32_t>(),
-                                             sl.d_sizes.as<uint32_t>(), g, sl.d_keys[0].as<unsigned long long>(),
-                                             sl.d_vals[0].as<uint32_t>(), d_npts, cap);
+                                             sl.d_sizes.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g,
+                                             sl.d_recs[0].as<unsigned long long>(), d_npts, cap);
         LAUNCH_CHECK("k_edges");
     }
     tm.mark();  // 4: after edges
     int cur = 0;
-    {
-        int shifts[16], ns = 0;
-        for (int s = 0; s < c.key_bits; s += RS_BITS) shifts[ns++] = s;
-        for (int s = 0; s < c.key_bits; s += RS_BITS) shifts[ns++] = 32 + s;
-        for (int i = 0; i < ns; i++) {
-            const int shift = shifts[i];
-            dim3 grid(c.nblk_max, n);
-            k_sort_hist<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_keys[cur].as<unsigned long long>(), d_npts, cap, shift,
-                                                            sl.d_hist.as<uint32_t>(), c.nblk_max);
-            LAUNCH_CHECK("k_sort_hist");
-            k_sort_scan<<<n, 1024, 0, sl.stream>>>(d_npts, cap, sl.d_hist.as<uint32_t>(), sl.d_dbase.as<uint32_t>(), c.nblk_max);
-            LAUNCH_CHECK("k_sort_scan");
-            k_sort_scatter<<<grid, RS_THREADS, 0, sl.stream>>>(
-                sl.d_keys[cur].as<unsigned long long>(), sl.d_vals[cur].as<uint32_t>(),
-                sl.d_keys[cur ^ 1].as<unsigned long long>(), sl.d_vals[cur ^ 1].as<uint32_t>(), d_npts, cap, shift,
-                sl.d_hist.as<uint32_t>(), sl.d_dbase.as<uint32_t>(), c.nblk_max);
-            LAUNCH_CHECK("k_sort_scatter");
-            cur ^= 1;
-        }
+    for (int shift = 32; shift < 64; shift += RS_BITS) {   // the 32 key bits of the record: 3 passes of 11 bits
+        dim3 grid(c.nblk_max, n);
+        k_sort_hist<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(), d_npts, cap, shift,
+                                                        sl.d_hist.as<uint32_t>(), c.nblk_max);
+        LAUNCH_CHECK("k_sort_hist");
+        k_sort_scan<<<dim3(n, RS_SCAN_PARTS), RS_RADIX / RS_SCAN_PARTS, 0, sl.stream>>>(
+            d_npts, cap, sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
+        LAUNCH_CHECK("k_sort_scan");
+        k_sort_scatter<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(),
+                                                           sl.d_recs[cur ^ 1].as<unsigned long long>(), d_npts, cap, shift,
+                                                           sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
+        LAUNCH_CHECK("k_sort_scatter");
+        cur ^= 1;
     }
     tm.mark();  // 5: after sort
-    const unsigned long long* skeys = sl.d_keys[cur].as<unsigned long long>();
-    const uint32_t* svals = sl.d_vals[cur].as<uint32_t>();
+    const unsigned long long* srecs = sl.d_recs[cur].as<unsigned long long>();
     {
         ClusterLists cl;
         for (int t = 0; t < AGPU_NTIERS; t++) {
@@ -509,10 +509,10 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         cl.dbg_heads = h->cfg.debug ? sl.d_dbg_heads.as<ClusterRef>() : nullptr;
         cl.cap_dbg = (int)(sl.d_dbg_heads.bytes / sizeof(ClusterRef));
         dim3 grid(std::max(1, std::min(64, ceil_div(cap, 256))), n);   // grid-stride over the live points
-        k_cluster_heads<<<grid, 256, 0, sl.stream>>>(skeys, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
+        k_cluster_heads<<<grid, 256, 0, sl.stream>>>(srecs, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
         LAUNCH_CHECK("k_cluster_heads");
         QuadFitArgs qa;
-        qa.vals = svals; qa.keys = skeys; qa.cap = cap;
+        qa.recs = srecs; qa.dense2rep = sl.d_dense2rep.as<uint32_t>(); qa.cap = cap;
         qa.quad_im = quad_im; qa.q_pitch = q_pitch; qa.q_frame = q_frame;
         qa.g = g;
         qa.lfps = sl.d_lfps.as<double>();
@@ -617,6 +617,12 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     const int* h_npts = hc + CNT_FIXED;
     const int* h_nd = h_npts + 2 * chunk;
     const int* h_oc = h_nd + chunk;
+    const int* h_ndense = h_oc + 2 * chunk;
+    for (int i = 0; i < n; i++)
+        if (h_ndense[i] > AGPU_MAX_DENSE) {
+            h->set_err("more than 65536 connected components of >= 25 pixels in one frame");
+            return AGPU_E_WORKSPACE;
+        }
     int max_pts = 0, max_cl = 0;
     for (int i = 0; i < n; i++) max_pts = std::max(max_pts, h_npts[i]);
     for (int t = 0; t < AGPU_NTIERS; t++) max_cl = std::max(max_cl, hc[CNT_TIER0 + t]);
@@ -708,7 +714,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     c.cap = (c.cap + RS_TILE - 1) / RS_TILE * RS_TILE;
     c.maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
     c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
-    c.ncnt = CNT_FIXED + (size_t)5 * chunk;
+    c.ncnt = CNT_FIXED + (size_t)6 * chunk;
     c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
     if (on_device) {   // order every slot stream after the producer's stream
@@ -1069,12 +1075,19 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
         int nh = std::min<long long>(cnt[CNT_HEADS], (long long)(sl.d_dbg_heads.bytes / sizeof(ClusterRef)));
         std::vector<ClusterRef> heads(nh);
         if (nh) cudaMemcpy(heads.data(), sl.d_dbg_heads.p, (size_t)nh * sizeof(ClusterRef), cudaMemcpyDeviceToHost);
-        std::vector<unsigned long long> keys((size_t)h->last_cap);
-        cudaMemcpy(keys.data(), sl.d_keys[sl.sorted].as<unsigned long long>() + (size_t)frame * h->last_cap,
+        std::vector<unsigned long long> recs((size_t)h->last_cap);
+        cudaMemcpy(recs.data(), sl.d_recs[sl.sorted].as<unsigned long long>() + (size_t)frame * h->last_cap,
                    (size_t)h->last_cap * 8, cudaMemcpyDeviceToHost);
+        std::vector<uint32_t> d2r(AGPU_MAX_DENSE);
+        cudaMemcpy(d2r.data(), sl.d_dense2rep.as<uint32_t>() + (size_t)frame * AGPU_MAX_DENSE, AGPU_MAX_DENSE * 4,
+                   cudaMemcpyDeviceToHost);
         std::vector<std::pair<unsigned long long, int>> v;
         for (const ClusterRef& r : heads)
-            if (r.frame == frame) v.push_back({unpitch_key(keys[r.start]), r.size});
+            if (r.frame == frame) {
+                const uint32_t ck = (uint32_t)(recs[r.start] >> 32);
+                const uint32_t ra = d2r[ck >> 16], rb = d2r[ck & 0xffff];
+                v.push_back({unpitch_key(((unsigned long long)std::max(ra, rb) << 32) | std::min(ra, rb)), r.size});
+            }
         std::sort(v.begin(), v.end());
         long long n = (long long)v.size();
         if (w == "cluster_keys") {
@@ -1148,7 +1161,7 @@ int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint3
     CK(cudaMemcpy2DAsync(sl.d_thresh.p, g.wp, thresh, W, W, H, cudaMemcpyHostToDevice, sl.stream));
     CK(sl.d_counters.ensure(64));
     CK(cudaMemsetAsync(sl.d_counters.p, 0, 64, sl.stream));
-    int rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), 1, g, sl.d_counters.as<int>(), true);
+    int rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), 1, g, sl.d_counters.as<int>(), nullptr, true);
     if (rc) return rc;
     std::vector<uint32_t> lab(g.plane), sz(g.plane);
     CK(cudaMemcpyAsync(lab.data(), sl.d_labels.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));

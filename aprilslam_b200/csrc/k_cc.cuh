@@ -294,6 +294,32 @@ k_cc_sizes(const uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, co
     }
 }
 
+// Dense ids for the components that can carry an edge point (final roots of >= 25 pixels): the edge-cluster key
+// becomes a pair of 16-bit ids instead of a pair of 21..23-bit pixel ids, which halves the radix-sort record
+// and its number of passes.  dense[rep] is only defined for those components; dense2rep maps back.
+#define AGPU_MAX_DENSE 65536
+__global__ void __launch_bounds__(256)
+k_cc_dense(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
+           const int* __restrict__ nroots, uint32_t* __restrict__ dense, uint32_t* __restrict__ dense2rep,
+           int* __restrict__ ndense, Geom g) {
+    const int frame = blockIdx.y;
+    const int n = nroots[frame];
+    const uint32_t* fl = labels + (size_t)frame * g.plane;
+    const uint32_t* fs = sizes + (size_t)frame * g.plane;
+    const uint32_t* fr = roots + (size_t)frame * g.plane;
+    uint32_t* fd = dense + (size_t)frame * g.plane;
+    uint32_t* f2 = dense2rep + (size_t)frame * AGPU_MAX_DENSE;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t a = fr[i];
+        if (__ldcg(&fl[a]) != a || __ldcg(&fs[a]) < 25u) continue;
+        const int d = atomicAdd(&ndense[frame], 1);
+        if (d < AGPU_MAX_DENSE) {
+            fd[a] = (uint32_t)d;
+            f2[d] = a;
+        }
+    }
+}
+
 // Pointer jumping to the global root (= smallest pixel id of the component): the canonical labelling.  The
 // pipeline itself resolves representatives on the fly (k_edges); this pass runs for the stage dumps.
 __global__ void __launch_bounds__(256)

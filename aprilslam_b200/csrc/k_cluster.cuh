@@ -1,9 +1,10 @@
 // k_cluster.cuh -- gradient-edge clusters (upstream stage U5; part of the native call
 // at /root/reference/src/detection/tag_detector.py:26).
 //
-//   k_edges          one thread per pixel: emits up to four edge points keyed by the unordered pair
-//                    of component representatives, (max(rep0,rep1) << 32) | min(rep0,rep1); points go
-//                    to the frame's own segment of the point list (warp-aggregated atomics).
+//   k_edges          four pixels per thread: emits up to four edge points per pixel as ONE 64-bit record
+//                    (pair key << 32) | packed point, the key being the unordered pair of the two
+//                    components' dense 16-bit ids (k_cc_dense); records go to the frame's own segment
+//                    of the point list (warp-aggregated atomics).
 //   k_sort_hist / k_sort_scan / k_sort_scatter
 //                    hand-written SEGMENTED least-significant-digit radix sort (8-bit digits, stable):
 //                    every frame's segment is sorted independently, grid = (blocks, frames).
@@ -21,12 +22,13 @@
 #define EDGE_CAND_PER_WARP 512   // 32 lanes x 4 pixels x 4 directions
 __global__ void __launch_bounds__(256)
 k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes,
-        Geom g, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ npts, int cap) {
+        const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts, int cap) {
     __shared__ uint16_t scand[8][EDGE_CAND_PER_WARP];
     const int frame = blockIdx.z;
     const uint8_t* ft = thresh + (size_t)frame * g.plane;
     const uint32_t* fl = labels + (size_t)frame * g.plane;
     const uint32_t* fs = sizes + (size_t)frame * g.plane;
+    const uint32_t* fd = dense + (size_t)frame * g.plane;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int kx = blockIdx.x * 32 + lane;          // word index in the row
     const int y = blockIdx.y * 8 + w;
@@ -78,13 +80,11 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
         }
     }
     __syncwarp();
-    unsigned long long* fk = keys + (size_t)frame * cap;
-    uint32_t* fv = vals + (size_t)frame * cap;
+    unsigned long long* fk = recs + (size_t)frame * cap;
     const int xbase = blockIdx.x * 128;
     for (int b = 0; b < total; b += 32) {
         bool ok = false;
-        unsigned long long key = 0;
-        uint32_t val = 0;
+        unsigned long long rec = 0;
         if (b + lane < total) {
             const uint32_t c = scand[w][b + lane];
             const int x = xbase + (int)(c & 127), d = (c >> 7) & 3, pos = (c >> 9) & 1;
@@ -95,9 +95,9 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
                 const uint32_t rep1 = gfind(fl, (uint32_t)(id + (size_t)dy * g.wp + dx));
                 if (fs[rep1] >= 25u) {
                     ok = true;
-                    const uint32_t hi = max(rep0, rep1), lo = min(rep0, rep1);
-                    key = ((unsigned long long)hi << 32) | lo;
-                    val = pack_point(2 * x + dx, 2 * y + dy, d, pos);
+                    const uint32_t d0 = fd[rep0], d1 = fd[rep1];
+                    const uint32_t key = (max(d0, d1) << 16) | min(d0, d1);
+                    rec = ((unsigned long long)key << 32) | pack_point(2 * x + dx, 2 * y + dy, d, pos);
                 }
             }
         }
@@ -107,25 +107,23 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
         if (lane == 0) base = atomicAdd(&npts[frame], __popc(okm));
         base = __shfl_sync(FULL_MASK, base, 0);
         const int p = base + __popc(okm & ((1u << lane) - 1u));
-        if (ok && p < cap) {
-            fk[p] = key;
-            fv[p] = val;
-        }
+        if (ok && p < cap) fk[p] = rec;
     }
 }
 
 // ---- segmented LSD radix sort ---------------------------------------------------------------
-// 11-bit digits (2048 bins): component ids of a 1080p frame have 21 bits, so each half of the
-// (rep_hi, rep_lo) key takes two passes -- four passes in all.
+// Records are single 64-bit words, (pair key << 32) | point; only the 32 key bits are sorted: three passes of
+// 11-bit digits (2048 bins).
 #define RS_THREADS 256
 #define RS_ITEMS 8
-#define RS_TILE (RS_THREADS * RS_ITEMS)  // 2048 keys per block
+#define RS_TILE (RS_THREADS * RS_ITEMS)  // 2048 records per block
 #define RS_BITS 11
 #define RS_RADIX (1 << RS_BITS)
+#define RS_SCAN_PARTS 8
 
-// per frame: hist[block][digit] (block-major, frame stride RS_RADIX * nblk_max) and digit_base[digit]
+// per frame: hist[block][digit] (block-major, frame stride RS_RADIX * nblk_max)
 __global__ void __launch_bounds__(RS_THREADS)
-k_sort_hist(const unsigned long long* __restrict__ keys, const int* __restrict__ npts, int cap, int shift,
+k_sort_hist(const unsigned long long* __restrict__ recs, const int* __restrict__ npts, int cap, int shift,
             uint32_t* __restrict__ hist, int nblk_max) {
     __shared__ uint32_t h[RS_RADIX];
     const int frame = blockIdx.y, b = blockIdx.x;
@@ -134,7 +132,7 @@ k_sort_hist(const unsigned long long* __restrict__ keys, const int* __restrict__
     if (b >= nblk) return;
     for (int i = threadIdx.x; i < RS_RADIX; i += RS_THREADS) h[i] = 0;
     __syncthreads();
-    const unsigned long long* fk = keys + (size_t)frame * cap;
+    const unsigned long long* fk = recs + (size_t)frame * cap;
     const int base = b * RS_TILE;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
@@ -146,61 +144,33 @@ k_sort_hist(const unsigned long long* __restrict__ keys, const int* __restrict__
     for (int i = threadIdx.x; i < RS_RADIX; i += RS_THREADS) out[i] = h[i];
 }
 
-// one CTA per frame, thread t owns digits t and t + 1024: exclusive prefix over the blocks (in place) and the
-// exclusive prefix over the digit totals (digit_base)
-__global__ void __launch_bounds__(1024)
-k_sort_scan(const int* __restrict__ npts, int cap, uint32_t* __restrict__ hist, uint32_t* __restrict__ digit_base,
+// grid (frames, RS_SCAN_PARTS): thread = one digit; exclusive prefix over the blocks (in place) and the digit's
+// total; the prefix over the digit totals is taken by every scatter block itself
+__global__ void __launch_bounds__(RS_RADIX / RS_SCAN_PARTS)
+k_sort_scan(const int* __restrict__ npts, int cap, uint32_t* __restrict__ hist, uint32_t* __restrict__ digit_total,
             int nblk_max) {
-    __shared__ uint32_t warp_tot[32];
     const int frame = blockIdx.x;
     const int n = min(npts[frame], cap);
     const int nblk = (n + RS_TILE - 1) / RS_TILE;
-    if (nblk == 0) return;
-    uint32_t* fh = hist + (size_t)frame * nblk_max * RS_RADIX;
-    const int d0 = 2 * threadIdx.x;   // two adjacent digits per thread -> one 64-bit access per block row
-    uint32_t run0 = 0, run1 = 0;
-#pragma unroll 4
+    const int d = blockIdx.y * blockDim.x + threadIdx.x;
+    uint32_t* fh = hist + (size_t)frame * nblk_max * RS_RADIX + d;
+    uint32_t run = 0;
+#pragma unroll 8
     for (int b = 0; b < nblk; b++) {
-        uint2* p = reinterpret_cast<uint2*>(fh + (size_t)b * RS_RADIX + d0);
-        uint2 c = *p;
-        *p = make_uint2(run0, run1);
-        run0 += c.x;
-        run1 += c.y;
+        const uint32_t c = fh[(size_t)b * RS_RADIX];
+        fh[(size_t)b * RS_RADIX] = run;
+        run += c;
     }
-    // block exclusive scan of the per-thread pair totals
-    const uint32_t sum = run0 + run1;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t incl = sum;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        uint32_t t = __shfl_up_sync(FULL_MASK, incl, off);
-        if (lane >= off) incl += t;
-    }
-    if (lane == 31) warp_tot[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-        uint32_t t = warp_tot[lane], ti = t;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t u = __shfl_up_sync(FULL_MASK, ti, off);
-            if (lane >= off) ti += u;
-        }
-        warp_tot[lane] = ti - t;
-    }
-    __syncthreads();
-    const uint32_t excl = warp_tot[w] + incl - sum;
-    uint32_t* db = digit_base + (size_t)frame * RS_RADIX;
-    db[d0] = excl;
-    db[d0 + 1] = excl + run0;
+    digit_total[(size_t)frame * RS_RADIX + d] = run;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
-k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-               unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long long* __restrict__ recs_out,
                const int* __restrict__ npts, int cap, int shift, const uint32_t* __restrict__ hist,
-               const uint32_t* __restrict__ digit_base, int nblk_max) {
+               const uint32_t* __restrict__ digit_total, int nblk_max) {
     __shared__ uint16_t wcnt[RS_THREADS / 32][RS_RADIX];   // per-warp digit counts (<= 256), then warp prefixes
     __shared__ uint32_t dbase[RS_RADIX];                   // first output slot of digit d for this block
+    __shared__ uint32_t wtot[RS_THREADS / 32];
     const int frame = blockIdx.y, b = blockIdx.x;
     const int n = min(npts[frame], cap);
     const int nblk = (n + RS_TILE - 1) / RS_TILE;
@@ -210,24 +180,47 @@ k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* _
         uint32_t* z = reinterpret_cast<uint32_t*>(&wcnt[0][0]);
         for (int i = threadIdx.x; i < (RS_THREADS / 32) * RS_RADIX / 2; i += RS_THREADS) z[i] = 0;
     }
-    __syncthreads();
     const size_t seg = (size_t)frame * cap;
     const int base = b * RS_TILE + w * (32 * RS_ITEMS);
-    unsigned long long key[RS_ITEMS];
-    uint32_t val[RS_ITEMS];
+    unsigned long long rec[RS_ITEMS];
     uint32_t rank[RS_ITEMS];
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
         const int i = base + r * 32 + lane;
-        const bool valid = i < n;
-        key[r] = valid ? keys_in[seg + i] : 0xffffffffffffffffull;
-        val[r] = valid ? vals_in[seg + i] : 0u;
+        rec[r] = i < n ? recs_in[seg + i] : 0xffffffffffffffffull;
     }
+    // exclusive prefix of the frame's digit totals: thread t owns digits 8t .. 8t+7
+    {
+        const uint32_t* dt = digit_total + (size_t)frame * RS_RADIX + threadIdx.x * 8;
+        const uint4 a = *reinterpret_cast<const uint4*>(dt), c = *reinterpret_cast<const uint4*>(dt + 4);
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += v[k];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_up_sync(FULL_MASK, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) wtot[w] = incl;
+        __syncthreads();
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int ww = 0; ww < RS_THREADS / 32; ww++)
+            if (ww < w) run += wtot[ww];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            dbase[threadIdx.x * 8 + k] = run;
+            run += v[k];
+        }
+    }
+    __syncthreads();
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
         const int i = base + r * 32 + lane;
         const bool valid = i < n;
-        const uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & (RS_RADIX - 1)) : 0xffffffffu;
+        const uint32_t d = valid ? ((uint32_t)(rec[r] >> shift) & (RS_RADIX - 1)) : 0xffffffffu;
         const uint32_t peers = __match_any_sync(FULL_MASK, d);
         const int leader = __ffs(peers) - 1;
         uint32_t before = 0;
@@ -240,9 +233,8 @@ k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* _
         __syncwarp();
     }
     __syncthreads();
-    {   // turn per-warp counts into exclusive warp prefixes and the block's global digit offsets
+    {   // per-warp counts -> exclusive warp prefixes; add the block's offset inside each digit
         const uint32_t* bh = hist + ((size_t)frame * nblk_max + b) * RS_RADIX;
-        const uint32_t* db = digit_base + (size_t)frame * RS_RADIX;
         for (int d = threadIdx.x; d < RS_RADIX; d += RS_THREADS) {
             uint32_t run = 0;
 #pragma unroll
@@ -251,7 +243,7 @@ k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* _
                 wcnt[ww][d] = (uint16_t)run;
                 run += c;
             }
-            dbase[d] = db[d] + bh[d];
+            dbase[d] += bh[d];
         }
     }
     __syncthreads();
@@ -259,10 +251,8 @@ k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* _
     for (int r = 0; r < RS_ITEMS; r++) {
         const int i = base + r * 32 + lane;
         if (i < n) {
-            const uint32_t d = (uint32_t)(key[r] >> shift) & (RS_RADIX - 1);
-            const uint32_t pos = dbase[d] + wcnt[w][d] + rank[r];
-            keys_out[seg + pos] = key[r];
-            vals_out[seg + pos] = val[r];
+            const uint32_t d = (uint32_t)(rec[r] >> shift) & (RS_RADIX - 1);
+            recs_out[seg + dbase[d] + wcnt[w][d] + rank[r]] = rec[r];
         }
     }
 }
@@ -279,19 +269,19 @@ struct ClusterLists {
 };
 
 __global__ void __launch_bounds__(256)
-k_cluster_heads(const unsigned long long* __restrict__ keys, const int* __restrict__ npts, int cap, Geom g,
+k_cluster_heads(const unsigned long long* __restrict__ recs, const int* __restrict__ npts, int cap, Geom g,
                 int min_size, ClusterLists cl) {
     const int frame = blockIdx.y;
     const int n = min(npts[frame], cap);
-    const unsigned long long* fk = keys + (size_t)frame * cap;
+    const unsigned long long* fk = recs + (size_t)frame * cap;
     const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned long long k = fk[i];
-        if (i > 0 && fk[i - 1] == k) continue;
+        const uint32_t k = (uint32_t)(fk[i] >> 32);
+        if (i > 0 && (uint32_t)(fk[i - 1] >> 32) == k) continue;
         int lo = i + 1, hi = n;  // first index in (i, n] whose key differs
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
-            if (fk[mid] == k) lo = mid + 1; else hi = mid;
+            if ((uint32_t)(fk[mid] >> 32) == k) lo = mid + 1; else hi = mid;
         }
         const int size = lo - i;
         ClusterRef ref;

@@ -8,10 +8,11 @@
 // -> exhaustive 4-corner search over a pre-computed table of pairwise line fits -> corners + gates.
 #pragma once
 #include "common.cuh"
+#include "k_cc.cuh"
 
 struct QuadFitArgs {
-    const uint32_t* vals;       // sorted packed points, per-frame segments of `cap`
-    const unsigned long long* keys;
+    const unsigned long long* recs;   // sorted records (pair key << 32 | packed point), per-frame segments of `cap`
+    const uint32_t* dense2rep;        // [nframes][AGPU_MAX_DENSE] dense component id -> representative pixel id
     int cap;
     const uint8_t* quad_im;     // decimated gray image (may alias the source frames)
     size_t q_pitch, q_frame;    // bytes per row / per frame of quad_im
@@ -165,14 +166,14 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     constexpr int T = QGroup<NW>::T;
     const int tid = G.tid, lane = G.lane;
     const size_t seg = (size_t)ref.frame * a.cap + ref.start;
-    const uint32_t* pv = a.vals + seg;
+    const unsigned long long* pv = a.recs + seg;
     int sz = ref.size;
 
     // ---- bounding box and polarity sums
     int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
     long long Sxgx = 0, Sygy = 0, Sgx = 0, Sgy = 0;
     for (int i = tid; i < sz; i += T) {
-        uint32_t v = pv[i];
+        uint32_t v = (uint32_t)pv[i];
         int px = v & 0x3fff, py = (v >> 14) & 0x3fff, dir = (v >> 28) & 3;
         int s = ((v >> 30) & 1) ? 255 : -255;
         int dx = (dir == 0 || dir == 3) ? 1 : (dir == 2 ? -1 : 0);
@@ -201,7 +202,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     for (int i = tid; i < n2; i += T) {
         unsigned long long key = ~0ull;
         if (i < sz) {
-            uint32_t v = pv[i];
+            uint32_t v = (uint32_t)pv[i];
             int px = v & 0x3fff, py = (v >> 14) & 0x3fff;
             float dx = (float)px - cx, dy = (float)py - cy;
             float qd;
@@ -525,7 +526,12 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     }
     q.frame = ref.frame;
     q.reversed_border = reversed;
-    q.key = a.keys[seg];
+    {
+        const uint32_t ck = (uint32_t)(a.recs[seg] >> 32);
+        const uint32_t* f2 = a.dense2rep + (size_t)ref.frame * AGPU_MAX_DENSE;
+        const uint32_t ra = f2[ck >> 16], rb = f2[ck & 0xffff];
+        q.key = ((unsigned long long)max(ra, rb) << 32) | min(ra, rb);
+    }
     return true;
 }
 
