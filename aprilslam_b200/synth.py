@@ -328,3 +328,27 @@ def grid_scene(width: int, height: int, frame_index: int, grid: Tuple[int, int],
             M[:3, 3] = (X, Y, -Z)
             sc.tags.append(SceneTag(fam, tid, M, 0.5 * inner * tw / wb, 0.5 * inner))
     return sc
+
+
+# --------------------------------------------------------------------------------------
+# C5 augmentations (builder-defined, seeded): the reference's randomised
+# config only perturbs tag poses, so blur / noise / lighting are defined here
+# --------------------------------------------------------------------------------------
+def augment(img: np.ndarray, seed: int) -> np.ndarray:
+    """Gaussian blur sigma~U(0,1.5) px, gain U(0.6,1.2), linear illumination ramp +-30, additive N(0, U(0,8))."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    sigma = float(rng.uniform(0.0, 1.5))
+    out = img.astype(np.float32)
+    if sigma > 0.05:
+        out = cv2.GaussianBlur(out, (0, 0), sigma)
+    gain = float(rng.uniform(0.6, 1.2))
+    H, W = img.shape
+    ang = float(rng.uniform(0, 2 * math.pi))
+    amp = float(rng.uniform(0, 30))
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    ramp = amp * ((xx / W - 0.5) * math.cos(ang) + (yy / H - 0.5) * math.sin(ang)) * 2
+    out = out * gain + ramp
+    sn = float(rng.uniform(0, 8))
+    out = out + rng.normal(0, sn, img.shape).astype(np.float32)
+    return np.clip(np.floor(out + 0.5), 0, 255).astype(np.uint8)

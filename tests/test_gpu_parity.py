@@ -298,3 +298,52 @@ def test_instrumentation_counts_launches_and_stages():
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+# ---- BASELINE configs[3] / [4]: 4K frames and mixed families under blur / noise / lighting ----------------------
+@pytest.mark.parametrize("fams,famspec,d,size,grid", [
+    ("tag36h11", (("tag36h11", range(587)),), 1.0, (1920, 1080), (10, 5)),
+    ("tag25h9 tagStandard41h12", (("tag25h9", range(35)), ("tagStandard41h12", range(5))), 1.0, (1920, 1080), (10, 5)),
+    ("tag16h5", (("tag16h5", range(30)),), 2.0, (1280, 720), (6, 3)),
+])
+def test_augmented_frames_match_oracle(ob, fams, famspec, d, size, grid):
+    """C5-style frames (seeded Gaussian blur, gain, illumination ramp, additive noise; synth.augment)."""
+    W, H = size
+    frames = np.stack([synth.augment(synth.render(synth.grid_scene(W, H, 300 + s, grid, families=famspec,
+                                                                    px_range=(60, 110))), 900 + s) for s in range(4)])
+    g = Detector(fams, decimate=d)
+    dets = g.detect_batch(frames, cap_per_frame=128)
+    o = ob.OracleDetector(fams, decimate=d)
+    total = 0
+    for b in range(len(frames)):
+        ref = o.detect_records(frames[b])
+        assert_same_detections(dets[b], ref)
+        total += len(ref)
+    assert total >= 4 * 8
+    g.close()
+
+
+@pytest.mark.parametrize("d", [2.0, 1.0])
+def test_4k_frame_matches_oracle(ob, d):
+    """BASELINE configs[3]: 3840x2160, ~200 tag36h11 tags."""
+    sc = synth.grid_scene(3840, 2160, 77, (20, 10))
+    img = synth.render(sc)
+    g = Detector("tag36h11", decimate=d)
+    recs = g.detect_batch(img, cap_per_frame=256)[0]
+    ref = ob.OracleDetector("tag36h11", decimate=d).detect_records(img)
+    assert_same_detections(recs, ref)
+    assert sorted(recs["id"].tolist()) == sorted(t.tag_id for t in sc.tags)
+    g.close()
+
+
+def test_noise_frames_match_oracle(ob):
+    rng = np.random.default_rng(5)
+    g = Detector("tag36h11", decimate=1.0)
+    o = ob.OracleDetector("tag36h11", decimate=1.0)
+    ims = [rng.integers(0, 256, (720, 1280), dtype=np.uint8),
+           np.kron(rng.integers(0, 2, (90, 160), dtype=np.uint8) * 200 + 25, np.ones((8, 8), np.uint8)).astype(np.uint8)]
+    for im in ims:
+        recs = g.detect_batch(im, cap_per_frame=256)[0]
+        assert_same_detections(recs, o.detect_records(im))
+        assert g.counters()["edge_points"] > 100000          # hundreds of thousands of edge points, thousands of clusters
+    g.close()
