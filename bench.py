@@ -289,11 +289,19 @@ def run_b200(args):
     pipe_gbs = 12 * N * B * nsteps / (pipe_ms / 1e3) / 1e9
     dom = max((k for k in stage if k in alg), key=lambda k: stage[k])
     nchunks = -(-B // max(1, det_chunk(det, args)))
-    kernels_per_launchgroup = {"image": 1, "cc": 3, "edges": 1}
-    roofline = {"kernel": {"image": "k_decimate_threshold<1>", "cc": "k_cc_local+k_cc_boundary+k_cc_finalize",
+    kernels_per_launchgroup = {"image": 1, "cc": 4, "edges": 1}
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = tr[dom]
+        # bytes per launch of the dominant kernel at the profiled chunk size, scaled to this run's chunk
+        traffic = (ent["dram_read_mb"] + ent["dram_write_mb"]) * 1e6 / tr["frames_per_launch"] * min(B, det_chunk(det, args))
+    except Exception:
+        pass
+    roofline = {"kernel": {"image": "k_decimate_threshold<1>", "cc": "k_cc_local (+k_cc_boundary, k_cc_sizes, k_cc_dense)",
                            "edges": "k_edges"}[dom],
                 "stage": dom, "bound": "hbm", "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom] * min(B, det_chunk(det, args)),
                 "launches_per_step": nchunks * kernels_per_launchgroup[dom],
                 "image_stage": {"kernel": "k_decimate_threshold<1>", "achieved": stages["image"]["achieved_gbs"],
