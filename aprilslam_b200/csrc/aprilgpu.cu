@@ -77,7 +77,7 @@ constexpr int TIER_CAP[AGPU_NTIERS] = {256, 1024, 2048, 16384};
 constexpr int TIER_NW[AGPU_NTIERS] = {1, 2, 4, 8};
 constexpr int TIER_CTAS_PER_SM[AGPU_NTIERS] = {3, 16, 8, 1};
 // counter block layout (ints): [0..3] clusters per tier
-enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_FIXED = 8 };
+enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_CURSOR0 = 8, CNT_FIXED = 16 };
 
 }  // namespace
 
@@ -474,7 +474,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     if (rc) return rc;
     tm.mark();  // 3: after CC
     {
-        dim3 grid(ceil_div(g.wp >> 2, 32), ceil_div(g.hd - 1, 8), n);
+        dim3 grid(ceil_div(g.wp >> 2, 32 * EDGE_WORDS), ceil_div(g.hd - 1, 8), n);
         k_edges<<<grid, 256, 0, sl.stream>>>(sl.d_thresh.as<uint8_t>(), sl.d_labels.as<uint32_t>(),
                                              sl.d_sizes.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g,
                                              sl.d_recs[0].as<unsigned long long>(), d_npts, cap);
@@ -530,6 +530,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             if (t > 0) CK(cudaStreamWaitEvent(st, sl.ev_fork, 0));
             qa.list = sl.d_clusters[t].as<ClusterRef>();
             qa.list_count = d_cnt + CNT_TIER0 + t;
+            qa.cursor = d_cnt + CNT_CURSOR0 + t;
             const int nblk = h->num_sms * TIER_CTAS_PER_SM[t];
             if (t == 0) {
                 const size_t smem = 8 * qf_smem_per_group(TIER_CAP[t]);

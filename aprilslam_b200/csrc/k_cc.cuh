@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(CC_THREADS)
 k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes,
            uint32_t* __restrict__ roots, int* __restrict__ nroots, Geom g) {
     __shared__ uint32_t sL[CC_WARPS][CC_TH * CC_PITCH];
-    __shared__ uint32_t sX[CC_WARPS][CC_TH * CC_PITCH];
+    __shared__ uint16_t sX[CC_WARPS][CC_TH * CC_PITCH];   // root (local id < 1024) of every run
     const int frame = blockIdx.z;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x0 = (blockIdx.x * CC_WARPS + w) * CC_TW, y0 = blockIdx.y * CC_TH;
@@ -103,7 +103,7 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
     uint32_t* fl = labels + (size_t)frame * g.plane;
     uint32_t* fs = sizes + (size_t)frame * g.plane;
     uint32_t* L = sL[w];
-    uint32_t* X = sX[w];
+    uint16_t* X = sX[w];
     const bool second = x0 + 32 <= g.wp;   // the row pitch is a multiple of 16, not of 32
 
     // ---- row masks
@@ -171,7 +171,7 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
     // ---- root of every run, then pixel counts per tile-local root (L is reused as the counter array)
     for (uint32_t m = S; m; m &= m - 1) {
         const uint32_t id = (uint32_t)(lane * 32 + __ffs(m) - 1);
-        X[cc_slot(id)] = sfind(L, id);
+        X[cc_slot(id)] = (uint16_t)sfind(L, id);
     }
     __syncwarp();
     int nroot = 0;

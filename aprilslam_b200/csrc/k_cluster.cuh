@@ -19,7 +19,8 @@
 // (pixel, direction) candidates of a warp are compacted through shared memory and then handled ONE PER LANE
 // (label + size look-ups, ballot compaction, one atomic per 32 candidates), so the expensive part is not
 // serialised inside the few threads that sit on an edge.
-#define EDGE_CAND_PER_WARP 512   // 32 lanes x 4 pixels x 4 directions
+#define EDGE_WORDS 4                                  // 16 pixels (one 128-bit load) per thread
+#define EDGE_CAND_PER_WARP (32 * EDGE_WORDS * 16)     // lanes x pixels x directions
 __global__ void __launch_bounds__(256)
 k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes,
         const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts, int cap) {
@@ -30,37 +31,49 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
     const uint32_t* fs = sizes + (size_t)frame * g.plane;
     const uint32_t* fd = dense + (size_t)frame * g.plane;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int kx = blockIdx.x * 32 + lane;          // word index in the row
+    const int kx = (blockIdx.x * 32 + lane) * EDGE_WORDS;   // first word of this thread in the row
     const int y = blockIdx.y * 8 + w;
-    const int wpr = g.wp >> 2;
+    const int wpr = g.wp >> 2;                              // words per row (a multiple of 4)
     const int x0 = kx * 4;
 
-    uint32_t m[4] = {0, 0, 0, 0}, cur = 0;
+    uint32_t m[EDGE_WORDS][4];
+    uint32_t cur[EDGE_WORDS];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < EDGE_WORDS; j++) {
+        cur[j] = 0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) m[j][d] = 0;
+    }
     if (y <= g.hd - 2 && kx < wpr && x0 <= g.wd - 2) {
         const uint32_t* r0 = reinterpret_cast<const uint32_t*>(ft + (size_t)y * g.wp);
         const uint32_t* r1 = r0 + wpr;
         const uint32_t none = 0x7f7f7f7fu;
-        cur = r0[kx];
-        const uint32_t nxt = kx + 1 < wpr ? r0[kx + 1] : none;
-        const uint32_t prv1 = kx > 0 ? r1[kx - 1] : none;
-        const uint32_t cur1 = r1[kx];
-        const uint32_t nxt1 = kx + 1 < wpr ? r1[kx + 1] : none;
-        uint32_t nb[4];
-        nb[0] = __funnelshift_r(cur, nxt, 8);       // (x+1, y)
-        nb[1] = cur1;                               // (x,   y+1)
-        nb[2] = __funnelshift_l(prv1, cur1, 8);     // (x-1, y+1)
-        nb[3] = __funnelshift_r(cur1, nxt1, 8);     // (x+1, y+1)
-        uint32_t xm = 0;                            // initiators: 1 <= x <= w-2
+        const uint4 c4 = *reinterpret_cast<const uint4*>(r0 + kx), d4 = *reinterpret_cast<const uint4*>(r1 + kx);
+        const uint32_t c[6] = {0, c4.x, c4.y, c4.z, c4.w, kx + 4 < wpr ? r0[kx + 4] : none};
+        const uint32_t e[6] = {kx > 0 ? r1[kx - 1] : none, d4.x, d4.y, d4.z, d4.w, kx + 4 < wpr ? r1[kx + 4] : none};
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (x0 + i >= 1 && x0 + i <= g.wd - 2) xm |= 1u << (8 * i);
+        for (int j = 0; j < EDGE_WORDS; j++) {
+            cur[j] = c[j + 1];
+            uint32_t nb[4];
+            nb[0] = __funnelshift_r(c[j + 1], c[j + 2], 8);   // (x+1, y)
+            nb[1] = e[j + 1];                                 // (x,   y+1)
+            nb[2] = __funnelshift_l(e[j], e[j + 1], 8);       // (x-1, y+1)
+            nb[3] = __funnelshift_r(e[j + 1], e[j + 2], 8);   // (x+1, y+1)
+            uint32_t xm = 0;                                  // initiators: 1 <= x <= w-2
 #pragma unroll
-        for (int d = 0; d < 4; d++) {
-            const uint32_t e = cur ^ nb[d];
-            m[d] = (e >> 7) & e & xm;
+            for (int i = 0; i < 4; i++) {
+                const int x = x0 + 4 * j + i;
+                if (x >= 1 && x <= g.wd - 2) xm |= 1u << (8 * i);
+            }
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                const uint32_t t = cur[j] ^ nb[d];
+                m[j][d] = (t >> 7) & t & xm;
+                cnt += __popc(m[j][d]);
+            }
         }
     }
-    const int cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
     int incl = cnt;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -72,22 +85,27 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
     if (cnt) {
         int o = incl - cnt;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t pos = ((cur >> (8 * i)) & 0xff) == 0 ? 1u : 0u;   // v1 > v0  <=>  v0 == 0
+        for (int j = 0; j < EDGE_WORDS; j++) {
+            if (!(m[j][0] | m[j][1] | m[j][2] | m[j][3])) continue;
 #pragma unroll
-            for (int d = 0; d < 4; d++)
-                if ((m[d] >> (8 * i)) & 1u) scand[w][o++] = (uint16_t)((lane * 4 + i) | (d << 7) | (pos << 9));
+            for (int i = 0; i < 4; i++) {
+                const uint32_t pos = ((cur[j] >> (8 * i)) & 0xff) == 0 ? 1u : 0u;   // v1 > v0  <=>  v0 == 0
+#pragma unroll
+                for (int d = 0; d < 4; d++)
+                    if ((m[j][d] >> (8 * i)) & 1u)
+                        scand[w][o++] = (uint16_t)((lane * 16 + j * 4 + i) | (d << 9) | (pos << 11));
+            }
         }
     }
     __syncwarp();
     unsigned long long* fk = recs + (size_t)frame * cap;
-    const int xbase = blockIdx.x * 128;
+    const int xbase = blockIdx.x * (32 * EDGE_WORDS * 4);
     for (int b = 0; b < total; b += 32) {
         bool ok = false;
         unsigned long long rec = 0;
         if (b + lane < total) {
             const uint32_t c = scand[w][b + lane];
-            const int x = xbase + (int)(c & 127), d = (c >> 7) & 3, pos = (c >> 9) & 1;
+            const int x = xbase + (int)(c & 511), d = (c >> 9) & 3, pos = (c >> 11) & 1;
             const int dx = (d == 0 || d == 3) ? 1 : (d == 2 ? -1 : 0), dy = d == 0 ? 0 : 1;
             const size_t id = (size_t)y * g.wp + x;
             const uint32_t rep0 = gfind(fl, (uint32_t)id);   // labels are parent links until k_cc_flatten (stage dumps only)
@@ -155,11 +173,16 @@ k_sort_scan(const int* __restrict__ npts, int cap, uint32_t* __restrict__ hist, 
     const int d = blockIdx.y * blockDim.x + threadIdx.x;
     uint32_t* fh = hist + (size_t)frame * nblk_max * RS_RADIX + d;
     uint32_t run = 0;
-#pragma unroll 8
-    for (int b = 0; b < nblk; b++) {
-        const uint32_t c = fh[(size_t)b * RS_RADIX];
-        fh[(size_t)b * RS_RADIX] = run;
-        run += c;
+    for (int b0 = 0; b0 < nblk; b0 += 8) {   // batches of 8 independent loads, then the 8 dependent stores
+        uint32_t c[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = b0 + k < nblk ? fh[(size_t)(b0 + k) * RS_RADIX] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (b0 + k < nblk) {
+                fh[(size_t)(b0 + k) * RS_RADIX] = run;
+                run += c[k];
+            }
     }
     digit_total[(size_t)frame * RS_RADIX + d] = run;
 }
@@ -262,7 +285,7 @@ k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long lon
 struct ClusterLists {
     ClusterRef* list[AGPU_NTIERS];
     int cap[AGPU_NTIERS];    // largest cluster size of the tier
-    int* counters;           // [0..3] tier counts, [4] oversize (skipped), [5] all heads (debug)
+    int* counters;           // [0..3] tier counts, [4] oversize (skipped), [5] all heads (debug), [8..11] tier work cursors
     int cap_list;
     ClusterRef* dbg_heads;   // all run heads (debug only, may be null)
     int cap_dbg;

@@ -21,6 +21,7 @@ struct QuadFitArgs {
     double* errs;               // [nframes*cap]   smoothed line-fit errors
     const ClusterRef* list;
     const int* list_count;
+    int* cursor;                // next unclaimed cluster of the list (dynamic work distribution)
     int list_cap;
     QuadRec* quads;
     int* nquads;
@@ -556,15 +557,25 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
     G.tid = NW == 1 ? G.lane : threadIdx.x;
     G.si = s_i;
     G.sd = s_d;
-    const int groups_per_cta = NW == 1 ? (blockDim.x >> 5) : 1;
     const int gi = NW == 1 ? (threadIdx.x >> 5) : 0;
     unsigned char* base = smem_raw + qf_smem_per_group(wcap) * gi;
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(base);
     int* sidx = reinterpret_cast<int*>(base + (size_t)wcap * 8);
     double* ptab = wcap >= 1024 ? reinterpret_cast<double*>(base) : reinterpret_cast<double*>(base + (size_t)wcap * 8 + 64);
     const int n = min(*a.list_count, a.list_cap);
-    const int ngroups = gridDim.x * groups_per_cta;
-    for (int ci = blockIdx.x * groups_per_cta + gi; ci < n; ci += ngroups) {
+    // clusters differ by two orders of magnitude in cost: groups claim them one at a time from a shared cursor
+    for (;;) {
+        int ci = 0;
+        if (NW == 1) {
+            if (G.lane == 0) ci = atomicAdd(a.cursor, 1);
+            ci = __shfl_sync(FULL_MASK, ci, 0);
+        } else {
+            if (threadIdx.x == 0) s_ok = atomicAdd(a.cursor, 1);
+            __syncthreads();
+            ci = s_ok;
+            __syncthreads();
+        }
+        if (ci >= n) break;
         const ClusterRef ref = a.list[ci];
         QuadRec q;
         const bool ok = fit_cluster_group<NW>(G, a, P, ref, sbuf, ptab, sidx, q);
@@ -573,7 +584,6 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
             atomicAdd(&a.per_frame_quads[ref.frame], 1);
             if (s < a.cap_quads) a.quads[s] = q;
         }
-        (void)s_ok;
         G.sync();
     }
 }
