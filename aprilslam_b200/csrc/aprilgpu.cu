@@ -490,7 +490,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         k_sort_scan<<<dim3(n, RS_SCAN_PARTS), RS_RADIX / RS_SCAN_PARTS, 0, sl.stream>>>(
             d_npts, cap, sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
         LAUNCH_CHECK("k_sort_scan");
-        k_sort_scatter<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(),
+        k_sort_scatter<<<grid, RS_THREADS, RS_SCATTER_SMEM, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(),
                                                            sl.d_recs[cur ^ 1].as<unsigned long long>(), d_npts, cap, shift,
                                                            sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
         LAUNCH_CHECK("k_sort_scatter");
@@ -906,6 +906,8 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     // the large quad-fit tiers need more than 48 KB of dynamic shared memory
     ce = cudaFuncSetAttribute(k_fit_quads<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)qf_smem_per_group(TIER_CAP[AGPU_NTIERS - 1]));
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(k_fit_quads<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(8 * qf_smem_per_group(TIER_CAP[0])));

@@ -278,25 +278,31 @@ k_cc_boundary(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels,
     }
 }
 
-// Fold the pixel counts of the tile-local roots into the final roots (after the boundary merges).
+// Fold the pixel counts of the tile-local roots into the final roots (after the boundary merges) and point every
+// tile-local root straight at its final root: afterwards the representative of ANY pixel is labels[labels[id]]
+// (pixel -> tile-local root -> final root), two loads instead of a chain walk.
 __global__ void __launch_bounds__(256)
-k_cc_sizes(const uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
+k_cc_sizes(uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
            const int* __restrict__ nroots, Geom g) {
     const int frame = blockIdx.y;
     const int n = nroots[frame];
-    const uint32_t* fl = labels + (size_t)frame * g.plane;
+    uint32_t* fl = labels + (size_t)frame * g.plane;
     uint32_t* fs = sizes + (size_t)frame * g.plane;
     const uint32_t* fr = roots + (size_t)frame * g.plane;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t a = fr[i];
         const uint32_t r = gfind(fl, a);
-        if (r != a) atomicAdd(&fs[r], fs[a]);
+        if (r != a) {
+            atomicAdd(&fs[r], fs[a]);
+            fl[a] = r;   // (monotone: still an ancestor for any concurrent walk)
+        }
     }
 }
 
 // Dense ids for the components that can carry an edge point (final roots of >= 25 pixels): the edge-cluster key
 // becomes a pair of 16-bit ids instead of a pair of 21..23-bit pixel ids, which halves the radix-sort record
-// and its number of passes.  dense[rep] is only defined for those components; dense2rep maps back.
+// and its number of passes.  dense[rep] is defined at every final root (0xffffffff: component smaller than 25
+// pixels, upstream's edge-point filter); dense2rep maps back.
 #define AGPU_MAX_DENSE 65536
 __global__ void __launch_bounds__(256)
 k_cc_dense(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
@@ -311,7 +317,8 @@ k_cc_dense(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ siz
     uint32_t* f2 = dense2rep + (size_t)frame * AGPU_MAX_DENSE;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t a = fr[i];
-        if (__ldcg(&fl[a]) != a || __ldcg(&fs[a]) < 25u) continue;
+        if (__ldcg(&fl[a]) != a) continue;                             // not a final root
+        if (__ldcg(&fs[a]) < 25u) { fd[a] = 0xffffffffu; continue; }   // too small to carry edge points
         const int d = atomicAdd(&ndense[frame], 1);
         if (d < AGPU_MAX_DENSE) {
             fd[a] = (uint32_t)d;

@@ -108,15 +108,15 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
             const int x = xbase + (int)(c & 511), d = (c >> 9) & 3, pos = (c >> 11) & 1;
             const int dx = (d == 0 || d == 3) ? 1 : (d == 2 ? -1 : 0), dy = d == 0 ? 0 : 1;
             const size_t id = (size_t)y * g.wp + x;
-            const uint32_t rep0 = gfind(fl, (uint32_t)id);   // labels are parent links until k_cc_flatten (stage dumps only)
-            if (fs[rep0] >= 25u) {
-                const uint32_t rep1 = gfind(fl, (uint32_t)(id + (size_t)dy * g.wp + dx));
-                if (fs[rep1] >= 25u) {
-                    ok = true;
-                    const uint32_t d0 = fd[rep0], d1 = fd[rep1];
-                    const uint32_t key = (max(d0, d1) << 16) | min(d0, d1);
-                    rec = ((unsigned long long)key << 32) | pack_point(2 * x + dx, 2 * y + dy, d, pos);
-                }
+            // pixel -> tile-local root -> final root (k_cc_sizes compressed the second hop)
+            const uint32_t id1 = (uint32_t)(id + (size_t)dy * g.wp + dx);
+            const uint32_t l0 = fl[id], l1 = fl[id1];
+            const uint32_t rep0 = fl[l0], rep1 = fl[l1];
+            const uint32_t d0 = fd[rep0], d1 = fd[rep1];
+            if (d0 != 0xffffffffu && d1 != 0xffffffffu) {   // both components have >= 25 pixels
+                ok = true;
+                const uint32_t key = (max(d0, d1) << 16) | min(d0, d1);
+                rec = ((unsigned long long)key << 32) | pack_point(2 * x + dx, 2 * y + dy, d, pos);
             }
         }
         const uint32_t okm = __ballot_sync(FULL_MASK, ok);
@@ -132,12 +132,13 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
 // ---- segmented LSD radix sort ---------------------------------------------------------------
 // Records are single 64-bit words, (pair key << 32) | point; only the 32 key bits are sorted: three passes of
 // 11-bit digits (2048 bins).
-#define RS_THREADS 256
-#define RS_ITEMS 8
-#define RS_TILE (RS_THREADS * RS_ITEMS)  // 2048 records per block
+#define RS_THREADS 512
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS)  // 8192 records per block: 1 byte of histogram traffic per record
 #define RS_BITS 11
 #define RS_RADIX (1 << RS_BITS)
 #define RS_SCAN_PARTS 8
+#define RS_SCATTER_SMEM ((RS_THREADS / 32) * RS_RADIX * 2 + RS_RADIX * 4)
 
 // per frame: hist[block][digit] (block-major, frame stride RS_RADIX * nblk_max)
 __global__ void __launch_bounds__(RS_THREADS)
@@ -191,8 +192,9 @@ __global__ void __launch_bounds__(RS_THREADS)
 k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long long* __restrict__ recs_out,
                const int* __restrict__ npts, int cap, int shift, const uint32_t* __restrict__ hist,
                const uint32_t* __restrict__ digit_total, int nblk_max) {
-    __shared__ uint16_t wcnt[RS_THREADS / 32][RS_RADIX];   // per-warp digit counts (<= 256), then warp prefixes
-    __shared__ uint32_t dbase[RS_RADIX];                   // first output slot of digit d for this block
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint16_t (*wcnt)[RS_RADIX] = reinterpret_cast<uint16_t (*)[RS_RADIX]>(rs_smem);   // per-warp digit counts (<= 512), then warp prefixes
+    uint32_t* dbase = reinterpret_cast<uint32_t*>(rs_smem + (RS_THREADS / 32) * RS_RADIX * 2);   // first output slot of digit d
     __shared__ uint32_t wtot[RS_THREADS / 32];
     const int frame = blockIdx.y, b = blockIdx.x;
     const int n = min(npts[frame], cap);
@@ -203,6 +205,7 @@ k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long lon
         uint32_t* z = reinterpret_cast<uint32_t*>(&wcnt[0][0]);
         for (int i = threadIdx.x; i < (RS_THREADS / 32) * RS_RADIX / 2; i += RS_THREADS) z[i] = 0;
     }
+    static_assert(RS_RADIX / RS_THREADS == 4, "digit ownership below assumes 4 digits per thread");
     const size_t seg = (size_t)frame * cap;
     const int base = b * RS_TILE + w * (32 * RS_ITEMS);
     unsigned long long rec[RS_ITEMS];
@@ -212,14 +215,15 @@ k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long lon
         const int i = base + r * 32 + lane;
         rec[r] = i < n ? recs_in[seg + i] : 0xffffffffffffffffull;
     }
-    // exclusive prefix of the frame's digit totals: thread t owns digits 8t .. 8t+7
+    // exclusive prefix of the frame's digit totals: thread t owns digits 4t .. 4t+3
     {
-        const uint32_t* dt = digit_total + (size_t)frame * RS_RADIX + threadIdx.x * 8;
-        const uint4 a = *reinterpret_cast<const uint4*>(dt), c = *reinterpret_cast<const uint4*>(dt + 4);
-        const uint32_t v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        constexpr int DPT = RS_RADIX / RS_THREADS;
+        const uint32_t* dt = digit_total + (size_t)frame * RS_RADIX + threadIdx.x * DPT;
+        const uint4 a = *reinterpret_cast<const uint4*>(dt);
+        const uint32_t v[DPT] = {a.x, a.y, a.z, a.w};
         uint32_t sum = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) sum += v[k];
+        for (int k = 0; k < DPT; k++) sum += v[k];
         uint32_t incl = sum;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -233,8 +237,8 @@ k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long lon
         for (int ww = 0; ww < RS_THREADS / 32; ww++)
             if (ww < w) run += wtot[ww];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            dbase[threadIdx.x * 8 + k] = run;
+        for (int k = 0; k < DPT; k++) {
+            dbase[threadIdx.x * DPT + k] = run;
             run += v[k];
         }
     }

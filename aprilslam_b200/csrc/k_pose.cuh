@@ -336,7 +336,7 @@ k_pose(PoseArgs a) {
             if (!improved) break;
             residual(R, t, ru, rv, Jr, true);
             double tn2 = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
-            if (step_norm < 1e-13 * (1 + tn2)) { iters++; break; }
+            if (step_norm < 1e-11 * (1 + tn2)) { iters++; break; }   // quadratic convergence: the next step would be ~1e-20
         }
         orthogonalize(R);
     } else {
