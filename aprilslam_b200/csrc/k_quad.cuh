@@ -125,6 +125,25 @@ struct QGroup {
         return r;
     }
     __device__ __forceinline__ int reduce_max(int v) const { return -reduce_min(-v); }
+    // (max of the 64-bit keys, how many threads-worth of `cnt` carry it): cnt is only summed where v == max
+    __device__ __forceinline__ unsigned long long reduce_max_count(unsigned long long v, int cnt, int& total) const {
+        unsigned long long m = v;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(FULL_MASK, m, off);
+            m = o > m ? o : m;
+        }
+        if (NW > 1) {
+            unsigned long long* sl = reinterpret_cast<unsigned long long*>(sd);
+            if (lane == 0) sl[w] = m;
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < NW; i++) m = sl[i] > m ? sl[i] : m;
+            __syncthreads();
+        }
+        total = (int)reduce_sum(v == m ? (long long)cnt : 0ll);
+        return m;
+    }
     __device__ __forceinline__ long long reduce_sum(long long v) const {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL_MASK, v, off);
@@ -372,13 +391,24 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     G.sync();
     if (nmax < 4) return false;
     if (nmax > P.max_nmaxima) {
-        int p2 = 64;
-        while (p2 < nmax) p2 <<= 1;
-        for (int i = nmax + tid; i < p2; i += T) mvals[i] = 0ull;
-        G.sync();
-        group_bitonic_sort<NW>(G, mvals, p2, true);
-        const unsigned long long thr = mvals[P.max_nmaxima];
-        G.sync();
+        // threshold = the (max_nmaxima+1)-th largest value, multiplicities counted (what upstream reads off a
+        // descending sort): walk down the distinct values, at most max_nmaxima+1 group reductions
+        unsigned long long thr = 0ull, bound = ~0ull;
+        int taken = 0;
+        for (int it = 0; it <= P.max_nmaxima; it++) {
+            unsigned long long best = 0ull;   // largest value strictly below `bound` among this thread's elements
+            for (int i = tid; i < nmax; i += T) {
+                const unsigned long long v = mvals[i];
+                if (v < bound && v > best) best = v;
+            }
+            int mine = 0;                     // multiplicity of `best` among this thread's elements
+            for (int i = tid; i < nmax; i += T) mine += (mvals[i] == best);
+            int cnt;
+            const unsigned long long m = G.reduce_max_count(best, mine, cnt);
+            if (taken + cnt > P.max_nmaxima) { thr = m; break; }
+            taken += cnt;
+            bound = m;
+        }
         int outn = 0;
         for (int base = 0; base < nmax; base += T) {
             const int i = base + tid;
@@ -412,34 +442,39 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     }
     G.sync();
 
-    // ---- exhaustive search over 4-subsets (lexicographic order; first minimum wins)
+    // ---- exhaustive search over 4-subsets (first minimum in lexicographic order wins).  The (m0, m1) pairs are
+    //      dealt to the threads; the tie-break key is the subset itself packed most-significant-first, which
+    //      orders exactly like upstream's nested loops.
     double best = HUGE_VALF;
     int best_c = 0x7fffffff, best_pack = 0;
     {
         const double max_mse = P.max_line_fit_mse, max_dot = P.cos_critical_rad;
-        int c = 0;
+        int pr = 0;
         for (int m0 = 0; m0 < nmax - 3; m0++)
-            for (int m1 = m0 + 1; m1 < nmax - 2; m1++)
-                for (int m2 = m1 + 1; m2 < nmax - 1; m2++)
-                    for (int m3 = m2 + 1; m3 < nmax; m3++, c++) {
-                        if ((c % T) != tid) continue;
-                        const double* e01 = ptab + (m0 * 10 + m1) * 6;
-                        const double* e12 = ptab + (m1 * 10 + m2) * 6;
+            for (int m1 = m0 + 1; m1 < nmax - 2; m1++, pr++) {
+                if ((pr % T) != tid) continue;
+                const double* e01 = ptab + (m0 * 10 + m1) * 6;
+                if (e01[5] > max_mse) continue;
+                for (int m2 = m1 + 1; m2 < nmax - 1; m2++) {
+                    const double* e12 = ptab + (m1 * 10 + m2) * 6;
+                    if (e12[5] > max_mse) continue;
+                    const double d = e01[2] * e12[2] + e01[3] * e12[3];
+                    if (fabs(d) > max_dot) continue;
+                    for (int m3 = m2 + 1; m3 < nmax; m3++) {
                         const double* e23 = ptab + (m2 * 10 + m3) * 6;
                         const double* e30 = ptab + (m3 * 10 + m0) * 6;
-                        if (e01[5] > max_mse) continue;
-                        if (e12[5] > max_mse) continue;
-                        double d = e01[2] * e12[2] + e01[3] * e12[3];
-                        if (fabs(d) > max_dot) continue;
                         if (e23[5] > max_mse) continue;
                         if (e30[5] > max_mse) continue;
-                        double err = e01[4] + e12[4] + e23[4] + e30[4];
-                        if (err < best) {
+                        const double err = e01[4] + e12[4] + e23[4] + e30[4];
+                        const int lex = (m0 << 12) | (m1 << 8) | (m2 << 4) | m3;
+                        if (err < best || (err == best && lex < best_c)) {
                             best = err;
-                            best_c = c;
+                            best_c = lex;
                             best_pack = m0 | (m1 << 4) | (m2 << 8) | (m3 << 12);
                         }
                     }
+                }
+            }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
