@@ -22,7 +22,7 @@
 #define CC_TH 32
 #define CC_WARPS 4
 #define CC_THREADS (CC_WARPS * 32)
-#define CC_PITCH 33   // run-start slots of row r live at r*33 + c: rows that touch the same column hit different banks
+#define CC_PITCH 33   // run-start slots of row r live at r*33 + c (16-bit entries)
 // tile of the flatten pass (8-pixel runs per thread)
 #define CCF_TW 64
 #define CCF_TH 32
@@ -49,10 +49,25 @@ __device__ __forceinline__ void gunion(uint32_t* L, uint32_t a, uint32_t b) {
     }
 }
 
-// logical run id r*32+c -> shared-memory slot
+// A run is identified inside its tile by the local pixel id of its first pixel, row*32 + col (< 1024, 16 bits):
+// the whole union-find state of a tile is 2 x 2 KB of shared memory, so an SM holds ~50 tiles at a time.
 __device__ __forceinline__ uint32_t cc_slot(uint32_t id) { return id + (id >> 5); }
 
-__device__ __forceinline__ uint32_t sfind(volatile uint32_t* L, uint32_t a) {
+// atomicMin on a 16-bit shared-memory entry (CAS on the containing word); returns the previous value
+__device__ __forceinline__ uint32_t atomic_min_u16(uint16_t* base, uint32_t slot, uint32_t val) {
+    uint32_t* word = reinterpret_cast<uint32_t*>(base) + (slot >> 1);
+    const int sh = (slot & 1) * 16;
+    uint32_t old = *reinterpret_cast<volatile uint32_t*>(word);
+    for (;;) {
+        const uint32_t cur = (old >> sh) & 0xffffu;
+        if (cur <= val) return cur;
+        const uint32_t assumed = old;
+        old = atomicCAS(word, assumed, (assumed & ~(0xffffu << sh)) | (val << sh));
+        if (old == assumed) return cur;
+    }
+}
+
+__device__ __forceinline__ uint32_t sfind(volatile uint16_t* L, uint32_t a) {
     uint32_t p = L[cc_slot(a)];
     while (p != a) {
         a = p;
@@ -61,13 +76,13 @@ __device__ __forceinline__ uint32_t sfind(volatile uint32_t* L, uint32_t a) {
     return a;
 }
 
-__device__ __forceinline__ void sunion(uint32_t* L, uint32_t a, uint32_t b) {
+__device__ __forceinline__ void sunion(uint16_t* L, uint32_t a, uint32_t b) {
     for (;;) {
         a = sfind(L, a);
         b = sfind(L, b);
         if (a == b) return;
         if (a < b) { uint32_t t = a; a = b; b = t; }
-        uint32_t old = atomicMin(&L[cc_slot(a)], b);
+        uint32_t old = atomic_min_u16(L, cc_slot(a), b);
         if (old == a) return;
         a = old;
     }
@@ -92,8 +107,8 @@ __device__ __forceinline__ uint32_t run_mask(uint32_t cont, int s) {
 __global__ void __launch_bounds__(CC_THREADS)
 k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes,
            uint32_t* __restrict__ roots, int* __restrict__ nroots, Geom g) {
-    __shared__ uint32_t sL[CC_WARPS][CC_TH * CC_PITCH];
-    __shared__ uint16_t sX[CC_WARPS][CC_TH * CC_PITCH];   // root (local id < 1024) of every run
+    __shared__ __align__(16) uint16_t sL[CC_WARPS][CC_TH * CC_PITCH + 8];   // parent links, then pixel counters
+    __shared__ __align__(16) uint16_t sX[CC_WARPS][CC_TH * CC_PITCH + 8];   // root of every run
     const int frame = blockIdx.z;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x0 = (blockIdx.x * CC_WARPS + w) * CC_TW, y0 = blockIdx.y * CC_TH;
@@ -102,7 +117,7 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
     const uint8_t* ft = thresh + (size_t)frame * g.plane;
     uint32_t* fl = labels + (size_t)frame * g.plane;
     uint32_t* fs = sizes + (size_t)frame * g.plane;
-    uint32_t* L = sL[w];
+    uint16_t* L = sL[w];
     uint16_t* X = sX[w];
     const bool second = x0 + 32 <= g.wp;   // the row pitch is a multiple of 16, not of 32
 
@@ -131,9 +146,10 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
     const uint32_t cw = Wm & (Wm << 1) & I, cb = Bm & (Bm << 1) & I;   // bit x: x continues the run of x-1
     const uint32_t Sw = Wm & ~cw, Sb = Bm & ~cb;                       // run starts
     const uint32_t S = Sw | Sb;
+    const uint32_t rid0 = (uint32_t)(lane * 32);
     for (uint32_t m = S; m; m &= m - 1) {
-        const uint32_t id = (uint32_t)(lane * 32 + __ffs(m) - 1);
-        L[cc_slot(id)] = id;
+        const uint32_t id = rid0 + __ffs(m) - 1;
+        L[cc_slot(id)] = (uint16_t)id;
     }
     __syncwarp();
 
@@ -151,7 +167,7 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
             while (touched) {
                 const int x = __ffs(touched) - 1;
                 const int su = 31 - __clz(Swu & (0xffffffffu >> (31 - x)));
-                sunion(L, (uint32_t)(lane * 32 + s), (uint32_t)((lane - 1) * 32 + su));
+                sunion(L, rid0 + s, rid0 - 32 + su);
                 touched &= ~run_mask(cwu, su);
             }
         }
@@ -161,32 +177,31 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
             while (touched) {
                 const int x = __ffs(touched) - 1;
                 const int su = 31 - __clz(Sbu & (0xffffffffu >> (31 - x)));
-                sunion(L, (uint32_t)(lane * 32 + s), (uint32_t)((lane - 1) * 32 + su));
+                sunion(L, rid0 + s, rid0 - 32 + su);
                 touched &= ~run_mask(cbu, su);
             }
         }
     }
     __syncwarp();
 
-    // ---- root of every run, then pixel counts per tile-local root (L is reused as the counter array)
+    // ---- root of every run, then pixel counts per tile-local root (L is reused as the counter array: two 16-bit
+    //      counters per word, a tile holds 1024 pixels so a carry can never reach the upper counter)
     for (uint32_t m = S; m; m &= m - 1) {
-        const uint32_t id = (uint32_t)(lane * 32 + __ffs(m) - 1);
+        const uint32_t id = rid0 + __ffs(m) - 1;
         X[cc_slot(id)] = (uint16_t)sfind(L, id);
     }
     __syncwarp();
     int nroot = 0;
     for (uint32_t m = S; m; m &= m - 1) {
-        const uint32_t id = (uint32_t)(lane * 32 + __ffs(m) - 1);
+        const uint32_t id = rid0 + __ffs(m) - 1;
         if (X[cc_slot(id)] == id) { L[cc_slot(id)] = 0; nroot++; }
     }
     __syncwarp();
-    for (uint32_t m = Sw; m; m &= m - 1) {
+    for (uint32_t m = S; m; m &= m - 1) {
         const int s = __ffs(m) - 1;
-        atomicAdd(&L[cc_slot(X[cc_slot((uint32_t)(lane * 32 + s))])], (uint32_t)__popc(run_mask(cw, s)));
-    }
-    for (uint32_t m = Sb; m; m &= m - 1) {
-        const int s = __ffs(m) - 1;
-        atomicAdd(&L[cc_slot(X[cc_slot((uint32_t)(lane * 32 + s))])], (uint32_t)__popc(run_mask(cb, s)));
+        const uint32_t cont = ((Sw >> s) & 1u) ? cw : cb;
+        const uint32_t slot = cc_slot(X[cc_slot(rid0 + s)]);
+        atomicAdd(reinterpret_cast<uint32_t*>(L) + (slot >> 1), (uint32_t)__popc(run_mask(cont, s)) << ((slot & 1) * 16));
     }
     __syncwarp();
     // append the tile's roots to the frame's root list (one atomic per tile) and publish their counts
@@ -204,10 +219,10 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
         int o = base + incl - nroot;
         uint32_t* fr = roots + (size_t)frame * g.plane;
         for (uint32_t m = S; m; m &= m - 1) {
-            const uint32_t id = (uint32_t)(lane * 32 + __ffs(m) - 1);
-            if (X[cc_slot(id)] == id) {
-                const uint32_t gid = (uint32_t)((y0 + (int)(id >> 5)) * g.wp + x0 + (int)(id & 31));
-                fs[gid] = L[cc_slot(id)];
+            const int s = __ffs(m) - 1;
+            if (X[cc_slot(rid0 + s)] == rid0 + s) {
+                const uint32_t gid = (uint32_t)(y * g.wp + x0 + s);   // a root is a run of this very row
+                fs[gid] = L[cc_slot(rid0 + s)];
                 fr[o++] = gid;
             }
         }
@@ -225,7 +240,7 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
             for (int k = 0; k < 4; k++) {
                 const int c = q * 4 + k;
                 if ((S >> c) & 1u) {
-                    const uint32_t r = X[cc_slot((uint32_t)(lane * 32 + c))];
+                    const uint32_t r = X[cc_slot(rid0 + c)];
                     cur = (uint32_t)((y0 + (int)(r >> 5)) * g.wp + x0 + (int)(r & 31));
                 }
                 o4[k] = ((fg >> c) & 1u) ? cur : own0 + c;
