@@ -317,15 +317,18 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         const int vec_ok = (s_stride % 16 == 0) && (s_frame % 16 == 0) && (((uintptr_t)src) % 16 == 0);
         const int md = h->prm.min_white_black_diff;
         uint8_t* th_out = sl.d_thresh.as<uint8_t>();
-        if (F == 1)
-            k_decimate_threshold<1><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
-                                                                   nstrips, nsegs, seg_tiles, n, md, vec_ok);
-        else if (F == 2)
-            k_decimate_threshold<2><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
-                                                                   nstrips, nsegs, seg_tiles, n, md, vec_ok);
-        else
-            k_decimate_threshold<4><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, th_out, g,
-                                                                   nstrips, nsegs, seg_tiles, n, md, vec_ok);
+        int minb = 4;
+        if (const char* e = getenv("AGPU_IMG_MINB")) minb = atoi(e);
+#define LAUNCH_DT(FF, MB) k_decimate_threshold<FF, MB><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, \
+                                                                               th_out, g, nstrips, nsegs, seg_tiles, n, md, vec_ok)
+        if (F == 1) {
+            if (minb == 4) LAUNCH_DT(1, 4); else if (minb == 5) LAUNCH_DT(1, 5); else if (minb == 6) LAUNCH_DT(1, 6); else LAUNCH_DT(1, 3);
+        } else if (F == 2) {
+            LAUNCH_DT(2, 4);
+        } else {
+            LAUNCH_DT(4, 4);
+        }
+#undef LAUNCH_DT
         LAUNCH_CHECK("k_decimate_threshold");
     }
     if (F > 1) {
@@ -693,12 +696,14 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     for (int b = 0; b < B; b++) counts[b] = 0;
     if (g.wd < 8 || g.hd < 8) return AGPU_OK;  // nothing detectable (and the tile grid would be empty)
 
-    // chunking: ~128 Mpx of working image per pass (61 frames of 1080p), several chunks in flight
+    // chunking: ~256 Mpx of working image per pass (129 frames of 1080p), several chunks in flight; a batch that is
+    // big enough is cut into at least three chunks so that the slots overlap
     int chunk = h->cfg.chunk_frames;
     if (chunk <= 0) {
-        const size_t target_px = (size_t)128 << 20;
+        const size_t target_px = (size_t)256 << 20;
         chunk = (int)std::max<size_t>(1, target_px / g.plane);
         chunk = std::min(chunk, 256);
+        if (B >= 48) chunk = std::min(chunk, (B + 2) / 3);
     }
     chunk = std::min(chunk, B);
     c.chunk = chunk;

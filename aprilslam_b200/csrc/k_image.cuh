@@ -40,8 +40,8 @@ __device__ __forceinline__ __half2 px_hi(uint32_t w) { return u2h(__byte_perm(w,
 #define H2_BIG 0x7bff7bffu   // 65504: neutral element of min
 #define H2_ZERO 0x00000000u  // 0 < 1024: neutral element of max
 
-template <int F>
-__global__ void __launch_bounds__(128)
+template <int F, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_stride, size_t src_frame_stride,
                      uint8_t* __restrict__ quad_im, uint8_t* __restrict__ thresh, Geom g, int nstrips, int nsegs,
                      int seg_tiles, int nframes, int min_diff, int vec_ok) {

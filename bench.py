@@ -350,7 +350,10 @@ def det_chunk(det, args):
     if args.chunk > 0:
         return args.chunk
     plane = ((W + 15) // 16 * 16) * H
-    return max(1, min(256, (128 << 20) // plane))
+    chunk = max(1, min(256, (256 << 20) // plane))
+    if args.batch >= 48:
+        chunk = min(chunk, (args.batch + 2) // 3)
+    return min(chunk, args.batch)
 
 
 def main():

@@ -56,7 +56,7 @@ typedef struct agpu_config {
     int debug;                /* (0)  1: keep stage buffers of the last chunk for agpu_debug_fetch */
     /* B200 side */
     int device;               /* CUDA device ordinal */
-    int chunk_frames;         /* frames processed per pipeline pass (0 = auto: ~128 Mpx of working image) */
+    int chunk_frames;         /* frames processed per pipeline pass (0 = auto: ~256 Mpx of working image) */
     int pipeline_slots;       /* chunks in flight on independent streams (0 = auto: 3) */
     int max_points_per_frame; /* edge-point list capacity per frame (0 = auto: decimated pixels / 4, >= 65536) */
     int max_clusters_per_frame; /* (0 = auto) */
