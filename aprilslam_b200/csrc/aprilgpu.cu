@@ -536,14 +536,14 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             qa.cursor = d_cnt + CNT_CURSOR0 + t;
             const int nblk = h->num_sms * TIER_CTAS_PER_SM[t];
             if (t == 0) {
-                const size_t smem = 8 * qf_smem_per_group(TIER_CAP[t]);
+                const size_t smem = 8 * qf_smem_per_group(TIER_CAP[t], 1);
                 k_fit_quads<1><<<nblk, 256, smem, st>>>(qa, h->prm, TIER_CAP[t]);
             } else if (t == 1) {
-                k_fit_quads<2><<<nblk, 64, qf_smem_per_group(TIER_CAP[t]), st>>>(qa, h->prm, TIER_CAP[t]);
+                k_fit_quads<2><<<nblk, 64, qf_smem_per_group(TIER_CAP[t], 2), st>>>(qa, h->prm, TIER_CAP[t]);
             } else if (t == 2) {
-                k_fit_quads<4><<<nblk, 128, qf_smem_per_group(TIER_CAP[t]), st>>>(qa, h->prm, TIER_CAP[t]);
+                k_fit_quads<4><<<nblk, 128, qf_smem_per_group(TIER_CAP[t], 4), st>>>(qa, h->prm, TIER_CAP[t]);
             } else {
-                k_fit_quads<8><<<nblk, 256, qf_smem_per_group(TIER_CAP[t]), st>>>(qa, h->prm, TIER_CAP[t]);
+                k_fit_quads<8><<<nblk, 256, qf_smem_per_group(TIER_CAP[t], 8), st>>>(qa, h->prm, TIER_CAP[t]);
             }
             LAUNCH_CHECK("k_fit_quads");
             if (t > 0) {
@@ -910,12 +910,12 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     }
     // the large quad-fit tiers need more than 48 KB of dynamic shared memory
     ce = cudaFuncSetAttribute(k_fit_quads<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)qf_smem_per_group(TIER_CAP[AGPU_NTIERS - 1]));
+                              (int)qf_smem_per_group(TIER_CAP[AGPU_NTIERS - 1], 8));
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(k_fit_quads<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(8 * qf_smem_per_group(TIER_CAP[0])));
+                                  (int)(8 * qf_smem_per_group(TIER_CAP[0], 1)));
     if (ce != cudaSuccess) return fail(AGPU_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
     *out = h;
     return AGPU_OK;

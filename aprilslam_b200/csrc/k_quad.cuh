@@ -179,10 +179,126 @@ __device__ __forceinline__ void group_bitonic_sort(const QGroup<NW>& G, unsigned
     }
 }
 
+// Stable LSD radix sort of n 64-bit keys by their upper 32 bits (the slope), 8-bit digits, four passes that
+// ping-pong between the shared-memory buffer and a global scratch (ends in shared memory).  Warp w owns the
+// contiguous chunk [w*cw, (w+1)*cw) of the source; ranks come from __match_any_sync, so the order of equal
+// digits is preserved.  cnt: NW*256 16-bit counters.  Roughly a third of the instructions of the bitonic
+// network for the cluster sizes that matter (1000-2000 points).
+template <int NW>
+__device__ void group_radix_sort_hi32(const QGroup<NW>& G, unsigned long long* sbuf, unsigned long long* gbuf, int n,
+                                      uint16_t* cnt) {
+    constexpr int T = QGroup<NW>::T;
+    const int lane = G.lane, w = G.w, tid = G.tid;
+    const int cw = ((n + NW - 1) / NW + 31) & ~31;          // chunk per warp, whole rounds of 32
+    const int lo = w * cw, hi = min(lo + cw, n);
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 32 + 8 * pass;
+        const bool from_smem = (pass & 1) == 0;
+        for (int i = tid; i < NW * 256; i += T) cnt[i] = 0;
+        G.sync();
+        // sweep 1: per-warp digit counts
+        for (int base = lo; base < hi; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < hi;
+            const unsigned long long k = valid ? (from_smem ? sbuf[i] : __ldcg(gbuf + i)) : 0ull;
+            const uint32_t d = valid ? (uint32_t)(k >> shift) & 255u : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(FULL_MASK, d);
+            if (valid && lane == __ffs(peers) - 1) cnt[w * 256 + d] += (uint16_t)__popc(peers);
+            __syncwarp();
+        }
+        G.sync();
+        // exclusive prefix over (digit, warp): thread t owns digits t*DPT .. t*DPT+DPT-1
+        {
+            constexpr int DPT = 256 / T > 0 ? 256 / T : 1;   // T <= 256 here
+            uint32_t tot[DPT];
+            uint32_t sum = 0;
+#pragma unroll
+            for (int q = 0; q < DPT; q++) {
+                const int d = tid * DPT + q;
+                uint32_t run = 0;
+#pragma unroll
+                for (int ww = 0; ww < NW; ww++) {
+                    const uint32_t c = cnt[ww * 256 + d];
+                    cnt[ww * 256 + d] = (uint16_t)run;      // offset of warp ww inside digit d
+                    run += c;
+                }
+                tot[q] = run;
+                sum += run;
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL_MASK, incl, off);
+                if (lane >= off) incl += t;
+            }
+            uint32_t excl = incl - sum;
+            if (NW > 1) {
+                if (lane == 31) G.si[w] = (int)incl;
+                __syncthreads();
+#pragma unroll
+                for (int ww = 0; ww < NW; ww++)
+                    if (ww < w) excl += (uint32_t)G.si[ww];
+                __syncthreads();
+            }
+#pragma unroll
+            for (int q = 0; q < DPT; q++) {
+                const int d = tid * DPT + q;
+#pragma unroll
+                for (int ww = 0; ww < NW; ww++) cnt[ww * 256 + d] = (uint16_t)(cnt[ww * 256 + d] + excl);
+                excl += tot[q];
+            }
+        }
+        G.sync();
+        // sweep 2: scatter
+        for (int base = lo; base < hi; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < hi;
+            const unsigned long long k = valid ? (from_smem ? sbuf[i] : __ldcg(gbuf + i)) : 0ull;
+            const uint32_t d = valid ? (uint32_t)(k >> shift) & 255u : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(FULL_MASK, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t start = 0;
+            if (valid && lane == leader) {
+                start = cnt[w * 256 + d];
+                cnt[w * 256 + d] = (uint16_t)(start + __popc(peers));
+            }
+            start = __shfl_sync(FULL_MASK, start, leader);
+            if (valid) {
+                const uint32_t pos = start + __popc(peers & ((1u << lane) - 1u));
+                if (from_smem) __stcg(gbuf + pos, k); else sbuf[pos] = k;
+            }
+            __syncwarp();
+        }
+        __threadfence_block();
+        G.sync();
+    }
+}
+
+// After the slope sort: order the (rare) runs of equal slope by (y, x), i.e. finish the sort on the full 64-bit key
+// with odd-even transposition rounds until nothing moves (equal points -- duplicates -- never move).
+template <int NW>
+__device__ void group_fix_ties(const QGroup<NW>& G, unsigned long long* s, int n) {
+    constexpr int T = QGroup<NW>::T;
+    for (;;) {
+        bool moved = false;
+#pragma unroll
+        for (int phase = 0; phase < 2; phase++) {
+            for (int i = 2 * G.tid + phase; i + 1 < n; i += 2 * T) {
+                const unsigned long long a = s[i], b = s[i + 1];
+                if (a > b) { s[i] = b; s[i + 1] = a; moved = true; }
+            }
+            G.sync();
+        }
+        int total;
+        (void)G.compact_pos(moved, total);
+        if (total == 0) break;
+    }
+}
+
 // Returns true (uniformly over the group) and fills q when the cluster yields a quad.
 template <int NW>
 __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, const DevParams& P, const ClusterRef ref,
-                                  unsigned long long* sbuf, double* ptab, int* sidx, QuadRec& q) {
+                                  unsigned long long* sbuf, double* ptab, int* sidx, uint16_t* scnt, QuadRec& q) {
     constexpr int T = QGroup<NW>::T;
     const int tid = G.tid, lane = G.lane;
     const size_t seg = (size_t)ref.frame * a.cap + ref.start;
@@ -219,9 +335,9 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     // ---- slope keys
     int n2 = 64;
     while (n2 < sz) n2 <<= 1;
-    for (int i = tid; i < n2; i += T) {
+    for (int i = tid; i < sz; i += T) {
         unsigned long long key = ~0ull;
-        if (i < sz) {
+        {
             uint32_t v = (uint32_t)pv[i];
             int px = v & 0x3fff, py = (v >> 14) & 0x3fff;
             float dx = (float)px - cx, dy = (float)py - cy;
@@ -236,7 +352,8 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         sbuf[i] = key;
     }
     G.sync();
-    group_bitonic_sort<NW>(G, sbuf, n2, false);
+    group_radix_sort_hi32<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(a.lfps + seg * 6), sz, scnt);
+    group_fix_ties<NW>(G, sbuf, sz);
 
     // ---- remove consecutive duplicates (same x, y); in place: a tile is read completely before it is written,
     //      and writes only go to positions at or below the ones read
@@ -573,8 +690,8 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
 
 // Dynamic shared memory per GROUP: `wcap` u64 (sort buffer; from 1024 keys on it also hosts the 600-double pair
 // table once the sort is over) + 16 ints, plus a separate pair table for the small tier.
-__host__ __device__ inline size_t qf_smem_per_group(int wcap) {
-    return (size_t)wcap * 8 + 64 + (wcap >= 1024 ? 0 : QF_PTAB_DOUBLES * 8);
+__host__ __device__ inline size_t qf_smem_per_group(int wcap, int nw) {
+    return (size_t)wcap * 8 + 64 + (size_t)nw * 512 + (wcap >= 1024 ? 0 : QF_PTAB_DOUBLES * 8);
 }
 
 // Persistent groups: group i takes clusters i, i + ngroups, ...   NW == 1: blockDim/32 warp groups per CTA;
@@ -593,10 +710,12 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
     G.si = s_i;
     G.sd = s_d;
     const int gi = NW == 1 ? (threadIdx.x >> 5) : 0;
-    unsigned char* base = smem_raw + qf_smem_per_group(wcap) * gi;
+    unsigned char* base = smem_raw + qf_smem_per_group(wcap, NW) * gi;
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(base);
     int* sidx = reinterpret_cast<int*>(base + (size_t)wcap * 8);
-    double* ptab = wcap >= 1024 ? reinterpret_cast<double*>(base) : reinterpret_cast<double*>(base + (size_t)wcap * 8 + 64);
+    uint16_t* scnt = reinterpret_cast<uint16_t*>(base + (size_t)wcap * 8 + 64);
+    double* ptab = wcap >= 1024 ? reinterpret_cast<double*>(base)
+                                : reinterpret_cast<double*>(base + (size_t)wcap * 8 + 64 + (size_t)NW * 512);
     const int n = min(*a.list_count, a.list_cap);
     // clusters differ by two orders of magnitude in cost: groups claim them one at a time from a shared cursor
     for (;;) {
@@ -613,7 +732,7 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
         if (ci >= n) break;
         const ClusterRef ref = a.list[ci];
         QuadRec q;
-        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sbuf, ptab, sidx, q);
+        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sbuf, ptab, sidx, scnt, q);
         if (ok && G.tid == 0) {
             int s = atomicAdd(a.nquads, 1);
             atomicAdd(&a.per_frame_quads[ref.frame], 1);
