@@ -477,7 +477,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     if (rc) return rc;
     tm.mark();  // 3: after CC
     {
-        dim3 grid(ceil_div(g.wp >> 2, 32 * EDGE_WORDS), ceil_div(g.hd - 1, 8), n);
+        dim3 grid(n, ceil_div(g.wp >> 2, 32 * EDGE_WORDS), ceil_div(g.hd - 1, 8));
         k_edges<<<grid, 256, 0, sl.stream>>>(sl.d_thresh.as<uint8_t>(), sl.d_labels.as<uint32_t>(),
                                              sl.d_sizes.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g,
                                              sl.d_recs[0].as<unsigned long long>(), d_npts, cap);

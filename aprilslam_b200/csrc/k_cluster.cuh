@@ -25,14 +25,16 @@ __global__ void __launch_bounds__(256)
 k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes,
         const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts, int cap) {
     __shared__ uint16_t scand[8][EDGE_CAND_PER_WARP];
-    const int frame = blockIdx.z;
+    // grid = (frames, x blocks, y blocks): consecutive CTAs belong to DIFFERENT frames, so the per-frame append
+    // counters are not hammered by every resident warp at once
+    const int frame = blockIdx.x;
     const uint8_t* ft = thresh + (size_t)frame * g.plane;
     const uint32_t* fl = labels + (size_t)frame * g.plane;
     const uint32_t* fs = sizes + (size_t)frame * g.plane;
     const uint32_t* fd = dense + (size_t)frame * g.plane;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int kx = (blockIdx.x * 32 + lane) * EDGE_WORDS;   // first word of this thread in the row
-    const int y = blockIdx.y * 8 + w;
+    const int kx = (blockIdx.y * 32 + lane) * EDGE_WORDS;   // first word of this thread in the row
+    const int y = blockIdx.z * 8 + w;
     const int wpr = g.wp >> 2;                              // words per row (a multiple of 4)
     const int x0 = kx * 4;
 
@@ -99,25 +101,37 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
     }
     __syncwarp();
     unsigned long long* fk = recs + (size_t)frame * cap;
-    const int xbase = blockIdx.x * (32 * EDGE_WORDS * 4);
+    const int xbase = blockIdx.y * (32 * EDGE_WORDS * 4);
     for (int b = 0; b < total; b += 32) {
         bool ok = false;
         unsigned long long rec = 0;
-        if (b + lane < total) {
+        const bool have = b + lane < total;
+        int x = 0, d = 0, pos = 0, dx = 0, dy = 0;
+        uint32_t l0 = 0xffffffffu, l1 = 0xfffffffeu;
+        if (have) {
             const uint32_t c = scand[w][b + lane];
-            const int x = xbase + (int)(c & 511), d = (c >> 9) & 3, pos = (c >> 11) & 1;
-            const int dx = (d == 0 || d == 3) ? 1 : (d == 2 ? -1 : 0), dy = d == 0 ? 0 : 1;
+            x = xbase + (int)(c & 511); d = (c >> 9) & 3; pos = (c >> 11) & 1;
+            dx = (d == 0 || d == 3) ? 1 : (d == 2 ? -1 : 0); dy = d == 0 ? 0 : 1;
             const size_t id = (size_t)y * g.wp + x;
-            // pixel -> tile-local root -> final root (k_cc_sizes compressed the second hop)
-            const uint32_t id1 = (uint32_t)(id + (size_t)dy * g.wp + dx);
-            const uint32_t l0 = fl[id], l1 = fl[id1];
-            const uint32_t rep0 = fl[l0], rep1 = fl[l1];
-            const uint32_t d0 = fd[rep0], d1 = fd[rep1];
-            if (d0 != 0xffffffffu && d1 != 0xffffffffu) {   // both components have >= 25 pixels
-                ok = true;
-                const uint32_t key = (max(d0, d1) << 16) | min(d0, d1);
-                rec = ((unsigned long long)key << 32) | pack_point(2 * x + dx, 2 * y + dy, d, pos);
-            }
+            // pixel -> tile-local root (k_cc_local)
+            l0 = fl[id];
+            l1 = fl[id + (size_t)dy * g.wp + dx];
+        }
+        // tile-local root -> final root -> dense id (k_cc_sizes / k_cc_dense).  The candidates of a warp sit on a
+        // handful of components, so one lane per distinct tile-local root does the two dependent loads.
+        uint32_t d0 = 0xffffffffu, d1 = 0xffffffffu;
+        {
+            const uint32_t p0 = __match_any_sync(FULL_MASK, l0), p1 = __match_any_sync(FULL_MASK, l1);
+            const int ld0 = __ffs(p0) - 1, ld1 = __ffs(p1) - 1;
+            if (have && lane == ld0) d0 = fd[fl[l0]];
+            if (have && lane == ld1) d1 = fd[fl[l1]];
+            d0 = __shfl_sync(FULL_MASK, d0, ld0);
+            d1 = __shfl_sync(FULL_MASK, d1, ld1);
+        }
+        if (have && d0 != 0xffffffffu && d1 != 0xffffffffu) {   // both components have >= 25 pixels
+            ok = true;
+            const uint32_t key = (max(d0, d1) << 16) | min(d0, d1);
+            rec = ((unsigned long long)key << 32) | pack_point(2 * x + dx, 2 * y + dy, d, pos);
         }
         const uint32_t okm = __ballot_sync(FULL_MASK, ok);
         if (okm == 0) continue;
