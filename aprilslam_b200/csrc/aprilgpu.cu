@@ -91,7 +91,7 @@ struct Slot {
     std::vector<cudaEvent_t> events;   // stage timing
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes, d_roots, d_dense, d_dense2rep;
     DevBuf d_recs[2], d_hist, d_dtot, d_lfps, d_errs;
-    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], nroots[chunk], ndense[chunk]
+    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
     bool pending = false;
@@ -352,7 +352,7 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
     dim3 gridb(ceil_div((long long)tx * ty * CCB_ITEMS, 256), 1, n);
     k_cc_boundary<<<gridb, 256, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), g, tx, ty);
     LAUNCH_CHECK("k_cc_boundary");
-    dim3 grids(std::max(1, std::min(64, ceil_div(g.plane / 64, 256))), n);
+    dim3 grids(std::max(1, std::min(8, ceil_div(g.plane / 1024, 256))), n * CC_SUBLISTS);
     k_cc_sizes<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
                                              d_nroots, g);
     LAUNCH_CHECK("k_cc_sizes");
@@ -453,8 +453,8 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int* d_frame_quads = d_npts + chunk;
     int* d_ndets = d_frame_quads + chunk;
     int* d_out_counts = d_ndets + chunk;
-    int* d_nroots = d_out_counts + chunk;
-    int* d_ndense = d_nroots + chunk;
+    int* d_ndense = d_out_counts + chunk;
+    int* d_nroots = d_ndense + chunk;          // CC_SUBLISTS counters per frame
     StageTimer tm(h, sl);
     tm.mark();  // 0
     const uint8_t* d_src;
@@ -621,7 +621,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     const int* h_npts = hc + CNT_FIXED;
     const int* h_nd = h_npts + 2 * chunk;
     const int* h_oc = h_nd + chunk;
-    const int* h_ndense = h_oc + 2 * chunk;
+    const int* h_ndense = h_oc + chunk;
     for (int i = 0; i < n; i++)
         if (h_ndense[i] > AGPU_MAX_DENSE) {
             h->set_err("more than 65536 connected components of >= 25 pixels in one frame");
@@ -720,7 +720,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     c.cap = (c.cap + RS_TILE - 1) / RS_TILE * RS_TILE;
     c.maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
     c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
-    c.ncnt = CNT_FIXED + (size_t)6 * chunk;
+    c.ncnt = CNT_FIXED + (size_t)(5 + CC_SUBLISTS) * chunk;
     c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
     if (on_device) {   // order every slot stream after the producer's stream
@@ -1167,8 +1167,8 @@ int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint3
     CK(sl.d_thresh.ensure(g.plane));
     CK(cudaMemsetAsync(sl.d_thresh.p, 127, g.plane, sl.stream));
     CK(cudaMemcpy2DAsync(sl.d_thresh.p, g.wp, thresh, W, W, H, cudaMemcpyHostToDevice, sl.stream));
-    CK(sl.d_counters.ensure(64));
-    CK(cudaMemsetAsync(sl.d_counters.p, 0, 64, sl.stream));
+    CK(sl.d_counters.ensure(256));
+    CK(cudaMemsetAsync(sl.d_counters.p, 0, 256, sl.stream));
     int rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), 1, g, sl.d_counters.as<int>(), nullptr, true);
     if (rc) return rc;
     std::vector<uint32_t> lab(g.plane), sz(g.plane);

@@ -22,6 +22,7 @@
 #define CC_TH 32
 #define CC_WARPS 4
 #define CC_THREADS (CC_WARPS * 32)
+#define CC_SUBLISTS 16   // root sub-lists per frame (tile row mod 16): spreads the append atomics over 16 counters
 #define CC_PITCH 33   // run-start slots of row r live at r*33 + c (16-bit entries)
 // tile of the flatten pass (8-pixel runs per thread)
 #define CCF_TW 64
@@ -213,11 +214,12 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
             if (lane >= off) incl += n;
         }
         const int total = __shfl_sync(FULL_MASK, incl, 31);
+        const int sub = blockIdx.y & (CC_SUBLISTS - 1);
         int base = 0;
-        if (lane == 31 && total) base = atomicAdd(&nroots[frame], total);
+        if (lane == 31 && total) base = atomicAdd(&nroots[frame * CC_SUBLISTS + sub], total);
         base = __shfl_sync(FULL_MASK, base, 31);
         int o = base + incl - nroot;
-        uint32_t* fr = roots + (size_t)frame * g.plane;
+        uint32_t* fr = roots + (size_t)frame * g.plane + (size_t)sub * (g.plane / CC_SUBLISTS);
         for (uint32_t m = S; m; m &= m - 1) {
             const int s = __ffs(m) - 1;
             if (X[cc_slot(rid0 + s)] == rid0 + s) {
@@ -299,11 +301,11 @@ k_cc_boundary(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels,
 __global__ void __launch_bounds__(256)
 k_cc_sizes(uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
            const int* __restrict__ nroots, Geom g) {
-    const int frame = blockIdx.y;
-    const int n = nroots[frame];
+    const int frame = blockIdx.y / CC_SUBLISTS, sub = blockIdx.y % CC_SUBLISTS;
+    const int n = nroots[blockIdx.y];
     uint32_t* fl = labels + (size_t)frame * g.plane;
     uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const uint32_t* fr = roots + (size_t)frame * g.plane;
+    const uint32_t* fr = roots + (size_t)frame * g.plane + (size_t)sub * (g.plane / CC_SUBLISTS);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t a = fr[i];
         const uint32_t r = gfind(fl, a);
@@ -323,11 +325,11 @@ __global__ void __launch_bounds__(256)
 k_cc_dense(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
            const int* __restrict__ nroots, uint32_t* __restrict__ dense, uint32_t* __restrict__ dense2rep,
            int* __restrict__ ndense, Geom g) {
-    const int frame = blockIdx.y;
-    const int n = nroots[frame];
+    const int frame = blockIdx.y / CC_SUBLISTS, sub = blockIdx.y % CC_SUBLISTS;
+    const int n = nroots[blockIdx.y];
     const uint32_t* fl = labels + (size_t)frame * g.plane;
     const uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const uint32_t* fr = roots + (size_t)frame * g.plane;
+    const uint32_t* fr = roots + (size_t)frame * g.plane + (size_t)sub * (g.plane / CC_SUBLISTS);
     uint32_t* fd = dense + (size_t)frame * g.plane;
     uint32_t* f2 = dense2rep + (size_t)frame * AGPU_MAX_DENSE;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
