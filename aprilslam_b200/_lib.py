@@ -88,6 +88,7 @@ def load():
     L.agpu_debug_dims.argtypes = [vp, vp, vp]
     L.agpu_stage_threshold.argtypes = [vp, vp, ci, ci, vp, vp]
     L.agpu_stage_labels.argtypes = [vp, vp, ci, ci, vp, vp]
+    L.agpu_render.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, vp]
     _lib = L
     return L
 
@@ -95,4 +96,4 @@ def load():
 EXPORTS = ["agpu_version", "agpu_default_config", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_detect",
            "agpu_detect_bgr", "agpu_detect_pose", "agpu_pose", "agpu_set_profiling", "agpu_get_stage_ms",
            "agpu_get_launch_count", "agpu_get_counters", "agpu_debug_fetch", "agpu_debug_dims",
-           "agpu_stage_threshold", "agpu_stage_labels"]
+           "agpu_stage_threshold", "agpu_stage_labels", "agpu_render"]

@@ -21,6 +21,7 @@
 #include "k_quad.cuh"
 #include "k_decode.cuh"
 #include "k_pose.cuh"
+#include "k_render.cuh"
 
 #include "families_data.inc"
 
@@ -1138,6 +1139,36 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
     }
     h->set_err("agpu_debug_fetch: unknown buffer name");
     return AGPU_E_INVALID;
+}
+
+int agpu_render(agpu_handle* h, const void* tags_host, const int* tag_offsets_host, const uint8_t* backgrounds_host, int B,
+                int W, int H, uint8_t* frames_dev, void* cuda_stream) {
+    if (!h) return AGPU_E_INVALID;
+    if (!tags_host || !tag_offsets_host || !backgrounds_host || !frames_dev || B <= 0 || W <= 0 || H <= 0 || B > 65535) {
+        h->set_err("agpu_render: invalid argument");
+        return AGPU_E_INVALID;
+    }
+    CK(cudaSetDevice(h->device));
+    const int ntags = tag_offsets_host[B];
+    DevBuf d_tags, d_off, d_bg;
+    CK(d_tags.ensure(std::max<size_t>(1, (size_t)ntags) * sizeof(RenderTag)));
+    CK(d_off.ensure((size_t)(B + 1) * 4));
+    CK(d_bg.ensure((size_t)B));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CK(cudaMemcpyAsync(d_tags.p, tags_host, (size_t)ntags * sizeof(RenderTag), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_off.p, tag_offsets_host, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_bg.p, backgrounds_host, (size_t)B, cudaMemcpyHostToDevice, st));
+    dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B);
+    k_render<<<grid, 256, 0, st>>>(d_tags.as<RenderTag>(), d_off.as<int>(), d_bg.as<uint8_t>(), frames_dev, W, H, B);
+    h->launches = 1;
+    cudaError_t le = cudaGetLastError();
+    cudaError_t se = cudaStreamSynchronize(st);
+    d_tags.release(); d_off.release(); d_bg.release();
+    if (le != cudaSuccess || se != cudaSuccess) {
+        h->set_err(std::string("agpu_render: ") + cudaGetErrorString(le != cudaSuccess ? le : se));
+        return AGPU_E_CUDA;
+    }
+    return AGPU_OK;
 }
 
 int agpu_stage_threshold(agpu_handle* h, const uint8_t* im, int W, int H, uint8_t* quad_im_out, uint8_t* thresh_out) {

@@ -192,13 +192,26 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     B = args.batch
     K = synth.intrinsics(W, H, 45.0)
-    t_gen = time.time()
-    frames_host = make_frames(args.distinct, B, seed0=rank * args.distinct)
-    t_gen = time.time() - t_gen
-    pinned = torch.from_numpy(frames_host).pin_memory()
-    frames_dev = pinned.to(dev, non_blocking=False)
     det = Detector("tag36h11", decimate=1.0, refine_edges=True, device=local_rank, chunk_frames=args.chunk,
                    pipeline_slots=args.slots)
+    t_gen = time.time()
+    if args.distinct <= 0:
+        # every frame of the batch is a distinct seeded scene (default_rng(1000 + global frame index)), rendered
+        # straight into HBM by the GPU restatement of the reference's renderer (bit-identical to synth.render)
+        from aprilslam_b200.render import render_batch
+        scenes = [synth.grid_scene(W, H, rank * B + i, GRID) for i in range(B)]
+        frames_dev = render_batch(det, scenes)
+        torch.cuda.synchronize()
+        pinned = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+        pinned.copy_(frames_dev)
+        frames_host = pinned.numpy()
+        distinct = B
+    else:
+        frames_host = make_frames(args.distinct, B, seed0=rank * args.distinct)
+        pinned = torch.from_numpy(frames_host).pin_memory()
+        frames_dev = pinned.to(dev, non_blocking=False)
+        distinct = args.distinct
+    t_gen = time.time() - t_gen
 
     def step_dev():
         return det.detect_pose_batch(frames_dev, K, None, TAG_SIZE, cap_per_frame=CAP)
@@ -320,7 +333,7 @@ def run_b200(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
         "config": {"workload": "C3: 1920x1080 gray, batch %d per GPU, quad_decimate=1, refine_edges=1, "
                                "~50 tag36h11/frame, detect + per-tag pose" % B,
-                   "batch_per_gpu": B, "distinct_frames": args.distinct, "tags_per_frame": tags_per_frame,
+                   "batch_per_gpu": B, "distinct_frames": distinct, "tags_per_frame": tags_per_frame,
                    "pose_ok_fraction": pose_ok, "l2": "inputs (%.1f GB per GPU) larger than L2" % (B * N / 1e9),
                    "chunk_frames": det_chunk(det, args), "pipeline_slots": args.slots or 3,
                    "stages_note": "stage times / roofline measured with pipeline_slots=1 (%.1f frames/s in that mode)" % (
@@ -363,7 +376,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step (BASELINE config C3: 1024)")
-    ap.add_argument("--distinct", type=int, default=64, help="distinct rendered frames per rank")
+    ap.add_argument("--distinct", type=int, default=0,
+                    help="0: every frame distinct, rendered on the GPU; N>0: N host-rendered frames replicated")
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline pass (0 = library default)")
     ap.add_argument("--slots", type=int, default=0, help="chunks in flight (0 = library default: 3)")
     ap.add_argument("--ref-frames", type=int, default=0)

@@ -145,6 +145,16 @@ int agpu_debug_dims(agpu_handle* h, int* wd, int* hd);
 int agpu_stage_threshold(agpu_handle* h, const uint8_t* im, int W, int H, uint8_t* quad_im_out, uint8_t* thresh_out);
 int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint32_t* labels_out, uint32_t* sizes_out);
 
+/* ---- synthetic frame source (the step before the path) -------------------------- */
+
+/* Renders B gray frames of W x H into DEVICE memory frames_dev[B][H][W] with the geometry of the reference's
+ * OpenGL renderer (src/simulation/renderer.py:91-96,188-251,253-274), bit-identical to aprilslam_b200/synth.py.
+ * tags_host: array of 112-byte records {double Gi[9]; uint64 cells[2]; int32 total_width, ppc, x0, x1, y0, y1}
+ * (aprilslam_b200.render.TAG_DTYPE); frame b owns tags [tag_offsets[b], tag_offsets[b+1]); backgrounds: one gray
+ * level per frame.  The call returns after the frames are complete. */
+int agpu_render(agpu_handle* h, const void* tags_host, const int* tag_offsets_host, const uint8_t* backgrounds_host,
+                int B, int W, int H, uint8_t* frames_dev, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

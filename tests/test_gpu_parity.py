@@ -347,3 +347,17 @@ def test_noise_frames_match_oracle(ob):
         assert_same_detections(recs, o.detect_records(im))
         assert g.counters()["edge_points"] > 100000          # hundreds of thousands of edge points, thousands of clusters
     g.close()
+
+
+def test_gpu_renderer_is_bit_identical_to_the_numpy_restatement():
+    """agpu_render (frame source) == synth.render (renderer.py geometry), byte for byte."""
+    from aprilslam_b200.render import render_batch
+    g = Detector("tag36h11", decimate=2.0)
+    scenes = [synth.grid_scene(1280, 720, s, (5, 2), px_range=(60, 110)) for s in range(3)]
+    scenes.append(synth.grid_scene(1280, 720, 9, (4, 3), families=(("tag25h9", range(35)), ("tagStandard41h12", range(5)))))
+    frames = render_batch(g, scenes).cpu().numpy()
+    for sc, f in zip(scenes, frames):
+        assert np.array_equal(f, synth.render(sc))
+    sim = synth.sim_settings_scene(1000, 1000)
+    assert np.array_equal(render_batch(g, [sim]).cpu().numpy()[0], synth.render(sim))
+    g.close()
