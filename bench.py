@@ -148,8 +148,8 @@ def run_reference_arm(args):
     ge.build()
     from aprilslam_b200 import synth
     threads = os.cpu_count() or 1
-    nframes = args.ref_frames or max(8, min(64, 2 * threads))
-    frames = make_frames(min(nframes, 16), nframes)
+    nframes = args.ref_frames or max(16, min(128, 8 * threads))
+    frames = make_frames(min(nframes, 32), nframes)
     K = synth.intrinsics(W, H, 45.0)
     sec, dpf = cpu_reference_run(frames, K, args.steps, args.warmup, threads)
     val = nframes / sec
@@ -322,7 +322,7 @@ def run_b200(args):
                 "dense_pipeline": {"achieved": pipe_gbs, "frac": pipe_gbs / peak, "algorithmic_bytes_per_frame": 12 * N}}
     # CPU baseline on this box's host cores (bounded sample of the same workload)
     threads = os.cpu_count() or 1
-    nref = max(8, min(64, 2 * threads))
+    nref = max(16, min(256, 16 * threads, B))     # ~10-30 core-seconds of CPU work
     t0 = time.time()
     sec_cpu, _ = cpu_reference_run(frames_host[:nref], K, 1, 0, threads)
     sec_cpu1, _ = cpu_reference_run(frames_host[:4], K, 1, 0, 1)

@@ -361,3 +361,42 @@ def test_gpu_renderer_is_bit_identical_to_the_numpy_restatement():
     sim = synth.sim_settings_scene(1000, 1000)
     assert np.array_equal(render_batch(g, [sim]).cpu().numpy()[0], synth.render(sim))
     g.close()
+
+
+def test_row_stride_and_bgr_device_input_through_the_c_abi(ob, det_gold):
+    """agpu_detect with stride > W (padded rows, device memory) and agpu_detect_bgr on a CUDA tensor."""
+    import torch
+    from aprilslam_b200 import _lib
+    gray = det_gold["grid720_36h11_d2_frame"]
+    H, W = gray.shape
+    ref = ob.OracleDetector("tag36h11", decimate=2.0).detect_records(gray)
+    g = Detector("tag36h11", decimate=2.0)
+    for pad in (16, 40, 3):                                    # 16-byte aligned, 8-byte aligned and odd strides
+        stride = W + pad
+        padded = torch.zeros((2, H, stride), dtype=torch.uint8, device="cuda")
+        padded[:, :, :W] = torch.from_numpy(gray).cuda()
+        padded[:, :, W:] = 200                                 # garbage in the padding must not leak in
+        out = np.zeros((2, 64), _lib.DET_DTYPE)
+        counts = np.zeros(2, np.int32)
+        rc = g._L.agpu_detect(g._h, padded.data_ptr(), 1, 2, W, H, stride, torch.cuda.current_stream().cuda_stream,
+                              out.ctypes.data, 64, counts.ctypes.data)
+        assert rc == 0 and counts.tolist() == [len(ref), len(ref)]
+        for b in range(2):
+            assert_same_detections(out[b, :counts[b]], ref)
+    bgr = torch.from_numpy(np.repeat(gray[..., None], 3, axis=2)).cuda()
+    recs = g.detect_batch(bgr, bgr=True)[0]
+    assert_same_detections(recs, ref)
+    g.close()
+
+
+def test_two_detectors_side_by_side(ob, det_gold):
+    """Distinct handles are independent (different families / decimation, interleaved calls)."""
+    a = Detector("tag36h11", decimate=2.0)
+    b = Detector("tagStandard41h12", decimate=2.0)
+    fa, fb = det_gold["grid720_36h11_d2_frame"], det_gold["sim1000_41h12_d2_frame"]
+    for _ in range(2):
+        ra = a.detect_batch(fa)[0]
+        rb = b.detect_batch(fb)[0]
+        assert ra["id"].tolist() == det_gold["grid720_36h11_d2_id"].tolist()
+        assert rb["id"].tolist() == det_gold["sim1000_41h12_d2_id"].tolist()
+    a.close(); b.close()
