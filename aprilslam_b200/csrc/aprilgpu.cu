@@ -137,10 +137,13 @@ struct agpu_handle {
 
     // growable per-frame list capacities (0 = not chosen yet)
     int cap_points = 0, cap_clusters = 0, cap_quads = 0;
+    // most dense component ids seen in a frame so far (-1: nothing seen): decides between 11-bit ids (two radix
+    // passes) and 16-bit ids (three); a chunk whose frames do not fit is simply run again with wider ids
+    int max_dense_seen = -1;
 
     // state of the last finished chunk (debug fetch)
     Geom geom;
-    int last_slot = 0, last_chunk = 0, last_cap = 0;
+    int last_slot = 0, last_chunk = 0, last_cap = 0, last_id_bits = 16;
     bool have_last = false;
 
     void set_err(const std::string& s) { err = s; }
@@ -412,6 +415,7 @@ struct CallCtx {   // constants of one agpu_detect* call
     size_t frame_bytes;
     Geom g;
     int chunk, cap, maxcl, maxq, cap_out, key_bits, nblk_max;
+    int id_bits;   // bits per dense component id in the pair key (11: two sort passes, 16: three)
     size_t ncnt;
     const PoseSpec* pose;
 };
@@ -481,12 +485,12 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         dim3 grid(n, ceil_div(g.wp >> 2, 32 * EDGE_WORDS), ceil_div(g.hd - 1, 8));
         k_edges<<<grid, 256, 0, sl.stream>>>(sl.d_thresh.as<uint8_t>(), sl.d_labels.as<uint32_t>(),
                                              sl.d_sizes.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g,
-                                             sl.d_recs[0].as<unsigned long long>(), d_npts, cap);
+                                             sl.d_recs[0].as<unsigned long long>(), d_npts, cap, c.id_bits);
         LAUNCH_CHECK("k_edges");
     }
     tm.mark();  // 4: after edges
     int cur = 0;
-    for (int shift = 32; shift < 64; shift += RS_BITS) {   // the 32 key bits of the record: 3 passes of 11 bits
+    for (int shift = 32; shift < 32 + 2 * c.id_bits; shift += RS_BITS) {   // the 2*id_bits key bits: 2 or 3 passes of 11 bits
         dim3 grid(c.nblk_max, n);
         k_sort_hist<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(), d_npts, cap, shift,
                                                         sl.d_hist.as<uint32_t>(), c.nblk_max);
@@ -516,7 +520,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         k_cluster_heads<<<grid, 256, 0, sl.stream>>>(srecs, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
         LAUNCH_CHECK("k_cluster_heads");
         QuadFitArgs qa;
-        qa.recs = srecs; qa.dense2rep = sl.d_dense2rep.as<uint32_t>(); qa.cap = cap;
+        qa.recs = srecs; qa.dense2rep = sl.d_dense2rep.as<uint32_t>(); qa.id_bits = c.id_bits; qa.cap = cap;
         qa.quad_im = quad_im; qa.q_pitch = q_pitch; qa.q_frame = q_frame;
         qa.g = g;
         qa.lfps = sl.d_lfps.as<double>();
@@ -601,7 +605,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
 }
 
 struct Overflow {
-    int max_pts = 0, max_cl_per_frame = 0, max_q_per_frame = 0;
+    int max_pts = 0, max_cl_per_frame = 0, max_q_per_frame = 0, max_dense = 0;
     bool any = false;
 };
 
@@ -623,15 +627,18 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     const int* h_nd = h_npts + 2 * chunk;
     const int* h_oc = h_nd + chunk;
     const int* h_ndense = h_oc + chunk;
-    for (int i = 0; i < n; i++)
-        if (h_ndense[i] > AGPU_MAX_DENSE) {
-            h->set_err("more than 65536 connected components of >= 25 pixels in one frame");
-            return AGPU_E_WORKSPACE;
-        }
+    int max_dense = 0;
+    for (int i = 0; i < n; i++) max_dense = std::max(max_dense, h_ndense[i]);
+    if (max_dense > AGPU_MAX_DENSE) {
+        h->set_err("more than 65536 connected components of >= 25 pixels in one frame");
+        return AGPU_E_WORKSPACE;
+    }
+    h->max_dense_seen = std::max(h->max_dense_seen, max_dense);
     int max_pts = 0, max_cl = 0;
     for (int i = 0; i < n; i++) max_pts = std::max(max_pts, h_npts[i]);
     for (int t = 0; t < AGPU_NTIERS; t++) max_cl = std::max(max_cl, hc[CNT_TIER0 + t]);
     bool redo = false;
+    if (max_dense > (1 << c.id_bits)) { ov.max_dense = std::max(ov.max_dense, max_dense); redo = true; }   // ids did not fit the key
     if (max_pts > c.cap) { ov.max_pts = std::max(ov.max_pts, max_pts); redo = true; }
     if (max_cl > n * c.maxcl) { ov.max_cl_per_frame = std::max(ov.max_cl_per_frame, (max_cl + n - 1) / n); redo = true; }
     if (hc[CNT_NQUADS] > n * c.maxq) { ov.max_q_per_frame = std::max(ov.max_q_per_frame, (hc[CNT_NQUADS] + n - 1) / n); redo = true; }
@@ -665,6 +672,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     h->last_slot = (int)(&sl - h->slots.data());
     h->last_chunk = n;
     h->last_cap = c.cap;
+    h->last_id_bits = c.id_bits;
     h->have_last = true;
     return 0;
 }
@@ -722,6 +730,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     c.maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
     c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
     c.ncnt = CNT_FIXED + (size_t)(5 + CC_SUBLISTS) * chunk;
+    c.id_bits = (h->max_dense_seen >= 0 && h->max_dense_seen <= 1536) ? 11 : 16;
     c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
     if (on_device) {   // order every slot stream after the producer's stream
@@ -771,6 +780,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
             if (!auto_cl) { h->set_err("cluster list overflow: raise agpu_config.max_clusters_per_frame"); return AGPU_E_WORKSPACE; }
             c.maxcl = ov.max_cl_per_frame * 2;
         }
+        if (ov.max_dense > (1 << c.id_bits)) c.id_bits = 16;
         if (ov.max_q_per_frame > c.maxq) {
             if (!auto_q) { h->set_err("quad list overflow: raise agpu_config.max_quads_per_frame"); return AGPU_E_WORKSPACE; }
             c.maxq = ov.max_q_per_frame * 2;
@@ -1094,7 +1104,7 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
         for (const ClusterRef& r : heads)
             if (r.frame == frame) {
                 const uint32_t ck = (uint32_t)(recs[r.start] >> 32);
-                const uint32_t ra = d2r[ck >> 16], rb = d2r[ck & 0xffff];
+                const uint32_t ra = d2r[ck >> h->last_id_bits], rb = d2r[ck & ((1u << h->last_id_bits) - 1u)];
                 v.push_back({unpitch_key(((unsigned long long)std::max(ra, rb) << 32) | std::min(ra, rb)), r.size});
             }
         std::sort(v.begin(), v.end());

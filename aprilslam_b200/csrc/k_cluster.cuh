@@ -23,7 +23,8 @@
 #define EDGE_CAND_PER_WARP (32 * EDGE_WORDS * 16)     // lanes x pixels x directions
 __global__ void __launch_bounds__(256)
 k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes,
-        const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts, int cap) {
+        const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts, int cap,
+        int id_bits) {
     __shared__ uint16_t scand[8][EDGE_CAND_PER_WARP];
     // grid = (frames, x blocks, y blocks): consecutive CTAs belong to DIFFERENT frames, so the per-frame append
     // counters are not hammered by every resident warp at once
@@ -130,7 +131,7 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
         }
         if (have && d0 != 0xffffffffu && d1 != 0xffffffffu) {   // both components have >= 25 pixels
             ok = true;
-            const uint32_t key = (max(d0, d1) << 16) | min(d0, d1);
+            const uint32_t key = (max(d0, d1) << id_bits) | min(d0, d1);   // 2*id_bits key bits: as few sort passes as needed
             rec = ((unsigned long long)key << 32) | pack_point(2 * x + dx, 2 * y + dy, d, pos);
         }
         const uint32_t okm = __ballot_sync(FULL_MASK, ok);

@@ -13,6 +13,7 @@
 struct QuadFitArgs {
     const unsigned long long* recs;   // sorted records (pair key << 32 | packed point), per-frame segments of `cap`
     const uint32_t* dense2rep;        // [nframes][AGPU_MAX_DENSE] dense component id -> representative pixel id
+    int id_bits;                      // bits per dense id inside the pair key
     int cap;
     const uint8_t* quad_im;     // decimated gray image (may alias the source frames)
     size_t q_pitch, q_frame;    // bytes per row / per frame of quad_im
@@ -682,7 +683,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     {
         const uint32_t ck = (uint32_t)(a.recs[seg] >> 32);
         const uint32_t* f2 = a.dense2rep + (size_t)ref.frame * AGPU_MAX_DENSE;
-        const uint32_t ra = f2[ck >> 16], rb = f2[ck & 0xffff];
+        const uint32_t ra = f2[ck >> a.id_bits], rb = f2[ck & ((1u << a.id_bits) - 1u)];
         q.key = ((unsigned long long)max(ra, rb) << 32) | min(ra, rb);
     }
     return true;

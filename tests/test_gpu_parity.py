@@ -400,3 +400,19 @@ def test_two_detectors_side_by_side(ob, det_gold):
         assert ra["id"].tolist() == det_gold["grid720_36h11_d2_id"].tolist()
         assert rb["id"].tolist() == det_gold["sim1000_41h12_d2_id"].tolist()
     a.close(); b.close()
+
+
+def test_id_width_switch_reruns_the_chunk(ob, det_gold):
+    """A handle that has only seen frames with few components packs 11-bit ids into the cluster key (two radix
+    passes); a later frame with thousands of components must transparently be re-run with 16-bit ids."""
+    rng = np.random.default_rng(11)
+    clean = det_gold["grid720_36h11_d2_frame"]
+    blocks = np.kron(rng.integers(0, 2, (90, 160), dtype=np.uint8) * 200 + 25, np.ones((8, 8), np.uint8)).astype(np.uint8)
+    g = Detector("tag36h11", decimate=1.0)
+    o = ob.OracleDetector("tag36h11", decimate=1.0)
+    for im in (clean, clean, blocks, clean, blocks):
+        assert_same_detections(g.detect_batch(im, cap_per_frame=256)[0], o.detect_records(im))
+    # the block image really has more components than 11 bits can number
+    _, sz = ob.stage_labels(ob.stage_threshold(blocks))
+    assert int((sz >= 25).sum()) > 2048
+    g.close()
