@@ -407,7 +407,7 @@ def test_id_width_switch_reruns_the_chunk(ob, det_gold):
     passes); a later frame with thousands of components must transparently be re-run with 16-bit ids."""
     rng = np.random.default_rng(11)
     clean = det_gold["grid720_36h11_d2_frame"]
-    blocks = np.kron(rng.integers(0, 2, (90, 160), dtype=np.uint8) * 200 + 25, np.ones((8, 8), np.uint8)).astype(np.uint8)
+    blocks = np.kron(rng.integers(0, 2, (180, 320), dtype=np.uint8) * 200 + 25, np.ones((6, 6), np.uint8)).astype(np.uint8)
     g = Detector("tag36h11", decimate=1.0)
     o = ob.OracleDetector("tag36h11", decimate=1.0)
     for im in (clean, clean, blocks, clean, blocks):
