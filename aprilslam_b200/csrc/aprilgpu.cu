@@ -347,24 +347,26 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
                  bool flatten) {
     CK(sl.d_labels.ensure(g.plane * n * 4));
     CK(sl.d_sizes.ensure(g.plane * n * 4));
-    CK(sl.d_roots.ensure(g.plane * n * 4));
     const int tx = ceil_div(g.wd, CC_TW), ty = ceil_div(g.hd, CC_TH);
+    // a root sub-list (tile rows r with r % 16 == s) can never hold more than 512 roots per tile
+    const size_t sub_stride = (size_t)tx * ceil_div(ty, CC_SUBLISTS) * 512;
+    CK(sl.d_roots.ensure(sub_stride * CC_SUBLISTS * n * 4));
     dim3 grid(ceil_div(tx, CC_WARPS), ty, n);
     k_cc_local<<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
-                                                   sl.d_roots.as<uint32_t>(), d_nroots, g);
+                                                   sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
     LAUNCH_CHECK("k_cc_local");
     dim3 gridb(ceil_div((long long)tx * ty * CCB_ITEMS, 256), 1, n);
     k_cc_boundary<<<gridb, 256, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), g, tx, ty);
     LAUNCH_CHECK("k_cc_boundary");
     dim3 grids(std::max(1, std::min(8, ceil_div(g.plane / 1024, 256))), n * CC_SUBLISTS);
     k_cc_sizes<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
-                                             d_nroots, g);
+                                             d_nroots, g, sub_stride);
     LAUNCH_CHECK("k_cc_sizes");
     if (d_ndense) {
         CK(sl.d_dense.ensure(g.plane * n * 4));
         CK(sl.d_dense2rep.ensure((size_t)n * AGPU_MAX_DENSE * 4));
         k_cc_dense<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
-                                                 d_nroots, sl.d_dense.as<uint32_t>(), sl.d_dense2rep.as<uint32_t>(), d_ndense, g);
+                                                 d_nroots, sl.d_dense.as<uint32_t>(), sl.d_dense2rep.as<uint32_t>(), d_ndense, g, sub_stride);
         LAUNCH_CHECK("k_cc_dense");
     }
     if (flatten) {

@@ -107,7 +107,7 @@ __device__ __forceinline__ uint32_t run_mask(uint32_t cont, int s) {
 // frame's root list (k_cc_sizes folds the counts into the final roots after the boundary merges).
 __global__ void __launch_bounds__(CC_THREADS)
 k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes,
-           uint32_t* __restrict__ roots, int* __restrict__ nroots, Geom g) {
+           uint32_t* __restrict__ roots, int* __restrict__ nroots, Geom g, size_t sub_stride) {
     __shared__ __align__(16) uint16_t sL[CC_WARPS][CC_TH * CC_PITCH + 8];   // parent links, then pixel counters
     __shared__ __align__(16) uint16_t sX[CC_WARPS][CC_TH * CC_PITCH + 8];   // root of every run
     const int frame = blockIdx.z;
@@ -185,6 +185,19 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
     }
     __syncwarp();
 
+    // ---- pointer jumping: rows hook to the row above concurrently, which leaves chains as deep as the tile is
+    //      tall; every round halves them (L[x] = L[L[x]] only ever moves an entry closer to its root)
+    for (int round = 0; round < 10; round++) {
+        bool changed = false;
+        for (uint32_t m = S; m; m &= m - 1) {
+            const uint32_t slot = cc_slot(rid0 + __ffs(m) - 1);
+            const uint32_t par = L[slot];
+            const uint32_t gpar = L[cc_slot(par)];
+            if (gpar != par) { L[slot] = (uint16_t)gpar; changed = true; }
+        }
+        __syncwarp();
+        if (!__any_sync(FULL_MASK, changed)) break;
+    }
     // ---- root of every run, then pixel counts per tile-local root (L is reused as the counter array: two 16-bit
     //      counters per word, a tile holds 1024 pixels so a carry can never reach the upper counter)
     for (uint32_t m = S; m; m &= m - 1) {
@@ -219,7 +232,7 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
         if (lane == 31 && total) base = atomicAdd(&nroots[frame * CC_SUBLISTS + sub], total);
         base = __shfl_sync(FULL_MASK, base, 31);
         int o = base + incl - nroot;
-        uint32_t* fr = roots + (size_t)frame * g.plane + (size_t)sub * (g.plane / CC_SUBLISTS);
+        uint32_t* fr = roots + ((size_t)frame * CC_SUBLISTS + sub) * sub_stride;
         for (uint32_t m = S; m; m &= m - 1) {
             const int s = __ffs(m) - 1;
             if (X[cc_slot(rid0 + s)] == rid0 + s) {
@@ -300,12 +313,12 @@ k_cc_boundary(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels,
 // (pixel -> tile-local root -> final root), two loads instead of a chain walk.
 __global__ void __launch_bounds__(256)
 k_cc_sizes(uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
-           const int* __restrict__ nroots, Geom g) {
-    const int frame = blockIdx.y / CC_SUBLISTS, sub = blockIdx.y % CC_SUBLISTS;
+           const int* __restrict__ nroots, Geom g, size_t sub_stride) {
+    const int frame = blockIdx.y / CC_SUBLISTS;
     const int n = nroots[blockIdx.y];
     uint32_t* fl = labels + (size_t)frame * g.plane;
     uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const uint32_t* fr = roots + (size_t)frame * g.plane + (size_t)sub * (g.plane / CC_SUBLISTS);
+    const uint32_t* fr = roots + (size_t)blockIdx.y * sub_stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t a = fr[i];
         const uint32_t r = gfind(fl, a);
@@ -324,12 +337,12 @@ k_cc_sizes(uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, const ui
 __global__ void __launch_bounds__(256)
 k_cc_dense(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
            const int* __restrict__ nroots, uint32_t* __restrict__ dense, uint32_t* __restrict__ dense2rep,
-           int* __restrict__ ndense, Geom g) {
-    const int frame = blockIdx.y / CC_SUBLISTS, sub = blockIdx.y % CC_SUBLISTS;
+           int* __restrict__ ndense, Geom g, size_t sub_stride) {
+    const int frame = blockIdx.y / CC_SUBLISTS;
     const int n = nroots[blockIdx.y];
     const uint32_t* fl = labels + (size_t)frame * g.plane;
     const uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const uint32_t* fr = roots + (size_t)frame * g.plane + (size_t)sub * (g.plane / CC_SUBLISTS);
+    const uint32_t* fr = roots + (size_t)blockIdx.y * sub_stride;
     uint32_t* fd = dense + (size_t)frame * g.plane;
     uint32_t* f2 = dense2rep + (size_t)frame * AGPU_MAX_DENSE;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

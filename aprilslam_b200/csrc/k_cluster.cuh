@@ -131,7 +131,12 @@ k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels,
         }
         if (have && d0 != 0xffffffffu && d1 != 0xffffffffu) {   // both components have >= 25 pixels
             ok = true;
-            const uint32_t key = (max(d0, d1) << id_bits) | min(d0, d1);   // 2*id_bits key bits: as few sort passes as needed
+            // 2*id_bits key bits: as few sort passes as needed.  Ids that do not fit (the host re-runs such a chunk
+            // with wider ids) are clamped so that nothing downstream indexes out of range in the meantime.
+            const uint32_t idmax = (1u << id_bits) - 1u;
+            d0 = min(d0, idmax);
+            d1 = min(d1, idmax);
+            const uint32_t key = (max(d0, d1) << id_bits) | min(d0, d1);
             rec = ((unsigned long long)key << 32) | pack_point(2 * x + dx, 2 * y + dy, d, pos);
         }
         const uint32_t okm = __ballot_sync(FULL_MASK, ok);
