@@ -76,7 +76,6 @@ struct HostBuf {
 constexpr int TIER_CAP[AGPU_NTIERS] = {256, 1024, 2048, 16384};
 // warps per cluster group (NW); tier 0 packs 8 one-warp groups into a CTA, the others use one CTA per cluster
 constexpr int TIER_NW[AGPU_NTIERS] = {1, 2, 4, 8};
-constexpr int TIER_CTAS_PER_SM[AGPU_NTIERS] = {3, 16, 8, 1};
 // counter block layout (ints): [0..3] clusters per tier
 enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_CURSOR0 = 8, CNT_FIXED = 16 };
 
@@ -86,11 +85,12 @@ enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_CURSO
 // slots run concurrently (each on its own stream) so that the latency-bound stages of one chunk (quad
 // fitting, decode, reconcile, pose, the radix-sort scans) overlap the bandwidth-bound stages of another.
 struct Slot {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // dense, bandwidth-bound front half: image, CC, edge points, radix sort
+    cudaStream_t tail = nullptr;       // latency-bound back half (quad fit, decode, reconcile, pose, D2H): HIGH priority
     cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};   // side streams: quad-fit tiers run concurrently
-    cudaEvent_t ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_mid = nullptr, ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;   // stage timing
-    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_labels, d_sizes, d_roots, d_dense, d_dense2rep;
+    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_labels, d_canon, d_sizes, d_roots, d_dense, d_dense2rep;
     DevBuf d_recs[2], d_hist, d_dtot, d_lfps, d_errs;
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
@@ -99,7 +99,7 @@ struct Slot {
     int b0 = 0, n = 0, sorted = 0;
 
     void release() {
-        DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_labels, &d_sizes, &d_roots,
+        DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_labels, &d_canon, &d_sizes, &d_roots,
                           &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_hist, &d_dtot, &d_lfps, &d_errs, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
@@ -113,8 +113,10 @@ struct Slot {
             aux[t] = nullptr; ev_join[t] = nullptr;
         }
         if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_mid) cudaEventDestroy(ev_mid);
+        if (tail) cudaStreamDestroy(tail);
         if (stream) cudaStreamDestroy(stream);
-        ev_fork = nullptr; stream = nullptr;
+        ev_fork = nullptr; ev_mid = nullptr; stream = nullptr; tail = nullptr;
     }
 };
 
@@ -131,6 +133,12 @@ struct agpu_handle {
     long long launches = 0;
     long long counters[8];
 
+    // scheduling knobs (defaults below; AGPU_PRIO / AGPU_TIER_CTAS / AGPU_DECODE_CTAS override them for experiments)
+    struct Tune {
+        int prio = 1;                                  // back half of a chunk on high-priority streams
+        int tier_ctas[AGPU_NTIERS] = {3, 16, 8, 1};    // persistent quad-fit CTAs per SM, by size tier
+        int decode_ctas = 4;                           // persistent decode CTAs per SM
+    } tune;
     DevBuf d_fams, d_codes, d_pose_in, d_pose_out;
     std::vector<Slot> slots;
     cudaEvent_t ev_user = nullptr;
@@ -205,12 +213,21 @@ int gaussian_kernel_host(float sigma, uint8_t* k) {
 
 int init_slot(agpu_handle* h, Slot& s) {
     if (s.stream) return AGPU_OK;
-    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    // The back half of a chunk is a handful of persistent, latency-bound kernels; the front half of the NEXT chunks
+    // are huge grids of short CTAs.  Giving the back half the higher stream priority lets its CTAs take the SM
+    // slots that the streaming kernels free all the time, so both kinds of work share every SM instead of
+    // alternating kernel by kernel.
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (!h->tune.prio) prio_hi = prio_lo;
+    CK(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&s.tail, cudaStreamNonBlocking, prio_hi));
     for (int t = 0; t < AGPU_NTIERS - 1; t++) {
-        CK(cudaStreamCreateWithFlags(&s.aux[t], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&s.aux[t], cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&s.ev_join[t], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_mid, cudaEventDisableTiming));
     return AGPU_OK;
 }
 
@@ -219,14 +236,14 @@ struct StageTimer {
     Slot& s;
     size_t next = 0;
     StageTimer(agpu_handle* hh, Slot& ss) : h(hh), s(ss) {}
-    void mark() {
+    void mark(cudaStream_t st = nullptr) {
         if (!h->profiling) return;
         if (next >= s.events.size()) {
             cudaEvent_t e;
             cudaEventCreate(&e);
             s.events.push_back(e);
         }
-        cudaEventRecord(s.events[next++], s.stream);
+        cudaEventRecord(s.events[next++], st ? st : s.stream);
     }
 };
 
@@ -344,19 +361,23 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
 }
 
 int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const Geom& g, int* d_nroots, int* d_ndense,
-                 bool flatten) {
+                 bool canonical) {
     CK(sl.d_labels.ensure(g.plane * n * 4));
     CK(sl.d_sizes.ensure(g.plane * n * 4));
-    const int tx = ceil_div(g.wd, CC_TW), ty = ceil_div(g.hd, CC_TH);
+    const int tx = cc_tiles_x(g), ty = cc_tiles_y(g);
+    CK(sl.d_masks.ensure((size_t)tx * ty * n * 32 * sizeof(uint2)));
+    CK(sl.d_l16.ensure((size_t)tx * ty * n * 1024 * sizeof(uint16_t)));
     // a root sub-list (tile rows r with r % 16 == s) can never hold more than 512 roots per tile
     const size_t sub_stride = (size_t)tx * ceil_div(ty, CC_SUBLISTS) * 512;
     CK(sl.d_roots.ensure(sub_stride * CC_SUBLISTS * n * 4));
     dim3 grid(ceil_div(tx, CC_WARPS), ty, n);
-    k_cc_local<<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
+    k_cc_local<<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
+                                                   sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
                                                    sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
     LAUNCH_CHECK("k_cc_local");
-    dim3 gridb(ceil_div((long long)tx * ty * CCB_ITEMS, 256), 1, n);
-    k_cc_boundary<<<gridb, 256, 0, sl.stream>>>(d_thresh, sl.d_labels.as<uint32_t>(), g, tx, ty);
+    dim3 gridb(ceil_div(tx * ty, CCB_WARPS), 1, n);
+    k_cc_boundary<<<gridb, CCB_WARPS * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
+                                                           sl.d_labels.as<uint32_t>(), g);
     LAUNCH_CHECK("k_cc_boundary");
     dim3 grids(std::max(1, std::min(8, ceil_div(g.plane / 1024, 256))), n * CC_SUBLISTS);
     k_cc_sizes<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
@@ -369,10 +390,12 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
                                                  d_nroots, sl.d_dense.as<uint32_t>(), sl.d_dense2rep.as<uint32_t>(), d_ndense, g, sub_stride);
         LAUNCH_CHECK("k_cc_dense");
     }
-    if (flatten) {
-        dim3 gridf(ceil_div(g.wd, CCF_TW), ceil_div(g.hd, CCF_TH), n);
-        k_cc_flatten<<<gridf, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), g);
-        LAUNCH_CHECK("k_cc_flatten");
+    if (canonical) {   // stage dumps only
+        CK(sl.d_canon.ensure(g.plane * n * 4));
+        dim3 gridf(ceil_div(g.wd, 32), ceil_div(g.hd, 8), n);
+        k_cc_canonical<<<gridf, 256, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
+                                                     sl.d_labels.as<uint32_t>(), sl.d_canon.as<uint32_t>(), g);
+        LAUNCH_CHECK("k_cc_canonical");
     }
     return AGPU_OK;
 }
@@ -484,10 +507,10 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     if (rc) return rc;
     tm.mark();  // 3: after CC
     {
-        dim3 grid(n, ceil_div(g.wp >> 2, 32 * EDGE_WORDS), ceil_div(g.hd - 1, 8));
-        k_edges<<<grid, 256, 0, sl.stream>>>(sl.d_thresh.as<uint8_t>(), sl.d_labels.as<uint32_t>(),
-                                             sl.d_sizes.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g,
-                                             sl.d_recs[0].as<unsigned long long>(), d_npts, cap, c.id_bits);
+        dim3 grid(n, ceil_div(cc_tiles_x(g), EDGE_WARPS), cc_tiles_y(g));
+        k_edges<<<grid, EDGE_WARPS * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
+                                                         sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g,
+                                                         sl.d_recs[0].as<unsigned long long>(), d_npts, cap, c.id_bits);
         LAUNCH_CHECK("k_edges");
     }
     tm.mark();  // 4: after edges
@@ -534,14 +557,16 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         qa.per_frame_quads = d_frame_quads;
         // the tiers are independent (own work list, atomic appends to the quad list): fork them over side
         // streams so that the latency-bound big-cluster warps overlap with the many small clusters
-        CK(cudaEventRecord(sl.ev_fork, sl.stream));
+        CK(cudaEventRecord(sl.ev_mid, sl.stream));
+        CK(cudaStreamWaitEvent(sl.tail, sl.ev_mid, 0));
+        CK(cudaEventRecord(sl.ev_fork, sl.tail));
         for (int t = AGPU_NTIERS - 1; t >= 0; t--) {
-            cudaStream_t st = t == 0 ? sl.stream : sl.aux[t - 1];
+            cudaStream_t st = t == 0 ? sl.tail : sl.aux[t - 1];
             if (t > 0) CK(cudaStreamWaitEvent(st, sl.ev_fork, 0));
             qa.list = sl.d_clusters[t].as<ClusterRef>();
             qa.list_count = d_cnt + CNT_TIER0 + t;
             qa.cursor = d_cnt + CNT_CURSOR0 + t;
-            const int nblk = h->num_sms * TIER_CTAS_PER_SM[t];
+            const int nblk = h->num_sms * h->tune.tier_ctas[t];
             if (t == 0) {
                 const size_t smem = 8 * qf_smem_per_group(TIER_CAP[t], 1);
                 k_fit_quads<1><<<nblk, 256, smem, st>>>(qa, h->prm, TIER_CAP[t]);
@@ -555,11 +580,11 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             LAUNCH_CHECK("k_fit_quads");
             if (t > 0) {
                 CK(cudaEventRecord(sl.ev_join[t - 1], st));
-                CK(cudaStreamWaitEvent(sl.stream, sl.ev_join[t - 1], 0));
+                CK(cudaStreamWaitEvent(sl.tail, sl.ev_join[t - 1], 0));
             }
         }
     }
-    tm.mark();  // 6: after quads
+    tm.mark(sl.tail);  // 6: after quads
     {
         DecodeArgs da;
         da.im = gray_full; da.pitch = gray_pitch; da.frame_stride = gray_frame;
@@ -573,11 +598,11 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         da.ndets = d_ndets;
         da.cap_dets = REC_CAP;
         da.dbg_refined = h->cfg.debug ? sl.d_refined.as<float>() : nullptr;
-        k_decode_quads<<<h->num_sms * 4, 128, 0, sl.stream>>>(da, h->prm);
+        k_decode_quads<<<h->num_sms * h->tune.decode_ctas, 128, 0, sl.tail>>>(da, h->prm);
         LAUNCH_CHECK("k_decode_quads");
     }
-    tm.mark();  // 7: after decode
-    k_reconcile<<<ceil_div(n, 4), 128, 0, sl.stream>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
+    tm.mark(sl.tail);  // 7: after decode
+    k_reconcile<<<ceil_div(n, 4), 128, 0, sl.tail>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
                                                       sl.d_out.as<DetRec>(), d_out_counts, c.cap_out);
     LAUNCH_CHECK("k_reconcile");
     if (c.pose->enabled) {
@@ -589,16 +614,16 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         pa.per_frame = c.cap_out;
         pa.M = n * c.cap_out;
         pa.out = sl.d_poses.as<PoseRec>();
-        k_pose<<<ceil_div((long long)pa.M * 4, 128), 128, 0, sl.stream>>>(pa);
+        k_pose<<<ceil_div((long long)pa.M * 4, 128), 128, 0, sl.tail>>>(pa);
         LAUNCH_CHECK("k_pose");
     }
-    tm.mark();  // 8: after reconcile/pose
-    CK(cudaMemcpyAsync(sl.h_counts.p, d_cnt, c.ncnt * 4, cudaMemcpyDeviceToHost, sl.stream));
-    CK(cudaMemcpyAsync(sl.h_out.p, sl.d_out.p, (size_t)n * c.cap_out * sizeof(DetRec), cudaMemcpyDeviceToHost, sl.stream));
+    tm.mark(sl.tail);  // 8: after reconcile/pose
+    CK(cudaMemcpyAsync(sl.h_counts.p, d_cnt, c.ncnt * 4, cudaMemcpyDeviceToHost, sl.tail));
+    CK(cudaMemcpyAsync(sl.h_out.p, sl.d_out.p, (size_t)n * c.cap_out * sizeof(DetRec), cudaMemcpyDeviceToHost, sl.tail));
     if (c.pose->enabled)
         CK(cudaMemcpyAsync(sl.h_poses.p, sl.d_poses.p, (size_t)n * c.cap_out * sizeof(PoseRec), cudaMemcpyDeviceToHost,
-                           sl.stream));
-    tm.mark();  // 9: after D2H
+                           sl.tail));
+    tm.mark(sl.tail);  // 9: after D2H
     sl.pending = true;
     sl.b0 = b0;
     sl.n = n;
@@ -614,7 +639,7 @@ struct Overflow {
 // wait for the slot's chunk and move its results into the caller's arrays; 1 = a work list overflowed (redo)
 int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out, agpu_pose_t* poses, int* counts,
                  Overflow& ov, int& rc_final) {
-    CK(cudaStreamSynchronize(sl.stream));
+    CK(cudaStreamSynchronize(sl.tail));   // (ordered after everything on sl.stream through ev_mid)
     sl.pending = false;
     const int n = sl.n, b0 = sl.b0, chunk = c.chunk;
     if (h->profiling) {
@@ -827,6 +852,13 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     h->cfg = *cfg;
     h->families_str = cfg->families;
     h->cfg.families = h->families_str.c_str();
+    if (const char* e = getenv("AGPU_PRIO")) h->tune.prio = atoi(e) != 0;
+    if (const char* e = getenv("AGPU_DECODE_CTAS")) h->tune.decode_ctas = std::max(1, std::min(16, atoi(e)));
+    if (const char* e = getenv("AGPU_TIER_CTAS")) {
+        int v[AGPU_NTIERS];
+        if (sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+            for (int t = 0; t < AGPU_NTIERS; t++) h->tune.tier_ctas[t] = std::max(1, std::min(32, v[t]));
+    }
     auto fail = [&](int rc, const std::string& msg) {
         g_create_error = msg;
         delete h;
@@ -939,6 +971,7 @@ int agpu_destroy(agpu_handle* h) {
     cudaSetDevice(h->device);
     for (Slot& s : h->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.tail) cudaStreamSynchronize(s.tail);
         s.release();
     }
     h->d_fams.release(); h->d_codes.release(); h->d_pose_in.release(); h->d_pose_out.release();
@@ -1068,7 +1101,7 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
     if (w == "labels" || w == "sizes") {
         if ((size_t)cap_bytes < npx * 4) return (long long)npx;
         std::vector<uint32_t> tmp(g.plane), lab;
-        const uint32_t* src = (w == "labels" ? sl.d_labels.as<uint32_t>() : sl.d_sizes.as<uint32_t>()) + (size_t)frame * g.plane;
+        const uint32_t* src = (w == "labels" ? sl.d_canon.as<uint32_t>() : sl.d_sizes.as<uint32_t>()) + (size_t)frame * g.plane;
         if (cudaMemcpy(tmp.data(), src, g.plane * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
         uint32_t* o = (uint32_t*)host_out;
         if (w == "labels") {
@@ -1077,7 +1110,7 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
         } else {
             lab.resize(g.plane);
             std::vector<uint8_t> th(g.plane);
-            cudaMemcpy(lab.data(), sl.d_labels.as<uint32_t>() + (size_t)frame * g.plane, g.plane * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(lab.data(), sl.d_canon.as<uint32_t>() + (size_t)frame * g.plane, g.plane * 4, cudaMemcpyDeviceToHost);
             cudaMemcpy(th.data(), sl.d_thresh.as<uint8_t>() + (size_t)frame * g.plane, g.plane, cudaMemcpyDeviceToHost);
             for (int y = 0; y < g.hd; y++)
                 for (int x = 0; x < g.wd; x++) {
@@ -1215,7 +1248,7 @@ int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint3
     int rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), 1, g, sl.d_counters.as<int>(), nullptr, true);
     if (rc) return rc;
     std::vector<uint32_t> lab(g.plane), sz(g.plane);
-    CK(cudaMemcpyAsync(lab.data(), sl.d_labels.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaMemcpyAsync(lab.data(), sl.d_canon.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));
     CK(cudaMemcpyAsync(sz.data(), sl.d_sizes.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));
     CK(cudaStreamSynchronize(sl.stream));
     for (int y = 0; y < H; y++)

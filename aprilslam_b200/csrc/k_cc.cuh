@@ -5,14 +5,24 @@
 // links to its equal-valued neighbours left (x-1, y) and, for y >= 1, up (x, y-1); white (255)
 // pixels additionally link up-left and up-right.  Columns 0 and w-1 never initiate links.
 //
+// Data layout (per frame, TILE-MAJOR: tile t = ty * tiles_x + tx covers 32x32 pixels):
+//   masks  uint2 [tiles][32]     row r of the tile as two bit masks {white, black} (bit c = column c); everything
+//                                downstream of the local pass (boundary merge, edge points) works on these
+//                                2 bits per pixel instead of the threshold bytes
+//   l16    u16   [tiles][1024]   SPARSE: defined only at the first pixel of every run; the tile-local root of the
+//                                run as a local pixel id (row * 32 + col).  A pixel finds its run start with two
+//                                bit operations on its row mask, so no per-pixel label image is ever written.
+//   links  u32   [plane]         SPARSE: union-find parent links between tile-local roots, indexed by raster pixel
+//                                id y * wp + x (root of a set = its smallest pixel id: canonical by construction)
+//
 // Kernels (block-local union-find + boundary merge + sizes [+ canonical relabel]):
 //   k_cc_local    32x32-pixel tile per warp, bit-parallel row runs + union-find over runs in shared memory
-//                 (atomicMin hooks: the root of a set is always its smallest pixel id); writes labels as
-//                 global pixel ids, the pixel count of every tile-local root, and the list of those roots.
-//   k_cc_boundary one thread per tile-border pixel, lock-free unions across tile edges in global memory.
+//                 (atomicMin hooks: the root of a set is always its smallest pixel id); writes the masks, the
+//                 run-start labels, the pixel count of every tile-local root, and the list of those roots.
+//   k_cc_boundary one warp per tile, bit-parallel contact tests along the tile's top / left / right border,
+//                 lock-free unions between the tile-local roots in global memory.
 //   k_cc_sizes    folds the counts of the tile-local roots into the final roots.
-//   k_cc_flatten  pointer jumping to the global root (= smallest pixel id of the component, so the
-//                 labelling is canonical by construction); only needed for the stage dumps, the
+//   k_cc_canonical per-pixel canonical labels (smallest pixel id of the component); stage dumps only, the
 //                 pipeline resolves representatives on the fly.
 #pragma once
 #include "common.cuh"
@@ -24,10 +34,6 @@
 #define CC_THREADS (CC_WARPS * 32)
 #define CC_SUBLISTS 16   // root sub-lists per frame (tile row mod 16): spreads the append atomics over 16 counters
 #define CC_PITCH 33   // run-start slots of row r live at r*33 + c (16-bit entries)
-// tile of the flatten pass (8-pixel runs per thread)
-#define CCF_TW 64
-#define CCF_TH 32
-#define CC_RUN 8
 
 __device__ __forceinline__ uint32_t gfind(const uint32_t* L, uint32_t a) {
     uint32_t p = __ldcg(&L[a]);
@@ -100,14 +106,44 @@ __device__ __forceinline__ uint32_t run_mask(uint32_t cont, int s) {
     return hi & ~((1u << s) - 1u);
 }
 
+__host__ __device__ __forceinline__ int cc_tiles_x(const Geom& g) { return (g.wd + CC_TW - 1) / CC_TW; }
+__host__ __device__ __forceinline__ int cc_tiles_y(const Geom& g) { return (g.hd + CC_TH - 1) / CC_TH; }
+__host__ __device__ __forceinline__ size_t cc_tile_index(const Geom& g, int frame, int tx, int ty) {
+    return ((size_t)frame * cc_tiles_y(g) + ty) * cc_tiles_x(g) + tx;
+}
+
+// initiator columns of the tile column block that starts at x0: 1 <= x <= wd-2
+__device__ __forceinline__ uint32_t cc_initiators(int x0, int wd) {
+    const int ncols = min(32, wd - x0);
+    uint32_t I = ncols >= 32 ? 0xffffffffu : (ncols <= 0 ? 0u : ((1u << ncols) - 1u));
+    if (x0 == 0) I &= ~1u;
+    if (wd - 1 - x0 < 32 && wd - 1 - x0 >= 0) I &= ~(1u << (wd - 1 - x0));
+    return I;
+}
+
+// first column of the run that contains column c (M: the row mask of the pixel's own colour, bit c set)
+__device__ __forceinline__ int cc_run_start(uint32_t M, uint32_t I, int c) {
+    const uint32_t S = M & ~(M & (M << 1) & I);
+    return 31 - __clz(S & (0xffffffffu >> (31 - c)));
+}
+
+// tile-local root (as raster pixel id) of the foreground pixel (column c, row r) of tile `tile` at (x0, y0)
+__device__ __forceinline__ uint32_t cc_pixel_root(const uint16_t* __restrict__ l16, size_t tile, int x0, int y0, int r,
+                                                  int c, uint32_t M, uint32_t I, int wp) {
+    const int s = cc_run_start(M, I, c);
+    const uint32_t loc = l16[tile * 1024 + r * 32 + s];
+    return (uint32_t)((y0 + (int)(loc >> 5)) * wp + x0 + (int)(loc & 31u));
+}
+
 // Local pass, bit-parallel.  A lane owns one ROW of the 32x32 tile as two bit masks (white / black); the runs of
 // the row come from shifts and ANDs of the lane's own word, the contacts with the row above from the masks of
 // the lane above (one shuffle), and only runs -- not pixels -- take part in the shared-memory union-find.
 // Besides the labels the pass leaves, for every tile-local root: its pixel count in sizes[] and its id in the
 // frame's root list (k_cc_sizes folds the counts into the final roots after the boundary merges).
 __global__ void __launch_bounds__(CC_THREADS)
-k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes,
-           uint32_t* __restrict__ roots, int* __restrict__ nroots, Geom g, size_t sub_stride) {
+k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16_t* __restrict__ l16,
+           uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, uint32_t* __restrict__ roots,
+           int* __restrict__ nroots, Geom g, size_t sub_stride) {
     __shared__ __align__(16) uint16_t sL[CC_WARPS][CC_TH * CC_PITCH + 8];   // parent links, then pixel counters
     __shared__ __align__(16) uint16_t sX[CC_WARPS][CC_TH * CC_PITCH + 8];   // root of every run
     const int frame = blockIdx.z;
@@ -140,10 +176,10 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
     const uint32_t V = ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u);
     Wm &= V;
     Bm &= V;
-    // initiator columns: 1 <= x <= w-2
-    uint32_t I = V;
-    if (x0 == 0) I &= ~1u;
-    if (g.wd - 1 - x0 < 32) I &= ~(1u << (g.wd - 1 - x0));
+    const size_t tile = cc_tile_index(g, frame, blockIdx.x * CC_WARPS + w, blockIdx.y);
+    masks[tile * 32 + lane] = make_uint2(Wm, Bm);
+    if (!__any_sync(FULL_MASK, (Wm | Bm) != 0u)) return;   // nothing but 127-pixels: no runs, no labels
+    const uint32_t I = cc_initiators(x0, g.wd);   // initiator columns: 1 <= x <= w-2
     const uint32_t cw = Wm & (Wm << 1) & I, cb = Bm & (Bm << 1) & I;   // bit x: x continues the run of x-1
     const uint32_t Sw = Wm & ~cw, Sb = Bm & ~cb;                       // run starts
     const uint32_t S = Sw | Sb;
@@ -238,72 +274,110 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, ui
             if (X[cc_slot(rid0 + s)] == rid0 + s) {
                 const uint32_t gid = (uint32_t)(y * g.wp + x0 + s);   // a root is a run of this very row
                 fs[gid] = L[cc_slot(rid0 + s)];
+                fl[gid] = gid;
                 fr[o++] = gid;
             }
         }
     }
-    // ---- labels: every pixel of a run gets the global id of the run's root, everything else its own id
-    if (y < g.hd) {
-        const uint32_t own0 = (uint32_t)(y * g.wp + x0);
-        const uint32_t fg = Wm | Bm;
-        uint32_t cur = 0;
-        uint4* dst = reinterpret_cast<uint4*>(fl + (size_t)y * g.wp + x0);
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            uint32_t o4[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int c = q * 4 + k;
-                if ((S >> c) & 1u) {
-                    const uint32_t r = X[cc_slot(rid0 + c)];
-                    cur = (uint32_t)((y0 + (int)(r >> 5)) * g.wp + x0 + (int)(r & 31));
-                }
-                o4[k] = ((fg >> c) & 1u) ? cur : own0 + c;
-            }
-            if (q < 4 || second) dst[q] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+    // ---- run-start labels: the tile-local root of every run (sparse, 2 bytes per run)
+    {
+        uint16_t* tl = l16 + tile * 1024 + lane * 32;
+        for (uint32_t m = S; m; m &= m - 1) {
+            const int c = __ffs(m) - 1;
+            tl[c] = X[cc_slot(rid0 + c)];
         }
     }
 }
 
-// One thread per tile-border pixel (top row, left column, right column of every 32x32 tile): lock-free unions
-// across tile borders.  As in the local pass only the first pixel of every contact issues a union.
-#define CCB_ITEMS (CC_TW + 2 * CC_TH)
-__global__ void __launch_bounds__(256)
-k_cc_boundary(const uint8_t* __restrict__ thresh, uint32_t* __restrict__ labels, Geom g, int tiles_x, int tiles_y) {
+// Boundary merge: one warp per tile.  All contact tests are bit operations on the row masks of the tile and of its
+// left / right / upper neighbours; only real, non-implied contacts reach the lock-free union in global memory, and
+// the unions run between TILE-LOCAL ROOTS (found through the run-start labels), never between pixels.
+// As in the local pass only initiator pixels (1 <= x <= wd-2) issue links: left and up for both colours, up-left
+// and up-right for white.  Top row: lane = column; left / right column: lane = row.
+#define CCB_WARPS 8
+__device__ __forceinline__ uint2 cc_ld_mask(const uint2* __restrict__ fm, const Geom& g, int tx, int ty, int r) {
+    if (tx < 0 || ty < 0 || tx >= cc_tiles_x(g) || ty >= cc_tiles_y(g)) return make_uint2(0u, 0u);
+    return __ldg(&fm[((size_t)ty * cc_tiles_x(g) + tx) * 32 + r]);
+}
+
+__global__ void __launch_bounds__(CCB_WARPS * 32)
+k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, uint32_t* __restrict__ labels, Geom g) {
     const int frame = blockIdx.z;
-    const uint8_t* ft = thresh + (size_t)frame * g.plane;
-    uint32_t* fl = labels + (size_t)frame * g.plane;
-    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)tiles_x * tiles_y * CCB_ITEMS;
-    if (item >= total) return;
-    const int tile = (int)(item / CCB_ITEMS), t = (int)(item - (long long)tile * CCB_ITEMS);
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int lane = threadIdx.x & 31;
+    const int tiles_x = cc_tiles_x(g), tiles_y = cc_tiles_y(g);
+    const int t = blockIdx.x * CCB_WARPS + (threadIdx.x >> 5);
+    if (t >= tiles_x * tiles_y) return;
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int x0 = tx * CC_TW, y0 = ty * CC_TH;
-    int x, y;
-    if (t < CC_TW) { x = x0 + t; y = y0; }
-    else if (t < CC_TW + CC_TH) { x = x0; y = y0 + (t - CC_TW); if (t == CC_TW) return; }          // corner: top row's job
-    else { x = x0 + CC_TW - 1; y = y0 + (t - CC_TW - CC_TH); if (t == CC_TW + CC_TH) return; }
-    if (x < 1 || x > g.wd - 2 || y >= g.hd) return;
-    const uint8_t* row = ft + (size_t)y * g.wp;
-    const uint8_t c = row[x];
-    if (c == 127) return;
-    const uint32_t id = (uint32_t)(y * g.wp + x);
-    const bool left_edge = (x == x0), top_edge = (y == y0), right_edge = (x == x0 + CC_TW - 1);
-    const uint8_t* up = y >= 1 ? row - g.wp : nullptr;
-    if (left_edge && row[x - 1] == c) {
-        // implied when the row above carries the same contact and both pixels hang on it
-        const bool implied = !top_edge && y >= 1 && up[x] == c && up[x - 1] == c && x - 1 >= 1;
-        if (!implied) gunion(fl, id, id - 1);
-    }
-    if (y >= 1) {
-        const bool upsame = up[x] == c;
-        if (top_edge && upsame) {
-            const bool implied = x - 1 >= 1 && row[x - 1] == c && up[x - 1] == c;
-            if (!implied) gunion(fl, id, id - g.wp);
+    const uint2* fm = masks + (size_t)frame * tiles_x * tiles_y * 32;
+    const uint16_t* f16 = l16 + (size_t)frame * tiles_x * tiles_y * 1024;
+    uint32_t* fl = labels + (size_t)frame * g.plane;
+    const uint2 M = fm[(size_t)t * 32 + lane];
+    if (!__any_sync(FULL_MASK, (M.x | M.y) != 0u)) return;
+    const uint2 ML = cc_ld_mask(fm, g, tx - 1, ty, lane), MR = cc_ld_mask(fm, g, tx + 1, ty, lane);
+    const uint32_t I = cc_initiators(x0, g.wd), IL = cc_initiators(x0 - 32, g.wd), IR = cc_initiators(x0 + 32, g.wd);
+    const size_t tl = (size_t)t, tL = tl - 1, tR = tl + 1, tU = tl - tiles_x;
+
+    // ---- top row of the tile (y = y0): lane = column
+    {
+        const uint2 R0 = make_uint2(__shfl_sync(FULL_MASK, M.x, 0), __shfl_sync(FULL_MASK, M.y, 0));
+        const uint2 L0 = make_uint2(__shfl_sync(FULL_MASK, ML.x, 0), __shfl_sync(FULL_MASK, ML.y, 0));
+        const uint2 U = cc_ld_mask(fm, g, tx, ty - 1, 31), UL = cc_ld_mask(fm, g, tx - 1, ty - 1, 31),
+                    UR = cc_ld_mask(fm, g, tx + 1, ty - 1, 31);
+        const int c = lane, x = x0 + c;
+        if ((I >> c) & 1u) {
+#pragma unroll
+            for (int col = 0; col < 2; col++) {   // 0: white, 1: black
+                const uint32_t P0 = col ? R0.y : R0.x;
+                if (!((P0 >> c) & 1u)) continue;
+                const uint32_t PL0 = col ? L0.y : L0.x, PU = col ? U.y : U.x, PUL = col ? UL.y : UL.x, PUR = col ? UR.y : UR.x;
+                const bool row_l = c > 0 ? ((P0 >> (c - 1)) & 1u) : (PL0 >> 31);
+                const bool up_c = (PU >> c) & 1u;
+                const bool up_l = c > 0 ? ((PU >> (c - 1)) & 1u) : (PUL >> 31);
+                const bool up_r = c < 31 ? ((PU >> (c + 1)) & 1u) : (PUR & 1u);
+                const bool do_left = c == 0 && row_l;
+                const bool do_up = up_c && !(x - 1 >= 1 && row_l && up_l);
+                const bool do_ul = col == 0 && up_l && !up_c;
+                const bool do_ur = col == 0 && up_r && (!up_c || x + 1 > g.wd - 2);
+                if (!(do_left || do_up || do_ul || do_ur)) continue;
+                const uint32_t me = cc_pixel_root(f16, tl, x0, y0, 0, c, P0, I, g.wp);
+                if (do_left) gunion(fl, me, cc_pixel_root(f16, tL, x0 - 32, y0, 0, 31, PL0, IL, g.wp));
+                if (do_up) gunion(fl, me, cc_pixel_root(f16, tU, x0, y0 - 32, 31, c, PU, I, g.wp));
+                if (do_ul) {
+                    if (c > 0) gunion(fl, me, cc_pixel_root(f16, tU, x0, y0 - 32, 31, c - 1, PU, I, g.wp));
+                    else gunion(fl, me, cc_pixel_root(f16, tU - 1, x0 - 32, y0 - 32, 31, 31, PUL, IL, g.wp));
+                }
+                if (do_ur) {
+                    if (c < 31) gunion(fl, me, cc_pixel_root(f16, tU, x0, y0 - 32, 31, c + 1, PU, I, g.wp));
+                    else gunion(fl, me, cc_pixel_root(f16, tU + 1, x0 + 32, y0 - 32, 31, 0, PUR, IR, g.wp));
+                }
+            }
         }
-        if (c == 255) {
-            if ((top_edge || left_edge) && up[x - 1] == c && !upsame) gunion(fl, id, id - g.wp - 1);
-            if ((top_edge || right_edge) && up[x + 1] == c && (!upsame || x + 1 > g.wd - 2)) gunion(fl, id, id - g.wp + 1);
+    }
+    // ---- left and right column (rows 1..31; the corners belong to the top row): lane = row
+    const uint2 Mu = make_uint2(__shfl_up_sync(FULL_MASK, M.x, 1), __shfl_up_sync(FULL_MASK, M.y, 1));
+    const uint2 MLu = make_uint2(__shfl_up_sync(FULL_MASK, ML.x, 1), __shfl_up_sync(FULL_MASK, ML.y, 1));
+    const uint32_t MRu_w = __shfl_up_sync(FULL_MASK, MR.x, 1);
+    if (lane == 0 || y0 + lane >= g.hd) return;
+    if (I & 1u) {   // x = x0 is an initiator (x0 >= 1: there is a left tile)
+#pragma unroll
+        for (int col = 0; col < 2; col++) {
+            const uint32_t P = col ? M.y : M.x;
+            if (!(P & 1u)) continue;
+            const uint32_t PL = col ? ML.y : ML.x, Pu = col ? Mu.y : Mu.x, PLu = col ? MLu.y : MLu.x;
+            const bool left = PL >> 31, up = Pu & 1u, upleft = PLu >> 31;
+            const bool do_left = left && !(up && upleft);
+            const bool do_ul = col == 0 && upleft && !up;
+            if (!(do_left || do_ul)) continue;
+            const uint32_t me = cc_pixel_root(f16, tl, x0, y0, lane, 0, P, I, g.wp);
+            if (do_left) gunion(fl, me, cc_pixel_root(f16, tL, x0 - 32, y0, lane, 31, PL, IL, g.wp));
+            if (do_ul) gunion(fl, me, cc_pixel_root(f16, tL, x0 - 32, y0, lane - 1, 31, PLu, IL, g.wp));
+        }
+    }
+    if ((I >> 31) & 1u) {   // x = x0 + 31 is an initiator: white up-right contact into the right tile
+        if ((M.x >> 31) && (MRu_w & 1u) && (!(Mu.x >> 31) || x0 + 32 > g.wd - 2)) {
+            const uint32_t me = cc_pixel_root(f16, tl, x0, y0, lane, 31, M.x, I, g.wp);
+            gunion(fl, me, cc_pixel_root(f16, tR, x0 + 32, y0, lane - 1, 0, MRu_w, IR, g.wp));
         }
     }
 }
@@ -357,34 +431,25 @@ k_cc_dense(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ siz
     }
 }
 
-// Pointer jumping to the global root (= smallest pixel id of the component): the canonical labelling.  The
-// pipeline itself resolves representatives on the fly (k_edges); this pass runs for the stage dumps.
+// Canonical per-pixel labels (smallest pixel id of the component; 127-pixels are singletons) for the stage dumps.
+// The pipeline itself never materialises a label image: k_edges resolves representatives on the fly.
 __global__ void __launch_bounds__(256)
-k_cc_flatten(uint32_t* __restrict__ labels, Geom g) {
+k_cc_canonical(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
+               uint32_t* __restrict__ out, Geom g) {
     const int frame = blockIdx.z;
-    const int x0 = blockIdx.x * CCF_TW, y0 = blockIdx.y * CCF_TH;
-    uint32_t* fl = labels + (size_t)frame * g.plane;
-    const int t = threadIdx.x;
-    const int ry = t >> 3, rx = (t & 7) * CC_RUN;
-    const int gy = y0 + ry, gx = x0 + rx;
-    if (gy < g.hd && gx < g.wp) {
-        uint4* lp = reinterpret_cast<uint4*>(fl + (size_t)gy * g.wp + gx);
-        uint4 a = __ldcg(lp), b = __ldcg(lp + 1);
-        uint32_t lab[CC_RUN] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t root[CC_RUN];
-        uint32_t prev_lab = 0xffffffffu, prev_root = 0;
-        bool changed = false;
-#pragma unroll
-        for (int k = 0; k < CC_RUN; k++) {
-            uint32_t r = lab[k] == prev_lab ? prev_root : gfind(fl, lab[k]);
-            prev_lab = lab[k];
-            prev_root = r;
-            root[k] = r;
-            changed |= (r != lab[k]);
-        }
-        if (changed) {
-            lp[0] = make_uint4(root[0], root[1], root[2], root[3]);
-            lp[1] = make_uint4(root[4], root[5], root[6], root[7]);
-        }
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= g.wd || y >= g.hd) return;
+    const int tiles_x = cc_tiles_x(g), tiles_y = cc_tiles_y(g);
+    const int tx = x >> 5, ty = y >> 5, c = x & 31, r = y & 31;
+    const size_t t = (size_t)ty * tiles_x + tx;
+    const uint2 M = masks[((size_t)frame * tiles_x * tiles_y + t) * 32 + r];
+    const uint32_t id = (uint32_t)(y * g.wp + x);
+    uint32_t lab = id;
+    const uint32_t P = ((M.x >> c) & 1u) ? M.x : (((M.y >> c) & 1u) ? M.y : 0u);
+    if (P) {
+        const uint32_t root = cc_pixel_root(l16 + (size_t)frame * tiles_x * tiles_y * 1024, t, tx * 32, ty * 32, r, c, P,
+                                            cc_initiators(tx * 32, g.wd), g.wp);
+        lab = gfind(labels + (size_t)frame * g.plane, root);
     }
+    out[(size_t)frame * g.plane + id] = lab;
 }

@@ -1,10 +1,10 @@
 // k_cluster.cuh -- gradient-edge clusters (upstream stage U5; part of the native call
 // at /root/reference/src/detection/tag_detector.py:26).
 //
-//   k_edges          four pixels per thread: emits up to four edge points per pixel as ONE 64-bit record
-//                    (pair key << 32) | packed point, the key being the unordered pair of the two
-//                    components' dense 16-bit ids (k_cc_dense); records go to the frame's own segment
-//                    of the point list (warp-aggregated atomics).
+//   k_edges          one warp per 32x32 tile on the bit masks: emits up to four edge points per pixel as ONE
+//                    64-bit record (pair key << 32) | packed point, the key being the unordered pair of the
+//                    two components' dense ids (k_cc_dense); records go to the frame's own segment of the
+//                    point list (warp-aggregated atomics).
 //   k_sort_hist / k_sort_scan / k_sort_scatter
 //                    hand-written SEGMENTED least-significant-digit radix sort (8-bit digits, stable):
 //                    every frame's segment is sorted independently, grid = (blocks, frames).
@@ -13,139 +13,138 @@
 #include "common.cuh"
 #include "k_cc.cuh"
 
-// Four pixels (one 32-bit word of the threshold image) per thread.  An edge between v0 and v1 means
-// v0 ^ v1 == 0xff (values are 0 / 127 / 255), tested for all four pixels and one direction at a time with
-// three word operations; the vast majority of warps see no edge and leave after five word loads.  The
-// (pixel, direction) candidates of a warp are compacted through shared memory and then handled ONE PER LANE
-// (label + size look-ups, ballot compaction, one atomic per 32 candidates), so the expensive part is not
-// serialised inside the few threads that sit on an edge.
-#define EDGE_WORDS 4                                  // 16 pixels (one 128-bit load) per thread
-#define EDGE_CAND_PER_WARP (32 * EDGE_WORDS * 16)     // lanes x pixels x directions
-__global__ void __launch_bounds__(256)
-k_edges(const uint8_t* __restrict__ thresh, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes,
+// One warp per 32x32 tile, lane = row, everything on the tile-major bit masks of k_cc_local (2 bits per pixel).
+// An edge between v0 and v1 (one white, one black) in direction d is one AND of the row's white mask with the
+// neighbour row's shifted black mask (and vice versa): a lane tests its 32 pixels x 4 directions with ~20 bit
+// operations, and a tile without any edge leaves after three coalesced 256-byte loads.  The (pixel, direction)
+// candidates of a warp are compacted through shared memory and then handled ONE PER LANE (run-start label +
+// representative + dense-id look-ups, ballot compaction, one atomic per 32 candidates), so the expensive part is
+// not serialised inside the few rows that sit on an edge.
+#define EDGE_WARPS 8
+#define EDGE_CAND_PER_PASS (16 * 32 * 4)   // rows of one half tile x columns x directions
+__global__ void __launch_bounds__(EDGE_WARPS * 32)
+k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
         const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts, int cap,
         int id_bits) {
-    __shared__ uint16_t scand[8][EDGE_CAND_PER_WARP];
-    // grid = (frames, x blocks, y blocks): consecutive CTAs belong to DIFFERENT frames, so the per-frame append
+    __shared__ uint16_t scand[EDGE_WARPS][EDGE_CAND_PER_PASS];
+    // grid = (frames, x blocks, tile rows): consecutive CTAs belong to DIFFERENT frames, so the per-frame append
     // counters are not hammered by every resident warp at once
     const int frame = blockIdx.x;
-    const uint8_t* ft = thresh + (size_t)frame * g.plane;
-    const uint32_t* fl = labels + (size_t)frame * g.plane;
-    const uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const uint32_t* fd = dense + (size_t)frame * g.plane;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int kx = (blockIdx.y * 32 + lane) * EDGE_WORDS;   // first word of this thread in the row
-    const int y = blockIdx.z * 8 + w;
-    const int wpr = g.wp >> 2;                              // words per row (a multiple of 4)
-    const int x0 = kx * 4;
-
-    uint32_t m[EDGE_WORDS][4];
-    uint32_t cur[EDGE_WORDS];
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < EDGE_WORDS; j++) {
-        cur[j] = 0;
-#pragma unroll
-        for (int d = 0; d < 4; d++) m[j][d] = 0;
+    const int tiles_x = cc_tiles_x(g), tiles_y = cc_tiles_y(g);
+    const int tx = blockIdx.y * EDGE_WARPS + w, ty = blockIdx.z;
+    if (tx >= tiles_x) return;   // (no block-level synchronisation anywhere below)
+    const size_t t = (size_t)ty * tiles_x + tx;
+    const uint2* fm = masks + (size_t)frame * tiles_x * tiles_y * 32;
+    const uint16_t* f16 = l16 + (size_t)frame * tiles_x * tiles_y * 1024;
+    const uint32_t* fl = labels + (size_t)frame * g.plane;
+    const uint32_t* fd = dense + (size_t)frame * g.plane;
+    const uint2 M = fm[t * 32 + lane];
+    if (!__any_sync(FULL_MASK, (M.x | M.y) != 0u)) return;
+    const int x0 = tx * 32, y0 = ty * 32;
+    const uint2 ML = cc_ld_mask(fm, g, tx - 1, ty, lane), MR = cc_ld_mask(fm, g, tx + 1, ty, lane);
+    uint2 N = make_uint2(__shfl_down_sync(FULL_MASK, M.x, 1), __shfl_down_sync(FULL_MASK, M.y, 1));
+    uint2 NL = make_uint2(__shfl_down_sync(FULL_MASK, ML.x, 1), __shfl_down_sync(FULL_MASK, ML.y, 1));
+    uint2 NR = make_uint2(__shfl_down_sync(FULL_MASK, MR.x, 1), __shfl_down_sync(FULL_MASK, MR.y, 1));
+    if (lane == 31) {
+        N = cc_ld_mask(fm, g, tx, ty + 1, 0);
+        NL = cc_ld_mask(fm, g, tx - 1, ty + 1, 0);
+        NR = cc_ld_mask(fm, g, tx + 1, ty + 1, 0);
     }
-    if (y <= g.hd - 2 && kx < wpr && x0 <= g.wd - 2) {
-        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(ft + (size_t)y * g.wp);
-        const uint32_t* r1 = r0 + wpr;
-        const uint32_t none = 0x7f7f7f7fu;
-        const uint4 c4 = *reinterpret_cast<const uint4*>(r0 + kx), d4 = *reinterpret_cast<const uint4*>(r1 + kx);
-        const uint32_t c[6] = {0, c4.x, c4.y, c4.z, c4.w, kx + 4 < wpr ? r0[kx + 4] : none};
-        const uint32_t e[6] = {kx > 0 ? r1[kx - 1] : none, d4.x, d4.y, d4.z, d4.w, kx + 4 < wpr ? r1[kx + 4] : none};
-#pragma unroll
-        for (int j = 0; j < EDGE_WORDS; j++) {
-            cur[j] = c[j + 1];
-            uint32_t nb[4];
-            nb[0] = __funnelshift_r(c[j + 1], c[j + 2], 8);   // (x+1, y)
-            nb[1] = e[j + 1];                                 // (x,   y+1)
-            nb[2] = __funnelshift_l(e[j], e[j + 1], 8);       // (x-1, y+1)
-            nb[3] = __funnelshift_r(e[j + 1], e[j + 2], 8);   // (x+1, y+1)
-            uint32_t xm = 0;                                  // initiators: 1 <= x <= w-2
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int x = x0 + 4 * j + i;
-                if (x >= 1 && x <= g.wd - 2) xm |= 1u << (8 * i);
-            }
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                const uint32_t t = cur[j] ^ nb[d];
-                m[j][d] = (t >> 7) & t & xm;
-                cnt += __popc(m[j][d]);
-            }
-        }
+    const uint32_t Ix = cc_initiators(x0, g.wd);
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
+    if (y0 + lane <= g.hd - 2) {
+        const uint32_t W = M.x, B = M.y;
+        const uint32_t rW = (W >> 1) | (MR.x << 31), rB = (B >> 1) | (MR.y << 31);           // (x+1, y)
+        const uint32_t dlW = (N.x << 1) | (NL.x >> 31), dlB = (N.y << 1) | (NL.y >> 31);     // (x-1, y+1)
+        const uint32_t drW = (N.x >> 1) | (NR.x << 31), drB = (N.y >> 1) | (NR.y << 31);     // (x+1, y+1)
+        m[0] = ((W & rB) | (B & rW)) & Ix;
+        m[1] = ((W & N.y) | (B & N.x)) & Ix;                                                 // (x,   y+1)
+        m[2] = ((W & dlB) | (B & dlW)) & Ix;
+        m[3] = ((W & drB) | (B & drW)) & Ix;
     }
-    int incl = cnt;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        int n = __shfl_up_sync(FULL_MASK, incl, off);
-        if (lane >= off) incl += n;
-    }
-    const int total = __shfl_sync(FULL_MASK, incl, 31);
-    if (total == 0) return;
-    if (cnt) {
-        int o = incl - cnt;
-#pragma unroll
-        for (int j = 0; j < EDGE_WORDS; j++) {
-            if (!(m[j][0] | m[j][1] | m[j][2] | m[j][3])) continue;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t pos = ((cur[j] >> (8 * i)) & 0xff) == 0 ? 1u : 0u;   // v1 > v0  <=>  v0 == 0
-#pragma unroll
-                for (int d = 0; d < 4; d++)
-                    if ((m[j][d] >> (8 * i)) & 1u)
-                        scand[w][o++] = (uint16_t)((lane * 16 + j * 4 + i) | (d << 9) | (pos << 11));
-            }
-        }
-    }
-    __syncwarp();
+    const int cnt_all = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+    if (!__any_sync(FULL_MASK, cnt_all != 0)) return;
     unsigned long long* fk = recs + (size_t)frame * cap;
-    const int xbase = blockIdx.y * (32 * EDGE_WORDS * 4);
-    for (int b = 0; b < total; b += 32) {
-        bool ok = false;
-        unsigned long long rec = 0;
-        const bool have = b + lane < total;
-        int x = 0, d = 0, pos = 0, dx = 0, dy = 0;
-        uint32_t l0 = 0xffffffffu, l1 = 0xfffffffeu;
-        if (have) {
-            const uint32_t c = scand[w][b + lane];
-            x = xbase + (int)(c & 511); d = (c >> 9) & 3; pos = (c >> 11) & 1;
-            dx = (d == 0 || d == 3) ? 1 : (d == 2 ? -1 : 0); dy = d == 0 ? 0 : 1;
-            const size_t id = (size_t)y * g.wp + x;
-            // pixel -> tile-local root (k_cc_local)
-            l0 = fl[id];
-            l1 = fl[id + (size_t)dy * g.wp + dx];
+    const uint32_t idmax = (1u << id_bits) - 1u;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        const int cnt = (lane >> 4) == half ? cnt_all : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int n = __shfl_up_sync(FULL_MASK, incl, off);
+            if (lane >= off) incl += n;
         }
-        // tile-local root -> final root -> dense id (k_cc_sizes / k_cc_dense).  The candidates of a warp sit on a
-        // handful of components, so one lane per distinct tile-local root does the two dependent loads.
-        uint32_t d0 = 0xffffffffu, d1 = 0xffffffffu;
-        {
-            const uint32_t p0 = __match_any_sync(FULL_MASK, l0), p1 = __match_any_sync(FULL_MASK, l1);
-            const int ld0 = __ffs(p0) - 1, ld1 = __ffs(p1) - 1;
-            if (have && lane == ld0) d0 = fd[fl[l0]];
-            if (have && lane == ld1) d1 = fd[fl[l1]];
-            d0 = __shfl_sync(FULL_MASK, d0, ld0);
-            d1 = __shfl_sync(FULL_MASK, d1, ld1);
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        if (total == 0) continue;
+        if (cnt) {
+            int o = incl - cnt;
+#pragma unroll
+            for (int d = 0; d < 4; d++)
+                for (uint32_t mm = m[d]; mm; mm &= mm - 1) {
+                    const int c = __ffs(mm) - 1;
+                    const uint32_t pos = (M.y >> c) & 1u;   // v1 > v0  <=>  v0 == 0 (black)
+                    scand[w][o++] = (uint16_t)(lane | (c << 5) | (d << 10) | (pos << 12));
+                }
         }
-        if (have && d0 != 0xffffffffu && d1 != 0xffffffffu) {   // both components have >= 25 pixels
-            ok = true;
-            // 2*id_bits key bits: as few sort passes as needed.  Ids that do not fit (the host re-runs such a chunk
-            // with wider ids) are clamped so that nothing downstream indexes out of range in the meantime.
-            const uint32_t idmax = (1u << id_bits) - 1u;
-            d0 = min(d0, idmax);
-            d1 = min(d1, idmax);
-            const uint32_t key = (max(d0, d1) << id_bits) | min(d0, d1);
-            rec = ((unsigned long long)key << 32) | pack_point(2 * x + dx, 2 * y + dy, d, pos);
+        __syncwarp();
+        for (int b = 0; b < total; b += 32) {
+            const bool have = b + lane < total;
+            const uint32_t cd = have ? scand[w][b + lane] : 0u;
+            const int r = cd & 31, c = (cd >> 5) & 31, d = (cd >> 10) & 3, pos = (cd >> 12) & 1;
+            const int dx = (d == 0 || d == 3) ? 1 : (d == 2 ? -1 : 0), dy = d == 0 ? 0 : 1;
+            int qc = c + dx, qr = r + dy;
+            const int qtx = tx + (qc < 0 ? -1 : (qc > 31 ? 1 : 0)), qty = ty + (qr > 31 ? 1 : 0);
+            qc &= 31;
+            qr &= 31;
+            // row masks of p (own tile) and q (own tile: shuffle; neighbour tile: one cached 8-byte load)
+            const uint32_t Wp = __shfl_sync(FULL_MASK, M.x, r), Bp = __shfl_sync(FULL_MASK, M.y, r);
+            uint32_t Wq = __shfl_sync(FULL_MASK, M.x, qr), Bq = __shfl_sync(FULL_MASK, M.y, qr);
+            const bool same_tile = qtx == tx && qty == ty;
+            uint32_t l0 = 0xffffffffu, l1 = 0xfffffffeu;
+            if (have) {
+                if (!same_tile) {
+                    const uint2 Q = cc_ld_mask(fm, g, qtx, qty, qr);
+                    Wq = Q.x;
+                    Bq = Q.y;
+                }
+                // pixel -> tile-local root (k_cc_local's run-start labels)
+                l0 = cc_pixel_root(f16, t, x0, y0, r, c, pos ? Bp : Wp, Ix, g.wp);
+                l1 = cc_pixel_root(f16, (size_t)qty * tiles_x + qtx, qtx * 32, qty * 32, qr, qc, pos ? Wq : Bq,
+                                   same_tile ? Ix : cc_initiators(qtx * 32, g.wd), g.wp);
+            }
+            // tile-local root -> final root -> dense id (k_cc_sizes / k_cc_dense).  The candidates of a warp sit on a
+            // handful of components, so one lane per distinct tile-local root does the two dependent loads.
+            uint32_t d0 = 0xffffffffu, d1 = 0xffffffffu;
+            {
+                const uint32_t p0 = __match_any_sync(FULL_MASK, l0), p1 = __match_any_sync(FULL_MASK, l1);
+                const int ld0 = __ffs(p0) - 1, ld1 = __ffs(p1) - 1;
+                if (have && lane == ld0) d0 = fd[fl[l0]];
+                if (have && lane == ld1) d1 = fd[fl[l1]];
+                d0 = __shfl_sync(FULL_MASK, d0, ld0);
+                d1 = __shfl_sync(FULL_MASK, d1, ld1);
+            }
+            bool ok = false;
+            unsigned long long rec = 0;
+            if (have && d0 != 0xffffffffu && d1 != 0xffffffffu) {   // both components have >= 25 pixels
+                ok = true;
+                // 2*id_bits key bits: as few sort passes as needed.  Ids that do not fit (the host re-runs such a chunk
+                // with wider ids) are clamped so that nothing downstream indexes out of range in the meantime.
+                d0 = min(d0, idmax);
+                d1 = min(d1, idmax);
+                const uint32_t key = (max(d0, d1) << id_bits) | min(d0, d1);
+                rec = ((unsigned long long)key << 32) | pack_point(2 * (x0 + c) + dx, 2 * (y0 + r) + dy, d, pos);
+            }
+            const uint32_t okm = __ballot_sync(FULL_MASK, ok);
+            if (okm == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&npts[frame], __popc(okm));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            const int p = base + __popc(okm & ((1u << lane) - 1u));
+            if (ok && p < cap) fk[p] = rec;
         }
-        const uint32_t okm = __ballot_sync(FULL_MASK, ok);
-        if (okm == 0) continue;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&npts[frame], __popc(okm));
-        base = __shfl_sync(FULL_MASK, base, 0);
-        const int p = base + __popc(okm & ((1u << lane) - 1u));
-        if (ok && p < cap) fk[p] = rec;
+        __syncwarp();
     }
 }
 
