@@ -137,7 +137,9 @@ struct agpu_handle {
     struct Tune {
         int prio = 1;                                  // back half of a chunk on high-priority streams
         int tier_ctas[AGPU_NTIERS] = {3, 16, 8, 1};    // persistent quad-fit CTAs per SM, by size tier
-        int decode_ctas = 4;                           // persistent decode CTAs per SM
+        int decode_ctas = 4;                           // persistent decode CTAs (of 4 warps) per SM
+        int tail_threads = 32;                         // CTA size of decode / reconcile / pose: small CTAs find room on SMs
+                                                       // that the streaming kernels of the next chunk keep full
     } tune;
     DevBuf d_fams, d_codes, d_pose_in, d_pose_out;
     std::vector<Slot> slots;
@@ -598,11 +600,11 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         da.ndets = d_ndets;
         da.cap_dets = REC_CAP;
         da.dbg_refined = h->cfg.debug ? sl.d_refined.as<float>() : nullptr;
-        k_decode_quads<<<h->num_sms * h->tune.decode_ctas, 128, 0, sl.tail>>>(da, h->prm);
+        k_decode_quads<<<h->num_sms * h->tune.decode_ctas * (128 / h->tune.tail_threads), h->tune.tail_threads, 0, sl.tail>>>(da, h->prm);
         LAUNCH_CHECK("k_decode_quads");
     }
     tm.mark(sl.tail);  // 7: after decode
-    k_reconcile<<<ceil_div(n, 4), 128, 0, sl.tail>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
+    k_reconcile<<<ceil_div(n, h->tune.tail_threads / 32), h->tune.tail_threads, 0, sl.tail>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
                                                       sl.d_out.as<DetRec>(), d_out_counts, c.cap_out);
     LAUNCH_CHECK("k_reconcile");
     if (c.pose->enabled) {
@@ -614,7 +616,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         pa.per_frame = c.cap_out;
         pa.M = n * c.cap_out;
         pa.out = sl.d_poses.as<PoseRec>();
-        k_pose<<<ceil_div((long long)pa.M * 4, 128), 128, 0, sl.tail>>>(pa);
+        k_pose<<<ceil_div((long long)pa.M * 4, h->tune.tail_threads), h->tune.tail_threads, 0, sl.tail>>>(pa);
         LAUNCH_CHECK("k_pose");
     }
     tm.mark(sl.tail);  // 8: after reconcile/pose
@@ -657,7 +659,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     int max_dense = 0;
     for (int i = 0; i < n; i++) max_dense = std::max(max_dense, h_ndense[i]);
     if (max_dense > AGPU_MAX_DENSE) {
-        h->set_err("more than 65536 connected components of >= 25 pixels in one frame");
+        h->set_err("more than 65535 connected components of >= 25 pixels in one frame");
         return AGPU_E_WORKSPACE;
     }
     h->max_dense_seen = std::max(h->max_dense_seen, max_dense);
@@ -853,6 +855,7 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     h->families_str = cfg->families;
     h->cfg.families = h->families_str.c_str();
     if (const char* e = getenv("AGPU_PRIO")) h->tune.prio = atoi(e) != 0;
+    if (const char* e = getenv("AGPU_TAIL_THREADS")) h->tune.tail_threads = atoi(e) >= 128 ? 128 : (atoi(e) >= 64 ? 64 : 32);
     if (const char* e = getenv("AGPU_DECODE_CTAS")) h->tune.decode_ctas = std::max(1, std::min(16, atoi(e)));
     if (const char* e = getenv("AGPU_TIER_CTAS")) {
         int v[AGPU_NTIERS];

@@ -407,7 +407,7 @@ k_cc_sizes(uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, const ui
 // becomes a pair of 16-bit ids instead of a pair of 21..23-bit pixel ids, which halves the radix-sort record
 // and its number of passes.  dense[rep] is defined at every final root (0xffffffff: component smaller than 25
 // pixels, upstream's edge-point filter); dense2rep maps back.
-#define AGPU_MAX_DENSE 65536
+#define AGPU_MAX_DENSE 65535   // ids 0 .. 65534 (0xffff marks "no id" in 16-bit tables)
 __global__ void __launch_bounds__(256)
 k_cc_dense(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
            const int* __restrict__ nroots, uint32_t* __restrict__ dense, uint32_t* __restrict__ dense2rep,

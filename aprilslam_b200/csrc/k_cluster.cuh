@@ -21,12 +21,13 @@
 // representative + dense-id look-ups, ballot compaction, one atomic per 32 candidates), so the expensive part is
 // not serialised inside the few rows that sit on an edge.
 #define EDGE_WARPS 8
-#define EDGE_CAND_PER_PASS (16 * 32 * 4)   // rows of one half tile x columns x directions
+#define EDGE_CAND_PER_PASS 1024   // a tile with more candidates is handled in four passes of 8 rows (8 x 32 x 4)
 __global__ void __launch_bounds__(EDGE_WARPS * 32)
 k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
         const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts, int cap,
         int id_bits) {
     __shared__ uint16_t scand[EDGE_WARPS][EDGE_CAND_PER_PASS];
+    __shared__ uint16_t sdense[EDGE_WARPS][1024];   // dense component id of every run of the tile, at its start pixel
     // grid = (frames, x blocks, tile rows): consecutive CTAs belong to DIFFERENT frames, so the per-frame append
     // counters are not hammered by every resident warp at once
     const int frame = blockIdx.x;
@@ -64,12 +65,42 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
         m[3] = ((W & drB) | (B & drW)) & Ix;
     }
     const int cnt_all = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-    if (!__any_sync(FULL_MASK, cnt_all != 0)) return;
+    int total_all = cnt_all;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total_all += __shfl_xor_sync(FULL_MASK, total_all, off);
+    if (total_all == 0) return;
+
+    // ---- dense id of every run of this tile: run start -> tile-local root -> final root -> dense id.  The runs of a
+    //      tile hang on a handful of roots, so one lane per distinct root does the two dependent loads.
+    {
+        const uint32_t Sw = M.x & ~(M.x & (M.x << 1) & Ix), Sb = M.y & ~(M.y & (M.y << 1) & Ix);
+        uint32_t S = Sw | Sb;
+        const uint16_t* tl = f16 + t * 1024 + lane * 32;
+        while (__any_sync(FULL_MASK, S != 0u)) {
+            const bool have = S != 0u;
+            const int c = have ? __ffs(S) - 1 : 0;
+            S &= S - 1;
+            const uint32_t loc = have ? (uint32_t)tl[c] : 0xffffffffu - lane;
+            const uint32_t peers = __match_any_sync(FULL_MASK, loc);
+            const int leader = __ffs(peers) - 1;
+            uint32_t d = 0xffffu;
+            if (have && lane == leader) {
+                const uint32_t gid = (uint32_t)((y0 + (int)(loc >> 5)) * g.wp + x0 + (int)(loc & 31u));
+                d = min(fd[fl[gid]], 0xffffu);
+            }
+            d = __shfl_sync(FULL_MASK, d, leader);
+            if (have) sdense[w][lane * 32 + c] = (uint16_t)d;
+        }
+    }
+    __syncwarp();
+
     unsigned long long* fk = recs + (size_t)frame * cap;
     const uint32_t idmax = (1u << id_bits) - 1u;
+    const int npass = total_all <= EDGE_CAND_PER_PASS ? 1 : 4;
+    const int rsh = npass == 1 ? 5 : 3;   // rows per pass = 1 << rsh
 #pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        const int cnt = (lane >> 4) == half ? cnt_all : 0;
+    for (int pass = 0; pass < npass; pass++) {
+        const int cnt = (lane >> rsh) == pass ? cnt_all : 0;
         int incl = cnt;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -98,36 +129,24 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
             const int qtx = tx + (qc < 0 ? -1 : (qc > 31 ? 1 : 0)), qty = ty + (qr > 31 ? 1 : 0);
             qc &= 31;
             qr &= 31;
-            // row masks of p (own tile) and q (own tile: shuffle; neighbour tile: one cached 8-byte load)
+            // row masks of p and q inside the tile: shuffles (every lane takes part)
             const uint32_t Wp = __shfl_sync(FULL_MASK, M.x, r), Bp = __shfl_sync(FULL_MASK, M.y, r);
-            uint32_t Wq = __shfl_sync(FULL_MASK, M.x, qr), Bq = __shfl_sync(FULL_MASK, M.y, qr);
-            const bool same_tile = qtx == tx && qty == ty;
-            uint32_t l0 = 0xffffffffu, l1 = 0xfffffffeu;
+            const uint32_t Wq = __shfl_sync(FULL_MASK, M.x, qr), Bq = __shfl_sync(FULL_MASK, M.y, qr);
+            uint32_t d0 = 0xffffu, d1 = 0xffffu;
             if (have) {
-                if (!same_tile) {
+                d0 = sdense[w][r * 32 + cc_run_start(pos ? Bp : Wp, Ix, c)];
+                if (qtx == tx && qty == ty) {
+                    d1 = sdense[w][qr * 32 + cc_run_start(pos ? Wq : Bq, Ix, qc)];
+                } else {   // neighbour tile (a tenth of the candidates): mask -> run start -> root -> dense id in global memory
                     const uint2 Q = cc_ld_mask(fm, g, qtx, qty, qr);
-                    Wq = Q.x;
-                    Bq = Q.y;
+                    const uint32_t l1 = cc_pixel_root(f16, (size_t)qty * tiles_x + qtx, qtx * 32, qty * 32, qr, qc,
+                                                      pos ? Q.x : Q.y, cc_initiators(qtx * 32, g.wd), g.wp);
+                    d1 = min(fd[fl[l1]], 0xffffu);
                 }
-                // pixel -> tile-local root (k_cc_local's run-start labels)
-                l0 = cc_pixel_root(f16, t, x0, y0, r, c, pos ? Bp : Wp, Ix, g.wp);
-                l1 = cc_pixel_root(f16, (size_t)qty * tiles_x + qtx, qtx * 32, qty * 32, qr, qc, pos ? Wq : Bq,
-                                   same_tile ? Ix : cc_initiators(qtx * 32, g.wd), g.wp);
-            }
-            // tile-local root -> final root -> dense id (k_cc_sizes / k_cc_dense).  The candidates of a warp sit on a
-            // handful of components, so one lane per distinct tile-local root does the two dependent loads.
-            uint32_t d0 = 0xffffffffu, d1 = 0xffffffffu;
-            {
-                const uint32_t p0 = __match_any_sync(FULL_MASK, l0), p1 = __match_any_sync(FULL_MASK, l1);
-                const int ld0 = __ffs(p0) - 1, ld1 = __ffs(p1) - 1;
-                if (have && lane == ld0) d0 = fd[fl[l0]];
-                if (have && lane == ld1) d1 = fd[fl[l1]];
-                d0 = __shfl_sync(FULL_MASK, d0, ld0);
-                d1 = __shfl_sync(FULL_MASK, d1, ld1);
             }
             bool ok = false;
             unsigned long long rec = 0;
-            if (have && d0 != 0xffffffffu && d1 != 0xffffffffu) {   // both components have >= 25 pixels
+            if (have && d0 != 0xffffu && d1 != 0xffffu) {   // both components have >= 25 pixels
                 ok = true;
                 // 2*id_bits key bits: as few sort passes as needed.  Ids that do not fit (the host re-runs such a chunk
                 // with wider ids) are clamped so that nothing downstream indexes out of range in the meantime.

@@ -29,10 +29,16 @@ __device__ __forceinline__ double bilinear_at(const uint8_t* im, size_t pitch, i
            (1 - a) * b * im[(size_t)(yi + 1) * pitch + xi] + a * b * im[(size_t)(yi + 1) * pitch + xi + 1];
 }
 
+// refine_edges: the (edge, sample) pairs of all four edges are dealt to the lanes as ONE flat list (a typical tag has
+// 4 x 16 samples: two full rounds instead of four half-empty ones); every sample runs the sequential search along the
+// edge normal on its own lane, and the per-edge moments are then accumulated in sample order (identical on every lane),
+// exactly the order of the sequential algorithm.
 __device__ void refine_edges_warp(const DevParams& P, const uint8_t* im, size_t pitch, int width, int height,
                                   float (&p)[4][2], int reversed) {
     const int lane = threadIdx.x & 31;
-    double lines[4][4];
+    double enx[4], eny[4];
+    int ens[4], eoff[5];
+    eoff[0] = 0;
 #pragma unroll
     for (int edge = 0; edge < 4; edge++) {
         const int a = edge, b = (edge + 1) & 3;
@@ -42,63 +48,87 @@ __device__ void refine_edges_warp(const DevParams& P, const uint8_t* im, size_t 
         nx /= mag;
         ny /= mag;
         if (reversed) { nx = -nx; ny = -ny; }
-        const int nsamples = max(16, (int)(mag / 8));
-        double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
-        const double range = P.quad_decimate + 1;
-        const int nsteps = (int)(2 * range * 4) + 1;
-        for (int s0 = 0; s0 < nsamples; s0 += 32) {
-            const int s = s0 + lane;
-            double bestx = 0, besty = 0;
-            int valid = 0;
-            if (s < nsamples) {
-                double alpha = (1.0 + s) / (nsamples + 1);
-                double x0 = alpha * p[a][0] + (1 - alpha) * p[b][0];
-                double y0 = alpha * p[a][1] + (1 - alpha) * p[b][1];
-                double Mn = 0, Mcount = 0;
-                for (int k = 0; k < nsteps; k++) {
-                    double n = -range + 0.25 * k;
-                    double grange = 1;
-                    double x1 = x0 + (n + grange) * nx - 0.5;
-                    double y1 = y0 + (n + grange) * ny - 0.5;
-                    int x1i = (int)floor(x1), y1i = (int)floor(y1);
-                    double a1 = x1 - x1i, b1 = y1 - y1i;
-                    if (x1i < 0 || x1i + 1 >= width || y1i < 0 || y1i + 1 >= height) continue;
-                    double x2 = x0 + (n - grange) * nx - 0.5;
-                    double y2 = y0 + (n - grange) * ny - 0.5;
-                    int x2i = (int)floor(x2), y2i = (int)floor(y2);
-                    double a2 = x2 - x2i, b2 = y2 - y2i;
-                    if (x2i < 0 || x2i + 1 >= width || y2i < 0 || y2i + 1 >= height) continue;
-                    double g1 = bilinear_at(im, pitch, x1i, y1i, a1, b1);
-                    double g2 = bilinear_at(im, pitch, x2i, y2i, a2, b2);
-                    if (g1 < g2) continue;
-                    double weight = (g2 - g1) * (g2 - g1);
-                    Mn += weight * n;
-                    Mcount += weight;
-                }
-                if (Mcount != 0) {
-                    double n0 = Mn / Mcount;
-                    bestx = x0 + n0 * nx;
-                    besty = y0 + n0 * ny;
-                    valid = 1;
-                }
-            }
-            const int cnt = min(32, nsamples - s0);
-            for (int k = 0; k < cnt; k++) {  // sequential-order accumulation, identical on every lane
-                int vk = __shfl_sync(FULL_MASK, valid, k);
-                double bx = __shfl_sync(FULL_MASK, bestx, k), by = __shfl_sync(FULL_MASK, besty, k);
-                if (vk) {
-                    Mx += bx; My += by; Mxx += bx * bx; Mxy += bx * by; Myy += by * by; N += 1;
-                }
-            }
-        }
+        enx[edge] = nx;
+        eny[edge] = ny;
+        ens[edge] = max(16, (int)(mag / 8));
+        eoff[edge + 1] = eoff[edge] + ens[edge];
+    }
+    const int total = eoff[4];
+    const double range = P.quad_decimate + 1;
+    const int nsteps = (int)(2 * range * 4) + 1;
+    double lines[4][4];
+    double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
+    int cur = 0;          // edge whose moments are being accumulated (uniform over the warp)
+    int cur_end = eoff[1];
+    auto finish_edge = [&]() {
         double Ex = Mx / N, Ey = My / N;
         double Cxx = Mxx / N - Ex * Ex, Cxy = Mxy / N - Ex * Ey, Cyy = Myy / N - Ey * Ey;
         double normal_theta = .5 * atan2f((float)(-2 * Cxy), (float)(Cyy - Cxx));
-        lines[edge][0] = Ex;
-        lines[edge][1] = Ey;
-        lines[edge][2] = cosf((float)normal_theta);
-        lines[edge][3] = sinf((float)normal_theta);
+        const double c = cosf((float)normal_theta), s = sinf((float)normal_theta);
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (e == cur) { lines[e][0] = Ex; lines[e][1] = Ey; lines[e][2] = c; lines[e][3] = s; }
+        cur++;
+        cur_end = cur == 1 ? eoff[2] : (cur == 2 ? eoff[3] : eoff[4]);
+        Mx = My = Mxx = Mxy = Myy = N = 0;
+    };
+    for (int base = 0; base < total; base += 32) {
+        const int item = base + lane;
+        double bestx = 0, besty = 0;
+        int valid = 0;
+        if (item < total) {
+            const int e = (item >= eoff[1]) + (item >= eoff[2]) + (item >= eoff[3]);
+            double nx = enx[0], ny = eny[0];
+            float pax = p[0][0], pay = p[0][1], pbx = p[1][0], pby = p[1][1];
+            int nsamples = ens[0], s = item;
+#pragma unroll
+            for (int k = 1; k < 4; k++)
+                if (e == k) {
+                    nx = enx[k]; ny = eny[k]; nsamples = ens[k]; s = item - eoff[k];
+                    pax = p[k][0]; pay = p[k][1]; pbx = p[(k + 1) & 3][0]; pby = p[(k + 1) & 3][1];
+                }
+            double alpha = (1.0 + s) / (nsamples + 1);
+            double x0 = alpha * pax + (1 - alpha) * pbx;
+            double y0 = alpha * pay + (1 - alpha) * pby;
+            double Mn = 0, Mcount = 0;
+            for (int k = 0; k < nsteps; k++) {
+                double n = -range + 0.25 * k;
+                double grange = 1;
+                double x1 = x0 + (n + grange) * nx - 0.5;
+                double y1 = y0 + (n + grange) * ny - 0.5;
+                int x1i = (int)floor(x1), y1i = (int)floor(y1);
+                double a1 = x1 - x1i, b1 = y1 - y1i;
+                if (x1i < 0 || x1i + 1 >= width || y1i < 0 || y1i + 1 >= height) continue;
+                double x2 = x0 + (n - grange) * nx - 0.5;
+                double y2 = y0 + (n - grange) * ny - 0.5;
+                int x2i = (int)floor(x2), y2i = (int)floor(y2);
+                double a2 = x2 - x2i, b2 = y2 - y2i;
+                if (x2i < 0 || x2i + 1 >= width || y2i < 0 || y2i + 1 >= height) continue;
+                double g1 = bilinear_at(im, pitch, x1i, y1i, a1, b1);
+                double g2 = bilinear_at(im, pitch, x2i, y2i, a2, b2);
+                if (g1 < g2) continue;
+                double weight = (g2 - g1) * (g2 - g1);
+                Mn += weight * n;
+                Mcount += weight;
+            }
+            if (Mcount != 0) {
+                double n0 = Mn / Mcount;
+                bestx = x0 + n0 * nx;
+                besty = y0 + n0 * ny;
+                valid = 1;
+            }
+        }
+        const int cnt = min(32, total - base);
+        for (int k = 0; k < cnt; k++) {  // sequential-order accumulation, identical on every lane
+            if (base + k >= cur_end) finish_edge();
+            int vk = __shfl_sync(FULL_MASK, valid, k);
+            double bx = __shfl_sync(FULL_MASK, bestx, k), by = __shfl_sync(FULL_MASK, besty, k);
+            if (vk) {
+                Mx += bx; My += by; Mxx += bx * bx; Mxy += bx * by; Myy += by * by; N += 1;
+            }
+        }
     }
+    finish_edge();   // the fourth edge (every edge has >= 16 samples, so edges 0..2 were closed inside the loop)
     float np[4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++) { np[i][0] = p[i][0]; np[i][1] = p[i][1]; }
@@ -120,47 +150,68 @@ __device__ void refine_edges_warp(const DevParams& P, const uint8_t* im, size_t 
     for (int i = 0; i < 4; i++) { p[i][0] = np[i][0]; p[i][1] = np[i][1]; }
 }
 
-// 8x9 Gaussian elimination with partial pivoting (upstream homography_compute2)
+// 8x9 Gaussian elimination with partial pivoting (upstream homography_compute2), spread over the warp: lane r (mod 8)
+// holds ROW r in nine registers, pivot search / row swap / pivot-row broadcast are shuffles.  Same operations in the
+// same order as the sequential algorithm (first largest pivot wins), so the result is bit-identical to it.
 __device__ bool homography_dev(const float (&p)[4][2], double (&H)[9]) {
-    double A[72];
+    const int row = threadIdx.x & 7;
+    double A[9];
+    {
+        const int i = row >> 1;
+        float c2f = p[0][0], c3f = p[0][1];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+        for (int k = 1; k < 4; k++)
+            if (i == k) { c2f = p[k][0]; c3f = p[k][1]; }
         const double c0 = (i == 0 || i == 3) ? -1 : 1, c1 = (i == 0 || i == 1) ? -1 : 1;
-        const double c2 = p[i][0], c3 = p[i][1];
-        double* r0 = &A[(2 * i) * 9];
-        double* r1 = &A[(2 * i + 1) * 9];
-        r0[0] = c0; r0[1] = c1; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0;
-        r0[6] = -c0 * c2; r0[7] = -c1 * c2; r0[8] = c2;
-        r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = c0; r1[4] = c1; r1[5] = 1;
-        r1[6] = -c0 * c3; r1[7] = -c1 * c3; r1[8] = c3;
+        const double c2 = c2f, c3 = c3f;
+        if ((row & 1) == 0) {
+            A[0] = c0; A[1] = c1; A[2] = 1; A[3] = 0; A[4] = 0; A[5] = 0;
+            A[6] = -c0 * c2; A[7] = -c1 * c2; A[8] = c2;
+        } else {
+            A[0] = 0; A[1] = 0; A[2] = 0; A[3] = c0; A[4] = c1; A[5] = 1;
+            A[6] = -c0 * c3; A[7] = -c1 * c3; A[8] = c3;
+        }
     }
     const double epsilon = 1e-10;
+#pragma unroll
     for (int col = 0; col < 8; col++) {
-        double max_val = 0;
-        int max_idx = -1;
-        for (int row = col; row < 8; row++) {
-            double val = fabs(A[row * 9 + col]);
-            if (val > max_val) { max_val = val; max_idx = row; }
+        // pivot: largest |A[r][col]| over rows r >= col, the first one on ties
+        const double val = row >= col ? fabs(A[col]) : -1.0;
+        double mx = val;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+            const double o = __shfl_xor_sync(FULL_MASK, mx, off);
+            mx = o > mx ? o : mx;
         }
-        if (max_idx < 0 || max_val < epsilon) return false;
-        if (max_idx != col)
-            for (int i = col; i < 9; i++) {
-                double t = A[col * 9 + i];
-                A[col * 9 + i] = A[max_idx * 9 + i];
-                A[max_idx * 9 + i] = t;
-            }
-        for (int i = col + 1; i < 8; i++) {
-            double f = A[i * 9 + col] / A[col * 9 + col];
-            A[i * 9 + col] = 0;
-            for (int j = col + 1; j < 9; j++) A[i * 9 + j] -= f * A[col * 9 + j];
+        if (!(mx >= epsilon)) return false;
+        const uint32_t cand = __ballot_sync(FULL_MASK, val == mx) & 0xffu;
+        const int max_idx = __ffs(cand) - 1;
+        if (max_idx != col) {   // (uniform) swap rows col and max_idx
+            const int partner = row == col ? max_idx : (row == max_idx ? col : row);
+#pragma unroll
+            for (int i = col; i < 9; i++) A[i] = __shfl_sync(FULL_MASK, A[i], (threadIdx.x & 24) | partner);
+        }
+        double pv[9];
+#pragma unroll
+        for (int j = col; j < 9; j++) pv[j] = __shfl_sync(FULL_MASK, A[j], (threadIdx.x & 24) | col);
+        if (row > col) {
+            const double f = A[col] / pv[col];
+            A[col] = 0;
+#pragma unroll
+            for (int j = col + 1; j < 9; j++) A[j] -= f * pv[j];
         }
     }
+    double x[8];
+#pragma unroll
     for (int col = 7; col >= 0; col--) {
         double sum = 0;
-        for (int i = col + 1; i < 8; i++) sum += A[col * 9 + i] * A[i * 9 + 8];
-        A[col * 9 + 8] = (A[col * 9 + 8] - sum) / A[col * 9 + col];
+#pragma unroll
+        for (int i = col + 1; i < 8; i++) sum += A[i] * x[i];
+        const double v = (A[8] - sum) / A[col];   // meaningful on the lanes that hold row `col`
+        x[col] = __shfl_sync(FULL_MASK, v, (threadIdx.x & 24) | col);
     }
-    for (int i = 0; i < 8; i++) H[i] = A[i * 9 + 8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) H[i] = x[i];
     H[8] = 1;
     return true;
 }
@@ -434,7 +485,7 @@ k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int 
     __shared__ int s_perm[4][REC_CAP];
     __shared__ unsigned char s_dead[4][REC_CAP];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int frame = blockIdx.x * 4 + w;
+    const int frame = blockIdx.x * (blockDim.x >> 5) + w;
     if (frame >= nframes) return;
     const int n = min(min(ndets[frame], cap_dets), REC_CAP);
     const DetRec* fd = dets + (size_t)frame * cap_dets;

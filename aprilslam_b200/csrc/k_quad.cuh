@@ -470,7 +470,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
 #pragma unroll 2
     for (int i = tid; i < sz; i += T) {
         LineFit f;
-        fit_line_dev(lf, sz, (i + sz - ksz) % sz, (i + ksz) % sz, f, false);
+        fit_line_dev(lf, sz, i - ksz < 0 ? i - ksz + sz : i - ksz, i + ksz >= sz ? i + ksz - sz : i + ksz, f, false);   // (index % sz without the division)
         sraw[i] = f.err;
     }
     G.sync();
@@ -478,7 +478,11 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     for (int i = tid; i < sz; i += T) {
         double acc = 0;
 #pragma unroll
-        for (int j = 0; j < 7; j++) acc += sraw[(i + j - 3 + sz) % sz] * P.smooth_f[j];
+        for (int j = 0; j < 7; j++) {
+            int q = i + j - 3;
+            q = q < 0 ? q + sz : (q >= sz ? q - sz : q);
+            acc += sraw[q] * P.smooth_f[j];
+        }
         __stcg(es + i, acc);
     }
     __threadfence_block();
@@ -495,7 +499,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         double e = 0;
         if (i < sz) {
             e = __ldcg(es + i);
-            const double en = __ldcg(es + (i + 1) % sz), ep = __ldcg(es + (i + sz - 1) % sz);
+            const double en = __ldcg(es + (i + 1 == sz ? 0 : i + 1)), ep = __ldcg(es + (i == 0 ? sz - 1 : i - 1));
             ismax = e > en && e > ep;
         }
         int total;
