@@ -92,7 +92,7 @@ struct Slot {
     std::vector<cudaEvent_t> events;   // stage timing
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_labels, d_canon, d_sizes, d_roots, d_dense, d_dense2rep;
     DevBuf d_recs[2], d_hist, d_dtot, d_lfps, d_errs;
-    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk]
+    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
     bool pending = false;
@@ -487,6 +487,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int* d_out_counts = d_ndets + chunk;
     int* d_ndense = d_out_counts + chunk;
     int* d_nroots = d_ndense + chunk;          // CC_SUBLISTS counters per frame
+    int* d_ndups = d_nroots + CC_SUBLISTS * chunk;   // merged duplicate points per frame (raw points = npts + ndups)
     StageTimer tm(h, sl);
     tm.mark();  // 0
     const uint8_t* d_src;
@@ -512,7 +513,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         dim3 grid(n, ceil_div(cc_tiles_x(g), EDGE_WARPS), cc_tiles_y(g));
         k_edges<<<grid, EDGE_WARPS * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
                                                          sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g,
-                                                         sl.d_recs[0].as<unsigned long long>(), d_npts, cap, c.id_bits);
+                                                         sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, cap, c.id_bits);
         LAUNCH_CHECK("k_edges");
     }
     tm.mark();  // 4: after edges
@@ -656,6 +657,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     const int* h_nd = h_npts + 2 * chunk;
     const int* h_oc = h_nd + chunk;
     const int* h_ndense = h_oc + chunk;
+    const int* h_ndups = h_ndense + chunk + CC_SUBLISTS * chunk;
     int max_dense = 0;
     for (int i = 0; i < n; i++) max_dense = std::max(max_dense, h_ndense[i]);
     if (max_dense > AGPU_MAX_DENSE) {
@@ -688,7 +690,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
             h->set_err("more detections than cap_per_frame; counts[] hold the true numbers");
             rc_final = AGPU_E_TRUNCATED;
         }
-        h->counters[0] += h_npts[i];
+        h->counters[0] += h_npts[i] + h_ndups[i];   // raw edge points, as upstream counts them
         h->counters[3] += h_nd[i];
         if (h_nd[i] > REC_CAP) {
             h->set_err("more than 256 raw detections in one frame");
@@ -758,7 +760,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     c.cap = (c.cap + RS_TILE - 1) / RS_TILE * RS_TILE;
     c.maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
     c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
-    c.ncnt = CNT_FIXED + (size_t)(5 + CC_SUBLISTS) * chunk;
+    c.ncnt = CNT_FIXED + (size_t)(6 + CC_SUBLISTS) * chunk;
     c.id_bits = (h->max_dense_seen >= 0 && h->max_dense_seen <= 1536) ? 11 : 16;
     c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
@@ -1143,7 +1145,9 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
             if (r.frame == frame) {
                 const uint32_t ck = (uint32_t)(recs[r.start] >> 32);
                 const uint32_t ra = d2r[ck >> h->last_id_bits], rb = d2r[ck & ((1u << h->last_id_bits) - 1u)];
-                v.push_back({unpitch_key(((unsigned long long)std::max(ra, rb) << 32) | std::min(ra, rb)), r.size});
+                int raw = r.size;   // upstream's cluster size counts the duplicate points that k_edges merged
+                for (int i = 0; i < r.size; i++) raw += ((uint32_t)recs[r.start + i] >> 28) >= 8u;
+                v.push_back({unpitch_key(((unsigned long long)std::max(ra, rb) << 32) | std::min(ra, rb)), raw});
             }
         std::sort(v.begin(), v.end());
         long long n = (long long)v.size();

@@ -52,9 +52,14 @@ struct Geom {
     size_t plane;    // wp*hd
 };
 
-// packed edge point: px (14b) | py (14b) << 14 | dir (2b) << 28 | positive (1b) << 30
-__host__ __device__ inline uint32_t pack_point(int px, int py, int dir, int positive) {
-    return (uint32_t)px | ((uint32_t)py << 14) | ((uint32_t)dir << 28) | ((uint32_t)positive << 30);
+// packed edge point: px (14b) | py (14b) << 14 | kind (4b) << 28
+//   kind 0..7 : one point, kind = dir | positive << 2   (dir 0..3 = offsets (1,0) (0,1) (-1,1) (1,1))
+//   kind 8..11: the point of direction 2 at (x, y) MERGED with the identical point that direction 3 emits at
+//               (x-1, y) -- always the same pair of components, see k_edges -- kind = 8 | positive(dir 2) |
+//               positive(dir 3) << 1.  Upstream emits both and drops the duplicate after the slope sort; merging
+//               them at emission keeps a third of all points out of both sorts.
+__host__ __device__ inline uint32_t pack_point(int px, int py, int kind) {
+    return (uint32_t)px | ((uint32_t)py << 14) | ((uint32_t)kind << 28);
 }
 
 struct ClusterRef {

@@ -24,8 +24,8 @@
 #define EDGE_CAND_PER_PASS 1024   // a tile with more candidates is handled in four passes of 8 rows (8 x 32 x 4)
 __global__ void __launch_bounds__(EDGE_WARPS * 32)
 k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
-        const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts, int cap,
-        int id_bits) {
+        const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts,
+        int* __restrict__ ndups, int cap, int id_bits) {
     __shared__ uint16_t scand[EDGE_WARPS][EDGE_CAND_PER_PASS];
     __shared__ uint16_t sdense[EDGE_WARPS][1024];   // dense component id of every run of the tile, at its start pixel
     // grid = (frames, x blocks, tile rows): consecutive CTAs belong to DIFFERENT frames, so the per-frame append
@@ -54,6 +54,7 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
     }
     const uint32_t Ix = cc_initiators(x0, g.wd);
     uint32_t m[4] = {0u, 0u, 0u, 0u};
+    uint32_t dup2 = 0u;   // direction-2 candidates that absorb the identical point of direction 3 at x-1
     if (y0 + lane <= g.hd - 2) {
         const uint32_t W = M.x, B = M.y;
         const uint32_t rW = (W >> 1) | (MR.x << 31), rB = (B >> 1) | (MR.y << 31);           // (x+1, y)
@@ -63,6 +64,14 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
         m[1] = ((W & N.y) | (B & N.x)) & Ix;                                                 // (x,   y+1)
         m[2] = ((W & dlB) | (B & dlW)) & Ix;
         m[3] = ((W & drB) | (B & drW)) & Ix;
+        // Duplicates.  (x, y, dir 2) and (x-1, y, dir 3) are the two diagonals of one 2x2 block and give the same
+        // point (2x-1, 2y+1).  When both exist the four pixels are two vertical or two horizontal same-coloured
+        // pairs, each pair linked by the component rules (all of x-1, x are initiators), so both candidates carry
+        // the SAME pair of components: the duplicate upstream removes after its slope sort.  Keep dir 2, flag it.
+        const uint32_t c3_left = ((ML.x >> 31) & N.y & 1u) | ((ML.y >> 31) & N.x & 1u);                 // dir 3 at (x0-1, y)
+        const uint32_t c2_right = x0 + 32 <= g.wd - 2 ? ((MR.x & (N.y >> 31)) | (MR.y & (N.x >> 31))) & 1u : 0u;   // dir 2 at (x0+32, y)
+        dup2 = m[2] & ((m[3] << 1) | c3_left);
+        m[3] &= ~((m[2] >> 1) | (c2_right << 31));
     }
     const int cnt_all = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
     int total_all = cnt_all;
@@ -116,7 +125,10 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
                 for (uint32_t mm = m[d]; mm; mm &= mm - 1) {
                     const int c = __ffs(mm) - 1;
                     const uint32_t pos = (M.y >> c) & 1u;   // v1 > v0  <=>  v0 == 0 (black)
-                    scand[w][o++] = (uint16_t)(lane | (c << 5) | (d << 10) | (pos << 12));
+                    uint32_t e = lane | (c << 5) | (d << 10) | (pos << 12);
+                    if (d == 2 && ((dup2 >> c) & 1u))       // merged: + polarity of the dir-3 point, whose v0 is (x-1, y)
+                        e |= (1u << 13) | ((c > 0 ? (M.y >> (c - 1)) & 1u : ML.y >> 31) << 14);
+                    scand[w][o++] = (uint16_t)e;
                 }
         }
         __syncwarp();
@@ -153,12 +165,18 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
                 d0 = min(d0, idmax);
                 d1 = min(d1, idmax);
                 const uint32_t key = (max(d0, d1) << id_bits) | min(d0, d1);
-                rec = ((unsigned long long)key << 32) | pack_point(2 * (x0 + c) + dx, 2 * (y0 + r) + dy, d, pos);
+                const int merged = (cd >> 13) & 1;
+                const int kind = merged ? (8 | pos | (((cd >> 14) & 1) << 1)) : (d | (pos << 2));
+                rec = ((unsigned long long)key << 32) | pack_point(2 * (x0 + c) + dx, 2 * (y0 + r) + dy, kind);
             }
             const uint32_t okm = __ballot_sync(FULL_MASK, ok);
             if (okm == 0) continue;
+            const uint32_t dupm = __ballot_sync(FULL_MASK, ok && ((cd >> 13) & 1u));
             int base = 0;
-            if (lane == 0) base = atomicAdd(&npts[frame], __popc(okm));
+            if (lane == 0) {
+                base = atomicAdd(&npts[frame], __popc(okm));
+                if (dupm) atomicAdd(&ndups[frame], __popc(dupm));   // (raw point count = npts + ndups)
+            }
             base = __shfl_sync(FULL_MASK, base, 0);
             const int p = base + __popc(okm & ((1u << lane) - 1u));
             if (ok && p < cap) fk[p] = rec;

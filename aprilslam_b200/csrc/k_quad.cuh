@@ -309,13 +309,22 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     // ---- bounding box and polarity sums
     int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
     long long Sxgx = 0, Sygy = 0, Sgx = 0, Sgy = 0;
+    int nmerged = 0;
     for (int i = tid; i < sz; i += T) {
         uint32_t v = (uint32_t)pv[i];
-        int px = v & 0x3fff, py = (v >> 14) & 0x3fff, dir = (v >> 28) & 3;
-        int s = ((v >> 30) & 1) ? 255 : -255;
-        int dx = (dir == 0 || dir == 3) ? 1 : (dir == 2 ? -1 : 0);
-        int dy = dir == 0 ? 0 : 1;
-        int gx = dx * s, gy = dy * s;
+        int px = v & 0x3fff, py = (v >> 14) & 0x3fff;
+        const int kind = v >> 28;
+        int gx, gy;
+        if (kind < 8) {
+            const int dir = kind & 3, s = (kind & 4) ? 255 : -255;
+            const int dx = (dir == 0 || dir == 3) ? 1 : (dir == 2 ? -1 : 0);
+            const int dy = dir == 0 ? 0 : 1;
+            gx = dx * s; gy = dy * s;
+        } else {   // two raw points at this (x, y): direction 2 (-1, 1) and direction 3 (1, 1)
+            const int s2 = (kind & 1) ? 255 : -255, s3 = (kind & 2) ? 255 : -255;
+            gx = s3 - s2; gy = s2 + s3;
+            nmerged++;
+        }
         xmin = min(xmin, px); xmax = max(xmax, px);
         ymin = min(ymin, py); ymax = max(ymax, py);
         Sxgx += (long long)px * gx; Sgx += gx;
@@ -325,6 +334,8 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     ymin = G.reduce_min(ymin); ymax = G.reduce_max(ymax);
     Sxgx = G.reduce_sum(Sxgx); Sygy = G.reduce_sum(Sygy);
     Sgx = G.reduce_sum(Sgx); Sgy = G.reduce_sum(Sgy);
+    // upstream's size limit counts the raw points (duplicates included)
+    if (sz + (int)G.reduce_sum((long long)nmerged) > 3 * (2 * a.g.wd + 2 * a.g.hd)) return false;
     if ((xmax - xmin) * (ymax - ymin) < P.min_tag_width) return false;
     const float cx = (xmin + xmax) * 0.5f + 0.05118f;
     const float cy = (ymin + ymax) * 0.5f - 0.028581f;
@@ -356,28 +367,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     group_radix_sort_hi32<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(a.lfps + seg * 6), sz, scnt);
     group_fix_ties<NW>(G, sbuf, sz);
 
-    // ---- remove consecutive duplicates (same x, y); in place: a tile is read completely before it is written,
-    //      and writes only go to positions at or below the ones read
-    {
-        int outn = 0;
-        for (int base = 0; base < sz; base += T) {
-            const int i = base + tid;
-            unsigned long long kk = 0ull;
-            bool keep = false;
-            if (i < sz) {
-                kk = sbuf[i];
-                const uint32_t pxy = i > 0 ? (uint32_t)sbuf[i - 1] : 0xffffffffu;
-                keep = (uint32_t)kk != pxy;
-            }
-            G.sync();
-            int total;
-            const int pos = G.compact_pos(keep, total);
-            if (keep) sbuf[outn + pos] = kk;
-            outn += total;
-            G.sync();
-        }
-        sz = outn;
-    }
+    // (no duplicate points to remove here: the only duplicates upstream produces were merged at emission, k_edges)
     if (sz < 24) return false;
 
     // ---- gradient weights: squared gradient magnitude of the decimated image at every point, gathered in a
