@@ -605,7 +605,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         LAUNCH_CHECK("k_decode_quads");
     }
     tm.mark(sl.tail);  // 7: after decode
-    k_reconcile<<<ceil_div(n, h->tune.tail_threads / 32), h->tune.tail_threads, 0, sl.tail>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
+    k_reconcile<<<n, 32, 0, sl.tail>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
                                                       sl.d_out.as<DetRec>(), d_out_counts, c.cap_out);
     LAUNCH_CHECK("k_reconcile");
     if (c.pose->enabled) {

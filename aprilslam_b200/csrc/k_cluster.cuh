@@ -244,7 +244,7 @@ k_sort_scan(const int* __restrict__ npts, int cap, uint32_t* __restrict__ hist, 
     digit_total[(size_t)frame * RS_RADIX + d] = run;
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 2)
 k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long long* __restrict__ recs_out,
                const int* __restrict__ npts, int cap, int shift, const uint32_t* __restrict__ hist,
                const uint32_t* __restrict__ digit_total, int nblk_max) {

@@ -471,30 +471,37 @@ __device__ int prefer_dev(const DetRec& a, const DetRec& b) {
 
 #define REC_CAP 256  // internal per-frame detection capacity before reconcile
 
-// order 0: (id, family, cx, cy)   order 1: (id, cx, cy)
-__device__ __forceinline__ bool det_less(const DetRec& a, const DetRec& b, int order) {
-    if (a.id != b.id) return a.id < b.id;
-    if (order == 0 && a.family != b.family) return a.family < b.family;
-    if (a.c[0] != b.c[0]) return a.c[0] < b.c[0];
-    return a.c[1] < b.c[1];
-}
-
-__global__ void __launch_bounds__(128)
+// One warp (= one CTA) per frame.  The sort keys (id, family, centre) are staged in shared memory once, so the two
+// rank sorts run out of shared memory instead of re-reading the 168-byte records n times.
+__global__ void __launch_bounds__(32)
 k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int cap_dets, int nframes,
             DetRec* __restrict__ out, int* __restrict__ out_counts, int cap_out) {
-    __shared__ int s_perm[4][REC_CAP];
-    __shared__ unsigned char s_dead[4][REC_CAP];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int frame = blockIdx.x * (blockDim.x >> 5) + w;
+    __shared__ int s_perm[REC_CAP];
+    __shared__ unsigned char s_dead[REC_CAP];
+    __shared__ int s_id[REC_CAP], s_fam[REC_CAP];
+    __shared__ double s_cx[REC_CAP], s_cy[REC_CAP];
+    const int lane = threadIdx.x & 31;
+    const int frame = blockIdx.x;
     if (frame >= nframes) return;
     const int n = min(min(ndets[frame], cap_dets), REC_CAP);
     const DetRec* fd = dets + (size_t)frame * cap_dets;
-    int* perm = s_perm[w];
-    unsigned char* dead = s_dead[w];
+    int* perm = s_perm;
+    unsigned char* dead = s_dead;
+    for (int i = lane; i < n; i += 32) {
+        s_id[i] = fd[i].id; s_fam[i] = fd[i].family; s_cx[i] = fd[i].c[0]; s_cy[i] = fd[i].c[1];
+    }
+    __syncwarp();
+    // order 0: (id, family, cx, cy)   order 1: (id, cx, cy)
+    auto less = [&](int a, int b, int order) {
+        if (s_id[a] != s_id[b]) return s_id[a] < s_id[b];
+        if (order == 0 && s_fam[a] != s_fam[b]) return s_fam[a] < s_fam[b];
+        if (s_cx[a] != s_cx[b]) return s_cx[a] < s_cx[b];
+        return s_cy[a] < s_cy[b];
+    };
     for (int i = lane; i < n; i += 32) {
         int rank = 0;
         for (int j = 0; j < n; j++)
-            if (det_less(fd[j], fd[i], 0) || (!det_less(fd[i], fd[j], 0) && j < i)) rank++;
+            if (less(j, i, 0) || (!less(i, j, 0) && j < i)) rank++;
         perm[rank] = i;
         dead[i] = 0;
     }
@@ -505,8 +512,8 @@ k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int 
             if (dead[i]) continue;
             for (int b = a + 1; b < n; b++) {
                 const int j = perm[b];
-                if (fd[j].id != fd[i].id) break;
-                if (dead[j] || fd[j].family != fd[i].family) continue;
+                if (s_id[j] != s_id[i]) break;
+                if (dead[j] || s_fam[j] != s_fam[i]) continue;
                 if (!polys_overlap_dev(fd[i].p, fd[j].p)) continue;
                 if (prefer_dev(fd[i], fd[j]) < 0) dead[j] = 1;
                 else { dead[i] = 1; break; }
@@ -520,7 +527,7 @@ k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int 
         int rank = 0;
         for (int j = 0; j < n; j++) {
             if (dead[j]) continue;
-            if (det_less(fd[j], fd[i], 1) || (!det_less(fd[i], fd[j], 1) && j < i)) rank++;
+            if (less(j, i, 1) || (!less(i, j, 1) && j < i)) rank++;
         }
         if (rank < cap_out) out[(size_t)frame * cap_out + rank] = fd[i];
         alive_total++;
