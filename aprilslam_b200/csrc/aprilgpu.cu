@@ -73,7 +73,7 @@ struct HostBuf {
 };
 
 // cluster size tiers of the quad-fit kernel: {largest cluster, warps per CTA, CTAs per SM}
-constexpr int TIER_CAP[AGPU_NTIERS] = {256, 1024, 2048, 16384};
+constexpr int TIER_CAP_DEFAULT[AGPU_NTIERS] = {256, 1024, 2048, 16384};
 // warps per cluster group (NW); tier 0 packs 8 one-warp groups into a CTA, the others use one CTA per cluster
 constexpr int TIER_NW[AGPU_NTIERS] = {1, 2, 4, 8};
 // counter block layout (ints): [0..3] clusters per tier
@@ -137,7 +137,9 @@ struct agpu_handle {
     struct Tune {
         int prio = 1;                                  // back half of a chunk on high-priority streams
         int tier_ctas[AGPU_NTIERS] = {3, 16, 8, 1};    // persistent quad-fit CTAs per SM, by size tier
+        int tier_cap[AGPU_NTIERS] = {TIER_CAP_DEFAULT[0], TIER_CAP_DEFAULT[1], TIER_CAP_DEFAULT[2], TIER_CAP_DEFAULT[3]};
         int decode_ctas = 4;                           // persistent decode CTAs (of 4 warps) per SM
+        int edge_warps = 2, boundary_warps = 8;        // tiles (warps) per CTA of k_edges / k_cc_boundary
         int tail_threads = 32;                         // CTA size of decode / reconcile / pose: small CTAs find room on SMs
                                                        // that the streaming kernels of the next chunk keep full
     } tune;
@@ -377,9 +379,13 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
                                                    sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
                                                    sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
     LAUNCH_CHECK("k_cc_local");
-    dim3 gridb(ceil_div(tx * ty, CCB_WARPS), 1, n);
-    k_cc_boundary<<<gridb, CCB_WARPS * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
-                                                           sl.d_labels.as<uint32_t>(), g);
+    {
+        const int bw = h->tune.boundary_warps;
+        dim3 gridb(ceil_div(tx * ty, bw), 1, n);
+#define LAUNCH_CCB(BW) k_cc_boundary<BW><<<gridb, BW * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), sl.d_labels.as<uint32_t>(), g)
+        if (bw == 1) LAUNCH_CCB(1); else if (bw == 2) LAUNCH_CCB(2); else if (bw == 4) LAUNCH_CCB(4); else LAUNCH_CCB(8);
+#undef LAUNCH_CCB
+    }
     LAUNCH_CHECK("k_cc_boundary");
     dim3 grids(std::max(1, std::min(8, ceil_div(g.plane / 1024, 256))), n * CC_SUBLISTS);
     k_cc_sizes<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
@@ -510,10 +516,12 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     if (rc) return rc;
     tm.mark();  // 3: after CC
     {
-        dim3 grid(n, ceil_div(cc_tiles_x(g), EDGE_WARPS), cc_tiles_y(g));
-        k_edges<<<grid, EDGE_WARPS * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
-                                                         sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g,
-                                                         sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, cap, c.id_bits);
+        const int ew = h->tune.edge_warps;
+        dim3 grid(n, ceil_div(cc_tiles_x(g), ew), cc_tiles_y(g));
+#define LAUNCH_EDGES(EW) k_edges<EW><<<grid, EW * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), \
+            sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g, sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, cap, c.id_bits)
+        if (ew == 1) LAUNCH_EDGES(1); else if (ew == 2) LAUNCH_EDGES(2); else if (ew == 4) LAUNCH_EDGES(4); else LAUNCH_EDGES(8);
+#undef LAUNCH_EDGES
         LAUNCH_CHECK("k_edges");
     }
     tm.mark();  // 4: after edges
@@ -538,7 +546,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         ClusterLists cl;
         for (int t = 0; t < AGPU_NTIERS; t++) {
             cl.list[t] = sl.d_clusters[t].as<ClusterRef>();
-            cl.cap[t] = TIER_CAP[t];
+            cl.cap[t] = h->tune.tier_cap[t];
         }
         cl.counters = d_cnt;
         cl.cap_list = n * c.maxcl;
@@ -571,14 +579,14 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             qa.cursor = d_cnt + CNT_CURSOR0 + t;
             const int nblk = h->num_sms * h->tune.tier_ctas[t];
             if (t == 0) {
-                const size_t smem = 8 * qf_smem_per_group(TIER_CAP[t], 1);
-                k_fit_quads<1><<<nblk, 256, smem, st>>>(qa, h->prm, TIER_CAP[t]);
+                const size_t smem = 8 * qf_smem_per_group(h->tune.tier_cap[t], 1);
+                k_fit_quads<1><<<nblk, 256, smem, st>>>(qa, h->prm, h->tune.tier_cap[t]);
             } else if (t == 1) {
-                k_fit_quads<2><<<nblk, 64, qf_smem_per_group(TIER_CAP[t], 2), st>>>(qa, h->prm, TIER_CAP[t]);
+                k_fit_quads<2><<<nblk, 64, qf_smem_per_group(h->tune.tier_cap[t], 2), st>>>(qa, h->prm, h->tune.tier_cap[t]);
             } else if (t == 2) {
-                k_fit_quads<4><<<nblk, 128, qf_smem_per_group(TIER_CAP[t], 4), st>>>(qa, h->prm, TIER_CAP[t]);
+                k_fit_quads<4><<<nblk, 128, qf_smem_per_group(h->tune.tier_cap[t], 4), st>>>(qa, h->prm, h->tune.tier_cap[t]);
             } else {
-                k_fit_quads<8><<<nblk, 256, qf_smem_per_group(TIER_CAP[t], 8), st>>>(qa, h->prm, TIER_CAP[t]);
+                k_fit_quads<8><<<nblk, 256, qf_smem_per_group(h->tune.tier_cap[t], 8), st>>>(qa, h->prm, h->tune.tier_cap[t]);
             }
             LAUNCH_CHECK("k_fit_quads");
             if (t > 0) {
@@ -857,8 +865,15 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     h->families_str = cfg->families;
     h->cfg.families = h->families_str.c_str();
     if (const char* e = getenv("AGPU_PRIO")) h->tune.prio = atoi(e) != 0;
+    if (const char* e = getenv("AGPU_EDGE_WARPS")) h->tune.edge_warps = atoi(e);
+    if (const char* e = getenv("AGPU_BOUNDARY_WARPS")) h->tune.boundary_warps = atoi(e);
     if (const char* e = getenv("AGPU_TAIL_THREADS")) h->tune.tail_threads = atoi(e) >= 128 ? 128 : (atoi(e) >= 64 ? 64 : 32);
     if (const char* e = getenv("AGPU_DECODE_CTAS")) h->tune.decode_ctas = std::max(1, std::min(16, atoi(e)));
+    if (const char* e = getenv("AGPU_TIER_CAP")) {
+        int v[3];
+        if (sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3 && v[0] >= 64 && v[0] < v[1] && v[1] < v[2] && v[2] <= 4096)
+            for (int t = 0; t < 3; t++) h->tune.tier_cap[t] = v[t];
+    }
     if (const char* e = getenv("AGPU_TIER_CTAS")) {
         int v[AGPU_NTIERS];
         if (sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
@@ -960,12 +975,12 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     }
     // the large quad-fit tiers need more than 48 KB of dynamic shared memory
     ce = cudaFuncSetAttribute(k_fit_quads<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)qf_smem_per_group(TIER_CAP[AGPU_NTIERS - 1], 8));
+                              (int)qf_smem_per_group(h->tune.tier_cap[AGPU_NTIERS - 1], 8));
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(k_fit_quads<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(8 * qf_smem_per_group(TIER_CAP[0], 1)));
+                                  (int)(8 * qf_smem_per_group(h->tune.tier_cap[0], 1)));
     if (ce != cudaSuccess) return fail(AGPU_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
     *out = h;
     return AGPU_OK;

@@ -294,12 +294,12 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
 // the unions run between TILE-LOCAL ROOTS (found through the run-start labels), never between pixels.
 // As in the local pass only initiator pixels (1 <= x <= wd-2) issue links: left and up for both colours, up-left
 // and up-right for white.  Top row: lane = column; left / right column: lane = row.
-#define CCB_WARPS 8
 __device__ __forceinline__ uint2 cc_ld_mask(const uint2* __restrict__ fm, const Geom& g, int tx, int ty, int r) {
     if (tx < 0 || ty < 0 || tx >= cc_tiles_x(g) || ty >= cc_tiles_y(g)) return make_uint2(0u, 0u);
     return __ldg(&fm[((size_t)ty * cc_tiles_x(g) + tx) * 32 + r]);
 }
 
+template <int CCB_WARPS>
 __global__ void __launch_bounds__(CCB_WARPS * 32)
 k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, uint32_t* __restrict__ labels, Geom g) {
     const int frame = blockIdx.z;

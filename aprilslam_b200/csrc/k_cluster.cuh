@@ -20,8 +20,8 @@
 // candidates of a warp are compacted through shared memory and then handled ONE PER LANE (run-start label +
 // representative + dense-id look-ups, ballot compaction, one atomic per 32 candidates), so the expensive part is
 // not serialised inside the few rows that sit on an edge.
-#define EDGE_WARPS 8
 #define EDGE_CAND_PER_PASS 1024   // a tile with more candidates is handled in four passes of 8 rows (8 x 32 x 4)
+template <int EDGE_WARPS>
 __global__ void __launch_bounds__(EDGE_WARPS * 32)
 k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
         const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts,
