@@ -81,6 +81,7 @@ def load():
     L.agpu_pose.argtypes = [vp, vp, ci, vp, vp, ci, cd, ci, vp]
     L.agpu_set_profiling.argtypes = [vp, ci]
     L.agpu_get_stage_ms.argtypes = [vp, vp]
+    L.agpu_get_kernel_ms.argtypes = [vp, C.c_char_p, vp]
     L.agpu_get_launch_count.argtypes = [vp, vp]
     L.agpu_get_counters.argtypes = [vp, vp]
     L.agpu_debug_fetch.argtypes = [vp, C.c_char_p, ci, vp, C.c_longlong]
@@ -95,5 +96,5 @@ def load():
 
 EXPORTS = ["agpu_version", "agpu_default_config", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_detect",
            "agpu_detect_bgr", "agpu_detect_pose", "agpu_pose", "agpu_set_profiling", "agpu_get_stage_ms",
-           "agpu_get_launch_count", "agpu_get_counters", "agpu_debug_fetch", "agpu_debug_dims",
+           "agpu_get_kernel_ms", "agpu_get_launch_count", "agpu_get_counters", "agpu_debug_fetch", "agpu_debug_dims",
            "agpu_stage_threshold", "agpu_stage_labels", "agpu_render"]

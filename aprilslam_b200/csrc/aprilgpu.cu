@@ -90,6 +90,7 @@ struct Slot {
     cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};   // side streams: quad-fit tiers run concurrently
     cudaEvent_t ev_mid = nullptr, ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;   // stage timing
+    cudaEvent_t ev_k[2] = {nullptr, nullptr};   // around k_cc_local (the roofline kernel), profiling only
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_labels, d_canon, d_sizes, d_roots, d_dense, d_dense2rep;
     DevBuf d_recs[2], d_hist, d_dtot, d_lfps, d_errs;
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk]
@@ -107,6 +108,7 @@ struct Slot {
         h_out.release(); h_counts.release(); h_poses.release();
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         events.clear();
+        for (int i = 0; i < 2; i++) { if (ev_k[i]) cudaEventDestroy(ev_k[i]); ev_k[i] = nullptr; }
         for (int t = 0; t < AGPU_NTIERS - 1; t++) {
             if (aux[t]) cudaStreamDestroy(aux[t]);
             if (ev_join[t]) cudaEventDestroy(ev_join[t]);
@@ -130,6 +132,7 @@ struct agpu_handle {
     std::string err;
     bool profiling = false;
     float stage_ms[AGPU_NUM_STAGES];
+    float cc_local_ms = 0;   // k_cc_local alone (agpu_get_kernel_ms)
     long long launches = 0;
     long long counters[8];
 
@@ -375,10 +378,16 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
     const size_t sub_stride = (size_t)tx * ceil_div(ty, CC_SUBLISTS) * 512;
     CK(sl.d_roots.ensure(sub_stride * CC_SUBLISTS * n * 4));
     dim3 grid(ceil_div(tx, CC_WARPS), ty, n);
+    if (h->profiling) {
+        for (int i = 0; i < 2; i++)
+            if (!sl.ev_k[i]) CK(cudaEventCreate(&sl.ev_k[i]));
+        CK(cudaEventRecord(sl.ev_k[0], sl.stream));
+    }
     k_cc_local<<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
                                                    sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
                                                    sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
     LAUNCH_CHECK("k_cc_local");
+    if (h->profiling) CK(cudaEventRecord(sl.ev_k[1], sl.stream));
     {
         const int bw = h->tune.boundary_warps;
         dim3 gridb(ceil_div(tx * ty, bw), 1, n);
@@ -659,6 +668,8 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
             cudaEventElapsedTime(&ms, sl.events[s], sl.events[s + 1]);
             h->stage_ms[s] += ms;
         }
+        float kms = 0;
+        if (sl.ev_k[0] && cudaEventElapsedTime(&kms, sl.ev_k[0], sl.ev_k[1]) == cudaSuccess) h->cc_local_ms += kms;
     }
     const int* hc = sl.h_counts.as<int>();
     const int* h_npts = hc + CNT_FIXED;
@@ -732,6 +743,7 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     CK(cudaSetDevice(h->device));
     h->launches = 0;
     for (int i = 0; i < AGPU_NUM_STAGES; i++) h->stage_ms[i] = 0;
+    h->cc_local_ms = 0;
     for (int i = 0; i < 8; i++) h->counters[i] = 0;
     CallCtx c;
     c.frames = frames; c.on_device = on_device; c.channels = channels; c.B = B; c.W = W; c.H = H; c.stride = stride;
@@ -1073,6 +1085,16 @@ int agpu_set_profiling(agpu_handle* h, int on) {
 int agpu_get_stage_ms(agpu_handle* h, float* ms) {
     if (!h || !ms) return AGPU_E_INVALID;
     for (int i = 0; i < AGPU_NUM_STAGES; i++) ms[i] = h->stage_ms[i];
+    return AGPU_OK;
+}
+
+int agpu_get_kernel_ms(agpu_handle* h, const char* kernel, float* ms) {
+    if (!h || !kernel || !ms) return AGPU_E_INVALID;
+    if (std::string(kernel) != "k_cc_local") {
+        h->set_err("agpu_get_kernel_ms: only k_cc_local carries its own timer");
+        return AGPU_E_INVALID;
+    }
+    *ms = h->cc_local_ms;
     return AGPU_OK;
 }
 

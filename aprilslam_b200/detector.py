@@ -157,6 +157,12 @@ class Detector:
     def set_profiling(self, on: bool = True):
         self._check(self._L.agpu_set_profiling(self._h, int(on)))
 
+    def kernel_ms(self, kernel: str = "k_cc_local") -> float:
+        """CUDA-event time of one kernel over the last call (profiling on); only k_cc_local has its own timer."""
+        ms = np.zeros(1, np.float32)
+        self._check(self._L.agpu_get_kernel_ms(self._h, kernel.encode(), ms.ctypes.data))
+        return float(ms[0])
+
     def stage_ms(self) -> dict:
         ms = np.zeros(len(STAGE_NAMES), np.float32)
         self._check(self._L.agpu_get_stage_ms(self._h, ms.ctypes.data))

@@ -126,6 +126,9 @@ enum { AGPU_STAGE_H2D = 0, AGPU_STAGE_IMAGE, AGPU_STAGE_CC, AGPU_STAGE_EDGES, AG
  * chunks, measured on the library's own stream).  on != 0 enables it (adds event records only). */
 int agpu_set_profiling(agpu_handle* h, int on);
 int agpu_get_stage_ms(agpu_handle* h, float* ms /* [AGPU_NUM_STAGES] */);
+/* CUDA-event time of ONE kernel summed over the chunks of the last call (profiling on).  Only "k_cc_local", the
+ * kernel bench.py quotes the roofline fraction for, carries its own pair of events. */
+int agpu_get_kernel_ms(agpu_handle* h, const char* kernel, float* ms);
 /* Kernel launches issued by the last agpu_detect* / agpu_pose call. */
 int agpu_get_launch_count(agpu_handle* h, long long* launches);
 /* Work counters of the last call, summed over frames: [0] edge points, [1] clusters fitted,
