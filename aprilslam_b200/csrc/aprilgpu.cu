@@ -22,6 +22,7 @@
 #include "k_decode.cuh"
 #include "k_pose.cuh"
 #include "k_render.cuh"
+#include "k_graph.cuh"
 
 #include "families_data.inc"
 
@@ -162,6 +163,14 @@ struct agpu_handle {
     bool have_last = false;
 
     void set_err(const std::string& s) { err = s; }
+};
+
+// Tag graphs of S independent camera streams, resident in HBM between agpu_graph_update calls.
+struct agpu_graph {
+    agpu_handle* h = nullptr;
+    int S = 0, nid = 0;
+    DevBuf d_coord, d_est, d_present, d_updated, d_visible, d_reference, d_weight, d_local, d_world, d_skipped;
+    DevBuf d_dets, d_poses, d_counts, d_my_pose, d_valid;
 };
 
 namespace {
@@ -764,10 +773,13 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
         chunk = (int)std::max<size_t>(1, target_px / g.plane);
         chunk = std::min(chunk, 256);
         if (B >= 48) chunk = std::min(chunk, (B + 2) / 3);
+        // host frames: the call is bound by the host link, so what matters is that the link never idles and that
+        // little work is left once the last copy has landed -- small chunks, one more slot
+        if (!on_device) chunk = std::min(chunk, std::max(1, (int)(((size_t)64 << 20) / g.plane)));
     }
     chunk = std::min(chunk, B);
     c.chunk = chunk;
-    int nslots = h->cfg.pipeline_slots > 0 ? h->cfg.pipeline_slots : 3;
+    int nslots = h->cfg.pipeline_slots > 0 ? h->cfg.pipeline_slots : (on_device ? 3 : 4);
     if (const char* e = getenv("AGPU_SLOTS")) nslots = std::max(1, atoi(e));
     nslots = std::min(nslots, 8);
     nslots = std::min(nslots, ceil_div(B, chunk));
@@ -1306,6 +1318,113 @@ int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint3
                 sizes_out[(size_t)y * W + x] = v;
             }
         }
+    return AGPU_OK;
+}
+
+
+// ---- tag graph (the step after the path) ------------------------------------------------------
+int agpu_graph_create(agpu_handle* h, int nstreams, int max_tag_id, agpu_graph** out) {
+    if (!h || !out) return AGPU_E_INVALID;
+    *out = nullptr;
+    if (nstreams <= 0 || max_tag_id < 0 || max_tag_id > (1 << 20)) {
+        h->set_err("agpu_graph_create: nstreams > 0 and 0 <= max_tag_id <= 2^20 expected");
+        return AGPU_E_INVALID;
+    }
+    CK(cudaSetDevice(h->device));
+    agpu_graph* g = new agpu_graph();
+    g->h = h; g->S = nstreams; g->nid = max_tag_id + 1;
+    const size_t S = nstreams, n = (size_t)nstreams * g->nid;
+    cudaError_t e = cudaSuccess;
+    auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
+    need(g->d_coord, S * 4); need(g->d_est, S * 16 * 8); need(g->d_skipped, S * 4);
+    need(g->d_present, n); need(g->d_updated, n); need(g->d_visible, n);
+    need(g->d_reference, n * 4); need(g->d_weight, n * 4); need(g->d_local, n * 16 * 8); need(g->d_world, n * 16 * 8);
+    if (e != cudaSuccess) {
+        h->set_err(std::string("agpu_graph_create: ") + cudaGetErrorString(e));
+        agpu_graph_destroy(g);
+        return AGPU_E_CUDA;
+    }
+    *out = g;
+    return agpu_graph_reset(g);
+}
+
+int agpu_graph_reset(agpu_graph* g) {
+    if (!g) return AGPU_E_INVALID;
+    agpu_handle* h = g->h;
+    CK(cudaSetDevice(h->device));
+    const size_t S = g->S, n = (size_t)g->S * g->nid;
+    CK(cudaMemset(g->d_coord.p, 0xff, S * 4));   // coordinate_id = -1
+    CK(cudaMemset(g->d_est.p, 0, S * 16 * 8));
+    CK(cudaMemset(g->d_skipped.p, 0, S * 4));
+    CK(cudaMemset(g->d_present.p, 0, n)); CK(cudaMemset(g->d_updated.p, 0, n)); CK(cudaMemset(g->d_visible.p, 0, n));
+    CK(cudaMemset(g->d_reference.p, 0xff, n * 4)); CK(cudaMemset(g->d_weight.p, 0, n * 4));
+    CK(cudaMemset(g->d_local.p, 0, n * 16 * 8)); CK(cudaMemset(g->d_world.p, 0, n * 16 * 8));
+    return AGPU_OK;
+}
+
+int agpu_graph_destroy(agpu_graph* g) {
+    if (!g) return AGPU_E_INVALID;
+    cudaSetDevice(g->h->device);
+    DevBuf* bufs[] = {&g->d_coord, &g->d_est, &g->d_present, &g->d_updated, &g->d_visible, &g->d_reference, &g->d_weight,
+                      &g->d_local, &g->d_world, &g->d_skipped, &g->d_dets, &g->d_poses, &g->d_counts, &g->d_my_pose, &g->d_valid};
+    for (DevBuf* b : bufs) b->release();
+    delete g;
+    return AGPU_OK;
+}
+
+int agpu_graph_update(agpu_graph* g, int F, const agpu_detection* dets, const agpu_pose_t* poses, const int* counts,
+                      int cap_per_frame, double* my_pose, uint8_t* valid) {
+    if (!g) return AGPU_E_INVALID;
+    agpu_handle* h = g->h;
+    if (F <= 0 || cap_per_frame <= 0 || !dets || !poses || !counts || !my_pose || !valid) {
+        h->set_err("agpu_graph_update: invalid argument");
+        return AGPU_E_INVALID;
+    }
+    CK(cudaSetDevice(h->device));
+    const size_t SF = (size_t)g->S * F, recs = SF * cap_per_frame;
+    CK(g->d_dets.ensure(recs * sizeof(DetRec))); CK(g->d_poses.ensure(recs * sizeof(PoseRec)));
+    CK(g->d_counts.ensure(SF * 4)); CK(g->d_my_pose.ensure(SF * 16 * 8)); CK(g->d_valid.ensure(SF));
+    cudaStream_t st = h->slots[0].stream;
+    CK(cudaMemcpyAsync(g->d_dets.p, dets, recs * sizeof(DetRec), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g->d_poses.p, poses, recs * sizeof(PoseRec), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g->d_counts.p, counts, SF * 4, cudaMemcpyHostToDevice, st));
+    GraphArgs a;
+    a.S = g->S; a.F = F; a.cap = cap_per_frame; a.nid = g->nid;
+    a.dets = g->d_dets.as<DetRec>(); a.poses = g->d_poses.as<PoseRec>(); a.counts = g->d_counts.as<int>();
+    a.coordinate_id = g->d_coord.as<int>(); a.estimated_pose = g->d_est.as<double>();
+    a.present = g->d_present.as<unsigned char>(); a.updated = g->d_updated.as<unsigned char>();
+    a.visible = g->d_visible.as<unsigned char>(); a.reference = g->d_reference.as<int>(); a.weight = g->d_weight.as<int>();
+    a.local = g->d_local.as<double>(); a.world = g->d_world.as<double>();
+    a.my_pose = g->d_my_pose.as<double>(); a.valid = g->d_valid.as<unsigned char>(); a.skipped = g->d_skipped.as<int>();
+    h->launches = 0;
+    k_graph_update<<<ceil_div(g->S, 32), 32, 0, st>>>(a);
+    LAUNCH_CHECK("k_graph_update");
+    CK(cudaMemcpyAsync(my_pose, g->d_my_pose.p, SF * 16 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(valid, g->d_valid.p, SF, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AGPU_OK;
+}
+
+int agpu_graph_get(agpu_graph* g, int stream, int* coordinate_id, double* estimated_pose, uint8_t* present, int* reference,
+                   int* weight, uint8_t* updated, uint8_t* visible, double* local, double* world, int* skipped) {
+    if (!g) return AGPU_E_INVALID;
+    agpu_handle* h = g->h;
+    if (stream < 0 || stream >= g->S) {
+        h->set_err("agpu_graph_get: stream out of range");
+        return AGPU_E_INVALID;
+    }
+    CK(cudaSetDevice(h->device));
+    const size_t n = g->nid, o = (size_t)stream * n;
+    if (coordinate_id) CK(cudaMemcpy(coordinate_id, g->d_coord.as<int>() + stream, 4, cudaMemcpyDeviceToHost));
+    if (skipped) CK(cudaMemcpy(skipped, g->d_skipped.as<int>() + stream, 4, cudaMemcpyDeviceToHost));
+    if (estimated_pose) CK(cudaMemcpy(estimated_pose, g->d_est.as<double>() + (size_t)stream * 16, 128, cudaMemcpyDeviceToHost));
+    if (present) CK(cudaMemcpy(present, g->d_present.as<unsigned char>() + o, n, cudaMemcpyDeviceToHost));
+    if (updated) CK(cudaMemcpy(updated, g->d_updated.as<unsigned char>() + o, n, cudaMemcpyDeviceToHost));
+    if (visible) CK(cudaMemcpy(visible, g->d_visible.as<unsigned char>() + o, n, cudaMemcpyDeviceToHost));
+    if (reference) CK(cudaMemcpy(reference, g->d_reference.as<int>() + o, n * 4, cudaMemcpyDeviceToHost));
+    if (weight) CK(cudaMemcpy(weight, g->d_weight.as<int>() + o, n * 4, cudaMemcpyDeviceToHost));
+    if (local) CK(cudaMemcpy(local, g->d_local.as<double>() + o * 16, n * 128, cudaMemcpyDeviceToHost));
+    if (world) CK(cudaMemcpy(world, g->d_world.as<double>() + o * 16, n * 128, cudaMemcpyDeviceToHost));
     return AGPU_OK;
 }
 

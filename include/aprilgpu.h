@@ -12,6 +12,8 @@
  *                          + cv2.Rodrigues(rvec) -> 4x4 T         src/detection/tag_detector.py:45-52
  *   agpu_detect_pose   <-  the caller loop  detect(); for d in detections: get_pose(d)
  *                          src/core/slam.py:21-32, src/simulation/simulation_engine.py:219-223
+ *   agpu_graph_update  <-  SLAMGraph.add_or_update_node + SLAM.my_pose (the consumer of the path)
+ *                          src/core/slam_graph.py:29-70, src/core/slam.py:36-63
  *
  * Plain C: pointers and sizes only.  Nothing crosses this boundary as a C++ or torch type, and
  * no exception leaves the library.  Every function returns AGPU_OK (0) or a negative agpu_status;
@@ -56,8 +58,8 @@ typedef struct agpu_config {
     int debug;                /* (0)  1: keep stage buffers of the last chunk for agpu_debug_fetch */
     /* B200 side */
     int device;               /* CUDA device ordinal */
-    int chunk_frames;         /* frames processed per pipeline pass (0 = auto: ~256 Mpx of working image) */
-    int pipeline_slots;       /* chunks in flight on independent streams (0 = auto: 3) */
+    int chunk_frames;         /* frames processed per pipeline pass (0 = auto: ~256 Mpx of working image for device frames, ~64 Mpx for host frames) */
+    int pipeline_slots;       /* chunks in flight on independent streams (0 = auto: 3 for device frames, 4 for host frames) */
     int max_points_per_frame; /* edge-point list capacity per frame (0 = auto: decimated pixels / 4, >= 65536) */
     int max_clusters_per_frame; /* (0 = auto) */
     int max_quads_per_frame;  /* (0 = auto: 1024) */
@@ -157,6 +159,32 @@ int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint3
  * level per frame.  The call returns after the frames are complete. */
 int agpu_render(agpu_handle* h, const void* tags_host, const int* tag_offsets_host, const uint8_t* backgrounds_host,
                 int B, int W, int H, uint8_t* frames_dev, void* cuda_stream);
+
+/* ---- tag graph + camera pose estimate (the step after the path) ------------------- */
+
+/* The graph update of SLAMGraph.add_or_update_node / find_world / get_world (src/core/slam_graph.py:29-70) and
+ * the weighted pose average of SLAM.my_pose (src/core/slam.py:36-63), batched over S independent camera streams
+ * (multi-camera rigs, replayed sequences).  The update is sequential inside a stream, so the unit of parallelism is
+ * the stream; every stream's graph stays in device memory between calls.  Tag ids 0..max_tag_id. */
+typedef struct agpu_graph agpu_graph;
+int agpu_graph_create(agpu_handle* h, int nstreams, int max_tag_id, agpu_graph** out);
+int agpu_graph_reset(agpu_graph* g);
+int agpu_graph_destroy(agpu_graph* g);
+
+/* F consecutive frames for each of the S streams, as agpu_detect_pose returned them (records in ascending id order,
+ * TagDetector.detect's order): dets / poses host arrays [S][F][cap_per_frame], counts [S][F].  Per frame the call
+ * replays the reference's caller loop (simulation_engine.py:219-232): visible_tags = all ids of the frame; for every
+ * detection whose pose succeeded, add_or_update_node(id, T, visible_tags) with T = [R t; 0 1]; then my_pose().
+ * Outputs (host): my_pose [S][F][16] row-major 4x4, valid [S][F] (0 where my_pose() returns None). */
+int agpu_graph_update(agpu_graph* g, int F, const agpu_detection* dets, const agpu_pose_t* poses, const int* counts,
+                      int cap_per_frame, double* my_pose, uint8_t* valid);
+
+/* Node table of one stream (any output pointer may be NULL): arrays of max_tag_id+1 entries
+ * (present = the id is a key of SLAMGraph.graph; local / world 4x4 row major; reference, weight, updated, visible =
+ * the Node fields, slam_graph.py:5-12), coordinate_id, estimated_pose[16], and the number of detections the graph
+ * could not place so far (the reference prints "Cannot find world reference"). */
+int agpu_graph_get(agpu_graph* g, int stream, int* coordinate_id, double* estimated_pose, uint8_t* present, int* reference,
+                   int* weight, uint8_t* updated, uint8_t* visible, double* local, double* world, int* skipped);
 
 #ifdef __cplusplus
 }
