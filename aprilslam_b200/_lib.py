@@ -90,6 +90,7 @@ def load():
     L.agpu_stage_threshold.argtypes = [vp, vp, ci, ci, vp, vp]
     L.agpu_stage_labels.argtypes = [vp, vp, ci, ci, vp, vp]
     L.agpu_render.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, vp]
+    L.agpu_get_timeline.argtypes = [vp, vp, ci]
     L.agpu_graph_create.argtypes = [vp, ci, ci, C.POINTER(vp)]
     L.agpu_graph_reset.argtypes = [vp]
     L.agpu_graph_destroy.argtypes = [vp]
@@ -101,6 +102,6 @@ def load():
 
 EXPORTS = ["agpu_version", "agpu_default_config", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_detect",
            "agpu_detect_bgr", "agpu_detect_pose", "agpu_pose", "agpu_set_profiling", "agpu_get_stage_ms",
-           "agpu_get_kernel_ms", "agpu_get_launch_count", "agpu_get_counters", "agpu_debug_fetch", "agpu_debug_dims",
+           "agpu_get_kernel_ms", "agpu_get_timeline", "agpu_get_launch_count", "agpu_get_counters", "agpu_debug_fetch", "agpu_debug_dims",
            "agpu_stage_threshold", "agpu_stage_labels", "agpu_render", "agpu_graph_create", "agpu_graph_reset",
            "agpu_graph_destroy", "agpu_graph_update", "agpu_graph_get"]

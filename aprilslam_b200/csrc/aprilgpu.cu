@@ -150,6 +150,8 @@ struct agpu_handle {
     DevBuf d_fams, d_codes, d_pose_in, d_pose_out;
     std::vector<Slot> slots;
     cudaEvent_t ev_user = nullptr;
+    cudaEvent_t ev_t0 = nullptr;          // profiling: start of the call, origin of the timeline
+    std::vector<float> timeline;          // profiling: per finished chunk {b0, n, slot, marks[AGPU_NUM_STAGES + 1]} in ms since ev_t0
 
     // growable per-frame list capacities (0 = not chosen yet)
     int cap_points = 0, cap_clusters = 0, cap_quads = 0;
@@ -392,7 +394,7 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
             if (!sl.ev_k[i]) CK(cudaEventCreate(&sl.ev_k[i]));
         CK(cudaEventRecord(sl.ev_k[0], sl.stream));
     }
-    k_cc_local<<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
+    k_cc_local<false><<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
                                                    sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
                                                    sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
     LAUNCH_CHECK("k_cc_local");
@@ -677,6 +679,15 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
             cudaEventElapsedTime(&ms, sl.events[s], sl.events[s + 1]);
             h->stage_ms[s] += ms;
         }
+        if (h->ev_t0) {
+            h->timeline.push_back((float)sl.b0); h->timeline.push_back((float)sl.n);
+            h->timeline.push_back((float)(&sl - h->slots.data()));
+            for (int s = 0; s <= AGPU_NUM_STAGES; s++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, h->ev_t0, sl.events[s]);
+                h->timeline.push_back(ms);
+            }
+        }
         float kms = 0;
         if (sl.ev_k[0] && cudaEventElapsedTime(&kms, sl.ev_k[0], sl.ev_k[1]) == cudaSuccess) h->cc_local_ms += kms;
     }
@@ -799,6 +810,11 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
     if (on_device) {   // order every slot stream after the producer's stream
         if (!h->ev_user) CK(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
         CK(cudaEventRecord(h->ev_user, (cudaStream_t)cuda_stream));
+    }
+    h->timeline.clear();
+    if (h->profiling) {
+        if (!h->ev_t0) CK(cudaEventCreate(&h->ev_t0));
+        CK(cudaEventRecord(h->ev_t0, on_device ? (cudaStream_t)cuda_stream : h->slots[0].stream));
     }
     int rc_final = AGPU_OK;
     std::vector<std::pair<int, int>> todo, redo;
@@ -1098,6 +1114,13 @@ int agpu_get_stage_ms(agpu_handle* h, float* ms) {
     if (!h || !ms) return AGPU_E_INVALID;
     for (int i = 0; i < AGPU_NUM_STAGES; i++) ms[i] = h->stage_ms[i];
     return AGPU_OK;
+}
+
+int agpu_get_timeline(agpu_handle* h, float* out, int cap_floats) {
+    if (!h) return AGPU_E_INVALID;
+    const int n = (int)h->timeline.size();
+    if (out) memcpy(out, h->timeline.data(), sizeof(float) * std::min(n, std::max(cap_floats, 0)));
+    return n;
 }
 
 int agpu_get_kernel_ms(agpu_handle* h, const char* kernel, float* ms) {

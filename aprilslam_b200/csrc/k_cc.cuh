@@ -135,98 +135,119 @@ __device__ __forceinline__ uint32_t cc_pixel_root(const uint16_t* __restrict__ l
     return (uint32_t)((y0 + (int)(loc >> 5)) * wp + x0 + (int)(loc & 31u));
 }
 
-// Local pass, bit-parallel.  A lane owns one ROW of the 32x32 tile as two bit masks (white / black); the runs of
-// the row come from shifts and ANDs of the lane's own word, the contacts with the row above from the masks of
-// the lane above (one shuffle), and only runs -- not pixels -- take part in the shared-memory union-find.
+// Local pass, bit-parallel and RUN-BALANCED.  The row masks of the 32x32 tile are built with lane = row (two bit
+// masks, white / black); the runs of every row come from shifts and ANDs of the lane's own word.  Everything after
+// that works on the tile's RUN LIST (one 16-bit entry per run, in shared memory) dealt round-robin to the lanes:
+// a tile that crosses a tag has a few rows with many runs and many rows with one, so "lane = row" loops idle half
+// of the warp, while "lane = run j, j + 32, ..." keeps every lane busy in every phase (contacts with the row above,
+// pointer jumping, pixel counts, label stores).  Only runs -- not pixels -- take part in the shared-memory union-find.
 // Besides the labels the pass leaves, for every tile-local root: its pixel count in sizes[] and its id in the
 // frame's root list (k_cc_sizes folds the counts into the final roots after the boundary merges).
+// FROM_MASKS: the tile-major masks were already written by the threshold kernel (decimate 1); otherwise they are
+// built here from the threshold bytes and stored.
+#define CC_RUN_COLOUR 0x400u   // run list entry: local pixel id of the first pixel (10 bits) | colour (1 = black)
+template <bool FROM_MASKS>
 __global__ void __launch_bounds__(CC_THREADS)
 k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16_t* __restrict__ l16,
            uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, uint32_t* __restrict__ roots,
            int* __restrict__ nroots, Geom g, size_t sub_stride) {
-    __shared__ __align__(16) uint16_t sL[CC_WARPS][CC_TH * CC_PITCH + 8];   // parent links, then pixel counters
-    __shared__ __align__(16) uint16_t sX[CC_WARPS][CC_TH * CC_PITCH + 8];   // root of every run
+    __shared__ __align__(16) uint16_t sL[CC_WARPS][CC_TH * CC_PITCH + 8];   // parent links; at roots later the pixel counters
+    __shared__ __align__(16) uint16_t sR[CC_WARPS][CC_TW * CC_TH];          // run list
+    __shared__ uint2 sM[CC_WARPS][CC_TH];                                    // row masks {white, black}
     const int frame = blockIdx.z;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x0 = (blockIdx.x * CC_WARPS + w) * CC_TW, y0 = blockIdx.y * CC_TH;
     if (x0 >= g.wd) return;   // (no block-level synchronisation anywhere below)
     const int y = y0 + lane;
-    const uint8_t* ft = thresh + (size_t)frame * g.plane;
     uint32_t* fl = labels + (size_t)frame * g.plane;
     uint32_t* fs = sizes + (size_t)frame * g.plane;
     uint16_t* L = sL[w];
-    uint16_t* X = sX[w];
-    const bool second = x0 + 32 <= g.wp;   // the row pitch is a multiple of 16, not of 32
-
-    // ---- row masks
-    uint32_t Wm = 0, Bm = 0;
-    if (y < g.hd) {
-        const uint4* rp = reinterpret_cast<const uint4*>(ft + (size_t)y * g.wp + x0);
-        const uint4 a = __ldg(rp);
-        uint4 b = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
-        if (second) b = __ldg(rp + 1);
-        const uint32_t wd8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            Wm |= gather4((wd8[k] >> 7) & 0x01010101u) << (4 * k);   // 255: bit 7 set
-            Bm |= gather4(~wd8[k] & 0x01010101u) << (4 * k);          // 0: bit 0 clear (127 and 255 have it set)
-        }
-    }
-    const int ncols = min(32, g.wd - x0);
-    const uint32_t V = ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u);
-    Wm &= V;
-    Bm &= V;
+    uint16_t* R = sR[w];
+    uint2* Ms = sM[w];
     const size_t tile = cc_tile_index(g, frame, blockIdx.x * CC_WARPS + w, blockIdx.y);
-    masks[tile * 32 + lane] = make_uint2(Wm, Bm);
+
+    // ---- row masks (lane = row)
+    uint32_t Wm = 0, Bm = 0;
+    if (FROM_MASKS) {
+        const uint2 m = __ldg(&masks[tile * 32 + lane]);
+        Wm = m.x; Bm = m.y;
+    } else {
+        const uint8_t* ft = thresh + (size_t)frame * g.plane;
+        const bool second = x0 + 32 <= g.wp;   // the row pitch is a multiple of 16, not of 32
+        if (y < g.hd) {
+            const uint4* rp = reinterpret_cast<const uint4*>(ft + (size_t)y * g.wp + x0);
+            const uint4 a = __ldg(rp);
+            uint4 b = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+            if (second) b = __ldg(rp + 1);
+            const uint32_t wd8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                Wm |= gather4((wd8[k] >> 7) & 0x01010101u) << (4 * k);   // 255: bit 7 set
+                Bm |= gather4(~wd8[k] & 0x01010101u) << (4 * k);          // 0: bit 0 clear (127 and 255 have it set)
+            }
+        }
+        const int ncols = min(32, g.wd - x0);
+        const uint32_t V = ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u);
+        Wm &= V;
+        Bm &= V;
+        masks[tile * 32 + lane] = make_uint2(Wm, Bm);
+    }
     if (!__any_sync(FULL_MASK, (Wm | Bm) != 0u)) return;   // nothing but 127-pixels: no runs, no labels
     const uint32_t I = cc_initiators(x0, g.wd);   // initiator columns: 1 <= x <= w-2
-    const uint32_t cw = Wm & (Wm << 1) & I, cb = Bm & (Bm << 1) & I;   // bit x: x continues the run of x-1
-    const uint32_t Sw = Wm & ~cw, Sb = Bm & ~cb;                       // run starts
-    const uint32_t S = Sw | Sb;
-    const uint32_t rid0 = (uint32_t)(lane * 32);
-    for (uint32_t m = S; m; m &= m - 1) {
-        const uint32_t id = rid0 + __ffs(m) - 1;
-        L[cc_slot(id)] = (uint16_t)id;
-    }
-    __syncwarp();
 
-    // ---- contacts with the row above (lane 0's upper row belongs to another tile: k_cc_boundary)
+    // ---- run list: the runs of row r occupy the entries [off(r), off(r) + popc(S_r)), white and black in column order
+    int nrun;
     {
-        uint32_t Wu = __shfl_up_sync(FULL_MASK, Wm, 1), Bu = __shfl_up_sync(FULL_MASK, Bm, 1);
-        uint32_t cwu = __shfl_up_sync(FULL_MASK, cw, 1), cbu = __shfl_up_sync(FULL_MASK, cb, 1);
-        uint32_t Swu = __shfl_up_sync(FULL_MASK, Sw, 1), Sbu = __shfl_up_sync(FULL_MASK, Sb, 1);
-        if (lane == 0) { Wu = Bu = 0; }
-        // white: 8-connected (up-left, up, up-right), black: 4-connected (up)
-        for (uint32_t m = Sw; m; m &= m - 1) {
-            const int s = __ffs(m) - 1;
-            const uint32_t rI = run_mask(cw, s) & I;
-            uint32_t touched = ((rI << 1) | rI | (rI >> 1)) & Wu;
-            while (touched) {
-                const int x = __ffs(touched) - 1;
-                const int su = 31 - __clz(Swu & (0xffffffffu >> (31 - x)));
-                sunion(L, rid0 + s, rid0 - 32 + su);
-                touched &= ~run_mask(cwu, su);
-            }
+        const uint32_t cw = Wm & (Wm << 1) & I, cb = Bm & (Bm << 1) & I;   // bit x: x continues the run of x-1
+        const uint32_t Sw = Wm & ~cw, Sb = Bm & ~cb;                       // run starts
+        Ms[lane] = make_uint2(Wm, Bm);
+        const int mine = __popc(Sw | Sb);
+        int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int n = __shfl_up_sync(FULL_MASK, incl, off);
+            if (lane >= off) incl += n;
         }
-        for (uint32_t m = Sb; m; m &= m - 1) {
-            const int s = __ffs(m) - 1;
-            uint32_t touched = run_mask(cb, s) & I & Bu;
-            while (touched) {
-                const int x = __ffs(touched) - 1;
-                const int su = 31 - __clz(Sbu & (0xffffffffu >> (31 - x)));
-                sunion(L, rid0 + s, rid0 - 32 + su);
-                touched &= ~run_mask(cbu, su);
-            }
+        nrun = __shfl_sync(FULL_MASK, incl, 31);
+        int o = incl - mine;
+        const uint32_t rid0 = (uint32_t)(lane * 32);
+        for (uint32_t m = Sw | Sb; m; m &= m - 1) {
+            const int c = __ffs(m) - 1;
+            const uint32_t id = rid0 + c;
+            R[o++] = (uint16_t)(id | (((Sb >> c) & 1u) ? CC_RUN_COLOUR : 0u));
+            L[cc_slot(id)] = (uint16_t)id;
         }
     }
     __syncwarp();
 
-    // ---- pointer jumping: rows hook to the row above concurrently, which leaves chains as deep as the tile is
+    // ---- contacts with the row above (row 0's upper row belongs to another tile: k_cc_boundary); lane = run
+    for (int j = lane; j < nrun; j += 32) {
+        const uint32_t e = R[j];
+        const uint32_t id = e & 1023u;
+        const int r = id >> 5, s = id & 31;
+        if (r == 0) continue;
+        const bool black = (e & CC_RUN_COLOUR) != 0u;
+        const uint2 mr = Ms[r], mu = Ms[r - 1];
+        const uint32_t M = black ? mr.y : mr.x, Mu = black ? mu.y : mu.x;
+        const uint32_t cu = Mu & (Mu << 1) & I, Su = Mu & ~cu;
+        const uint32_t rI = run_mask(M & (M << 1) & I, s) & I;
+        // white: 8-connected (up-left, up, up-right), black: 4-connected (up)
+        uint32_t touched = (black ? rI : ((rI << 1) | rI | (rI >> 1))) & Mu;
+        while (touched) {
+            const int x = __ffs(touched) - 1;
+            const int su = 31 - __clz(Su & (0xffffffffu >> (31 - x)));
+            sunion(L, id, id - s - 32 + su);
+            touched &= ~run_mask(cu, su);
+        }
+    }
+    __syncwarp();
+
+    // ---- pointer jumping: runs hook to the row above concurrently, which leaves chains as deep as the tile is
     //      tall; every round halves them (L[x] = L[L[x]] only ever moves an entry closer to its root)
     for (int round = 0; round < 10; round++) {
         bool changed = false;
-        for (uint32_t m = S; m; m &= m - 1) {
-            const uint32_t slot = cc_slot(rid0 + __ffs(m) - 1);
+        for (int j = lane; j < nrun; j += 32) {
+            const uint32_t slot = cc_slot(R[j] & 1023u);
             const uint32_t par = L[slot];
             const uint32_t gpar = L[cc_slot(par)];
             if (gpar != par) { L[slot] = (uint16_t)gpar; changed = true; }
@@ -234,27 +255,36 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
         __syncwarp();
         if (!__any_sync(FULL_MASK, changed)) break;
     }
-    // ---- root of every run, then pixel counts per tile-local root (L is reused as the counter array: two 16-bit
-    //      counters per word, a tile holds 1024 pixels so a carry can never reach the upper counter)
-    for (uint32_t m = S; m; m &= m - 1) {
-        const uint32_t id = rid0 + __ffs(m) - 1;
-        X[cc_slot(id)] = (uint16_t)sfind(L, id);
-    }
-    __syncwarp();
+    // ---- root of every run; the entry of a ROOT then becomes its pixel counter (two 16-bit entries per word; a tile
+    //      holds 1024 pixels, so a carry can never leave a counter), the entries of the other runs keep their root.
+    //      A lane remembers which of its runs are roots in a bit mask (run j = lane + 32 k -> bit k).
+    uint32_t rootbits = 0u;
     int nroot = 0;
-    for (uint32_t m = S; m; m &= m - 1) {
-        const uint32_t id = rid0 + __ffs(m) - 1;
-        if (X[cc_slot(id)] == id) { L[cc_slot(id)] = 0; nroot++; }
+    for (int j = lane, k = 0; j < nrun; j += 32, k++) {
+        const uint32_t id = R[j] & 1023u;
+        const uint32_t root = sfind(L, id);
+        if (root == id) { rootbits |= 1u << k; nroot++; }
+        else L[cc_slot(id)] = (uint16_t)root;
     }
     __syncwarp();
-    for (uint32_t m = S; m; m &= m - 1) {
-        const int s = __ffs(m) - 1;
-        const uint32_t cont = ((Sw >> s) & 1u) ? cw : cb;
-        const uint32_t slot = cc_slot(X[cc_slot(rid0 + s)]);
-        atomicAdd(reinterpret_cast<uint32_t*>(L) + (slot >> 1), (uint32_t)__popc(run_mask(cont, s)) << ((slot & 1) * 16));
+    for (int j = lane, k = 0; j < nrun; j += 32, k++)
+        if ((rootbits >> k) & 1u) L[cc_slot(R[j] & 1023u)] = 0;
+    __syncwarp();
+    uint16_t* tl = l16 + tile * 1024;
+    for (int j = lane, k = 0; j < nrun; j += 32, k++) {
+        const uint32_t e = R[j];
+        const uint32_t id = e & 1023u;
+        const int r = id >> 5, s = id & 31;
+        const uint2 mr = Ms[r];
+        const uint32_t M = (e & CC_RUN_COLOUR) ? mr.y : mr.x;
+        const uint32_t root = ((rootbits >> k) & 1u) ? id : (uint32_t)L[cc_slot(id)];
+        const uint32_t slot = cc_slot(root);
+        atomicAdd(reinterpret_cast<uint32_t*>(L) + (slot >> 1),
+                  (uint32_t)__popc(run_mask(M & (M << 1) & I, s)) << ((slot & 1) * 16));
+        tl[id] = (uint16_t)root;   // run-start label: the tile-local root of the run (sparse, 2 bytes per run)
     }
     __syncwarp();
-    // append the tile's roots to the frame's root list (one atomic per tile) and publish their counts
+    // ---- append the tile's roots to the frame's root list (one atomic per tile) and publish their counts
     {
         int incl = nroot;
 #pragma unroll
@@ -269,22 +299,13 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
         base = __shfl_sync(FULL_MASK, base, 31);
         int o = base + incl - nroot;
         uint32_t* fr = roots + ((size_t)frame * CC_SUBLISTS + sub) * sub_stride;
-        for (uint32_t m = S; m; m &= m - 1) {
-            const int s = __ffs(m) - 1;
-            if (X[cc_slot(rid0 + s)] == rid0 + s) {
-                const uint32_t gid = (uint32_t)(y * g.wp + x0 + s);   // a root is a run of this very row
-                fs[gid] = L[cc_slot(rid0 + s)];
-                fl[gid] = gid;
-                fr[o++] = gid;
-            }
-        }
-    }
-    // ---- run-start labels: the tile-local root of every run (sparse, 2 bytes per run)
-    {
-        uint16_t* tl = l16 + tile * 1024 + lane * 32;
-        for (uint32_t m = S; m; m &= m - 1) {
-            const int c = __ffs(m) - 1;
-            tl[c] = X[cc_slot(rid0 + c)];
+        for (uint32_t m = rootbits; m; m &= m - 1) {
+            const int k = __ffs(m) - 1;
+            const uint32_t id = R[lane + 32 * k] & 1023u;
+            const uint32_t gid = (uint32_t)((y0 + (int)(id >> 5)) * g.wp + x0 + (int)(id & 31u));
+            fs[gid] = L[cc_slot(id)];
+            fl[gid] = gid;
+            fr[o++] = gid;
         }
     }
 }

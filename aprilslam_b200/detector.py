@@ -168,6 +168,13 @@ class Detector:
         self._check(self._L.agpu_get_stage_ms(self._h, ms.ctypes.data))
         return dict(zip(STAGE_NAMES, (float(v) for v in ms)))
 
+    def timeline(self) -> np.ndarray:
+        """Per chunk of the last call (profiling on): [first frame, frames, slot, 10 stage boundary marks in ms]."""
+        n = int(self._L.agpu_get_timeline(self._h, None, 0))
+        buf = np.zeros(max(n, 1), np.float32)
+        self._L.agpu_get_timeline(self._h, buf.ctypes.data, n)
+        return buf[:n].reshape(-1, len(STAGE_NAMES) + 4)
+
     def launch_count(self) -> int:
         v = C.c_longlong()
         self._check(self._L.agpu_get_launch_count(self._h, C.byref(v)))

@@ -131,6 +131,10 @@ int agpu_get_stage_ms(agpu_handle* h, float* ms /* [AGPU_NUM_STAGES] */);
 /* CUDA-event time of ONE kernel summed over the chunks of the last call (profiling on).  Only "k_cc_local", the
  * kernel bench.py quotes the roofline fraction for, carries its own pair of events. */
 int agpu_get_kernel_ms(agpu_handle* h, const char* kernel, float* ms);
+/* Timeline of the last call (profiling on): per finished chunk AGPU_NUM_STAGES + 4 floats {first frame, frames, slot,
+ * stage boundary marks in ms since the start of the call}.  Returns the number of floats available; copies at most
+ * cap_floats of them.  Shows how the chunks in flight overlap. */
+int agpu_get_timeline(agpu_handle* h, float* out, int cap_floats);
 /* Kernel launches issued by the last agpu_detect* / agpu_pose call. */
 int agpu_get_launch_count(agpu_handle* h, long long* launches);
 /* Work counters of the last call, summed over frames: [0] edge points, [1] clusters fitted,
