@@ -97,7 +97,7 @@ struct Slot {
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
-    bool pending = false;
+    bool pending = false, from_masks = false;
     int b0 = 0, n = 0, sorted = 0;
 
     void release() {
@@ -144,6 +144,9 @@ struct agpu_handle {
         int tier_cap[AGPU_NTIERS] = {TIER_CAP_DEFAULT[0], TIER_CAP_DEFAULT[1], TIER_CAP_DEFAULT[2], TIER_CAP_DEFAULT[3]};
         int decode_ctas = 4;                           // persistent decode CTAs (of 4 warps) per SM
         int edge_warps = 2, boundary_warps = 8;        // tiles (warps) per CTA of k_edges / k_cc_boundary
+        int masks = 0;                                 // 1 (AGPU_MASKS=1), decimate 1: the threshold kernel writes the CC bit masks instead of
+                                                       // threshold bytes -- 0.75 N less HBM traffic each way, but both kernels are issue-bound:
+                                                       // measured +-0 on the whole pipeline, so the simpler byte image stays the default
         int tail_threads = 32;                         // CTA size of decode / reconcile / pose: small CTAs find room on SMs
                                                        // that the streaming kernels of the next chunk keep full
     } tune;
@@ -162,7 +165,7 @@ struct agpu_handle {
     // state of the last finished chunk (debug fetch)
     Geom geom;
     int last_slot = 0, last_chunk = 0, last_cap = 0, last_id_bits = 16;
-    bool have_last = false;
+    bool have_last = false, last_from_masks = false;
 
     void set_err(const std::string& s) { err = s; }
 };
@@ -270,10 +273,13 @@ struct StageTimer {
 // ------------------------------------------------------------------------------------------
 int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels, int W, int H, size_t stride,
                     size_t frame_stride, int n, const Geom& g, const uint8_t** quad_im_out, size_t* q_pitch,
-                    size_t* q_frame, const uint8_t** gray_full, size_t* gray_pitch, size_t* gray_frame) {
+                    size_t* q_frame, const uint8_t** gray_full, size_t* gray_pitch, size_t* gray_frame,
+                    bool* masks_written = nullptr) {
+    // masks_written != null: the caller's next step is the CC pass and it can take the tile-major bit masks instead
+    // of the threshold bytes (pipeline, decimate 1, no stage dumps)
+    if (masks_written) *masks_written = false;
     const int f = h->prm.decim;
     const float sigma = h->cfg.quad_sigma;
-    CK(sl.d_thresh.ensure(g.plane * n));
     const uint8_t* src = d_src;
     size_t s_stride = stride, s_frame = frame_stride;
     int srcW = W, srcH = H;
@@ -342,6 +348,7 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         quad_out = sl.d_quad_im.as<uint8_t>();
     }
     if ((g.wd >> 2) == 0 || (g.hd >> 2) == 0) {
+        CK(sl.d_thresh.ensure(g.plane * n));
         CK(cudaMemsetAsync(sl.d_thresh.p, 127, g.plane * n, sl.stream));
     } else {
         const int TPL = 4 / F;
@@ -355,12 +362,20 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         const int blocks = ceil_div(warps * 32, 128);
         const int vec_ok = (s_stride % 16 == 0) && (s_frame % 16 == 0) && (((uintptr_t)src) % 16 == 0);
         const int md = h->prm.min_white_black_diff;
+        const bool use_masks = masks_written && F == 1 && h->tune.masks;
+        if (!use_masks) CK(sl.d_thresh.ensure(g.plane * n));
         uint8_t* th_out = sl.d_thresh.as<uint8_t>();
         int minb = 4;
         if (const char* e = getenv("AGPU_IMG_MINB")) minb = atoi(e);
 #define LAUNCH_DT(FF, MB) k_decimate_threshold<FF, MB><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, \
                                                                                th_out, g, nstrips, nsegs, seg_tiles, n, md, vec_ok)
-        if (F == 1) {
+        if (use_masks) {
+            CK(sl.d_masks.ensure((size_t)cc_tiles_x(g) * cc_tiles_y(g) * n * 32 * sizeof(uint2)));
+            k_decimate_threshold<1, 4, true><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, nullptr, nullptr, g,
+                                                                          nstrips, nsegs, seg_tiles, n, md, vec_ok,
+                                                                          sl.d_masks.as<uint2>());
+            *masks_written = true;
+        } else if (F == 1) {
             if (minb == 4) LAUNCH_DT(1, 4); else if (minb == 5) LAUNCH_DT(1, 5); else if (minb == 6) LAUNCH_DT(1, 6); else LAUNCH_DT(1, 3);
         } else if (F == 2) {
             LAUNCH_DT(2, 4);
@@ -379,7 +394,7 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
 }
 
 int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const Geom& g, int* d_nroots, int* d_ndense,
-                 bool canonical) {
+                 bool canonical, bool from_masks = false) {
     CK(sl.d_labels.ensure(g.plane * n * 4));
     CK(sl.d_sizes.ensure(g.plane * n * 4));
     const int tx = cc_tiles_x(g), ty = cc_tiles_y(g);
@@ -394,9 +409,14 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
             if (!sl.ev_k[i]) CK(cudaEventCreate(&sl.ev_k[i]));
         CK(cudaEventRecord(sl.ev_k[0], sl.stream));
     }
-    k_cc_local<false><<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
-                                                   sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
-                                                   sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
+    if (from_masks)
+        k_cc_local<true><<<grid, CC_THREADS, 0, sl.stream>>>(nullptr, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
+                                                             sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
+                                                             sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
+    else
+        k_cc_local<false><<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
+                                                              sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
+                                                              sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
     LAUNCH_CHECK("k_cc_local");
     if (h->profiling) CK(cudaEventRecord(sl.ev_k[1], sl.stream));
     {
@@ -528,11 +548,12 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     tm.mark();  // 1: after H2D
     const uint8_t *quad_im, *gray_full;
     size_t q_pitch, q_frame, gray_pitch, gray_frame;
+    bool from_masks = false;
     int rc = run_image_stage(h, sl, d_src, c.channels, c.W, c.H, c.stride, c.frame_bytes, n, g, &quad_im, &q_pitch,
-                             &q_frame, &gray_full, &gray_pitch, &gray_frame);
+                             &q_frame, &gray_full, &gray_pitch, &gray_frame, &from_masks);
     if (rc) return rc;
     tm.mark();  // 2: after image
-    rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), n, g, d_nroots, d_ndense, h->cfg.debug != 0);
+    rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), n, g, d_nroots, d_ndense, h->cfg.debug != 0, from_masks);
     if (rc) return rc;
     tm.mark();  // 3: after CC
     {
@@ -659,6 +680,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     sl.b0 = b0;
     sl.n = n;
     sl.sorted = cur;
+    sl.from_masks = from_masks;
     return AGPU_OK;
 }
 
@@ -743,6 +765,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     h->last_chunk = n;
     h->last_cap = c.cap;
     h->last_id_bits = c.id_bits;
+    h->last_from_masks = sl.from_masks;
     h->have_last = true;
     return 0;
 }
@@ -905,6 +928,7 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     h->families_str = cfg->families;
     h->cfg.families = h->families_str.c_str();
     if (const char* e = getenv("AGPU_PRIO")) h->tune.prio = atoi(e) != 0;
+    if (const char* e = getenv("AGPU_MASKS")) h->tune.masks = atoi(e) != 0;
     if (const char* e = getenv("AGPU_EDGE_WARPS")) h->tune.edge_warps = atoi(e);
     if (const char* e = getenv("AGPU_BOUNDARY_WARPS")) h->tune.boundary_warps = atoi(e);
     if (const char* e = getenv("AGPU_TAIL_THREADS")) h->tune.tail_threads = atoi(e) >= 128 ? 128 : (atoi(e) >= 64 ? 64 : 32);
@@ -1152,6 +1176,27 @@ int agpu_debug_dims(agpu_handle* h, int* wd, int* hd) {
     return AGPU_OK;
 }
 
+// threshold image of one frame of the last chunk, pitched (g.wp): straight from the byte image, or rebuilt from the
+// tile-major bit masks when the threshold kernel wrote those instead (white -> 255, black -> 0, neither -> 127)
+static bool fetch_thresh_frame(agpu_handle* h, Slot& sl, int frame, std::vector<uint8_t>& th) {
+    const Geom& g = h->geom;
+    th.assign(g.plane, 127);
+    if (!h->last_from_masks)
+        return cudaMemcpy(th.data(), sl.d_thresh.as<uint8_t>() + (size_t)frame * g.plane, g.plane, cudaMemcpyDeviceToHost) == cudaSuccess;
+    const int tx = cc_tiles_x(g), ty = cc_tiles_y(g);
+    std::vector<uint2> m((size_t)tx * ty * 32);
+    if (cudaMemcpy(m.data(), sl.d_masks.as<uint2>() + (size_t)frame * m.size(), m.size() * sizeof(uint2),
+                   cudaMemcpyDeviceToHost) != cudaSuccess)
+        return false;
+    for (int y = 0; y < g.hd; y++)
+        for (int x = 0; x < g.wd; x++) {
+            const uint2 r = m[((size_t)(y >> 5) * tx + (x >> 5)) * 32 + (y & 31)];
+            if ((r.x >> (x & 31)) & 1u) th[(size_t)y * g.wp + x] = 255;
+            else if ((r.y >> (x & 31)) & 1u) th[(size_t)y * g.wp + x] = 0;
+        }
+    return true;
+}
+
 long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* host_out, long long cap_bytes) {
     if (!h || !what || !host_out) return AGPU_E_INVALID;
     if (!h->have_last || !h->cfg.debug || frame < 0 || frame >= h->last_chunk) {
@@ -1167,8 +1212,15 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
     auto unpitch_key = [&](unsigned long long k) {
         return ((unsigned long long)unpitch((uint32_t)(k >> 32)) << 32) | unpitch((uint32_t)k);
     };
-    if (w == "quad_im" || w == "thresh") {
-        const uint8_t* src = (w == "thresh") ? sl.d_thresh.as<uint8_t>() : sl.d_quad_im.as<uint8_t>();
+    if (w == "thresh") {
+        if ((size_t)cap_bytes < npx) return (long long)npx;
+        std::vector<uint8_t> th;
+        if (!fetch_thresh_frame(h, sl, frame, th)) return AGPU_E_CUDA;
+        for (int y = 0; y < g.hd; y++) memcpy((uint8_t*)host_out + (size_t)y * g.wd, th.data() + (size_t)y * g.wp, g.wd);
+        return (long long)npx;
+    }
+    if (w == "quad_im") {
+        const uint8_t* src = sl.d_quad_im.as<uint8_t>();
         if (!src) { h->set_err("agpu_debug_fetch: buffer not materialised (decimate = 1 keeps no quad_im copy)"); return AGPU_E_INVALID; }
         if ((size_t)cap_bytes < npx) return (long long)npx;
         if (cudaMemcpy2D(host_out, g.wd, src + (size_t)frame * g.plane, g.wp, g.wd, g.hd, cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -1186,9 +1238,9 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
                 for (int x = 0; x < g.wd; x++) o[(size_t)y * g.wd + x] = unpitch(tmp[(size_t)y * g.wp + x]);
         } else {
             lab.resize(g.plane);
-            std::vector<uint8_t> th(g.plane);
+            std::vector<uint8_t> th;
             cudaMemcpy(lab.data(), sl.d_canon.as<uint32_t>() + (size_t)frame * g.plane, g.plane * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(th.data(), sl.d_thresh.as<uint8_t>() + (size_t)frame * g.plane, g.plane, cudaMemcpyDeviceToHost);
+            if (!fetch_thresh_frame(h, sl, frame, th)) return AGPU_E_CUDA;
             for (int y = 0; y < g.hd; y++)
                 for (int x = 0; x < g.wd; x++) {
                     size_t id = (size_t)y * g.wp + x;

@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "k_cc.cuh"   // tile-major mask layout (cc_tile_index)
 
 template <int F>
 __device__ __forceinline__ void unpack16(const uint4 v, uint32_t (&w)[4 / F]) {
@@ -40,11 +41,18 @@ __device__ __forceinline__ __half2 px_hi(uint32_t w) { return u2h(__byte_perm(w,
 #define H2_BIG 0x7bff7bffu   // 65504: neutral element of min
 #define H2_ZERO 0x00000000u  // 0 < 1024: neutral element of max
 
-template <int F, int MINB>
+// MASKS (decimate 1 only): instead of the threshold BYTES the kernel writes what the connected-components pass
+// actually consumes -- the tile-major bit masks (2 bits per pixel: white / black, neither = 127) of k_cc.cuh.  A lane's
+// 16 pixels are half a mask row; lanes pair up (1,2), (3,4), ... (a strip of 30 lanes starts on a 32-pixel tile
+// boundary), swap two rows' worth of bits with one shuffle each, and every lane stores ONE 16-byte word (two mask
+// rows) per tile row instead of four: the threshold image never reaches HBM (N/4 bytes written instead of N, and
+// k_cc_local reads N/4 instead of N).
+template <int F, int MINB, bool MASKS = false>
 __global__ void __launch_bounds__(128, MINB)
 k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_stride, size_t src_frame_stride,
                      uint8_t* __restrict__ quad_im, uint8_t* __restrict__ thresh, Geom g, int nstrips, int nsegs,
-                     int seg_tiles, int nframes, int min_diff, int vec_ok) {
+                     int seg_tiles, int nframes, int min_diff, int vec_ok, uint2* __restrict__ masks = nullptr) {
+    static_assert(!MASKS || F == 1, "mask output needs 16 pixels per lane");
     constexpr int TPL = 4 / F;  // tiles (4-pixel words) per lane per row
     const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -63,6 +71,26 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
     const bool is_out = lane >= 1 && lane <= 30 && px0 < g.wd;
     const bool lane_in = sc0 + 16 > 0 && sc0 < W;           // the lane's column chunk overlaps the frame
     const bool vec = vec_ok && sc0 >= 0 && sc0 + 16 <= W;   // ... and is a whole aligned 16-byte chunk
+    // mask output: this lane's half of the 32-pixel mask row, its partner, and the tile column of the pair
+    const bool m_low = (lane & 1) != 0;                         // lanes 1, 3, ...: columns 0-15 of the tile
+    const int m_partner = (m_low ? lane + 1 : lane - 1) & 31;
+    const int m_px0 = m_low ? px0 : px0 - 16;
+    const bool m_out = MASKS && lane >= 1 && lane <= 30 && m_px0 < g.wd;
+    uint32_t m_valid = 0;                                       // the lane's columns that exist in the image
+    if (MASKS && px0 >= 0 && px0 < g.wd) m_valid = g.wd - px0 >= 16 ? 0xffffu : ((1u << (g.wd - px0)) - 1u);
+    const int m_tiles_x = cc_tiles_x(g), m_tiles_y = cc_tiles_y(g);
+    auto store_mask_rows = [&](int gy0, const uint32_t(&v)[4]) {   // v[r]: white bits | black bits << 16 of row gy0 + r
+        // the low lane keeps rows 0-1 and takes the partner's, the high lane keeps rows 2-3
+        const uint32_t ra = __shfl_sync(FULL_MASK, m_low ? v[2] : v[0], m_partner);
+        const uint32_t rb = __shfl_sync(FULL_MASK, m_low ? v[3] : v[1], m_partner);
+        if (!m_out) return;
+        const uint32_t lo_a = m_low ? v[0] : ra, hi_a = m_low ? ra : v[2];
+        const uint32_t lo_b = m_low ? v[1] : rb, hi_b = m_low ? rb : v[3];
+        const size_t tile = ((size_t)frame * m_tiles_y + (gy0 >> 5)) * m_tiles_x + (m_px0 >> 5);
+        uint2* dst = masks + tile * 32 + (gy0 & 31) + (m_low ? 0 : 2);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(__byte_perm(lo_a, hi_a, 0x5410), __byte_perm(lo_a, hi_a, 0x7632),
+                                                    __byte_perm(lo_b, hi_b, 0x5410), __byte_perm(lo_b, hi_b, 0x7632));
+    };
 
     auto load_row = [&](int gy, uint32_t(&w)[TPL]) {
 #pragma unroll
@@ -142,6 +170,27 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
             const uint32_t thr = (uint32_t)(imn + (diff >> 1));
             thr2[j] = 0x64006400u | thr | (thr << 16);
         }
+        if (MASKS) {
+            uint32_t nf = 0;   // pixels of non-flat tiles (flat ones are 127: neither white nor black)
+#pragma unroll
+            for (int j = 0; j < TPL; j++) nf |= flat[j] ? 0u : (0xfu << (4 * j));
+            nf &= m_valid;
+            uint32_t v[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                uint32_t acc = 0;   // pixel 4j+k above the threshold -> bit 4j+k (after folding the two halves)
+#pragma unroll
+                for (int j = 0; j < TPL; j++) {
+                    const uint32_t m0 = __hgt2_mask(px_lo(px[r][j]), u2h(thr2[j]));
+                    const uint32_t m1 = __hgt2_mask(px_hi(px[r][j]), u2h(thr2[j]));
+                    acc |= ((m0 & 0x00020001u) | (m1 & 0x00080004u)) << (4 * j);
+                }
+                const uint32_t w16 = (acc | (acc >> 16)) & nf;
+                v[r] = (r < nrows && gy0 + r < g.hd) ? (w16 | ((~w16 & nf) << 16)) : 0u;
+            }
+            store_mask_rows(gy0, v);
+            return;
+        }
         if (!is_out) return;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
@@ -195,6 +244,10 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
 #pragma unroll
             for (int r = 0; r < 4; r++) load_row(th * 4 + r, lr[r]);
             store_rows(th * 4, g.hd - th * 4, lr, dmn, dmx);
+        }
+        if (MASKS && T == th - 1) {   // mask rows of the last tile row that lie below the image: empty
+            const uint32_t zero[4] = {0u, 0u, 0u, 0u};
+            for (int Tz = th + ((g.hd & 3) ? 1 : 0); Tz < m_tiles_y * 8; Tz++) store_mask_rows(Tz * 4, zero);
         }
 #pragma unroll
         for (int j = 0; j < TPL; j++) {

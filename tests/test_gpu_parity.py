@@ -78,6 +78,35 @@ def test_threshold_and_labels_bit_exact(ob, W, H, d):
     det.close()
 
 
+@pytest.mark.parametrize("W,H", [(643, 481), (1920, 1080), (333, 77), (100, 33), (479, 31), (97, 131), (1001, 997), (32, 32),
+                                 (496, 64), (481, 36)])
+def test_mask_front_end_bit_exact(ob, W, H, monkeypatch):
+    """decimate 1, AGPU_MASKS=1 (optional front end): the threshold kernel writes the tile-major bit masks the CC pass
+    consumes instead of threshold bytes.  The stage dumps of the PIPELINE (threshold image rebuilt from the masks,
+    canonical labels, sizes) are bit-exact against the oracle for both front ends."""
+    rng = np.random.default_rng(W * 11 + H)
+    images = [rng.integers(0, 256, (H, W), dtype=np.uint8),
+              (np.kron(rng.integers(0, 2, (H // 5 + 1, W // 5 + 1), dtype=np.uint8) * 180 + 30,
+                       np.ones((5, 5), np.uint8))[:H, :W] + rng.integers(0, 7, (H, W), dtype=np.uint8)).astype(np.uint8),
+              np.full((H, W), 93, np.uint8)]
+    monkeypatch.setenv("AGPU_MASKS", "1")
+    det = Detector("tag36h11", decimate=1.0, debug=True)
+    monkeypatch.setenv("AGPU_MASKS", "0")
+    det_bytes = Detector("tag36h11", decimate=1.0, debug=True)
+    monkeypatch.delenv("AGPU_MASKS")
+    for im in images:
+        im = np.ascontiguousarray(im)
+        t_ref = ob.stage_threshold(im)
+        lab_ref, sz_ref = ob.stage_labels(t_ref)
+        for d in (det, det_bytes):
+            recs = d.detect_batch(im, cap_per_frame=256)[0]
+            assert np.array_equal(d.debug_fetch("thresh"), t_ref)
+            assert np.array_equal(d.debug_fetch("labels"), lab_ref)
+            assert np.array_equal(d.debug_fetch("sizes"), sz_ref)
+    det.close()
+    det_bytes.close()
+
+
 @pytest.mark.parametrize("sigma", [0.8, 1.5, -0.8])
 def test_blur_front_end_bit_exact(ob, sigma):
     rng = np.random.default_rng(5)
