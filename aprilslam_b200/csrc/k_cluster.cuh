@@ -209,10 +209,26 @@ k_sort_hist(const unsigned long long* __restrict__ recs, const int* __restrict__
     __syncthreads();
     const unsigned long long* fk = recs + (size_t)frame * cap;
     const int base = b * RS_TILE;
+    // all loads first; then one shared-memory atomic per RUN of equal digits inside a warp: neighbouring records come
+    // from the same image tile (first pass) or the same low digit (later passes) and mostly share their digit, which
+    // would otherwise serialise 32 ways on one counter
+    const int lane = threadIdx.x & 31;
+    uint32_t dg[RS_ITEMS];
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
-        int i = base + r * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(uint32_t)(fk[i] >> shift) & (RS_RADIX - 1)], 1u);
+        const int i = base + r * RS_THREADS + threadIdx.x;
+        dg[r] = i < n ? ((uint32_t)(__ldg(&fk[i]) >> shift) & (RS_RADIX - 1)) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t d = dg[r];
+        const uint32_t d0 = __shfl_sync(FULL_MASK, d, 0);
+        const uint32_t same = __ballot_sync(FULL_MASK, d == d0);
+        if (d == d0) {
+            if (lane == 0 && d0 != 0xffffffffu) atomicAdd(&h[d0], (uint32_t)__popc(same));
+        } else if (d != 0xffffffffu) {
+            atomicAdd(&h[d], 1u);
+        }
     }
     __syncthreads();
     uint32_t* out = hist + ((size_t)frame * nblk_max + b) * RS_RADIX;
@@ -358,9 +374,25 @@ k_cluster_heads(const unsigned long long* __restrict__ recs, const int* __restri
     const int n = min(npts[frame], cap);
     const unsigned long long* fk = recs + (size_t)frame * cap;
     const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t k = (uint32_t)(fk[i] >> 32);
-        if (i > 0 && (uint32_t)(fk[i - 1] >> 32) == k) continue;
+    // four independent loads per thread and round (the kernel is a single streaming read of the sorted records: what
+    // bounds it is the number of bytes in flight); the predecessor's key comes from the neighbouring lane
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 - lane < n; i0 += 4 * stride) {   // (warp-uniform bound)
+        uint32_t kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * stride;
+            kk[u] = i < n ? (uint32_t)(__ldg(&fk[i]) >> 32) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * stride;
+        const uint32_t k = kk[u];
+        uint32_t prev = __shfl_up_sync(FULL_MASK, k, 1);
+        if (i >= n) continue;
+        if (lane == 0 && i > 0) prev = (uint32_t)(__ldg(&fk[i - 1]) >> 32);
+        if (i > 0 && prev == k) continue;
         int lo = i + 1, hi = n;  // first index in (i, n] whose key differs
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
@@ -383,5 +415,6 @@ k_cluster_heads(const unsigned long long* __restrict__ recs, const int* __restri
                 placed = true;
             }
         if (!placed) atomicAdd(&cl.counters[4], 1);
+        }
     }
 }
