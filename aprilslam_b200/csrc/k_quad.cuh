@@ -554,20 +554,23 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     }
     G.sync();
 
-    // ---- exhaustive search over 4-subsets (first minimum in lexicographic order wins).  The (m0, m1) pairs are
-    //      dealt to the threads; the tie-break key is the subset itself packed most-significant-first, which
-    //      orders exactly like upstream's nested loops.
+    // ---- exhaustive search over 4-subsets (first minimum in lexicographic order wins).  The work is dealt to the
+    //      threads; the tie-break key is the subset itself packed most-significant-first, which orders exactly
+    //      like upstream's nested loops.
     double best = HUGE_VALF;
     int best_c = 0x7fffffff, best_pack = 0;
     {
         const double max_mse = P.max_line_fit_mse, max_dot = P.cos_critical_rad;
+        // dealt by (m0, m1, m2) TRIPLES: the inner loop of a triple is at most seven candidates long, so the threads
+        // finish together (dealt by pairs, the pair (0, 1) alone carried 28 of the 210 subsets)
         int pr = 0;
         for (int m0 = 0; m0 < nmax - 3; m0++)
-            for (int m1 = m0 + 1; m1 < nmax - 2; m1++, pr++) {
-                if ((pr % T) != tid) continue;
+            for (int m1 = m0 + 1; m1 < nmax - 2; m1++) {
                 const double* e01 = ptab + (m0 * 10 + m1) * 6;
-                if (e01[5] > max_mse) continue;
-                for (int m2 = m1 + 1; m2 < nmax - 1; m2++) {
+                const bool ok01 = !(e01[5] > max_mse);
+                for (int m2 = m1 + 1; m2 < nmax - 1; m2++, pr++) {
+                    if (pr % T != tid) continue;
+                    if (!ok01) continue;
                     const double* e12 = ptab + (m1 * 10 + m2) * 6;
                     if (e12[5] > max_mse) continue;
                     const double d = e01[2] * e12[2] + e01[3] * e12[3];
@@ -609,6 +612,9 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     }
     if (best_c == 0x7fffffff) return false;
     if (!(best / sz < P.max_line_fit_mse)) return false;
+    // the rest is straight-line code that runs once per cluster (corners, area, angles): one warp is enough, the
+    // others would only fetch the same instructions again (the caller lets thread 0 write the quad)
+    if (NW > 1 && G.w != 0) return false;
 
     // ---- corners and gates (every thread computes the same values)
     int mi[4] = {best_pack & 15, (best_pack >> 4) & 15, (best_pack >> 8) & 15, (best_pack >> 12) & 15};

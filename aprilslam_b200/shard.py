@@ -27,6 +27,27 @@ def env_rank() -> Tuple[int, int, int]:
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
+def bind_to_gpu_numa(device_index: int) -> int:
+    """Pin this process to the CPU cores next to GPU `device_index` (NVML's ideal CPU affinity), so that the pinned
+    frame buffers it allocates afterwards live on the NUMA node the GPU's PCIe link hangs off -- with one process per
+    GPU every rank then streams its frames over its own socket's memory controllers.  Returns the number of CPUs
+    bound to (0: NVML unavailable or nothing to do; the process is left as it was)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * wi + b for wi, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def pack_lists(lists: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
     """Per-frame record arrays -> (counts int32[B], concatenated records)."""
     counts = np.array([len(x) for x in lists], np.int32)

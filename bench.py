@@ -190,6 +190,11 @@ def run_b200(args):
         dist.barrier()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: stay on the CPU cores / NUMA node next to this GPU before the pinned frame buffers exist
+    from aprilslam_b200.shard import bind_to_gpu_numa
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    phys = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
+    bound_cpus = bind_to_gpu_numa(phys)
     B = args.batch
     K = synth.intrinsics(W, H, 45.0)
     det = Detector("tag36h11", decimate=1.0, refine_edges=True, device=local_rank, chunk_frames=args.chunk,
@@ -369,6 +374,7 @@ def run_b200(args):
                    "stages_note": "stage times / roofline measured with pipeline_slots=1 (%.1f frames/s in that mode)" % (
                        B * prof_steps / sec_prof),
                    "parallelism": "frames sharded, %d rank(s), no collective" % world,
+                   "cpus_bound_rank0": bound_cpus,
                    "frame_generation_s": t_gen},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(B * N),
                 "d2h_bytes_per_step": int(B * CAP * (168 + 136) + 4 * (16 + 22 * B)), "steps": e2e_steps,

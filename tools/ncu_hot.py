@@ -5,8 +5,11 @@ import csv, subprocess, sys
 rep, kr = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 key = sys.argv[4] if len(sys.argv) > 4 else "inst"
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name",
-                      "regex:" + kr], capture_output=True, text=True).stdout
+import os
+sel = ["--launch-skip", os.environ["NCU_LAUNCH"], "--launch-count", "1"] if os.environ.get("NCU_LAUNCH") else \
+      ["--kernel-name", "regex:" + kr]          # NCU_LAUNCH=<index>: pick one launch by position (templated kernels)
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + sel,
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 func_pat = sys.argv[5] if len(sys.argv) > 5 else ""     # substring of the "Function Name" row (templated kernels)
 out, fname, h, kernels, func_ok = [], "", None, 0, True
