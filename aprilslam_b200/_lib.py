@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaprilgpu.so")
+LIB_PATH = os.environ.get("AGPU_LIB") or os.path.join(_HERE, "libaprilgpu.so")   # (AGPU_LIB: an experimental build)
 CSRC = os.path.join(_HERE, "csrc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

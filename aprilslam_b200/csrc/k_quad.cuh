@@ -697,8 +697,14 @@ __host__ __device__ inline size_t qf_smem_per_group(int wcap, int nw) {
 
 // Persistent groups: group i takes clusters i, i + ngroups, ...   NW == 1: blockDim/32 warp groups per CTA;
 // NW > 1: the CTA (NW warps) is the group.
+#ifndef QF_MINB2
+#define QF_MINB2 16
+#endif
+#ifndef QF_MINB4
+#define QF_MINB4 8
+#endif
 template <int NW>
-__global__ void __launch_bounds__(NW == 1 ? 256 : NW * 32, NW == 1 ? 4 : (NW == 2 ? 16 : (NW == 4 ? 8 : 2)))   // <= 64 registers
+__global__ void __launch_bounds__(NW == 1 ? 256 : NW * 32, NW == 1 ? 4 : (NW == 2 ? QF_MINB2 : (NW == 4 ? QF_MINB4 : 2)))   // <= 64 registers
 k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_i[2 * NW + 8];
