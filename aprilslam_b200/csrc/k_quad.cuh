@@ -41,7 +41,10 @@ __device__ __forceinline__ void ld_lfp(const double* lf, int i, double (&m)[6]) 
 }
 
 // same arithmetic as the oracle's fit_line (apriltag_oracle.cpp), moments by prefix differences
-__device__ void fit_line_dev(const double* lf, int sz, int i0, int i1, LineFit& out, bool want_params) {
+// (__noinline__ and the `unroll 1` pragmas below: a warp walks through most of this kernel ONCE per cluster, so the
+// kernel's instruction footprint -- not its instruction count -- is what the SM's instruction caches see; ncu showed
+// no_instruction as the top stall.  Every kilobyte of code less is measurable: -19 % SASS gave -10 % time.)
+__device__ __noinline__ void fit_line_dev(const double* lf, int sz, int i0, int i1, LineFit& out, bool want_params) {
     double M[6], T[6];
     int N;
     if (i0 < i1) {
@@ -192,12 +195,15 @@ __device__ void group_radix_sort_hi32(const QGroup<NW>& G, unsigned long long* s
     const int lane = G.lane, w = G.w, tid = G.tid;
     const int cw = ((n + NW - 1) / NW + 31) & ~31;          // chunk per warp, whole rounds of 32
     const int lo = w * cw, hi = min(lo + cw, n);
+#pragma unroll 1
     for (int pass = 0; pass < 4; pass++) {
         const int shift = 32 + 8 * pass;
         const bool from_smem = (pass & 1) == 0;
+#pragma unroll 1
         for (int i = tid; i < NW * 256; i += T) cnt[i] = 0;
         G.sync();
         // sweep 1: per-warp digit counts
+#pragma unroll 1
         for (int base = lo; base < hi; base += 32) {
             const int i = base + lane;
             const bool valid = i < hi;
@@ -251,6 +257,7 @@ __device__ void group_radix_sort_hi32(const QGroup<NW>& G, unsigned long long* s
         }
         G.sync();
         // sweep 2: scatter
+#pragma unroll 1
         for (int base = lo; base < hi; base += 32) {
             const int i = base + lane;
             const bool valid = i < hi;
@@ -284,6 +291,7 @@ __device__ void group_fix_ties(const QGroup<NW>& G, unsigned long long* s, int n
         bool moved = false;
 #pragma unroll
         for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
             for (int i = 2 * G.tid + phase; i + 1 < n; i += 2 * T) {
                 const unsigned long long a = s[i], b = s[i + 1];
                 if (a > b) { s[i] = b; s[i + 1] = a; moved = true; }
@@ -310,6 +318,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
     long long Sxgx = 0, Sygy = 0, Sgx = 0, Sgy = 0;
     int nmerged = 0;
+#pragma unroll 1
     for (int i = tid; i < sz; i += T) {
         uint32_t v = (uint32_t)pv[i];
         int px = v & 0x3fff, py = (v >> 14) & 0x3fff;
@@ -347,6 +356,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     // ---- slope keys
     int n2 = 64;
     while (n2 < sz) n2 <<= 1;
+#pragma unroll 1
     for (int i = tid; i < sz; i += T) {
         unsigned long long key = ~0ull;
         {
@@ -375,7 +385,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     //      are dead after the sort), so that the scan below never waits on global memory
     {
         const uint8_t* im = a.quad_im + (size_t)ref.frame * a.q_frame;
-#pragma unroll 4
+#pragma unroll 1
         for (int i = tid; i < sz; i += T) {
             const uint32_t xy = (uint32_t)sbuf[i];
             const int px = xy & 0xffff, py = xy >> 16;
@@ -395,6 +405,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     double* lf = a.lfps + seg * 6;
     {
         double carry[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
         for (int base = 0; base < sz; base += T) {
             const int i = base + tid;
             double t[6] = {0, 0, 0, 0, 0, 0};
@@ -457,7 +468,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     const int ksz = min(20, sz / 12);
     if (ksz < 2) return false;
     double* sraw = reinterpret_cast<double*>(sbuf);
-#pragma unroll 2
+#pragma unroll 1
     for (int i = tid; i < sz; i += T) {
         LineFit f;
         fit_line_dev(lf, sz, i - ksz < 0 ? i - ksz + sz : i - ksz, i + ksz >= sz ? i + ksz - sz : i + ksz, f, false);   // (index % sz without the division)
@@ -465,6 +476,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     }
     G.sync();
     double* es = a.errs + seg;
+#pragma unroll 1
     for (int i = tid; i < sz; i += T) {
         double acc = 0;
 #pragma unroll
@@ -483,6 +495,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     unsigned long long* mvals = sbuf;                       // [half]
     int* midx = reinterpret_cast<int*>(sbuf + half);        // [<= n2/2 ints]
     int nmax = 0;
+#pragma unroll 1
     for (int base = 0; base < sz; base += T) {
         const int i = base + tid;
         bool ismax = false;
@@ -507,13 +520,16 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         // descending sort): walk down the distinct values, at most max_nmaxima+1 group reductions
         unsigned long long thr = 0ull, bound = ~0ull;
         int taken = 0;
+#pragma unroll 1
         for (int it = 0; it <= P.max_nmaxima; it++) {
             unsigned long long best = 0ull;   // largest value strictly below `bound` among this thread's elements
+#pragma unroll 1
             for (int i = tid; i < nmax; i += T) {
                 const unsigned long long v = mvals[i];
                 if (v < bound && v > best) best = v;
             }
             int mine = 0;                     // multiplicity of `best` among this thread's elements
+#pragma unroll 1
             for (int i = tid; i < nmax; i += T) mine += (mvals[i] == best);
             int cnt;
             const unsigned long long m = G.reduce_max_count(best, mine, cnt);
@@ -522,6 +538,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
             bound = m;
         }
         int outn = 0;
+#pragma unroll 1
         for (int base = 0; base < nmax; base += T) {
             const int i = base + tid;
             int id = 0;
@@ -544,6 +561,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     G.sync();
 
     // ---- table of pairwise line fits between maxima (the table may alias sbuf: everything in it is dead now)
+#pragma unroll 1
     for (int t = tid; t < nmax * nmax; t += T) {
         int ia = t / nmax, ib = t - ia * nmax;
         if (ia == ib) continue;
@@ -568,6 +586,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
             for (int m1 = m0 + 1; m1 < nmax - 2; m1++) {
                 const double* e01 = ptab + (m0 * 10 + m1) * 6;
                 const bool ok01 = !(e01[5] > max_mse);
+#pragma unroll 1
                 for (int m2 = m1 + 1; m2 < nmax - 1; m2++, pr++) {
                     if (pr % T != tid) continue;
                     if (!ok01) continue;
@@ -575,6 +594,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
                     if (e12[5] > max_mse) continue;
                     const double d = e01[2] * e12[2] + e01[3] * e12[3];
                     if (fabs(d) > max_dot) continue;
+#pragma unroll 1
                     for (int m3 = m2 + 1; m3 < nmax; m3++) {
                         const double* e23 = ptab + (m2 * 10 + m3) * 6;
                         const double* e30 = ptab + (m3 * 10 + m0) * 6;
@@ -619,14 +639,14 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     // ---- corners and gates (every thread computes the same values)
     int mi[4] = {best_pack & 15, (best_pack >> 4) & 15, (best_pack >> 8) & 15, (best_pack >> 12) & 15};
     double lines[4][4];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         const double* e = ptab + (mi[i] * 10 + mi[(i + 1) & 3]) * 6;
         if (e[5] > P.max_line_fit_mse) return false;
         lines[i][0] = e[0]; lines[i][1] = e[1]; lines[i][2] = e[2]; lines[i][3] = e[3];
     }
     float p[4][2];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
         double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
@@ -641,7 +661,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     }
     {
         double area = 0, length[3], pp;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 3; i++) {
             int ia = i, ib = (i + 1) % 3;
             double ddx = p[ib][0] - p[ia][0], ddy = p[ib][1] - p[ia][1];
@@ -650,7 +670,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         pp = (length[0] + length[1] + length[2]) / 2;
         area += sqrt(pp * (pp - length[0]) * (pp - length[1]) * (pp - length[2]));
         const int idxs[4] = {2, 3, 0, 2};
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 3; i++) {
             int ia = idxs[i], ib = idxs[i + 1];
             double ddx = p[ib][0] - p[ia][0], ddy = p[ib][1] - p[ia][1];
@@ -660,7 +680,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         area += sqrt(pp * (pp - length[0]) * (pp - length[1]) * (pp - length[2]));
         if (area < 0.95 * P.min_tag_width * P.min_tag_width) return false;
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
         double dx1 = p[i1][0] - p[i0][0], dy1 = p[i1][1] - p[i0][1];
@@ -668,7 +688,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
         if ((cos_dtheta > P.cos_critical_rad || cos_dtheta < -P.cos_critical_rad) || dx1 * dy2 < dy1 * dx2) return false;
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         if (P.quad_decimate > 1) {
             q.p[i][0] = (p[i][0] - 0.5f) * P.quad_decimate + 0.5f;
