@@ -202,12 +202,17 @@ __device__ void group_radix_sort_hi32(const QGroup<NW>& G, unsigned long long* s
 #pragma unroll 1
         for (int i = tid; i < NW * 256; i += T) cnt[i] = 0;
         G.sync();
+        // (the key of the NEXT round is loaded before the current one is ranked: on the passes that read the global
+        // scratch the L2 round trip overlaps the match / counter chain instead of heading it)
+        auto ld_key = [&](int i) -> unsigned long long { return i < hi ? (from_smem ? sbuf[i] : __ldcg(gbuf + i)) : 0ull; };
         // sweep 1: per-warp digit counts
+        unsigned long long knext = ld_key(lo + lane);
 #pragma unroll 1
         for (int base = lo; base < hi; base += 32) {
             const int i = base + lane;
             const bool valid = i < hi;
-            const unsigned long long k = valid ? (from_smem ? sbuf[i] : __ldcg(gbuf + i)) : 0ull;
+            const unsigned long long k = knext;
+            knext = ld_key(i + 32);
             const uint32_t d = valid ? (uint32_t)(k >> shift) & 255u : 0xffffffffu;
             const uint32_t peers = __match_any_sync(FULL_MASK, d);
             if (valid && lane == __ffs(peers) - 1) cnt[w * 256 + d] += (uint16_t)__popc(peers);
@@ -257,11 +262,13 @@ __device__ void group_radix_sort_hi32(const QGroup<NW>& G, unsigned long long* s
         }
         G.sync();
         // sweep 2: scatter
+        knext = ld_key(lo + lane);
 #pragma unroll 1
         for (int base = lo; base < hi; base += 32) {
             const int i = base + lane;
             const bool valid = i < hi;
-            const unsigned long long k = valid ? (from_smem ? sbuf[i] : __ldcg(gbuf + i)) : 0ull;
+            const unsigned long long k = knext;
+            knext = ld_key(i + 32);
             const uint32_t d = valid ? (uint32_t)(k >> shift) & 255u : 0xffffffffu;
             const uint32_t peers = __match_any_sync(FULL_MASK, d);
             const int leader = __ffs(peers) - 1;
