@@ -379,7 +379,12 @@ __device__ float quad_decode_warp(const DevParams& P, const DevFamily& fam, cons
     return fminf(white_score / white_count, black_score / black_count);
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef DEC_MINB
+#define DEC_MINB 4   // 128 registers: all 16 persistent one-warp CTAs per SM (decode_ctas = 4) are resident; at the 155
+                     // the compiler takes unbounded only 12 were and a quarter of the grid ran as a second wave
+                     // (0.42 -> 0.32 ms per 128 frames; 96 registers spill too much)
+#endif
+__global__ void __launch_bounds__(128, DEC_MINB)
 k_decode_quads(DecodeArgs a, DevParams P) {
     __shared__ double s_values[4][DEC_GRID_MAX];
     __shared__ double s_sharp[4][DEC_GRID_MAX];
