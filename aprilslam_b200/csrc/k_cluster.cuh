@@ -21,8 +21,11 @@
 // representative + dense-id look-ups, ballot compaction, one atomic per 32 candidates), so the expensive part is
 // not serialised inside the few rows that sit on an edge.
 #define EDGE_CAND_PER_PASS 1024   // a tile with more candidates is handled in four passes of 8 rows (8 x 32 x 4)
+#ifndef EDGE_MINB
+#define EDGE_MINB 24   // 40 registers, 48 warps per SM: the kernel waits on dependent global look-ups (46 registers / 40 warps
+#endif                 // unbounded: +6 % time; 32 registers spill and gain nothing)
 template <int EDGE_WARPS>
-__global__ void __launch_bounds__(EDGE_WARPS * 32)
+__global__ void __launch_bounds__(EDGE_WARPS * 32, EDGE_WARPS == 2 ? EDGE_MINB : 1)
 k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
         const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts,
         int* __restrict__ ndups, int cap, int id_bits) {
