@@ -14,6 +14,8 @@ libaprilgpu.so.  Nothing here falls back to a CPU implementation.
 from __future__ import annotations
 
 import ctypes as C
+import sys
+from collections.abc import Sequence as _SequenceABC
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -22,6 +24,35 @@ from . import _lib
 from ._lib import DET_DTYPE, POSE_DTYPE, STAGE_NAMES, AgpuConfig
 
 KNOWN_FAMILIES = ("tag36h11", "tag25h9", "tag16h5", "tagStandard41h12")
+
+
+class FrameLists(_SequenceABC):
+    """Per-frame record arrays of one batch call: element b is a view `buf[b, :n[b]]`, created on demand (a batch of
+    1024 frames would otherwise cost a millisecond of Python just to slice).  Behaves like a list of arrays."""
+    __slots__ = ("_buf", "_n")
+
+    def __init__(self, buf: np.ndarray, n: np.ndarray):
+        self._buf, self._n = buf, n
+
+    def __len__(self) -> int:
+        return int(self._buf.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError("frame index out of range")
+        return self._buf[i, :int(self._n[i])]
+
+    def counts(self) -> np.ndarray:
+        """Number of records per frame."""
+        return self._n
+
+    def __repr__(self):
+        return "FrameLists(%d frames, %d records)" % (len(self), int(self._n.sum()))
 
 
 def _is_torch_cuda(x) -> bool:
@@ -40,6 +71,7 @@ class Detector:
         self.families = families.replace(",", " ").split()
         self.decimate = float(decimate)
         self._L = _lib.load()
+        self._pool = {}   # (B, cap, dtype) -> result buffers, see _result_buffer
         cfg = AgpuConfig()
         self._L.agpu_default_config(C.byref(cfg))
         self._fam_bytes = " ".join(self.families).encode()
@@ -112,25 +144,41 @@ class Detector:
         B, H, W = a.shape[:3]
         return a.ctypes.data, 0, B, W, H, W * channels, None, a
 
+    # -- result buffers -----------------------------------------------------------------------
+    def _result_buffer(self, B: int, cap: int, dtype) -> np.ndarray:
+        """[B, cap] record array for one call.  A fresh 10-20 MB array per call costs ~2 ms of page faults on a 1024-frame
+        batch (10 % of the whole step), so buffers are pooled and one is handed out again once NOTHING outside the pool
+        references it any more (the per-frame views a caller still holds keep their buffer alive and out of
+        circulation -- results never change under a caller's feet)."""
+        key = (B, cap, dtype.str if hasattr(dtype, "str") else str(dtype))
+        pool = self._pool.setdefault(key, [])
+        for i in range(len(pool)):
+            if sys.getrefcount(pool[i]) == 2:          # the pool's own reference + getrefcount's argument
+                return pool[i]
+        buf = np.empty((B, cap), dtype)
+        if len(pool) < 4:
+            pool.append(buf)
+        return buf
+
     # -- detection ----------------------------------------------------------------------------
-    def detect_batch(self, frames, cap_per_frame: int = 64, bgr: bool = False) -> List[np.ndarray]:
-        """frames: uint8 [B,H,W] (gray) or [B,H,W,3] (bgr=True) -> list of DET_DTYPE record arrays."""
+    def detect_batch(self, frames, cap_per_frame: int = 64, bgr: bool = False) -> FrameLists:
+        """frames: uint8 [B,H,W] (gray) or [B,H,W,3] (bgr=True) -> per-frame DET_DTYPE record arrays (a list-like)."""
         ch = 3 if bgr else 1
         ptr, on_dev, B, W, H, stride, stream, keep = self._frames(frames, ch)
-        out = np.zeros((B, cap_per_frame), DET_DTYPE)
+        out = self._result_buffer(B, cap_per_frame, DET_DTYPE)
         counts = np.zeros(B, np.int32)
         fn = self._L.agpu_detect_bgr if bgr else self._L.agpu_detect
         rc = fn(self._h, ptr, on_dev, B, W, H, stride, stream, out.ctypes.data, cap_per_frame, counts.ctypes.data)
         self._check(rc, allow_truncated=True)
-        return [out[b, :min(int(counts[b]), cap_per_frame)] for b in range(B)]
+        return FrameLists(out, np.minimum(counts, cap_per_frame))
 
     def detect_pose_batch(self, frames, camera_matrix, dist_coeffs, tag_size: float, cap_per_frame: int = 64,
-                          bgr: bool = False) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+                          bgr: bool = False) -> Tuple[FrameLists, FrameLists]:
         """Detection + per-tag pose in one pass: (detections, poses) per frame (POSE_DTYPE records)."""
         ch = 3 if bgr else 1
         ptr, on_dev, B, W, H, stride, stream, keep = self._frames(frames, ch)
-        out = np.zeros((B, cap_per_frame), DET_DTYPE)
-        poses = np.zeros((B, cap_per_frame), POSE_DTYPE)
+        out = self._result_buffer(B, cap_per_frame, DET_DTYPE)
+        poses = self._result_buffer(B, cap_per_frame, POSE_DTYPE)
         counts = np.zeros(B, np.int32)
         K = np.ascontiguousarray(np.asarray(camera_matrix, np.float64).reshape(3, 3))
         dist = np.ascontiguousarray(np.asarray(dist_coeffs if dist_coeffs is not None else [], np.float64).ravel())
@@ -138,8 +186,8 @@ class Detector:
                                       dist.ctypes.data if dist.size else None, int(dist.size), float(tag_size),
                                       out.ctypes.data, poses.ctypes.data, cap_per_frame, counts.ctypes.data)
         self._check(rc, allow_truncated=True)
-        n = [min(int(c), cap_per_frame) for c in counts]
-        return [out[b, :n[b]] for b in range(B)], [poses[b, :n[b]] for b in range(B)]
+        n = np.minimum(counts, cap_per_frame)
+        return FrameLists(out, n), FrameLists(poses, n)
 
     def estimate_pose(self, corners, camera_matrix, dist_coeffs, tag_size: float, method: int = 0) -> np.ndarray:
         """corners [M,4,2] (lb, rb, rt, lt) -> POSE_DTYPE[M] (ok, rvec, tvec, R)."""

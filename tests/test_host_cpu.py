@@ -153,3 +153,35 @@ def test_bench_reference_arm_prints_one_json_line():
     line = json.loads(out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_result_buffers_are_recycled_only_when_unreferenced():
+    """Detector._result_buffer hands a pooled [B, cap] array out again only when no FrameLists / view of it is alive."""
+    from aprilslam_b200._lib import DET_DTYPE
+    from aprilslam_b200.detector import Detector, FrameLists
+
+    class PoolOnly(Detector):          # (no GPU here: only the host-side pool logic)
+        def __init__(self):
+            self._pool = {}
+
+        def close(self):
+            pass
+
+    d = PoolOnly()
+    a = d._result_buffer(4, 8, DET_DTYPE)
+    ida = id(a)
+    fl = FrameLists(a, np.array([1, 2, 0, 3], np.int32))
+    del a
+    b = d._result_buffer(4, 8, DET_DTYPE)
+    assert id(b) != ida                                   # first buffer still referenced by `fl`
+    view = fl[1]
+    del fl
+    c = d._result_buffer(4, 8, DET_DTYPE)
+    assert id(c) != ida and len(view) == 2                # ... and by a per-frame view
+    del view, b, c
+    e = d._result_buffer(4, 8, DET_DTYPE)
+    assert id(e) in {id(x) for x in d._pool[(4, 8, DET_DTYPE.str)]}   # recycled from the pool
+    fl = FrameLists(e, np.array([1, 2, 0, 3], np.int32))
+    assert len(fl) == 4 and [len(x) for x in fl] == [1, 2, 0, 3] and len(fl[-1]) == 3 and len(fl[1:3]) == 2
+    with pytest.raises(IndexError):
+        fl[4]
