@@ -325,9 +325,20 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
     long long Sxgx = 0, Sygy = 0, Sgx = 0, Sgy = 0;
     int nmerged = 0;
+    // the cluster's records come in from L2 / HBM exactly once, four loads in flight per thread, and are parked in the
+    // sort buffer: the passes below (thread t always touches the entries t, t + T, ...) read shared memory
+#pragma unroll 1
+    for (int i0 = tid; i0 < sz; i0 += 4 * T) {
+        uint32_t v4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v4[u] = i0 + u * T < sz ? (uint32_t)__ldg(pv + i0 + u * T) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + u * T < sz) sbuf[i0 + u * T] = v4[u];
+    }
 #pragma unroll 1
     for (int i = tid; i < sz; i += T) {
-        uint32_t v = (uint32_t)pv[i];
+        uint32_t v = (uint32_t)sbuf[i];
         int px = v & 0x3fff, py = (v >> 14) & 0x3fff;
         const int kind = v >> 28;
         int gx, gy;
@@ -367,7 +378,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     for (int i = tid; i < sz; i += T) {
         unsigned long long key = ~0ull;
         {
-            uint32_t v = (uint32_t)pv[i];
+            uint32_t v = (uint32_t)sbuf[i];
             int px = v & 0x3fff, py = (v >> 14) & 0x3fff;
             float dx = (float)px - cx, dy = (float)py - cy;
             float qd;
@@ -392,7 +403,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     //      are dead after the sort), so that the scan below never waits on global memory
     {
         const uint8_t* im = a.quad_im + (size_t)ref.frame * a.q_frame;
-#pragma unroll 1
+#pragma unroll 2
         for (int i = tid; i < sz; i += T) {
             const uint32_t xy = (uint32_t)sbuf[i];
             const int px = xy & 0xffff, py = xy >> 16;
