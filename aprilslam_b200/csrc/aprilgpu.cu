@@ -73,10 +73,9 @@ struct HostBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// cluster size tiers of the quad-fit kernel: {largest cluster, warps per CTA, CTAs per SM}
+// cluster size tiers of the quad-fit kernel (largest cluster per tier; 1 / 2 / 4 / 8 warps per cluster: tier 0 packs
+// eight one-warp groups into a CTA, the others use one CTA per cluster)
 constexpr int TIER_CAP_DEFAULT[AGPU_NTIERS] = {256, 1024, 2048, 16384};
-// warps per cluster group (NW); tier 0 packs 8 one-warp groups into a CTA, the others use one CTA per cluster
-constexpr int TIER_NW[AGPU_NTIERS] = {1, 2, 4, 8};
 // counter block layout (ints): [0..3] clusters per tier
 enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_CURSOR0 = 8, CNT_FIXED = 16 };
 

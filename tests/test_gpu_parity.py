@@ -321,6 +321,8 @@ def test_instrumentation_counts_launches_and_stages():
     assert all(v >= 0 for v in ms.values()) and sum(ms.values()) > 0
     c = g.counters()
     assert c["edge_points"] > 0 and c["quads"] >= 6 and c["oversize_clusters"] == 0
+    tl = g.timeline()   # one row per chunk: first frame, frames, slot, then the ten stage boundary marks (ms, ascending)
+    assert tl.shape == (1, 13) and tl[0, 0] == 0 and tl[0, 1] == 1 and np.all(np.diff(tl[0, 3:]) >= 0)
     g.close()
 
 
