@@ -147,7 +147,7 @@ def run_reference_arm(args):
     import __graft_entry__ as ge
     ge.build()
     from aprilslam_b200 import synth
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) or 1
     nframes = args.ref_frames or max(16, min(128, 8 * threads))
     frames = make_frames(min(nframes, 32), nframes)
     K = synth.intrinsics(W, H, 45.0)
@@ -194,6 +194,7 @@ def run_b200(args):
     from aprilslam_b200.shard import bind_to_gpu_numa
     visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
     phys = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
+    cpus_before = os.sched_getaffinity(0)
     bound_cpus = bind_to_gpu_numa(phys)
     B = args.batch
     K = synth.intrinsics(W, H, 45.0)
@@ -356,7 +357,8 @@ def run_b200(args):
                                 "frac": stages["edges"]["frac"], "algorithmic_bytes_per_frame": alg["edges"]},
                 "dense_pipeline": {"achieved": pipe_gbs, "frac": pipe_gbs / peak, "algorithmic_bytes_per_frame": 12 * N}}
     # CPU baseline on this box's host cores (bounded sample of the same workload)
-    threads = os.cpu_count() or 1
+    os.sched_setaffinity(0, cpus_before)          # the CPU baseline may use every host core again
+    threads = len(os.sched_getaffinity(0)) or 1
     nref = max(16, min(256, 16 * threads, B))     # ~10-30 core-seconds of CPU work
     t0 = time.time()
     sec_cpu, _ = cpu_reference_run(frames_host[:nref], K, 1, 0, threads)
