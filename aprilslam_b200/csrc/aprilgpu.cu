@@ -1059,6 +1059,7 @@ int agpu_destroy(agpu_handle* h) {
     }
     h->d_fams.release(); h->d_codes.release(); h->d_pose_in.release(); h->d_pose_out.release();
     if (h->ev_user) cudaEventDestroy(h->ev_user);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     delete h;
     return AGPU_OK;
 }
