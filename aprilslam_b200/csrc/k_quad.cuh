@@ -2,10 +2,12 @@
 // quad_segment_maxima / fit_line; part of the native call at
 // /root/reference/src/detection/tag_detector.py:26).
 //
-// Per cluster: bounding box + border polarity (exact integer sums) -> slope keys -> bitonic sort in
-// shared memory on (slope, y, x) -> de-duplication -> prefix line-fit moments (warp scans, stored in
-// an L2-resident scratch) -> windowed line-fit error, 7-tap smoothing, local maxima, top-10 selection
-// -> exhaustive 4-corner search over a pre-computed table of pairwise line fits -> corners + gates.
+// Per cluster: records staged once in shared memory -> bounding box + border polarity (exact integer sums) -> slope
+// keys -> stable radix sort on the slope bits (ping-pong shared memory / L2 scratch) + tie fix on (y, x) -> prefix
+// line-fit moments (warp scans, stored in an L2-resident scratch) -> windowed line-fit error, 7-tap smoothing, local
+// maxima, top-10 selection -> exhaustive 4-corner search over a pre-computed table of pairwise line fits (dealt to
+// the threads by triples) -> corners + gates on one warp.  (The only duplicate points upstream produces are merged at
+// emission by k_edges, so there is no de-duplication pass.)
 #pragma once
 #include "common.cuh"
 #include "k_cc.cuh"
@@ -163,30 +165,10 @@ struct QGroup {
     }
 };
 
-// Bitonic sort of n2 (power of two >= 64) 64-bit keys in shared memory: every thread owns compare-exchange
-// PAIRS (no idle half), independent pairs per step for memory-level parallelism.
-template <int NW>
-__device__ __forceinline__ void group_bitonic_sort(const QGroup<NW>& G, unsigned long long* s, int n2, bool descending) {
-    const int npairs = n2 >> 1;
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 4
-            for (int t = G.tid; t < npairs; t += QGroup<NW>::T) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int ixj = i | j;
-                unsigned long long a = s[i], b = s[ixj];
-                const bool up = ((i & k) == 0) != descending;
-                if ((a > b) == up) { s[i] = b; s[ixj] = a; }
-            }
-            G.sync();
-        }
-    }
-}
-
 // Stable LSD radix sort of n 64-bit keys by their upper 32 bits (the slope), 8-bit digits, four passes that
 // ping-pong between the shared-memory buffer and a global scratch (ends in shared memory).  Warp w owns the
 // contiguous chunk [w*cw, (w+1)*cw) of the source; ranks come from __match_any_sync, so the order of equal
-// digits is preserved.  cnt: NW*256 16-bit counters.  Roughly a third of the instructions of the bitonic
+// digits is preserved.  cnt: NW*256 16-bit counters.  Roughly a third of the instructions of a bitonic
 // network for the cluster sizes that matter (1000-2000 points).
 template <int NW>
 __device__ void group_radix_sort_hi32(const QGroup<NW>& G, unsigned long long* sbuf, unsigned long long* gbuf, int n,
