@@ -185,3 +185,14 @@ def test_result_buffers_are_recycled_only_when_unreferenced():
     assert len(fl) == 4 and [len(x) for x in fl] == [1, 2, 0, 3] and len(fl[-1]) == 3 and len(fl[1:3]) == 2
     with pytest.raises(IndexError):
         fl[4]
+
+
+def test_bind_to_gpu_numa_degrades_without_nvml():
+    """No GPU / NVML here: the helper reports 0 bound CPUs and leaves the process affinity untouched."""
+    from aprilslam_b200.shard import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    n = bind_to_gpu_numa(0)
+    assert isinstance(n, int) and n >= 0
+    if n == 0:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
