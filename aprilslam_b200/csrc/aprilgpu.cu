@@ -74,8 +74,10 @@ struct HostBuf {
 };
 
 // cluster size tiers of the quad-fit kernel (largest cluster per tier; 1 / 2 / 4 / 8 warps per cluster: tier 0 packs
-// eight one-warp groups into a CTA, the others use one CTA per cluster)
-constexpr int TIER_CAP_DEFAULT[AGPU_NTIERS] = {256, 1024, 2048, 16384};
+// eight one-warp groups into a CTA, the others use one CTA per cluster).  The last tier takes everything up to
+// upstream's own size limit, 3(2w+2h) points (set per call from the frame geometry), so no cluster upstream would
+// fit is ever skipped.
+constexpr int TIER_CAP_DEFAULT[AGPU_NTIERS] = {256, 1024, 2048, 0};
 // counter block layout (ints): [0..3] clusters per tier
 enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_CURSOR0 = 8, CNT_FIXED = 16 };
 
@@ -92,7 +94,7 @@ struct Slot {
     std::vector<cudaEvent_t> events;   // stage timing
     cudaEvent_t ev_k[2] = {nullptr, nullptr};   // around k_cc_local (the roofline kernel), profiling only
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_labels, d_canon, d_sizes, d_roots, d_dense, d_dense2rep;
-    DevBuf d_recs[2], d_hist, d_dtot, d_lfps, d_errs;
+    DevBuf d_recs[2], d_hist, d_dtot, d_lfps, d_errs, d_gsort;
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
@@ -101,7 +103,7 @@ struct Slot {
 
     void release() {
         DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_labels, &d_canon, &d_sizes, &d_roots,
-                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_hist, &d_dtot, &d_lfps, &d_errs, &d_counters,
+                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_hist, &d_dtot, &d_lfps, &d_errs, &d_gsort, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
         for (DevBuf* bb : bufs) bb->release();
@@ -503,6 +505,12 @@ int alloc_slot(agpu_handle* h, Slot& s, const CallCtx& c) {
     CK(s.d_dense2rep.ensure((size_t)chunk * AGPU_MAX_DENSE * 4));
     CK(s.d_lfps.ensure((size_t)chunk * cap * 48));
     CK(s.d_errs.ensure((size_t)chunk * cap * 8));
+    {   // frames so large that a cluster of upstream's maximum size does not fit a CTA's shared memory (4K at decimate 1):
+        // the last tier then sorts such clusters in a per-CTA global buffer
+        const int max_cluster = 3 * (2 * c.g.wd + 2 * c.g.hd);
+        if (max_cluster > QF_SMEM_CAP)
+            CK(s.d_gsort.ensure((size_t)h->num_sms * h->tune.tier_ctas[AGPU_NTIERS - 1] * max_cluster * 8));
+    }
     CK(s.d_counters.ensure(c.ncnt * 4));
     for (int t = 0; t < AGPU_NTIERS; t++) CK(s.d_clusters[t].ensure((size_t)chunk * c.maxcl * sizeof(ClusterRef)));
     if (h->cfg.debug) {
@@ -584,9 +592,13 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     const unsigned long long* srecs = sl.d_recs[cur].as<unsigned long long>();
     {
         ClusterLists cl;
+        const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);   // upstream's cluster size limit
+        int tier_cap[AGPU_NTIERS], tier_smem[AGPU_NTIERS];    // largest cluster of a tier / capacity of its shared-memory sort buffer
         for (int t = 0; t < AGPU_NTIERS; t++) {
+            tier_cap[t] = t == AGPU_NTIERS - 1 ? std::max(max_cluster, h->tune.tier_cap[t - 1] + 1) : h->tune.tier_cap[t];
+            tier_smem[t] = std::min(tier_cap[t], QF_SMEM_CAP);
             cl.list[t] = sl.d_clusters[t].as<ClusterRef>();
-            cl.cap[t] = h->tune.tier_cap[t];
+            cl.cap[t] = tier_cap[t];
         }
         cl.counters = d_cnt;
         cl.cap_list = n * c.maxcl;
@@ -606,6 +618,9 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         qa.nquads = d_cnt + CNT_NQUADS;
         qa.cap_quads = n * c.maxq;
         qa.per_frame_quads = d_frame_quads;
+        qa.oversize = d_cnt + CNT_OVERSIZE;
+        qa.gsort = sl.d_gsort.as<unsigned long long>();
+        qa.gsort_stride = (size_t)max_cluster;
         // the tiers are independent (own work list, atomic appends to the quad list): fork them over side
         // streams so that the latency-bound big-cluster warps overlap with the many small clusters
         CK(cudaEventRecord(sl.ev_mid, sl.stream));
@@ -619,14 +634,14 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             qa.cursor = d_cnt + CNT_CURSOR0 + t;
             const int nblk = h->num_sms * h->tune.tier_ctas[t];
             if (t == 0) {
-                const size_t smem = 8 * qf_smem_per_group(h->tune.tier_cap[t], 1);
-                k_fit_quads<1><<<nblk, 256, smem, st>>>(qa, h->prm, h->tune.tier_cap[t]);
+                const size_t smem = 8 * qf_smem_per_group(tier_smem[t], 1);
+                k_fit_quads<1><<<nblk, 256, smem, st>>>(qa, h->prm, tier_smem[t]);
             } else if (t == 1) {
-                k_fit_quads<2><<<nblk, 64, qf_smem_per_group(h->tune.tier_cap[t], 2), st>>>(qa, h->prm, h->tune.tier_cap[t]);
+                k_fit_quads<2><<<nblk, 64, qf_smem_per_group(tier_smem[t], 2), st>>>(qa, h->prm, tier_smem[t]);
             } else if (t == 2) {
-                k_fit_quads<4><<<nblk, 128, qf_smem_per_group(h->tune.tier_cap[t], 4), st>>>(qa, h->prm, h->tune.tier_cap[t]);
+                k_fit_quads<4><<<nblk, 128, qf_smem_per_group(tier_smem[t], 4), st>>>(qa, h->prm, tier_smem[t]);
             } else {
-                k_fit_quads<8><<<nblk, 256, qf_smem_per_group(h->tune.tier_cap[t], 8), st>>>(qa, h->prm, h->tune.tier_cap[t]);
+                k_fit_quads<8><<<nblk, 256, qf_smem_per_group(tier_smem[t], 8), st>>>(qa, h->prm, tier_smem[t]);
             }
             LAUNCH_CHECK("k_fit_quads");
             if (t > 0) {
@@ -758,6 +773,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
         }
     }
     for (int t = 0; t < AGPU_NTIERS; t++) h->counters[1] += hc[CNT_TIER0 + t];
+    for (int t = 1; t < AGPU_NTIERS; t++) h->counters[4 + t] += hc[CNT_TIER0 + t];   // clusters per multi-warp tier
     h->counters[2] += hc[CNT_NQUADS];
     h->counters[4] += hc[CNT_OVERSIZE];
     h->last_slot = (int)(&sl - h->slots.data());
@@ -769,9 +785,23 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     return 0;
 }
 
-int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channels, int B, int W, int H, int stride,
-                void* cuda_stream, const PoseSpec& pose, agpu_detection* out, agpu_pose_t* poses, int cap_out,
-                int* counts) {
+// Wait for everything a slot still has in flight (kernels, the asynchronous copies from the caller's host frames and
+// into the pinned result buffers) and forget its chunk.  Every error exit of a detect call goes through this: a chunk
+// left pending would otherwise be "finished" by the NEXT call with that call's batch geometry.
+void drain_slots(agpu_handle* h) {
+    for (Slot& s : h->slots) {
+        if (!s.pending) continue;
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        for (int t = 0; t < AGPU_NTIERS - 1; t++)
+            if (s.aux[t]) cudaStreamSynchronize(s.aux[t]);
+        if (s.tail) cudaStreamSynchronize(s.tail);
+        s.pending = false;
+    }
+}
+
+int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channels, int B, int W, int H, int stride,
+               void* cuda_stream, const PoseSpec& pose, agpu_detection* out, agpu_pose_t* poses, int cap_out,
+               int* counts) {
     if (!h) return AGPU_E_INVALID;
     if (!frames || !out || !counts || B <= 0 || W <= 0 || H <= 0 || cap_out <= 0 || (channels != 1 && channels != 3) ||
         stride < W * channels) {
@@ -889,6 +919,15 @@ int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channe
         todo = redo;
     }
     return rc_final;
+}
+
+int detect_impl(agpu_handle* h, const uint8_t* frames, int on_device, int channels, int B, int W, int H, int stride,
+                void* cuda_stream, const PoseSpec& pose, agpu_detection* out, agpu_pose_t* poses, int cap_out,
+                int* counts) {
+    if (h) drain_slots(h);   // (safety net: nothing may be pending when a call starts)
+    const int rc = detect_run(h, frames, on_device, channels, B, W, H, stride, cuda_stream, pose, out, poses, cap_out, counts);
+    if (h) drain_slots(h);   // error exits leave chunks in flight; after a successful call this is a no-op
+    return rc;
 }
 
 }  // namespace
@@ -1038,7 +1077,7 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     }
     // the large quad-fit tiers need more than 48 KB of dynamic shared memory
     ce = cudaFuncSetAttribute(k_fit_quads<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)qf_smem_per_group(h->tune.tier_cap[AGPU_NTIERS - 1], 8));
+                              (int)qf_smem_per_group(QF_SMEM_CAP, 8));
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
     if (ce == cudaSuccess)

@@ -3,7 +3,9 @@
 //
 // Partition restated: pixels with value 127 are singletons.  A pixel (x, y) with 1 <= x <= w-2
 // links to its equal-valued neighbours left (x-1, y) and, for y >= 1, up (x, y-1); white (255)
-// pixels additionally link up-left and up-right.  Columns 0 and w-1 never initiate links.
+// pixels additionally link up-left and -- unless the upper neighbour is white as well (upstream's
+// guard; only at x = w-2 is that link not implied by the others) -- up-right.  Columns 0 and w-1
+// never initiate links.
 //
 // Data layout (per frame, TILE-MAJOR: tile t = ty * tiles_x + tx covers 32x32 pixels):
 //   masks  uint2 [tiles][32]     row r of the tile as two bit masks {white, black} (bit c = column c); everything
@@ -231,8 +233,10 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
         const uint32_t M = black ? mr.y : mr.x, Mu = black ? mu.y : mu.x;
         const uint32_t cu = Mu & (Mu << 1) & I, Su = Mu & ~cu;
         const uint32_t rI = run_mask(M & (M << 1) & I, s) & I;
-        // white: 8-connected (up-left, up, up-right), black: 4-connected (up)
-        uint32_t touched = (black ? rI : ((rI << 1) | rI | (rI >> 1))) & Mu;
+        // white: 8-connected (up-left, up, up-right), black: 4-connected (up).  Upstream skips the up-right link when the
+        // upper neighbour is white too; inside the image that link is implied (up + the upper row's own run), but at
+        // x = wd-2 it is not (column wd-1 never continues a run), and the partition has to be upstream's.
+        uint32_t touched = (black ? rI : (((rI & ~Mu) << 1) | rI | (rI >> 1))) & Mu;
         while (touched) {
             const int x = __ffs(touched) - 1;
             const int su = 31 - __clz(Su & (0xffffffffu >> (31 - x)));
@@ -359,7 +363,7 @@ k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16,
                 const bool do_left = c == 0 && row_l;
                 const bool do_up = up_c && !(x - 1 >= 1 && row_l && up_l);
                 const bool do_ul = col == 0 && up_l && !up_c;
-                const bool do_ur = col == 0 && up_r && (!up_c || x + 1 > g.wd - 2);
+                const bool do_ur = col == 0 && up_r && !up_c;   // (upstream: no up-right link when up is white)
                 if (!(do_left || do_up || do_ul || do_ur)) continue;
                 const uint32_t me = cc_pixel_root(f16, tl, x0, y0, 0, c, P0, I, g.wp);
                 if (do_left) gunion(fl, me, cc_pixel_root(f16, tL, x0 - 32, y0, 0, 31, PL0, IL, g.wp));
@@ -396,7 +400,7 @@ k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16,
         }
     }
     if ((I >> 31) & 1u) {   // x = x0 + 31 is an initiator: white up-right contact into the right tile
-        if ((M.x >> 31) && (MRu_w & 1u) && (!(Mu.x >> 31) || x0 + 32 > g.wd - 2)) {
+        if ((M.x >> 31) && (MRu_w & 1u) && !(Mu.x >> 31)) {
             const uint32_t me = cc_pixel_root(f16, tl, x0, y0, lane, 31, M.x, I, g.wp);
             gunion(fl, me, cc_pixel_root(f16, tR, x0 + 32, y0, lane - 1, 0, MRu_w, IR, g.wp));
         }

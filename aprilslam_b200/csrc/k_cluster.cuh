@@ -364,7 +364,7 @@ k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long lon
 struct ClusterLists {
     ClusterRef* list[AGPU_NTIERS];
     int cap[AGPU_NTIERS];    // largest cluster size of the tier
-    int* counters;           // [0..3] tier counts, [4] oversize (skipped), [5] all heads (debug), [8..11] tier work cursors
+    int* counters;           // [0..3] tier counts, [4] clusters over upstream's size limit, [5] all heads (debug), [8..11] tier work cursors
     int cap_list;
     ClusterRef* dbg_heads;   // all run heads (debug only, may be null)
     int cap_dbg;
@@ -408,7 +408,11 @@ k_cluster_heads(const unsigned long long* __restrict__ recs, const int* __restri
             int s = atomicAdd(&cl.counters[5], 1);
             if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
         }
-        if (size < min_size || size > max_cluster) continue;
+        if (size < min_size) continue;
+        // upstream drops clusters of more than 3(2w+2h) RAW points; a record stands for one or two raw points, so a
+        // cluster with more RECORDS than that is certainly over the limit (the exact raw count of the others is
+        // taken by the fitting group, which has to read the records anyway)
+        if (size > max_cluster) { atomicAdd(&cl.counters[4], 1); continue; }
         bool placed = false;
 #pragma unroll
         for (int t = 0; t < AGPU_NTIERS; t++)

@@ -153,8 +153,11 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
         }
     };
     // threshold + store the four rows of tile row T (or one leftover row) against dilated extrema d
+    // (leftover pixels -- right of the last full tile column, or the rows below the last full tile row (`bottom`) --
+    // are thresholded against the last full tile's extrema and never become 127: upstream's fix-up loop has no
+    // low-contrast test)
     auto store_rows = [&](int gy0, int nrows, const uint32_t(&px)[4][TPL], const uint32_t(&dmn)[TPL],
-                          const uint32_t(&dmx)[TPL]) {
+                          const uint32_t(&dmx)[TPL], bool bottom) {
         // the tile column left of this lane's first tile: right leftover pixels (x >= 4*tw) use tile tw-1
         const uint32_t lmn = __shfl_up_sync(FULL_MASK, dmn[TPL - 1], 1), lmx = __shfl_up_sync(FULL_MASK, dmx[TPL - 1], 1);
         uint32_t thr2[TPL];
@@ -166,7 +169,7 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
             if (tx >= tw) { a = j == 0 ? lmn : dmn[(j + TPL - 1) % TPL]; b = j == 0 ? lmx : dmx[(j + TPL - 1) % TPL]; }
             const int imn = a & 0xff, imx = b & 0xff;
             const int diff = imx - imn;
-            flat[j] = diff < min_diff;
+            flat[j] = !bottom && tx < tw && diff < min_diff;
             const uint32_t thr = (uint32_t)(imn + (diff >> 1));
             thr2[j] = 0x64006400u | thr | (thr << 16);
         }
@@ -238,12 +241,12 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
             dmn[j] = h2u(__hmin2(__hmin2(u2h(prevMn[j]), u2h(curMn[j])), u2h(nextMn[j])));
             dmx[j] = h2u(__hmax2(__hmax2(u2h(prevMx[j]), u2h(curMx[j])), u2h(nextMx[j])));
         }
-        store_rows(T * 4, 4, cur, dmn, dmx);
+        store_rows(T * 4, 4, cur, dmn, dmx, false);
         if (T == th - 1 && (g.hd & 3)) {  // bottom leftover rows use the last tile row
             uint32_t lr[4][TPL];
 #pragma unroll
             for (int r = 0; r < 4; r++) load_row(th * 4 + r, lr[r]);
-            store_rows(th * 4, g.hd - th * 4, lr, dmn, dmx);
+            store_rows(th * 4, g.hd - th * 4, lr, dmn, dmx, true);
         }
         if (MASKS && T == th - 1) {   // mask rows of the last tile row that lie below the image: empty
             const uint32_t zero[4] = {0u, 0u, 0u, 0u};

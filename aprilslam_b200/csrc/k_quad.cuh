@@ -30,6 +30,9 @@ struct QuadFitArgs {
     int* nquads;
     int cap_quads;              // per chunk
     int* per_frame_quads;       // [nframes] count per frame (limit check / debug)
+    int* oversize;              // clusters over upstream's raw-point limit 3(2w+2h) (counted, not fitted -- as upstream)
+    unsigned long long* gsort;  // last tier only: per-CTA sort buffer in global memory for clusters that do not fit the
+    size_t gsort_stride;        // shared-memory one (frames so large that 3(2w+2h) records exceed it); may be null
 };
 
 struct LineFit {
@@ -344,7 +347,10 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     Sxgx = G.reduce_sum(Sxgx); Sygy = G.reduce_sum(Sygy);
     Sgx = G.reduce_sum(Sgx); Sgy = G.reduce_sum(Sgy);
     // upstream's size limit counts the raw points (duplicates included)
-    if (sz + (int)G.reduce_sum((long long)nmerged) > 3 * (2 * a.g.wd + 2 * a.g.hd)) return false;
+    if (sz + (int)G.reduce_sum((long long)nmerged) > 3 * (2 * a.g.wd + 2 * a.g.hd)) {
+        if (tid == 0) atomicAdd(a.oversize, 1);
+        return false;
+    }
     if ((xmax - xmin) * (ymax - ymin) < P.min_tag_width) return false;
     const float cx = (xmin + xmax) * 0.5f + 0.05118f;
     const float cy = (ymin + ymax) * 0.5f - 0.028581f;
@@ -354,8 +360,6 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     if (!P.normal_border && !reversed) return false;
 
     // ---- slope keys
-    int n2 = 64;
-    while (n2 < sz) n2 <<= 1;
 #pragma unroll 1
     for (int i = tid; i < sz; i += T) {
         unsigned long long key = ~0ull;
@@ -491,9 +495,9 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     G.sync();
 
     // ---- local maxima, in index order
-    const int half = max(n2 >> 1, 64);                      // room for the padded (>= 64) sort of the maxima values
+    const int half = max((sz + 1) >> 1, 64);                // strict local maxima are never adjacent: at most sz/2 of them
     unsigned long long* mvals = sbuf;                       // [half]
-    int* midx = reinterpret_cast<int*>(sbuf + half);        // [<= n2/2 ints]
+    int* midx = reinterpret_cast<int*>(sbuf + half);        // [half] ints: 12 * half <= 8 * sz bytes in all
     int nmax = 0;
 #pragma unroll 1
     for (int base = 0; base < sz; base += T) {
@@ -710,7 +714,9 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
 }
 
 // Dynamic shared memory per GROUP: `wcap` u64 (sort buffer; from 1024 keys on it also hosts the 600-double pair
-// table once the sort is over) + 16 ints, plus a separate pair table for the small tier.
+// table once the sort is over) + 16 ints, plus a separate pair table for the small tier.  QF_SMEM_CAP: the largest
+// sort buffer one CTA can have (227 KB of shared memory per SM).
+#define QF_SMEM_CAP 28000
 __host__ __device__ inline size_t qf_smem_per_group(int wcap, int nw) {
     return (size_t)wcap * 8 + 64 + (size_t)nw * 512 + (wcap >= 1024 ? 0 : QF_PTAB_DOUBLES * 8);
 }
@@ -759,7 +765,9 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
         if (ci >= n) break;
         const ClusterRef ref = a.list[ci];
         QuadRec q;
-        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sbuf, ptab, sidx, scnt, q);
+        unsigned long long* sb = sbuf;
+        if (NW == 8 && ref.size > wcap) sb = a.gsort + (size_t)blockIdx.x * a.gsort_stride;   // (the pair table stays in shared memory)
+        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sb, ptab, sidx, scnt, q);
         if (ok && G.tid == 0) {
             int s = atomicAdd(a.nquads, 1);
             atomicAdd(&a.per_frame_quads[ref.frame], 1);

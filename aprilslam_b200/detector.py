@@ -232,7 +232,7 @@ class Detector:
         c = np.zeros(8, np.int64)
         self._check(self._L.agpu_get_counters(self._h, c.ctypes.data))
         return dict(edge_points=int(c[0]), clusters=int(c[1]), quads=int(c[2]), raw_detections=int(c[3]),
-                    oversize_clusters=int(c[4]))
+                    oversize_clusters=int(c[4]), tier_clusters=(int(c[1] - c[5] - c[6] - c[7]), int(c[5]), int(c[6]), int(c[7])))
 
     def debug_fetch(self, what: str, frame: int = 0) -> np.ndarray:
         wd, hd = C.c_int(), C.c_int()

@@ -124,6 +124,8 @@ class SceneTag:
     half_outer: float         # half size of the textured quad (tag_size_outer / 2)
     half_inner: float         # half size of the border square (tag_size_inner / 2)
     ppc: int = DEFAULT_PPC
+    texture: Optional[np.ndarray] = None   # gray uint8 image (row 0 = top) instead of the virtual cell texture,
+                                           # e.g. the reference's own assets/tags/tagN.png (renderer.py:150-176)
 
 
 @dataclass
@@ -198,6 +200,25 @@ def _sample_virtual(cells: np.ndarray, ppc: int, s: np.ndarray, t: np.ndarray) -
     return v
 
 
+def _sample_image(tex: np.ndarray, s: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """GL_LINEAR + GL_REPEAT lookup in an image texture (texel centres at +0.5; t = 0 is the bottom row, the way
+    renderer.py:164 uploads the PNG bottom-up)."""
+    h, w = tex.shape
+    xt = s * w - 0.5
+    yt = (1.0 - t) * h - 0.5
+    x0 = np.floor(xt)
+    y0 = np.floor(yt)
+    ax = xt - x0
+    ay = yt - y0
+    x0 = x0.astype(np.int64)
+    y0 = y0.astype(np.int64)
+    x0m, x1m = np.mod(x0, w), np.mod(x0 + 1, w)
+    y0m, y1m = np.mod(y0, h), np.mod(y0 + 1, h)
+    c = tex.astype(np.float64)
+    return ((1 - ax) * (1 - ay) * c[y0m, x0m] + ax * (1 - ay) * c[y0m, x1m]
+            + (1 - ax) * ay * c[y1m, x0m] + ax * ay * c[y1m, x1m])
+
+
 def render(scene: Scene) -> np.ndarray:
     """Gray uint8 [H, W] frame."""
     W, H = scene.width, scene.height
@@ -231,8 +252,11 @@ def render(scene: Scene) -> np.ndarray:
         ok &= q > zb
         if not ok.any():
             continue
-        cells = tag_cells(tag.family, tag.tag_id)
-        v = _sample_virtual(cells, tag.ppc, np.where(ok, s, 0.5), np.where(ok, t, 0.5))
+        if tag.texture is not None:
+            v = _sample_image(tag.texture, np.where(ok, s, 0.5), np.where(ok, t, 0.5))
+        else:
+            cells = tag_cells(tag.family, tag.tag_id)
+            v = _sample_virtual(cells, tag.ppc, np.where(ok, s, 0.5), np.where(ok, t, 0.5))
         sub = img[y0:y1, x0:x1]
         sub[ok] = np.floor(v[ok] + 0.5).astype(np.uint8)
         zb[ok] = q[ok]
@@ -259,8 +283,9 @@ SIM_SETTINGS_TAGS = [  # /root/reference/config/sim_settings.json:11-42
 
 def sim_settings_scene(width=1000, height=1000, cam_pos=(0.0, 0.0, 0.0), cam_rot=(0.0, 0.0, 0.0),
                        fov_y=45.0, family="tagStandard41h12", size_scale=2.0,
-                       tag_size_inner=5.0, tag_size_outer=9.0) -> Scene:
-    """The shipped 5-tag scene (sizes scaled by size_scale as config_manager.py:147 does)."""
+                       tag_size_inner=5.0, tag_size_outer=9.0, textures=None) -> Scene:
+    """The shipped 5-tag scene (sizes scaled by size_scale as config_manager.py:147 does).  textures: optional
+    gray images indexed by tag id (the reference's assets/tags/tag{0..4}.png) instead of code-book cell textures."""
     sc = Scene(width, height, intrinsics(width, height, fov_y))
     V = view_matrix(cam_pos, cam_rot)
     wb = FAMILIES[family]["width_at_border"]
@@ -268,7 +293,8 @@ def sim_settings_scene(width=1000, height=1000, cam_pos=(0.0, 0.0, 0.0), cam_rot
     inner = tag_size_inner * size_scale
     outer = tag_size_outer * size_scale if family == "tagStandard41h12" else inner * tw / wb
     for tid, pos, rot in SIM_SETTINGS_TAGS:
-        sc.tags.append(SceneTag(family, tid, V @ model_matrix(pos, rot), outer / 2, inner / 2))
+        sc.tags.append(SceneTag(family, tid, V @ model_matrix(pos, rot), outer / 2, inner / 2,
+                                texture=None if textures is None else textures[tid]))
     return sc
 
 

@@ -138,7 +138,9 @@ int agpu_get_timeline(agpu_handle* h, float* out, int cap_floats);
 /* Kernel launches issued by the last agpu_detect* / agpu_pose call. */
 int agpu_get_launch_count(agpu_handle* h, long long* launches);
 /* Work counters of the last call, summed over frames: [0] edge points, [1] clusters fitted,
- * [2] quads, [3] detections before reconcile, [4] oversize clusters skipped. */
+ * [2] quads, [3] detections before reconcile, [4] clusters over upstream's size limit of 3(2w+2h) raw points
+ * (dropped before fitting, exactly as upstream drops them), [5] / [6] / [7] clusters fitted by the 2- / 4- / 8-warp
+ * tiers of the quad-fit kernel (cluster size classes; [1] counts all tiers). */
 int agpu_get_counters(agpu_handle* h, long long* counters /* [8] */);
 
 /* Stage dumps for parity tests (cfg.debug = 1): buffers of frame `frame` of the LAST chunk.

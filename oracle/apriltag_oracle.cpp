@@ -100,6 +100,7 @@ struct ao_debug {  // every pointer optional (NULL = not wanted); sizes are call
     float* quads_refined;  // [cap_quads*8]
     uint64_t* quad_keys;   // [cap_quads]
     int cap_quads;
+    int noversize;         // out: clusters dropped by upstream's size limit (more than 3(2w+2h) points)
 };
 }
 
@@ -217,16 +218,27 @@ void threshold(const std::vector<uint8_t>& im, int w, int h, int min_wb_diff, st
             mn2[ty * tw + tx] = a;
             mx2[ty * tw + tx] = b;
         }
+    // full tiles: low-contrast tiles (max - min < min_white_black_diff) become 127 = "unknown"
+    for (int ty = 0; ty < th; ty++)
+        for (int tx = 0; tx < tw; tx++) {
+            int a = mn2[ty * tw + tx], b = mx2[ty * tw + tx];
+            if (b - a < min_wb_diff) continue;   // stays 127
+            uint8_t thr = (uint8_t)(a + (b - a) / 2);
+            for (int dy = 0; dy < ts; dy++)
+                for (int dx = 0; dx < ts; dx++) {
+                    size_t i = (size_t)(ty * ts + dy) * w + tx * ts + dx;
+                    out[i] = im[i] > thr ? 255 : 0;
+                }
+        }
+    // leftover right / bottom pixels (w or h not a multiple of 4): upstream's fix-up loop thresholds them against
+    // the last full tile's (dilated) extrema and NEVER writes 127 there -- no low-contrast test on this path
     for (int y = 0; y < h; y++) {
+        int x0 = y >= th * ts ? 0 : tw * ts;
         int ty = std::min(y / ts, th - 1);
-        for (int x = 0; x < w; x++) {
+        for (int x = x0; x < w; x++) {
             int tx = std::min(x / ts, tw - 1);
-            uint8_t a = mn2[ty * tw + tx], b = mx2[ty * tw + tx];
-            if (b - a < min_wb_diff) {
-                out[(size_t)y * w + x] = 127;
-                continue;
-            }
-            uint8_t thr = a + (b - a) / 2;
+            int a = mn2[ty * tw + tx], b = mx2[ty * tw + tx];
+            int thr = a + (b - a) / 2;
             out[(size_t)y * w + x] = im[(size_t)y * w + x] > thr ? 255 : 0;
         }
     }
@@ -262,6 +274,11 @@ void connected_components(const std::vector<uint8_t>& t, int w, int h, std::vect
                           std::vector<uint32_t>& sizes) {
     size_t n = (size_t)w * h;
     UF uf(n);
+    // upstream's do_unionfind_first_line / do_unionfind_line2, guards included.  The guards skip unions that
+    // are implied by others -- EXCEPT the up-right one: it is skipped whenever up == up-right, and at
+    // x = w-2 the implied link (w-1, y-1) ~ (w-2, y-1) does not exist (column w-1 never initiates a union),
+    // so a white pixel of the last column joins a component only through a diagonal from (w-2, y+1) whose
+    // upper neighbour is not white.  Restated literally so that the partition is upstream's.
     for (int y = 0; y < h; y++)
         for (int x = 1; x < w - 1; x++) {
             uint8_t v = t[(size_t)y * w + x];
@@ -269,10 +286,14 @@ void connected_components(const std::vector<uint8_t>& t, int w, int h, std::vect
             uint32_t id = (uint32_t)(y * w + x);
             if (t[id - 1] == v) uf.unite(id, id - 1);
             if (y == 0) continue;
-            if (t[id - w] == v) uf.unite(id, id - w);
+            const uint8_t v_m1_0 = t[id - 1], v_m1_m1 = t[id - w - 1], v_0_m1 = t[id - w], v_1_m1 = t[id - w + 1];
+            if (x == 1 || !(v_m1_0 == v_m1_m1 && v_m1_m1 == v_0_m1))
+                if (v_0_m1 == v) uf.unite(id, id - w);
             if (v == 255) {
-                if (t[id - w - 1] == v) uf.unite(id, id - w - 1);
-                if (t[id - w + 1] == v) uf.unite(id, id - w + 1);
+                if (x == 1 || !(v_m1_0 == v_m1_m1 || v_0_m1 == v_m1_m1))
+                    if (v_m1_m1 == v) uf.unite(id, id - w - 1);
+                if (!(v_0_m1 == v_1_m1))
+                    if (v_1_m1 == v) uf.unite(id, id - w + 1);
             }
         }
     labels.assign(n, 0xffffffffu);
@@ -942,6 +963,7 @@ int detect_one(const Detector& D, const uint8_t* im, int w, int h, int stride, s
         dbg->npoints = (int)kpts.size();
         dbg->nclusters = 0;
         dbg->nquads = 0;
+        dbg->noversize = 0;
     }
 
     std::vector<Quad> quads;
@@ -959,6 +981,7 @@ int detect_one(const Detector& D, const uint8_t* im, int w, int h, int stride, s
             }
             dbg->nclusters++;
         }
+        if (dbg && csz > max_cluster) dbg->noversize++;
         if (csz >= prm.min_cluster_pixels && csz <= max_cluster) {
             cl.clear();
             for (size_t i = s; i < e; i++) cl.push_back(kpts[i].p);

@@ -29,7 +29,7 @@ class AoDebug(C.Structure):
                 ("wd", C.c_int), ("hd", C.c_int), ("npoints", C.c_int), ("nclusters", C.c_int),
                 ("cluster_keys", C.c_void_p), ("cluster_sizes", C.c_void_p), ("cap_clusters", C.c_int),
                 ("nquads", C.c_int), ("quads", C.c_void_p), ("quads_refined", C.c_void_p),
-                ("quad_keys", C.c_void_p), ("cap_quads", C.c_int)]
+                ("quad_keys", C.c_void_p), ("cap_quads", C.c_int), ("noversize", C.c_int)]
 
 
 DET_DTYPE = np.dtype([("family", "<i4"), ("id", "<i4"), ("hamming", "<i4"), ("margin", "<f4"),
@@ -128,6 +128,7 @@ class OracleDetector:
         for k in ("quads", "quads_refined", "quad_keys"):
             keep[k] = keep[k][:nq].copy()
         keep["npoints"] = dbg.npoints
+        keep["noversize"] = dbg.noversize
         return recs, keep
 
     def detect(self, gray: np.ndarray):

@@ -138,6 +138,7 @@ def test_pipeline_matches_oracle_and_golden(ob, det_gold, name):
         assert np.abs(g.debug_fetch("quads") - dbg["quads"]).max() <= 1e-3
         assert np.abs(g.debug_fetch("quads_refined") - dbg["quads_refined"]).max() <= 1e-2
     assert g.counters()["edge_points"] == dbg["npoints"]
+    assert g.counters()["oversize_clusters"] == dbg["noversize"] == 0
     assert_same_detections(recs, ref)
     # committed fixture (generated through the reference's TagDetector.detect, tools/make_golden.py)
     assert recs["id"].tolist() == det_gold[name + "_id"].tolist()
@@ -446,4 +447,107 @@ def test_id_width_switch_reruns_the_chunk(ob, det_gold):
     # the block image really has more components than 11 bits can number
     _, sz = ob.stage_labels(ob.stage_threshold(blocks))
     assert int((sz >= 25).sum()) > 2048
+    g.close()
+
+
+# ---- upstream's cluster size limit: 3(2w+2h) RAW points ---------------------------------------------------------------
+def snake_frame(L2, W=1920, H=1080, x0=100, x1=1820, amp=40, thick=14, y1=300, y2=500, bg=200, fg=30):
+    """One black shape bounded by 45-degree zigzags (almost no duplicate edge points) inside one white region: the
+    whole contour is ONE cluster whose size is set by L2."""
+    im = np.full((H, W), bg, np.uint8)
+
+    def band(xa, xb, yb):
+        xs = np.arange(xa, xb)
+        tri = np.abs(((xs - x0) % (2 * amp)) - amp)
+        for x, t in zip(xs, tri):
+            im[yb + t:yb + t + thick, x] = fg
+        return int(tri[-1])
+
+    ta, tb = band(x0, x1, y1), band(x1 - L2, x1, y2)
+    im[y1 + ta:y2 + tb + thick, x1 - thick:x1] = fg
+    return im
+
+
+@pytest.mark.parametrize("L2,raw,over", [(300, 17346, 0), (420, 18306, 1), (480, 18786, 1)])
+def test_cluster_size_limit_is_upstreams_raw_point_count(ob, L2, raw, over):
+    """1080p: the limit is 18000 raw points.  L2 = 300: 17346 raw points = 16896 records after the duplicate merge --
+    upstream fits this cluster (a 16384-record cap would have skipped it); L2 = 420: 18306 raw points in 17856
+    records -- over the limit although the record count is not; L2 = 480: records alone exceed it."""
+    im = snake_frame(L2)
+    g = Detector("tag36h11", decimate=1.0, debug=True)
+    recs = g.detect_batch(im, cap_per_frame=64)[0]
+    ref, dbg = ob.OracleDetector("tag36h11", decimate=1.0).detect_records(im, debug=True)
+    assert int(dbg["cluster_sizes"].max()) == raw and dbg["noversize"] == over
+    assert np.array_equal(g.debug_fetch("cluster_keys"), dbg["cluster_keys"])
+    assert np.array_equal(g.debug_fetch("cluster_sizes"), dbg["cluster_sizes"])
+    assert np.array_equal(g.debug_fetch("quad_keys"), dbg["quad_keys"])
+    c = g.counters()
+    assert c["oversize_clusters"] == over
+    assert c["tier_clusters"][3] == (1 if L2 < 480 else 0)      # the 8-warp tier got it unless the head pass dropped it
+    assert_same_detections(recs, ref)
+    g.close()
+
+
+def test_noise_regime_1080p_exercises_every_quad_fit_tier(ob):
+    """BASELINE configs[4] regime: sensor noise over a non-flat background -- thousands of clusters per frame in all
+    four size classes, the 8-warp tier (k_fit_quads<8>) included; detections, cluster and quad sets equal the oracle's."""
+    famspec = (("tag25h9", range(35)), ("tagStandard41h12", range(5)))
+    sc = synth.grid_scene(1920, 1080, 303, (10, 5), families=famspec, px_range=(60, 110))
+    im = synth.render(sc).astype(np.float32)
+    rng = np.random.default_rng(42)
+    yy, xx = np.mgrid[0:1080, 0:1920].astype(np.float32)
+    im = im * 0.9 + 25 * (xx / 1920 - 0.5) + rng.normal(0, 7.0, im.shape).astype(np.float32)
+    im = np.clip(np.floor(im + 0.5), 0, 255).astype(np.uint8)
+    g = Detector("tag25h9 tagStandard41h12", decimate=1.0, debug=True)
+    recs = g.detect_batch(im, cap_per_frame=128)[0]
+    ref, dbg = ob.OracleDetector("tag25h9 tagStandard41h12", decimate=1.0).detect_records(im, debug=True)
+    c = g.counters()
+    assert all(n > 0 for n in c["tier_clusters"]), c
+    assert c["edge_points"] == dbg["npoints"] > 500000 and c["oversize_clusters"] == dbg["noversize"]
+    assert np.array_equal(g.debug_fetch("cluster_keys"), dbg["cluster_keys"])
+    assert np.array_equal(g.debug_fetch("cluster_sizes"), dbg["cluster_sizes"])
+    assert np.array_equal(g.debug_fetch("quad_keys"), dbg["quad_keys"])
+    assert_same_detections(recs, ref)
+    assert len(ref) >= 20
+    g.close()
+
+
+# ---- the reference's recorded run (tests/golden/reference_run.npz) through the GPU path --------------------------------
+def test_reference_run_through_the_gpu_chain():
+    """data/csv/slam_clustered_data.csv replayed: frames rendered with the reference's textures -> agpu_detect_pose ->
+    agpu_graph_update; the my_pose estimates equal the CPU oracle chain's and reproduce the LOGGED estimates of the
+    reference (real upstream detector + cv2.solvePnP + SLAMGraph) like the oracle chain does (tests/test_reference_run.py)."""
+    from aprilslam_b200.slam_graph import SLAMGraphBatch
+    from oracle import replay
+    gold = replay.load()
+    frames, K = [], None
+    for gt in gold["traj_gt"]:
+        sc, img = replay.render_frame(gold, replay.camera_of(gt, gold["tag0_pos"]))
+        frames.append(img)
+        K = sc.K
+    frames = np.stack(frames)
+    g = Detector("tagStandard41h12", decimate=2.0)
+    dets, poses = g.detect_pose_batch(frames, K, np.zeros(4), replay.TAG_SIZE, cap_per_frame=8)
+    F = len(frames)
+    D = np.zeros((1, F, 8), dets[0].dtype)
+    P = np.zeros((1, F, 8), poses[0].dtype)
+    n = np.zeros((1, F), np.int32)
+    for f in range(F):
+        n[0, f] = len(dets[f])
+        D[0, f, :n[0, f]], P[0, f, :n[0, f]] = dets[f], poses[f]
+    graph = SLAMGraphBatch(g, nstreams=1, max_tag_id=4)
+    my_pose, valid = graph.update(D, P, n)
+    chain = replay.chain_oracle(gold)
+    assert valid.all()
+    worst_vs_oracle = 0.0
+    for f, c in enumerate(chain):
+        assert dets[f]["id"].tolist() == c["visible"]
+        if 0 in c["visible"]:                                       # (entries 78..88 amplify pose noise: see the CPU test)
+            worst_vs_oracle = max(worst_vs_oracle, float(np.abs(my_pose[0, f] - c["my_pose"]).max()))
+    assert worst_vs_oracle < 2e-3, worst_vs_oracle
+    est = gold["traj_est"][:, :3]
+    with0 = [f for f, c in enumerate(chain) if 0 in c["visible"]]
+    d = np.abs(my_pose[0, with0, :3, 3] - est[with0])
+    assert d.max() <= 0.06 and np.median(d.max(axis=1)) <= 0.006, (d.max(), np.median(d.max(axis=1)))
+    graph.close()
     g.close()

@@ -196,6 +196,40 @@ def test_oracle_edge_cases():
         ob.OracleDetector("tag99h1")
 
 
+def test_threshold_leftover_pixels_follow_upstreams_fix_up_loop():
+    """Upstream thresholds the pixels right of / below the last full 4x4 tile in a separate fix-up loop that uses the
+    last full tile's (dilated) extrema and has NO low-contrast test: those pixels are 0 or 255, never 127."""
+    flat = np.full((9, 10), 93, np.uint8)                       # tw = 2, th = 2: column 8-9 and row 8 are leftovers
+    t = ob.stage_threshold(flat)
+    assert (t[:8, :8] == 127).all()                             # full tiles: max - min < 5 -> unknown
+    assert (t[:, 8:] == 0).all() and (t[8, :] == 0).all()       # leftovers: 93 > 93 + 0 is false -> 0, not 127
+    im = np.full((9, 10), 93, np.uint8)
+    im[0:4, 4:8] = [[10, 200, 10, 200]] * 4                     # tile (1, 0): min 10, max 200 -> threshold 105
+    im[1, 8], im[2, 9], im[8, 5] = 150, 60, 250
+    t = ob.stage_threshold(im)
+    assert t[1, 8] == 255 and t[2, 9] == 0                      # right leftovers of tile row 0 use tile (1, 0): 150 > 105
+    assert t[8, 5] == 255 and t[8, 1] == 0                      # bottom leftovers use tile row 1, whose dilation sees tile (1, 0)
+    assert set(np.unique(t[:, 8:])) <= {0, 255} and set(np.unique(t[8])) <= {0, 255}
+
+
+def test_connected_components_last_column_follows_upstreams_guards():
+    """Columns 0 and w-1 never initiate a union, and upstream skips the up-right union whenever the upper neighbour has
+    the pixel's value (do_unionfind_line2): a white pixel of the last column is reached only through the diagonal of
+    (w-2, y+1), and only when (w-2, y) is not white."""
+    t = np.full((5, 6), 255, np.uint8)
+    lab, sz = ob.stage_labels(t)
+    assert (lab[:, :5] == 0).all() and sz[0, 0] == 25           # columns 0..4: one component
+    assert np.array_equal(lab[:, 5], np.arange(5) * 6 + 5)      # column 5: singletons (up == up-right everywhere)
+    t[1, 4] = 0                                                 # now (4, 2)'s upper neighbour is black ...
+    lab, sz = ob.stage_labels(t)
+    assert lab[1, 5] == 0 and lab[2, 4] == 0                    # ... and its up-right union with (5, 1) happens
+    assert lab[0, 5] == 5 and lab[2, 5] == 17 and sz[0, 0] == 25
+    assert lab[1, 4] == 10 and sz[1, 4] == 1                    # the black pixel: alone (4-connectivity, no equal neighbour)
+    b = np.zeros((4, 5), np.uint8)                              # black: left + up only
+    lab, sz = ob.stage_labels(b)
+    assert (lab[:, :4] == 0).all() and np.array_equal(lab[:, 4], np.arange(4) * 5 + 4)
+
+
 def test_oracle_blur_and_threshold_stage_properties():
     rng = np.random.default_rng(1)
     im = rng.integers(0, 256, (61, 83), dtype=np.uint8)
