@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -92,9 +93,11 @@ struct Slot {
     cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};   // side streams: quad-fit tiers run concurrently
     cudaEvent_t ev_mid = nullptr, ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;   // stage timing
-    cudaEvent_t ev_k[2] = {nullptr, nullptr};   // around k_cc_local (the roofline kernel), profiling only
+    struct KEv { const char* name; cudaEvent_t a, b; };
+    std::vector<KEv> kev;              // profiling only: one event pair around EVERY kernel launch of the chunk
+    size_t kev_next = 0;
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_labels, d_canon, d_sizes, d_roots, d_dense, d_dense2rep;
-    DevBuf d_recs[2], d_hist, d_dtot, d_lfps, d_errs, d_gsort;
+    DevBuf d_recs[2], d_hist, d_dtot, d_qscratch, d_gsort;
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
@@ -103,14 +106,15 @@ struct Slot {
 
     void release() {
         DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_labels, &d_canon, &d_sizes, &d_roots,
-                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_hist, &d_dtot, &d_lfps, &d_errs, &d_gsort, &d_counters,
+                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_hist, &d_dtot, &d_qscratch, &d_gsort, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
         for (DevBuf* bb : bufs) bb->release();
         h_out.release(); h_counts.release(); h_poses.release();
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         events.clear();
-        for (int i = 0; i < 2; i++) { if (ev_k[i]) cudaEventDestroy(ev_k[i]); ev_k[i] = nullptr; }
+        for (KEv& k : kev) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+        kev.clear();
         for (int t = 0; t < AGPU_NTIERS - 1; t++) {
             if (aux[t]) cudaStreamDestroy(aux[t]);
             if (ev_join[t]) cudaEventDestroy(ev_join[t]);
@@ -134,7 +138,7 @@ struct agpu_handle {
     std::string err;
     bool profiling = false;
     float stage_ms[AGPU_NUM_STAGES];
-    float cc_local_ms = 0;   // k_cc_local alone (agpu_get_kernel_ms)
+    std::map<std::string, std::pair<float, int>> kernel_ms;   // profiling: per kernel {ms, launches} of the last call
     long long launches = 0;
     long long counters[8];
 
@@ -253,6 +257,27 @@ int init_slot(agpu_handle* h, Slot& s) {
     return AGPU_OK;
 }
 
+// Profiling only: CUDA events right before and after one kernel launch on the stream it is launched on.  With one
+// chunk in flight (and the quad-fit tiers serialised, see launch_chunk) the interval is that kernel alone.
+struct KScope {
+    agpu_handle* h;
+    Slot& s;
+    cudaStream_t st;
+    Slot::KEv* e = nullptr;
+    KScope(agpu_handle* hh, Slot& ss, const char* name, cudaStream_t stream) : h(hh), s(ss), st(stream) {
+        if (!h->profiling) return;
+        if (s.kev_next >= s.kev.size()) {
+            Slot::KEv k{name, nullptr, nullptr};
+            if (cudaEventCreate(&k.a) != cudaSuccess || cudaEventCreate(&k.b) != cudaSuccess) return;
+            s.kev.push_back(k);
+        }
+        e = &s.kev[s.kev_next++];
+        e->name = name;
+        cudaEventRecord(e->a, st);
+    }
+    ~KScope() { if (e) cudaEventRecord(e->b, st); }
+};
+
 struct StageTimer {
     agpu_handle* h;
     Slot& s;
@@ -290,8 +315,11 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         Geom gf = make_geom(W, H, 1);
         CK(sl.d_gray.ensure(gf.plane * n));
         size_t total = (size_t)n * gf.hd * (gf.wp >> 2);
-        k_pack<<<ceil_div(total, 256), 256, 0, sl.stream>>>(d_src, W, H, stride, frame_stride, 3, 1,
-                                                            sl.d_gray.as<uint8_t>(), gf, n);
+        {
+            KScope ks(h, sl, "k_pack(bgr)", sl.stream);
+            k_pack<<<ceil_div(total, 256), 256, 0, sl.stream>>>(d_src, W, H, stride, frame_stride, 3, 1,
+                                                                sl.d_gray.as<uint8_t>(), gf, n);
+        }
         LAUNCH_CHECK("k_pack(bgr)");
         *gray_full = sl.d_gray.as<uint8_t>();
         *gray_pitch = gf.wp;
@@ -365,13 +393,15 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         const int md = h->prm.min_white_black_diff;
         const bool use_masks = masks_written && F == 1 && h->tune.masks;
         if (!use_masks) CK(sl.d_thresh.ensure(g.plane * n));
+        if (use_masks) CK(sl.d_masks.ensure((size_t)cc_tiles_x(g) * cc_tiles_y(g) * n * 32 * sizeof(uint2)));
+        {
+        KScope ks(h, sl, "k_decimate_threshold", sl.stream);
         uint8_t* th_out = sl.d_thresh.as<uint8_t>();
         int minb = 4;
         if (const char* e = getenv("AGPU_IMG_MINB")) minb = atoi(e);
 #define LAUNCH_DT(FF, MB) k_decimate_threshold<FF, MB><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, \
                                                                                th_out, g, nstrips, nsegs, seg_tiles, n, md, vec_ok)
         if (use_masks) {
-            CK(sl.d_masks.ensure((size_t)cc_tiles_x(g) * cc_tiles_y(g) * n * 32 * sizeof(uint2)));
             k_decimate_threshold<1, 4, true><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, nullptr, nullptr, g,
                                                                           nstrips, nsegs, seg_tiles, n, md, vec_ok,
                                                                           sl.d_masks.as<uint2>());
@@ -385,6 +415,7 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         }
 #undef LAUNCH_DT
         LAUNCH_CHECK("k_decimate_threshold");
+        }
     }
     if (F > 1) {
         *quad_im_out = quad_out; *q_pitch = g.wp; *q_frame = g.plane;
@@ -405,11 +436,8 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
     const size_t sub_stride = (size_t)tx * ceil_div(ty, CC_SUBLISTS) * 512;
     CK(sl.d_roots.ensure(sub_stride * CC_SUBLISTS * n * 4));
     dim3 grid(ceil_div(tx, CC_WARPS), ty, n);
-    if (h->profiling) {
-        for (int i = 0; i < 2; i++)
-            if (!sl.ev_k[i]) CK(cudaEventCreate(&sl.ev_k[i]));
-        CK(cudaEventRecord(sl.ev_k[0], sl.stream));
-    }
+    {
+    KScope ks(h, sl, "k_cc_local", sl.stream);
     if (from_masks)
         k_cc_local<true><<<grid, CC_THREADS, 0, sl.stream>>>(nullptr, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
                                                              sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
@@ -418,9 +446,10 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
         k_cc_local<false><<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
                                                               sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
                                                               sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
+    }
     LAUNCH_CHECK("k_cc_local");
-    if (h->profiling) CK(cudaEventRecord(sl.ev_k[1], sl.stream));
     {
+        KScope ks(h, sl, "k_cc_boundary", sl.stream);
         const int bw = h->tune.boundary_warps;
         dim3 gridb(ceil_div(tx * ty, bw), 1, n);
 #define LAUNCH_CCB(BW) k_cc_boundary<BW><<<gridb, BW * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), sl.d_labels.as<uint32_t>(), g)
@@ -429,14 +458,20 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
     }
     LAUNCH_CHECK("k_cc_boundary");
     dim3 grids(std::max(1, std::min(8, ceil_div(g.plane / 1024, 256))), n * CC_SUBLISTS);
-    k_cc_sizes<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
-                                             d_nroots, g, sub_stride);
+    {
+        KScope ks(h, sl, "k_cc_sizes", sl.stream);
+        k_cc_sizes<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
+                                                 d_nroots, g, sub_stride);
+    }
     LAUNCH_CHECK("k_cc_sizes");
     if (d_ndense) {
         CK(sl.d_dense.ensure(g.plane * n * 4));
         CK(sl.d_dense2rep.ensure((size_t)n * AGPU_MAX_DENSE * 4));
-        k_cc_dense<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
-                                                 d_nroots, sl.d_dense.as<uint32_t>(), sl.d_dense2rep.as<uint32_t>(), d_ndense, g, sub_stride);
+        {
+            KScope ks(h, sl, "k_cc_dense", sl.stream);
+            k_cc_dense<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
+                                                     d_nroots, sl.d_dense.as<uint32_t>(), sl.d_dense2rep.as<uint32_t>(), d_ndense, g, sub_stride);
+        }
         LAUNCH_CHECK("k_cc_dense");
     }
     if (canonical) {   // stage dumps only
@@ -503,8 +538,16 @@ int alloc_slot(agpu_handle* h, Slot& s, const CallCtx& c) {
     CK(s.d_hist.ensure((size_t)chunk * RS_RADIX * c.nblk_max * 4));
     CK(s.d_dtot.ensure((size_t)chunk * RS_RADIX * 4));
     CK(s.d_dense2rep.ensure((size_t)chunk * AGPU_MAX_DENSE * 4));
-    CK(s.d_lfps.ensure((size_t)chunk * cap * 48));
-    CK(s.d_errs.ensure((size_t)chunk * cap * 8));
+    {   // quad-fit scratch: 56 bytes per point of the largest cluster of its tier for every persistent GROUP (re-used
+        // cluster after cluster, so it lives in L2), not per edge point of the chunk
+        const int max_cluster = 3 * (2 * c.g.wd + 2 * c.g.hd);
+        size_t pts = 0;
+        for (int t = 0; t < AGPU_NTIERS; t++) {
+            const int cap_t = t == AGPU_NTIERS - 1 ? std::max(max_cluster, h->tune.tier_cap[t - 1] + 1) : h->tune.tier_cap[t];
+            pts += (size_t)h->num_sms * h->tune.tier_ctas[t] * (t == 0 ? 8 : 1) * cap_t;
+        }
+        CK(s.d_qscratch.ensure(pts * 56));
+    }
     {   // frames so large that a cluster of upstream's maximum size does not fit a CTA's shared memory (4K at decimate 1):
         // the last tier then sorts such clusters in a per-CTA global buffer
         const int max_cluster = 3 * (2 * c.g.wd + 2 * c.g.hd);
@@ -542,6 +585,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int* d_nroots = d_ndense + chunk;          // CC_SUBLISTS counters per frame
     int* d_ndups = d_nroots + CC_SUBLISTS * chunk;   // merged duplicate points per frame (raw points = npts + ndups)
     StageTimer tm(h, sl);
+    sl.kev_next = 0;
     tm.mark();  // 0
     const uint8_t* d_src;
     if (c.on_device) {
@@ -568,7 +612,10 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         dim3 grid(n, ceil_div(cc_tiles_x(g), ew), cc_tiles_y(g));
 #define LAUNCH_EDGES(EW) k_edges<EW><<<grid, EW * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), \
             sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g, sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, cap, c.id_bits)
-        if (ew == 1) LAUNCH_EDGES(1); else if (ew == 2) LAUNCH_EDGES(2); else if (ew == 4) LAUNCH_EDGES(4); else LAUNCH_EDGES(8);
+        {
+            KScope ks(h, sl, "k_edges", sl.stream);
+            if (ew == 1) LAUNCH_EDGES(1); else if (ew == 2) LAUNCH_EDGES(2); else if (ew == 4) LAUNCH_EDGES(4); else LAUNCH_EDGES(8);
+        }
 #undef LAUNCH_EDGES
         LAUNCH_CHECK("k_edges");
     }
@@ -576,15 +623,24 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int cur = 0;
     for (int shift = 32; shift < 32 + 2 * c.id_bits; shift += RS_BITS) {   // the 2*id_bits key bits: 2 or 3 passes of 11 bits
         dim3 grid(c.nblk_max, n);
-        k_sort_hist<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(), d_npts, cap, shift,
-                                                        sl.d_hist.as<uint32_t>(), c.nblk_max);
+        {
+            KScope ks(h, sl, "k_sort_hist", sl.stream);
+            k_sort_hist<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(), d_npts, cap, shift,
+                                                            sl.d_hist.as<uint32_t>(), c.nblk_max);
+        }
         LAUNCH_CHECK("k_sort_hist");
-        k_sort_scan<<<dim3(n, RS_SCAN_PARTS), RS_RADIX / RS_SCAN_PARTS, 0, sl.stream>>>(
-            d_npts, cap, sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
+        {
+            KScope ks(h, sl, "k_sort_scan", sl.stream);
+            k_sort_scan<<<dim3(n, RS_SCAN_PARTS), RS_RADIX / RS_SCAN_PARTS, 0, sl.stream>>>(
+                d_npts, cap, sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
+        }
         LAUNCH_CHECK("k_sort_scan");
-        k_sort_scatter<<<grid, RS_THREADS, RS_SCATTER_SMEM, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(),
-                                                           sl.d_recs[cur ^ 1].as<unsigned long long>(), d_npts, cap, shift,
-                                                           sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
+        {
+            KScope ks(h, sl, "k_sort_scatter", sl.stream);
+            k_sort_scatter<<<grid, RS_THREADS, RS_SCATTER_SMEM, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(),
+                                                               sl.d_recs[cur ^ 1].as<unsigned long long>(), d_npts, cap, shift,
+                                                               sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
+        }
         LAUNCH_CHECK("k_sort_scatter");
         cur ^= 1;
     }
@@ -605,14 +661,15 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         cl.dbg_heads = h->cfg.debug ? sl.d_dbg_heads.as<ClusterRef>() : nullptr;
         cl.cap_dbg = (int)(sl.d_dbg_heads.bytes / sizeof(ClusterRef));
         dim3 grid(std::max(1, std::min(64, ceil_div(cap, 256))), n);   // grid-stride over the live points
-        k_cluster_heads<<<grid, 256, 0, sl.stream>>>(srecs, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
+        {
+            KScope ks(h, sl, "k_cluster_heads", sl.stream);
+            k_cluster_heads<<<grid, 256, 0, sl.stream>>>(srecs, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
+        }
         LAUNCH_CHECK("k_cluster_heads");
         QuadFitArgs qa;
         qa.recs = srecs; qa.dense2rep = sl.d_dense2rep.as<uint32_t>(); qa.id_bits = c.id_bits; qa.cap = cap;
         qa.quad_im = quad_im; qa.q_pitch = q_pitch; qa.q_frame = q_frame;
         qa.g = g;
-        qa.lfps = sl.d_lfps.as<double>();
-        qa.errs = sl.d_errs.as<double>();
         qa.list_cap = n * c.maxcl;
         qa.quads = sl.d_quads.as<QuadRec>();
         qa.nquads = d_cnt + CNT_NQUADS;
@@ -626,13 +683,25 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         CK(cudaEventRecord(sl.ev_mid, sl.stream));
         CK(cudaStreamWaitEvent(sl.tail, sl.ev_mid, 0));
         CK(cudaEventRecord(sl.ev_fork, sl.tail));
+        // (profiling: the tiers run one after the other on the tail stream so that every kernel's event pair times
+        // that kernel alone)
+        const bool fork = !h->profiling;
+        static const char* const tier_name[AGPU_NTIERS] = {"k_fit_quads<1>", "k_fit_quads<2>", "k_fit_quads<4>", "k_fit_quads<8>"};
         for (int t = AGPU_NTIERS - 1; t >= 0; t--) {
-            cudaStream_t st = t == 0 ? sl.tail : sl.aux[t - 1];
-            if (t > 0) CK(cudaStreamWaitEvent(st, sl.ev_fork, 0));
+            cudaStream_t st = (t == 0 || !fork) ? sl.tail : sl.aux[t - 1];
+            if (t > 0 && fork) CK(cudaStreamWaitEvent(st, sl.ev_fork, 0));
             qa.list = sl.d_clusters[t].as<ClusterRef>();
             qa.list_count = d_cnt + CNT_TIER0 + t;
             qa.cursor = d_cnt + CNT_CURSOR0 + t;
             const int nblk = h->num_sms * h->tune.tier_ctas[t];
+            {   // this tier's slice of the per-group scratch (tiers are visited from the last to the first)
+                size_t off = 0;
+                for (int u = AGPU_NTIERS - 1; u > t; u--) off += (size_t)h->num_sms * h->tune.tier_ctas[u] * (u == 0 ? 8 : 1) * tier_cap[u];
+                qa.scratch = sl.d_qscratch.as<double>() + off * 7;
+                qa.scratch_pts = tier_cap[t];
+            }
+            {
+            KScope ks(h, sl, tier_name[t], st);
             if (t == 0) {
                 const size_t smem = 8 * qf_smem_per_group(tier_smem[t], 1);
                 k_fit_quads<1><<<nblk, 256, smem, st>>>(qa, h->prm, tier_smem[t]);
@@ -643,8 +712,9 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             } else {
                 k_fit_quads<8><<<nblk, 256, qf_smem_per_group(tier_smem[t], 8), st>>>(qa, h->prm, tier_smem[t]);
             }
+            }
             LAUNCH_CHECK("k_fit_quads");
-            if (t > 0) {
+            if (t > 0 && fork) {
                 CK(cudaEventRecord(sl.ev_join[t - 1], st));
                 CK(cudaStreamWaitEvent(sl.tail, sl.ev_join[t - 1], 0));
             }
@@ -664,12 +734,18 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         da.ndets = d_ndets;
         da.cap_dets = REC_CAP;
         da.dbg_refined = h->cfg.debug ? sl.d_refined.as<float>() : nullptr;
-        k_decode_quads<<<h->num_sms * h->tune.decode_ctas * (128 / h->tune.tail_threads), h->tune.tail_threads, 0, sl.tail>>>(da, h->prm);
+        {
+            KScope ks(h, sl, "k_decode_quads", sl.tail);
+            k_decode_quads<<<h->num_sms * h->tune.decode_ctas * (128 / h->tune.tail_threads), h->tune.tail_threads, 0, sl.tail>>>(da, h->prm);
+        }
         LAUNCH_CHECK("k_decode_quads");
     }
     tm.mark(sl.tail);  // 7: after decode
-    k_reconcile<<<n, 32, 0, sl.tail>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
-                                                      sl.d_out.as<DetRec>(), d_out_counts, c.cap_out);
+    {
+        KScope ks(h, sl, "k_reconcile", sl.tail);
+        k_reconcile<<<n, 32, 0, sl.tail>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
+                                                          sl.d_out.as<DetRec>(), d_out_counts, c.cap_out);
+    }
     LAUNCH_CHECK("k_reconcile");
     if (c.pose->enabled) {
         PoseArgs pa;
@@ -680,7 +756,10 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         pa.per_frame = c.cap_out;
         pa.M = n * c.cap_out;
         pa.out = sl.d_poses.as<PoseRec>();
-        k_pose<<<ceil_div((long long)pa.M * 4, h->tune.tail_threads), h->tune.tail_threads, 0, sl.tail>>>(pa);
+        {
+            KScope ks(h, sl, "k_pose", sl.tail);
+            k_pose<<<ceil_div((long long)pa.M * 4, h->tune.tail_threads), h->tune.tail_threads, 0, sl.tail>>>(pa);
+        }
         LAUNCH_CHECK("k_pose");
     }
     tm.mark(sl.tail);  // 8: after reconcile/pose
@@ -724,8 +803,13 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
                 h->timeline.push_back(ms);
             }
         }
-        float kms = 0;
-        if (sl.ev_k[0] && cudaEventElapsedTime(&kms, sl.ev_k[0], sl.ev_k[1]) == cudaSuccess) h->cc_local_ms += kms;
+        for (size_t i = 0; i < sl.kev_next; i++) {
+            float kms = 0;
+            if (cudaEventElapsedTime(&kms, sl.kev[i].a, sl.kev[i].b) != cudaSuccess) continue;
+            auto& e = h->kernel_ms[sl.kev[i].name];
+            e.first += kms;
+            e.second += 1;
+        }
     }
     const int* hc = sl.h_counts.as<int>();
     const int* h_npts = hc + CNT_FIXED;
@@ -815,7 +899,7 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
     CK(cudaSetDevice(h->device));
     h->launches = 0;
     for (int i = 0; i < AGPU_NUM_STAGES; i++) h->stage_ms[i] = 0;
-    h->cc_local_ms = 0;
+    h->kernel_ms.clear();
     for (int i = 0; i < 8; i++) h->counters[i] = 0;
     CallCtx c;
     c.frames = frames; c.on_device = on_device; c.channels = channels; c.B = B; c.W = W; c.H = H; c.stride = stride;
@@ -1188,12 +1272,29 @@ int agpu_get_timeline(agpu_handle* h, float* out, int cap_floats) {
 
 int agpu_get_kernel_ms(agpu_handle* h, const char* kernel, float* ms) {
     if (!h || !kernel || !ms) return AGPU_E_INVALID;
-    if (std::string(kernel) != "k_cc_local") {
-        h->set_err("agpu_get_kernel_ms: only k_cc_local carries its own timer");
+    auto it = h->kernel_ms.find(kernel);
+    if (it == h->kernel_ms.end()) {
+        h->set_err(std::string("agpu_get_kernel_ms: no launch of '") + kernel + "' was timed in the last call (profiling on?)");
         return AGPU_E_INVALID;
     }
-    *ms = h->cc_local_ms;
+    *ms = it->second.first;
     return AGPU_OK;
+}
+
+int agpu_get_kernel_table(agpu_handle* h, char* buf, int cap) {
+    if (!h) return AGPU_E_INVALID;
+    std::string t;
+    char line[160];
+    for (const auto& kv : h->kernel_ms) {
+        snprintf(line, sizeof(line), "%s\t%.6f\t%d\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        t += line;
+    }
+    if (buf && cap > 0) {
+        const size_t ncopy = std::min(t.size(), (size_t)cap - 1);
+        memcpy(buf, t.data(), ncopy);
+        buf[ncopy] = 0;
+    }
+    return (int)t.size() + 1;
 }
 
 int agpu_get_launch_count(agpu_handle* h, long long* launches) {

@@ -4,7 +4,8 @@
 //
 // Per cluster: records staged once in shared memory -> bounding box + border polarity (exact integer sums) -> slope
 // keys -> stable radix sort on the slope bits (ping-pong shared memory / L2 scratch) + tie fix on (y, x) -> prefix
-// line-fit moments (warp scans, stored in an L2-resident scratch) -> windowed line-fit error, 7-tap smoothing, local
+// line-fit moments (terms in parallel, running sums in upstream's sequential order on six lanes; stored in the group's
+// own L2-resident scratch) -> windowed line-fit error, 7-tap smoothing, local
 // maxima, top-10 selection -> exhaustive 4-corner search over a pre-computed table of pairwise line fits (dealt to
 // the threads by triples) -> corners + gates on one warp.  (The only duplicate points upstream produces are merged at
 // emission by k_edges, so there is no de-duplication pass.)
@@ -20,8 +21,10 @@ struct QuadFitArgs {
     const uint8_t* quad_im;     // decimated gray image (may alias the source frames)
     size_t q_pitch, q_frame;    // bytes per row / per frame of quad_im
     Geom g;
-    double* lfps;               // [nframes*cap][6] prefix moments
-    double* errs;               // [nframes*cap]   smoothed line-fit errors
+    double* scratch;            // this tier's per-GROUP scratch, 7 * scratch_pts doubles each: [scratch_pts][6] prefix moments
+    int scratch_pts;            // (+ ping-pong partner of the in-cluster sort) and [scratch_pts] smoothed line-fit errors.
+                                // A persistent group re-uses ITS region for every cluster it fits, so the lines stay in L2
+                                // and are overwritten there instead of streaming through HBM once per cluster
     const ClusterRef* list;
     const int* list_count;
     int* cursor;                // next unclaimed cluster of the list (dynamic work distribution)
@@ -299,7 +302,7 @@ __device__ void group_fix_ties(const QGroup<NW>& G, unsigned long long* s, int n
 // Returns true (uniformly over the group) and fills q when the cluster yields a quad.
 template <int NW>
 __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, const DevParams& P, const ClusterRef ref,
-                                  unsigned long long* sbuf, double* ptab, int* sidx, uint16_t* scnt, QuadRec& q) {
+                                  unsigned long long* sbuf, double* ptab, int* sidx, uint16_t* scnt, double* lf, QuadRec& q) {
     constexpr int T = QGroup<NW>::T;
     const int tid = G.tid, lane = G.lane;
     const size_t seg = (size_t)ref.frame * a.cap + ref.start;
@@ -378,7 +381,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         sbuf[i] = key;
     }
     G.sync();
-    group_radix_sort_hi32<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(a.lfps + seg * 6), sz, scnt);
+    group_radix_sort_hi32<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(lf), sz, scnt);
     group_fix_ties<NW>(G, sbuf, sz);
 
     // (no duplicate points to remove here: the only duplicates upstream produces were merged at emission, k_edges)
@@ -405,65 +408,40 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         }
     }
     G.sync();
-    // ---- prefix moments (inclusive), written to the scratch at the cluster's own offset
-    double* lf = a.lfps + seg * 6;
-    {
-        double carry[6] = {0, 0, 0, 0, 0, 0};
+    // ---- prefix moments (inclusive).  Upstream accumulates them sequentially, P[i] = P[i-1] + t[i], and every line fit
+    //      below is a DIFFERENCE of two of these sums, so their rounding is part of the result: a parallel scan adds in
+    //      another order and the last bits -- sometimes a decision -- come out differently.  The terms t[i] are
+    //      therefore computed by all threads in parallel, and the six running sums are then taken in upstream's order
+    //      by six lanes of one warp (one lane per moment, eight loads in flight, ~10 cycles per point): bit-identical
+    //      to the sequential loop at a fraction of the issue slots of a 6 x double warp scan.
 #pragma unroll 1
-        for (int base = 0; base < sz; base += T) {
-            const int i = base + tid;
-            double t[6] = {0, 0, 0, 0, 0, 0};
-            if (i < sz) {
-                const unsigned long long e = sbuf[i];
-                const uint32_t xy = (uint32_t)e;
-                int px = xy & 0xffff, py = xy >> 16;
-                double x = px * .5 + 0.5, y = py * .5 + 0.5;
-                double W = sqrt((double)(uint32_t)(e >> 32)) + 1;
-                t[0] = W * x;
-                t[1] = W * y;
-                t[2] = W * x * x;
-                t[3] = W * x * y;
-                t[4] = W * y * y;
-                t[5] = W;
-            }
+    for (int i = tid; i < sz; i += T) {
+        const unsigned long long e = sbuf[i];
+        const uint32_t xy = (uint32_t)e;
+        const int px = xy & 0xffff, py = xy >> 16;
+        const double x = px * .5 + 0.5, y = py * .5 + 0.5;
+        const double W = sqrt((double)(uint32_t)(e >> 32)) + 1;
+        double2* p = reinterpret_cast<double2*>(lf + (size_t)i * 6);
+        __stcg(p, make_double2(W * x, W * y));
+        __stcg(p + 1, make_double2(W * x * x, W * x * y));
+        __stcg(p + 2, make_double2(W * y * y, W));
+    }
+    __threadfence_block();
+    G.sync();
+    if (G.w == 0 && lane < 6) {
+        double acc = 0;
+        double* p = lf + lane;
+        int i = 0;
+#pragma unroll 1
+        for (; i + 8 <= sz; i += 8) {
+            double v[8];
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
+            for (int u = 0; u < 8; u++) v[u] = __ldcg(p + (size_t)(i + u) * 6);
 #pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    double n = __shfl_up_sync(FULL_MASK, t[k], off);
-                    if (lane >= off) t[k] += n;
-                }
-            }
-            double add[6], tot[6];
-#pragma unroll
-            for (int k = 0; k < 6; k++) { add[k] = carry[k]; tot[k] = __shfl_sync(FULL_MASK, t[k], 31); }
-            if (NW > 1) {
-                if (lane == 31) {
-#pragma unroll
-                    for (int k = 0; k < 6; k++) G.sd[G.w * 8 + k] = t[k];
-                }
-                __syncthreads();
-#pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    double below = 0, all = 0;
-#pragma unroll
-                    for (int ww = 0; ww < NW; ww++) { const double v = G.sd[ww * 8 + k]; if (ww < G.w) below += v; all += v; }
-                    add[k] = carry[k] + below;
-                    tot[k] = all;
-                }
-                __syncthreads();
-            }
-#pragma unroll
-            for (int k = 0; k < 6; k++) t[k] = add[k] + t[k];
-            if (i < sz) {
-                double2* p = reinterpret_cast<double2*>(lf + (size_t)i * 6);
-                __stcg(p, make_double2(t[0], t[1]));
-                __stcg(p + 1, make_double2(t[2], t[3]));
-                __stcg(p + 2, make_double2(t[4], t[5]));
-            }
-#pragma unroll
-            for (int k = 0; k < 6; k++) carry[k] = carry[k] + tot[k];
+            for (int u = 0; u < 8; u++) { acc += v[u]; __stcg(p + (size_t)(i + u) * 6, acc); }
         }
+#pragma unroll 1
+        for (; i < sz; i++) { acc += __ldcg(p + (size_t)i * 6); __stcg(p + (size_t)i * 6, acc); }
     }
     __threadfence_block();
     G.sync();
@@ -479,7 +457,7 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         sraw[i] = f.err;
     }
     G.sync();
-    double* es = a.errs + seg;
+    double* es = lf + (size_t)a.scratch_pts * 6;
 #pragma unroll 1
     for (int i = tid; i < sz; i += T) {
         double acc = 0;
@@ -767,7 +745,8 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
         QuadRec q;
         unsigned long long* sb = sbuf;
         if (NW == 8 && ref.size > wcap) sb = a.gsort + (size_t)blockIdx.x * a.gsort_stride;   // (the pair table stays in shared memory)
-        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sb, ptab, sidx, scnt, q);
+        double* lf = a.scratch + (size_t)(NW == 1 ? blockIdx.x * 8 + gi : blockIdx.x) * a.scratch_pts * 7;
+        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sb, ptab, sidx, scnt, lf, q);
         if (ok && G.tid == 0) {
             int s = atomicAdd(a.nquads, 1);
             atomicAdd(&a.per_frame_quads[ref.frame], 1);

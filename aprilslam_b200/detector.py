@@ -206,10 +206,21 @@ class Detector:
         self._check(self._L.agpu_set_profiling(self._h, int(on)))
 
     def kernel_ms(self, kernel: str = "k_cc_local") -> float:
-        """CUDA-event time of one kernel over the last call (profiling on); only k_cc_local has its own timer."""
+        """CUDA-event time of one kernel summed over the chunks of the last call (profiling on)."""
         ms = np.zeros(1, np.float32)
         self._check(self._L.agpu_get_kernel_ms(self._h, kernel.encode(), ms.ctypes.data))
         return float(ms[0])
+
+    def kernel_table(self) -> dict:
+        """{kernel name: (milliseconds, launches)} of the last call (profiling on): every launch has its own event pair."""
+        n = int(self._L.agpu_get_kernel_table(self._h, None, 0))
+        buf = C.create_string_buffer(max(n, 1))
+        self._L.agpu_get_kernel_table(self._h, buf, n)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.split("\t")
+            out[name] = (float(ms), int(cnt))
+        return out
 
     def stage_ms(self) -> dict:
         ms = np.zeros(len(STAGE_NAMES), np.float32)

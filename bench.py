@@ -122,46 +122,63 @@ def measured_peak_gbs():
 
 def cpu_reference_run(frames: np.ndarray, K, steps: int, warmup: int, threads: int):
     """The reference's CPU path restated: detector (oracle, frames spread over `threads` host threads) +
-    cv2.solvePnP per detection exactly as tag_detector.py:30-43 calls it.  Returns seconds per step."""
+    cv2.solvePnP per detection exactly as tag_detector.py:30-43 calls it, the per-frame pose loops spread over the same
+    number of threads (cv2 releases the GIL inside solvePnP).  Returns (seconds per step, tags per frame,
+    seconds of the detector alone, seconds of the pose loop alone)."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle.binding import OracleDetector, reference_pose
     det = OracleDetector("tag36h11", decimate=1.0, refine_edges=True)
     dist = np.zeros((4, 1))
-    times, ndet = [], 0
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        lists = det.detect_batch(frames, nthreads=threads, cap=CAP)
-        for recs in lists:
-            for r in recs:
-                reference_pose(r["p"], K, dist, TAG_SIZE)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-            ndet += sum(len(x) for x in lists)
-    return float(np.mean(times)), ndet / max(1, steps * len(frames))
+
+    def poses_of(recs):
+        return [reference_pose(r["p"], K, dist, TAG_SIZE) for r in recs]
+
+    times, t_det, t_pose, ndet = [], [], [], 0
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            lists = det.detect_batch(frames, nthreads=threads, cap=CAP)
+            t1 = time.perf_counter()
+            if threads > 1:
+                list(pool.map(poses_of, lists))
+            else:
+                for recs in lists:
+                    poses_of(recs)
+            t2 = time.perf_counter()
+            if it >= warmup:
+                times.append(t2 - t0); t_det.append(t1 - t0); t_pose.append(t2 - t1)
+                ndet += sum(len(x) for x in lists)
+    return float(np.mean(times)), ndet / max(1, steps * len(frames)), float(np.mean(t_det)), float(np.mean(t_pose))
 
 
 def run_reference_arm(args):
+    """CPU arm: the oracle port of the reference's detector + the reference's own cv2.solvePnP call, all host threads.
+    Loads nothing of the product: only oracle/ is built and dlopen-ed here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import __graft_entry__ as ge
-    ge.build()
-    from aprilslam_b200 import synth
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    from aprilslam_b200 import synth                      # (pure numpy scene / frame generator, no native code)
     threads = len(os.sched_getaffinity(0)) or 1
     nframes = args.ref_frames or max(16, min(128, 8 * threads))
-    frames = make_frames(min(nframes, 32), nframes)
+    # the FIRST nframes frames of the GPU arm's batch: same seeds (default_rng(1000 + frame index)), all distinct
+    frames = make_frames(nframes, nframes)
     K = synth.intrinsics(W, H, 45.0)
-    sec, dpf = cpu_reference_run(frames, K, args.steps, args.warmup, threads)
+    sec, dpf, sec_det, sec_pose = cpu_reference_run(frames, K, args.steps, args.warmup, threads)
+    n1 = min(4, nframes)
+    sec1, _, _, _ = cpu_reference_run(frames[:n1], K, 1, 0, 1)
     val = nframes / sec
-    sample = "%d of the workload's 1080p frames per step, %d host threads (frames in parallel) + cv2.solvePnP per tag" % (
-        nframes, threads)
+    sample = ("frames 0..%d of the workload's 1024-frame batch per step (same seeds as the GPU arm), %d host threads: "
+              "detector %.2f s + cv2.solvePnP per tag %.2f s per step; 1 thread (the reference's own setting, "
+              "tag_detector.py:18): %.2f frames/s" % (nframes - 1, threads, sec_det, sec_pose, n1 / sec1))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
             "config": {"workload": "C3: 1920x1080 gray, quad_decimate=1, refine_edges=1, ~50 tag36h11/frame "
                                    "(bounded sample of the 1024-frame batch)", "frames_per_step": nframes,
-                       "tags_per_frame": dpf},
-            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+                       "tags_per_frame": dpf, "same_frames_as_gpu_arm": True},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
+                             "one_thread_value": n1 / sec1},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "restated CPU detector (oracle/), not the upstream apriltag binary (unavailable offline)"}
     print(json.dumps(line))
@@ -361,8 +378,8 @@ def run_b200(args):
     threads = len(os.sched_getaffinity(0)) or 1
     nref = max(16, min(256, 16 * threads, B))     # ~10-30 core-seconds of CPU work
     t0 = time.time()
-    sec_cpu, _ = cpu_reference_run(frames_host[:nref], K, 1, 0, threads)
-    sec_cpu1, _ = cpu_reference_run(frames_host[:4], K, 1, 0, 1)
+    sec_cpu, _, sec_cpu_det, sec_cpu_pose = cpu_reference_run(frames_host[:nref], K, 1, 0, threads)
+    sec_cpu1, _, _, _ = cpu_reference_run(frames_host[:4], K, 1, 0, 1)
     cpu_val = nref / sec_cpu
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -387,9 +404,11 @@ def run_b200(args):
         "roofline": roofline,
         "stages": stages,
         "cpu_baseline": {"value": cpu_val, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d frames of the same batch, oracle detector on %d host threads + cv2.solvePnP per tag; "
-                                   "1 thread (the reference's setting, tag_detector.py:18): %.2f frames/s" % (
-                                       nref, threads, 4 / sec_cpu1),
+                         "sample": "frames 0..%d of the same batch, oracle detector on %d host threads (%.2f s) + cv2.solvePnP "
+                                   "per tag on the same threads (%.2f s); 1 thread (the reference's setting, "
+                                   "tag_detector.py:18): %.2f frames/s" % (nref - 1, threads, sec_cpu_det, sec_cpu_pose,
+                                                                           4 / sec_cpu1),
+                         "one_thread_value": 4 / sec_cpu1,
                          "seconds": time.time() - t0},
     }
     print(json.dumps(line))

@@ -128,9 +128,15 @@ enum { AGPU_STAGE_H2D = 0, AGPU_STAGE_IMAGE, AGPU_STAGE_CC, AGPU_STAGE_EDGES, AG
  * chunks, measured on the library's own stream).  on != 0 enables it (adds event records only). */
 int agpu_set_profiling(agpu_handle* h, int on);
 int agpu_get_stage_ms(agpu_handle* h, float* ms /* [AGPU_NUM_STAGES] */);
-/* CUDA-event time of ONE kernel summed over the chunks of the last call (profiling on).  Only "k_cc_local", the
- * kernel bench.py quotes the roofline fraction for, carries its own pair of events. */
+/* Profiling on: EVERY kernel launch of a chunk is bracketed by its own pair of CUDA events on the stream it is launched
+ * on (and the quad-fit size tiers, normally concurrent on side streams, run one after the other), so with
+ * pipeline_slots = 1 each interval is that kernel alone.  agpu_get_kernel_ms: milliseconds of one kernel summed over
+ * the chunks of the last call; names: k_decimate_threshold, k_pack(bgr), k_cc_local, k_cc_boundary, k_cc_sizes,
+ * k_cc_dense, k_edges, k_sort_hist, k_sort_scan, k_sort_scatter, k_cluster_heads, k_fit_quads<1|2|4|8>,
+ * k_decode_quads, k_reconcile, k_pose.  agpu_get_kernel_table: all of them as text lines "name\tms\tlaunches\n";
+ * returns the bytes needed (terminator included) and copies at most cap. */
 int agpu_get_kernel_ms(agpu_handle* h, const char* kernel, float* ms);
+int agpu_get_kernel_table(agpu_handle* h, char* buf, int cap);
 /* Timeline of the last call (profiling on): per finished chunk AGPU_NUM_STAGES + 4 floats {first frame, frames, slot,
  * stage boundary marks in ms since the start of the call}.  Returns the number of floats available; copies at most
  * cap_floats of them.  Shows how the chunks in flight overlap. */
