@@ -85,6 +85,7 @@ def load():
     L.agpu_get_kernel_table.argtypes = [vp, vp, ci]
     L.agpu_get_launch_count.argtypes = [vp, vp]
     L.agpu_get_counters.argtypes = [vp, vp]
+    L.agpu_get_tier_stats.argtypes = [vp, vp]
     L.agpu_debug_fetch.argtypes = [vp, C.c_char_p, ci, vp, C.c_longlong]
     L.agpu_debug_fetch.restype = C.c_longlong
     L.agpu_debug_dims.argtypes = [vp, vp, vp]
@@ -103,6 +104,6 @@ def load():
 
 EXPORTS = ["agpu_version", "agpu_default_config", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_detect",
            "agpu_detect_bgr", "agpu_detect_pose", "agpu_pose", "agpu_set_profiling", "agpu_get_stage_ms",
-           "agpu_get_kernel_ms", "agpu_get_kernel_table", "agpu_get_timeline", "agpu_get_launch_count", "agpu_get_counters", "agpu_debug_fetch", "agpu_debug_dims",
+           "agpu_get_kernel_ms", "agpu_get_kernel_table", "agpu_get_timeline", "agpu_get_launch_count", "agpu_get_counters", "agpu_get_tier_stats", "agpu_debug_fetch", "agpu_debug_dims",
            "agpu_stage_threshold", "agpu_stage_labels", "agpu_render", "agpu_graph_create", "agpu_graph_reset",
            "agpu_graph_destroy", "agpu_graph_update", "agpu_graph_get"]

@@ -80,7 +80,7 @@ struct HostBuf {
 // fit is ever skipped.
 constexpr int TIER_CAP_DEFAULT[AGPU_NTIERS] = {256, 1024, 2048, 0};
 // counter block layout (ints): [0..3] clusters per tier
-enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_CURSOR0 = 8, CNT_FIXED = 16 };
+enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_CURSOR0 = 8, CNT_TIER_RECS0 = 12, CNT_FIXED = 16 };
 
 }  // namespace
 
@@ -141,6 +141,7 @@ struct agpu_handle {
     std::map<std::string, std::pair<float, int>> kernel_ms;   // profiling: per kernel {ms, launches} of the last call
     long long launches = 0;
     long long counters[8];
+    long long tier_stats[8];   // [0..3] clusters, [4..7] records handed to the quad-fit tiers in the last call
 
     // scheduling knobs (defaults below; AGPU_PRIO / AGPU_TIER_CTAS / AGPU_DECODE_CTAS override them for experiments)
     struct Tune {
@@ -858,6 +859,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     }
     for (int t = 0; t < AGPU_NTIERS; t++) h->counters[1] += hc[CNT_TIER0 + t];
     for (int t = 1; t < AGPU_NTIERS; t++) h->counters[4 + t] += hc[CNT_TIER0 + t];   // clusters per multi-warp tier
+    for (int t = 0; t < AGPU_NTIERS; t++) { h->tier_stats[t] += hc[CNT_TIER0 + t]; h->tier_stats[4 + t] += hc[CNT_TIER_RECS0 + t]; }
     h->counters[2] += hc[CNT_NQUADS];
     h->counters[4] += hc[CNT_OVERSIZE];
     h->last_slot = (int)(&sl - h->slots.data());
@@ -900,7 +902,7 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
     h->launches = 0;
     for (int i = 0; i < AGPU_NUM_STAGES; i++) h->stage_ms[i] = 0;
     h->kernel_ms.clear();
-    for (int i = 0; i < 8; i++) h->counters[i] = 0;
+    for (int i = 0; i < 8; i++) h->counters[i] = h->tier_stats[i] = 0;
     CallCtx c;
     c.frames = frames; c.on_device = on_device; c.channels = channels; c.B = B; c.W = W; c.H = H; c.stride = stride;
     c.frame_bytes = (size_t)H * stride;
@@ -1306,6 +1308,12 @@ int agpu_get_launch_count(agpu_handle* h, long long* launches) {
 int agpu_get_counters(agpu_handle* h, long long* counters) {
     if (!h || !counters) return AGPU_E_INVALID;
     for (int i = 0; i < 8; i++) counters[i] = h->counters[i];
+    return AGPU_OK;
+}
+
+int agpu_get_tier_stats(agpu_handle* h, long long* stats) {
+    if (!h || !stats) return AGPU_E_INVALID;
+    for (int i = 0; i < 8; i++) stats[i] = h->tier_stats[i];
     return AGPU_OK;
 }
 

@@ -364,7 +364,7 @@ k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long lon
 struct ClusterLists {
     ClusterRef* list[AGPU_NTIERS];
     int cap[AGPU_NTIERS];    // largest cluster size of the tier
-    int* counters;           // [0..3] tier counts, [4] clusters over upstream's size limit, [5] all heads (debug), [8..11] tier work cursors
+    int* counters;           // [0..3] tier counts, [4] clusters over upstream's size limit, [5] all heads (debug), [8..11] tier work cursors, [12..15] records per tier
     int cap_list;
     ClusterRef* dbg_heads;   // all run heads (debug only, may be null)
     int cap_dbg;
@@ -418,6 +418,7 @@ k_cluster_heads(const unsigned long long* __restrict__ recs, const int* __restri
         for (int t = 0; t < AGPU_NTIERS; t++)
             if (!placed && size <= cl.cap[t]) {
                 int s = atomicAdd(&cl.counters[t], 1);
+                atomicAdd(&cl.counters[12 + t], size);   // records handed to this tier (instrumentation)
                 if (s < cl.cap_list) cl.list[t][s] = ref;
                 placed = true;
             }

@@ -299,10 +299,110 @@ __device__ void group_fix_ties(const QGroup<NW>& G, unsigned long long* s, int n
     }
 }
 
+// Bucket sort of the n 64-bit keys (slope bits << 32 | y << 16 | x, all distinct) in `sbuf`: ONE counting pass instead
+// of four radix passes.  The bucket of a key is a monotone function of its slope float f -- quadrant k of the slope
+// key (f lives near -65536, 0, 65536, 131072) and r / (1 + r) of the remainder r = tan of the angle inside the
+// quadrant, i.e. roughly the polar angle of the point, which is what spreads the points of a contour evenly --, so the
+// buckets are in key order; inside a bucket (one or two keys on average) one thread finishes the order on the full
+// 64-bit key by insertion.  Counts with shared-memory atomics (two 16-bit counters per word), scatter through the L2
+// scratch.  Returns false -- nothing moved -- when some bucket holds more than QF_BUCKET_LIMIT keys (degenerate
+// contours); the caller then falls back to the radix sort.  The result is the same total order either way.
+#define QF_BUCKET_LIMIT 24
+__device__ __forceinline__ int qf_bucket(uint32_t orderable, int per_quadrant) {
+    const uint32_t bits = (orderable & 0x80000000u) ? (orderable ^ 0x80000000u) : ~orderable;
+    const float f = __uint_as_float(bits);
+    if (!(f == f)) return 4 * per_quadrant - 1;                      // NaN keys carry the largest bit pattern
+    const int k = f < 0.0f ? 0 : (f < 65536.0f ? 1 : (f < 131072.0f ? 2 : 3));
+    const float r = fmaxf(f - (float)(k - 1) * 65536.0f, 0.0f);      // (f below -65536 cannot occur: clamp)
+    const float h = r >= 1e30f ? 1.0f : r / (1.0f + r);              // IEEE division: monotone in r
+    return k * per_quadrant + min(per_quadrant - 1, (int)(h * (float)per_quadrant));
+}
+
+template <int NW>
+__device__ bool group_bucket_sort(const QGroup<NW>& G, unsigned long long* sbuf, unsigned long long* gbuf, int n,
+                                  uint32_t* cnt /* NB / 2 words */) {
+    constexpr int T = QGroup<NW>::T;
+    constexpr int PQ = NW == 1 ? 128 : 256, NB = 4 * PQ, NWORDS = NB / 2;
+    constexpr int WPT = NWORDS / T;                                  // counter words per thread: 8 (NW 1, 2), 4, 2
+    static_assert(WPT >= 1 && WPT * T == NWORDS, "bucket ownership");
+    const int tid = G.tid, lane = G.lane;
+#pragma unroll 1
+    for (int i = tid; i < NWORDS; i += T) cnt[i] = 0;
+    G.sync();
+#pragma unroll 1
+    for (int i = tid; i < n; i += T) {
+        const int b = qf_bucket((uint32_t)(sbuf[i] >> 32), PQ);
+        atomicAdd(&cnt[b >> 1], 1u << ((b & 1) * 16));
+    }
+    G.sync();
+    // thread t owns the buckets [2 * WPT * t, 2 * WPT * (t + 1)): largest bucket, then exclusive prefix -> start offsets
+    uint32_t w[WPT];
+    int mx = 0, sum = 0;
+#pragma unroll
+    for (int q = 0; q < WPT; q++) {
+        w[q] = cnt[tid * WPT + q];
+        const int lo = w[q] & 0xffffu, hi = w[q] >> 16;
+        mx = max(mx, max(lo, hi));
+        sum += lo + hi;
+    }
+    if (G.reduce_max(mx) > QF_BUCKET_LIMIT) return false;            // (uniform)
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= off) incl += t;
+    }
+    int excl = incl - sum;
+    if (NW > 1) {
+        if (lane == 31) G.si[G.w] = incl;
+        __syncthreads();
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++)
+            if (ww < G.w) excl += G.si[ww];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < WPT; q++) {
+        const int lo = w[q] & 0xffffu, hi = w[q] >> 16;
+        cnt[tid * WPT + q] = (uint32_t)excl | ((uint32_t)(excl + lo) << 16);
+        excl += lo + hi;
+    }
+    G.sync();
+    // scatter through the scratch (a bucket's keys arrive in any order; the insertion below fixes it), copy back
+#pragma unroll 1
+    for (int i = tid; i < n; i += T) {
+        const unsigned long long k = sbuf[i];
+        const int b = qf_bucket((uint32_t)(k >> 32), PQ);
+        const uint32_t old = atomicAdd(&cnt[b >> 1], 1u << ((b & 1) * 16));
+        __stcg(gbuf + ((old >> ((b & 1) * 16)) & 0xffffu), k);
+    }
+    __threadfence_block();
+    G.sync();
+#pragma unroll 1
+    for (int i = tid; i < n; i += T) sbuf[i] = __ldcg(gbuf + i);
+    G.sync();
+    // the counters now hold the END of every bucket: thread t finishes the buckets t, t + T, ...
+#pragma unroll 1
+    for (int b = tid; b < NB; b += T) {
+        const int e = (cnt[b >> 1] >> ((b & 1) * 16)) & 0xffff;
+        const int s0 = b == 0 ? 0 : (int)((cnt[(b - 1) >> 1] >> (((b - 1) & 1) * 16)) & 0xffff);
+#pragma unroll 1
+        for (int i = s0 + 1; i < e; i++) {
+            const unsigned long long k = sbuf[i];
+            int j = i - 1;
+            while (j >= s0 && sbuf[j] > k) { sbuf[j + 1] = sbuf[j]; j--; }
+            sbuf[j + 1] = k;
+        }
+    }
+    G.sync();
+    return true;
+}
+
 // Returns true (uniformly over the group) and fills q when the cluster yields a quad.
 template <int NW>
 __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, const DevParams& P, const ClusterRef ref,
-                                  unsigned long long* sbuf, double* ptab, int* sidx, uint16_t* scnt, double* lf, QuadRec& q) {
+                                  unsigned long long* sbuf, double* ptab, int* sidx, uint16_t* scnt, double* stage, double* lf,
+                                  QuadRec& q) {
     constexpr int T = QGroup<NW>::T;
     const int tid = G.tid, lane = G.lane;
     const size_t seg = (size_t)ref.frame * a.cap + ref.start;
@@ -381,8 +481,12 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         sbuf[i] = key;
     }
     G.sync();
-    group_radix_sort_hi32<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(lf), sz, scnt);
-    group_fix_ties<NW>(G, sbuf, sz);
+    // (the bucket counters borrow the prefix-moment stage: 1 KB / 2 KB of the 1.6 KB / 3+ KB it has)
+    if (sz > (NW == 1 ? 512 : 4096) ||
+        !group_bucket_sort<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(lf), sz, reinterpret_cast<uint32_t*>(stage))) {
+        group_radix_sort_hi32<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(lf), sz, scnt);
+        group_fix_ties<NW>(G, sbuf, sz);
+    }
 
     // (no duplicate points to remove here: the only duplicates upstream produces were merged at emission, k_edges)
     if (sz < 24) return false;
@@ -410,38 +514,49 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     G.sync();
     // ---- prefix moments (inclusive).  Upstream accumulates them sequentially, P[i] = P[i-1] + t[i], and every line fit
     //      below is a DIFFERENCE of two of these sums, so their rounding is part of the result: a parallel scan adds in
-    //      another order and the last bits -- sometimes a decision -- come out differently.  The terms t[i] are
-    //      therefore computed by all threads in parallel, and the six running sums are then taken in upstream's order
-    //      by six lanes of one warp (one lane per moment, eight loads in flight, ~10 cycles per point): bit-identical
-    //      to the sequential loop at a fraction of the issue slots of a 6 x double warp scan.
+    //      another order and the last bits -- sometimes a decision -- come out differently.  So: T points at a time, every
+    //      thread computes the six terms of its point into a shared-memory stage (moment-major, padded: conflict-free
+    //      both ways), six lanes of warp 0 -- one per moment -- run upstream's sequential sums over the stage in place
+    //      (LDS / DADD / STS per point, the DADD chain is the only dependency), and every thread writes its point's
+    //      six sums to the group's scratch.  Bit-identical to the sequential loop, and cheaper in issue slots than a
+    //      6 x double warp scan.
+    {
+        constexpr int SP = T + 2;   // stage pitch in doubles
+        double carry = 0;           // (lanes 0..5 of warp 0: running sum of "their" moment)
 #pragma unroll 1
-    for (int i = tid; i < sz; i += T) {
-        const unsigned long long e = sbuf[i];
-        const uint32_t xy = (uint32_t)e;
-        const int px = xy & 0xffff, py = xy >> 16;
-        const double x = px * .5 + 0.5, y = py * .5 + 0.5;
-        const double W = sqrt((double)(uint32_t)(e >> 32)) + 1;
-        double2* p = reinterpret_cast<double2*>(lf + (size_t)i * 6);
-        __stcg(p, make_double2(W * x, W * y));
-        __stcg(p + 1, make_double2(W * x * x, W * x * y));
-        __stcg(p + 2, make_double2(W * y * y, W));
-    }
-    __threadfence_block();
-    G.sync();
-    if (G.w == 0 && lane < 6) {
-        double acc = 0;
-        double* p = lf + lane;
-        int i = 0;
+        for (int base = 0; base < sz; base += T) {
+            const int i = base + tid;
+            double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+            if (i < sz) {
+                const unsigned long long e = sbuf[i];
+                const uint32_t xy = (uint32_t)e;
+                const int px = xy & 0xffff, py = xy >> 16;
+                const double x = px * .5 + 0.5, y = py * .5 + 0.5;
+                const double W = sqrt((double)(uint32_t)(e >> 32)) + 1;
+                t0 = W * x; t1 = W * y; t2 = W * x * x; t3 = W * x * y; t4 = W * y * y; t5 = W;
+            }
+            stage[0 * SP + tid] = t0; stage[1 * SP + tid] = t1; stage[2 * SP + tid] = t2;
+            stage[3 * SP + tid] = t3; stage[4 * SP + tid] = t4; stage[5 * SP + tid] = t5;
+            G.sync();
+            if (G.w == 0 && lane < 6) {
+                double* p = stage + lane * SP;
 #pragma unroll 1
-        for (; i + 8 <= sz; i += 8) {
-            double v[8];
+                for (int j = 0; j < T; j += 8) {   // (entries past the cluster's end hold zeros)
+                    double v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = __ldcg(p + (size_t)(i + u) * 6);
+                    for (int u = 0; u < 8; u++) v[u] = p[j + u];
 #pragma unroll
-            for (int u = 0; u < 8; u++) { acc += v[u]; __stcg(p + (size_t)(i + u) * 6, acc); }
+                    for (int u = 0; u < 8; u++) { carry += v[u]; p[j + u] = carry; }
+                }
+            }
+            G.sync();
+            if (i < sz) {
+                double2* p = reinterpret_cast<double2*>(lf + (size_t)i * 6);
+                __stcg(p, make_double2(stage[0 * SP + tid], stage[1 * SP + tid]));
+                __stcg(p + 1, make_double2(stage[2 * SP + tid], stage[3 * SP + tid]));
+                __stcg(p + 2, make_double2(stage[4 * SP + tid], stage[5 * SP + tid]));
+            }
         }
-#pragma unroll 1
-        for (; i < sz; i++) { acc += __ldcg(p + (size_t)i * 6); __stcg(p + (size_t)i * 6, acc); }
     }
     __threadfence_block();
     G.sync();
@@ -694,9 +809,10 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
 // Dynamic shared memory per GROUP: `wcap` u64 (sort buffer; from 1024 keys on it also hosts the 600-double pair
 // table once the sort is over) + 16 ints, plus a separate pair table for the small tier.  QF_SMEM_CAP: the largest
 // sort buffer one CTA can have (227 KB of shared memory per SM).
-#define QF_SMEM_CAP 28000
+#define QF_SMEM_CAP 26000
+__host__ __device__ inline size_t qf_stage_bytes(int nw) { return (size_t)6 * (nw * 32 + 2) * 8; }   // prefix-moment stage
 __host__ __device__ inline size_t qf_smem_per_group(int wcap, int nw) {
-    return (size_t)wcap * 8 + 64 + (size_t)nw * 512 + (wcap >= 1024 ? 0 : QF_PTAB_DOUBLES * 8);
+    return (size_t)wcap * 8 + 64 + (size_t)nw * 512 + qf_stage_bytes(nw) + (wcap >= 1024 ? 0 : QF_PTAB_DOUBLES * 8);
 }
 
 // Persistent groups: group i takes clusters i, i + ngroups, ...   NW == 1: blockDim/32 warp groups per CTA;
@@ -725,8 +841,9 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
     unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(base);
     int* sidx = reinterpret_cast<int*>(base + (size_t)wcap * 8);
     uint16_t* scnt = reinterpret_cast<uint16_t*>(base + (size_t)wcap * 8 + 64);
+    double* stage = reinterpret_cast<double*>(base + (size_t)wcap * 8 + 64 + (size_t)NW * 512);
     double* ptab = wcap >= 1024 ? reinterpret_cast<double*>(base)
-                                : reinterpret_cast<double*>(base + (size_t)wcap * 8 + 64 + (size_t)NW * 512);
+                                : reinterpret_cast<double*>(base + (size_t)wcap * 8 + 64 + (size_t)NW * 512 + qf_stage_bytes(NW));
     const int n = min(*a.list_count, a.list_cap);
     // clusters differ by two orders of magnitude in cost: groups claim them one at a time from a shared cursor
     for (;;) {
@@ -746,7 +863,7 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
         unsigned long long* sb = sbuf;
         if (NW == 8 && ref.size > wcap) sb = a.gsort + (size_t)blockIdx.x * a.gsort_stride;   // (the pair table stays in shared memory)
         double* lf = a.scratch + (size_t)(NW == 1 ? blockIdx.x * 8 + gi : blockIdx.x) * a.scratch_pts * 7;
-        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sb, ptab, sidx, scnt, lf, q);
+        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sb, ptab, sidx, scnt, stage, lf, q);
         if (ok && G.tid == 0) {
             int s = atomicAdd(a.nquads, 1);
             atomicAdd(&a.per_frame_quads[ref.frame], 1);

@@ -245,6 +245,12 @@ class Detector:
         return dict(edge_points=int(c[0]), clusters=int(c[1]), quads=int(c[2]), raw_detections=int(c[3]),
                     oversize_clusters=int(c[4]), tier_clusters=(int(c[1] - c[5] - c[6] - c[7]), int(c[5]), int(c[6]), int(c[7])))
 
+    def tier_stats(self) -> dict:
+        """Clusters and edge-point records handed to the four quad-fit size tiers in the last call."""
+        c = np.zeros(8, np.int64)
+        self._check(self._L.agpu_get_tier_stats(self._h, c.ctypes.data))
+        return dict(clusters=[int(v) for v in c[:4]], records=[int(v) for v in c[4:]])
+
     def debug_fetch(self, what: str, frame: int = 0) -> np.ndarray:
         wd, hd = C.c_int(), C.c_int()
         self._check(self._L.agpu_debug_dims(self._h, C.byref(wd), C.byref(hd)))

@@ -148,6 +148,9 @@ int agpu_get_launch_count(agpu_handle* h, long long* launches);
  * (dropped before fitting, exactly as upstream drops them), [5] / [6] / [7] clusters fitted by the 2- / 4- / 8-warp
  * tiers of the quad-fit kernel (cluster size classes; [1] counts all tiers). */
 int agpu_get_counters(agpu_handle* h, long long* counters /* [8] */);
+/* Quad-fit size tiers (1- / 2- / 4- / 8-warp groups) in the last call: [0..3] clusters, [4..7] edge-point records handed
+ * to each tier (8 bytes each: the algorithmic input of k_fit_quads<1|2|4|8>). */
+int agpu_get_tier_stats(agpu_handle* h, long long* stats /* [8] */);
 
 /* Stage dumps for parity tests (cfg.debug = 1): buffers of frame `frame` of the LAST chunk.
  * what: "quad_im" u8[hd*wd], "thresh" u8[hd*wd], "labels" u32[hd*wd] (min-index representative),

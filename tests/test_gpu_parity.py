@@ -17,8 +17,16 @@ from aprilslam_b200 import synth  # noqa: E402
 from aprilslam_b200.detector import Detector, TagDetector, apriltag  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CORNER_TOL_PX = 0.05
+CORNER_TOL_PX = 0.05      # the north-star bars ...
 POSE_TOL = 1e-4
+# ... and what is asserted: a few times the largest difference ever measured between the CUDA path and the oracle
+# (tools/gpu_tolerances.py over 19 frames / 934 detections incl. augmented 1080p and 4K, profiles/r3a_tolerances.json):
+# fitted quads bit-equal; corners 2.4e-4 px, centre 1.2e-4 px, margin 6.1e-5, pose 2.1e-7 units / 2.7e-6 rad.  What is
+# left comes from atan2f / cosf / sinf (CUDA's and glibc's differ by an ulp or two) inside refine_edges.
+CORNER_ACHIEVED_TOL_PX = 1e-3
+MARGIN_ACHIEVED_TOL = 5e-4
+REFINED_ACHIEVED_TOL_PX = 5e-4   # clean frames; junk quads of noisy frames (ill-conditioned edge fits) reach 1.4e-2
+POSE_ACHIEVED_TOL = 2e-6         # units (scene scale 1) and 2e-5 rad
 
 CASES = {
     "sim1000_41h12_d2": ("tagStandard41h12", 2.0), "sim640_41h12_d2": ("tagStandard41h12", 2.0),
@@ -43,7 +51,7 @@ def geodesic(Ra, Rb):
     return float(np.arccos(np.clip((np.trace(Ra @ Rb.T) - 1) / 2, -1, 1)))
 
 
-def assert_same_detections(recs, ref, tol=CORNER_TOL_PX):
+def assert_same_detections(recs, ref, tol=CORNER_ACHIEVED_TOL_PX):
     assert len(recs) == len(ref)
     assert recs["id"].tolist() == ref["id"].tolist()
     assert recs["hamming"].tolist() == ref["hamming"].tolist()
@@ -51,7 +59,7 @@ def assert_same_detections(recs, ref, tol=CORNER_TOL_PX):
     if len(ref):
         assert np.abs(recs["p"] - ref["p"]).max() <= tol
         assert np.abs(recs["c"] - ref["c"]).max() <= tol
-        assert np.abs(recs["margin"] - ref["margin"]).max() <= 1e-2
+        assert np.abs(recs["margin"] - ref["margin"]).max() <= MARGIN_ACHIEVED_TOL
 
 
 # ---- stage level: bit-exact -----------------------------------------------------------------------------
@@ -135,15 +143,15 @@ def test_pipeline_matches_oracle_and_golden(ob, det_gold, name):
     assert np.array_equal(g.debug_fetch("cluster_sizes"), dbg["cluster_sizes"])
     assert np.array_equal(g.debug_fetch("quad_keys"), dbg["quad_keys"])
     if len(dbg["quads"]):
-        assert np.abs(g.debug_fetch("quads") - dbg["quads"]).max() <= 1e-3
-        assert np.abs(g.debug_fetch("quads_refined") - dbg["quads_refined"]).max() <= 1e-2
+        assert np.array_equal(g.debug_fetch("quads"), dbg["quads"])       # fitted quads: bit-equal (sequential-order moments)
+        assert np.abs(g.debug_fetch("quads_refined") - dbg["quads_refined"]).max() <= REFINED_ACHIEVED_TOL_PX
     assert g.counters()["edge_points"] == dbg["npoints"]
     assert g.counters()["oversize_clusters"] == dbg["noversize"] == 0
     assert_same_detections(recs, ref)
     # committed fixture (generated through the reference's TagDetector.detect, tools/make_golden.py)
     assert recs["id"].tolist() == det_gold[name + "_id"].tolist()
     assert recs["hamming"].tolist() == det_gold[name + "_hamming"].tolist()
-    assert np.abs(recs["p"] - det_gold[name + "_corners"]).max() <= CORNER_TOL_PX
+    assert np.abs(recs["p"] - det_gold[name + "_corners"]).max() <= CORNER_ACHIEVED_TOL_PX
     g.close()
 
 
@@ -167,7 +175,7 @@ def test_bgr_front_end_and_tagdetector_drop_in(ob, det_gold):
         assert set(("hamming", "margin", "id", "center", "lb-rb-rt-lt", "tag_family", "tag_id", "decision_margin",
                     "corners", "homography")) <= set(x)
         assert x["lb-rb-rt-lt"].shape == (4, 2) and x["lb-rb-rt-lt"].dtype == np.float64
-        assert np.abs(x["lb-rb-rt-lt"] - r["p"]).max() <= CORNER_TOL_PX
+        assert np.abs(x["lb-rb-rt-lt"] - r["p"]).max() <= CORNER_ACHIEVED_TOL_PX
         retval, rvec, tvec, T = td.get_pose(x)
         ok, rv, tv, TT = ob.reference_pose(x["lb-rb-rt-lt"], K, np.zeros((4, 1)), 0.15)
         assert retval is True and rvec.shape == (3, 1) and tvec.shape == (3, 1) and T.shape == (4, 4)
@@ -182,7 +190,7 @@ def test_apriltag_shim_matches_upstream_wrapper_contract(ob, det_gold):
     assert isinstance(out, tuple) and [x["id"] for x in out] == [0, 1, 2]
     ref = ob.OracleDetector("tagStandard41h12").detect(img)
     for a, b in zip(out, ref):
-        assert a["hamming"] == b["hamming"] and np.abs(a["lb-rb-rt-lt"] - b["lb-rb-rt-lt"]).max() <= CORNER_TOL_PX
+        assert a["hamming"] == b["hamming"] and np.abs(a["lb-rb-rt-lt"] - b["lb-rb-rt-lt"]).max() <= CORNER_ACHIEVED_TOL_PX
     with pytest.raises(RuntimeError):
         d.detect(np.zeros((10, 10, 3), np.uint8))
     with pytest.raises(RuntimeError):
@@ -230,8 +238,8 @@ def test_batch_on_device_equals_per_frame_and_oracle(ob, det_gold):
         assert np.array_equal(dets_dev[b], dets_host[b])   # same kernels, same inputs: identical records
         for r, p in zip(dets_dev[b], poses_dev[b]):
             ok, rv, tv, T = ob.reference_pose(r["p"], K, np.zeros((4, 1)), 0.2)
-            assert p["ok"] == 1 and np.abs(p["tvec"] - tv.ravel()).max() < POSE_TOL
-            assert geodesic(p["R"].reshape(3, 3), T[:3, :3]) < POSE_TOL
+            assert p["ok"] == 1 and np.abs(p["tvec"] - tv.ravel()).max() < POSE_ACHIEVED_TOL
+            assert geodesic(p["R"].reshape(3, 3), T[:3, :3]) < 10 * POSE_ACHIEVED_TOL
     assert len(dets_dev[3]) == 0
     assert np.array_equal(dets_dev[4], dets_dev[1])
     g.close()
@@ -507,6 +515,7 @@ def test_noise_regime_1080p_exercises_every_quad_fit_tier(ob):
     assert np.array_equal(g.debug_fetch("cluster_keys"), dbg["cluster_keys"])
     assert np.array_equal(g.debug_fetch("cluster_sizes"), dbg["cluster_sizes"])
     assert np.array_equal(g.debug_fetch("quad_keys"), dbg["quad_keys"])
+    assert np.array_equal(g.debug_fetch("quads"), dbg["quads"])           # ~700 quads, most of them junk: still bit-equal
     assert_same_detections(recs, ref)
     assert len(ref) >= 20
     g.close()
