@@ -171,7 +171,7 @@ struct agpu_handle {
     // state of the last finished chunk (debug fetch)
     Geom geom;
     int last_slot = 0, last_chunk = 0, last_cap = 0, last_id_bits = 16;
-    bool have_last = false, last_from_masks = false;
+    bool have_last = false, last_from_masks = false, last_bgr = false;
 
     void set_err(const std::string& s) { err = s; }
 };
@@ -311,8 +311,17 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
     size_t s_stride = stride, s_frame = frame_stride;
     int srcW = W, srcH = H;
     int F = f;
-    // full-resolution gray image for refine_edges / decode
-    if (channels == 3) {
+    // full-resolution gray image for refine_edges / decode.  BGR frames (the reference's input, tag_detector.py:25) at
+    // decimate 1 / 2 / 4 without blur: the strip kernel converts, decimates and thresholds in one pass (`fused_bgr`);
+    // other settings convert first (k_pack) and continue on the gray plane
+    const bool fused_bgr = channels == 3 && (f == 1 || f == 2 || f == 4) && sigma == 0.0f && (g.wd >> 2) > 0 && (g.hd >> 2) > 0;
+    const Geom gfull = make_geom(W, H, 1);
+    if (fused_bgr) {
+        CK(sl.d_gray.ensure(gfull.plane * n));
+        *gray_full = sl.d_gray.as<uint8_t>();
+        *gray_pitch = gfull.wp;
+        *gray_frame = gfull.plane;
+    } else if (channels == 3) {
         Geom gf = make_geom(W, H, 1);
         CK(sl.d_gray.ensure(gf.plane * n));
         size_t total = (size_t)n * gf.hd * (gf.wp >> 2);
@@ -385,14 +394,14 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         const int strip_px = 30 * TPL * 4;
         const int nstrips = ceil_div(g.wp, strip_px);
         const int th = g.hd >> 2;
-        int seg_tiles = 8;
+        int seg_tiles = fused_bgr ? 16 : 8;   // (a segment re-converts its two halo tile rows: longer segments for BGR)
         if (const char* e = getenv("AGPU_SEG_TILES")) seg_tiles = std::max(1, atoi(e));
         const int nsegs = ceil_div(th, seg_tiles);
         const long long warps = (long long)n * nstrips * nsegs;
         const int blocks = ceil_div(warps * 32, 128);
         const int vec_ok = (s_stride % 16 == 0) && (s_frame % 16 == 0) && (((uintptr_t)src) % 16 == 0);
         const int md = h->prm.min_white_black_diff;
-        const bool use_masks = masks_written && F == 1 && h->tune.masks;
+        const bool use_masks = masks_written && F == 1 && h->tune.masks && !fused_bgr;
         if (!use_masks) CK(sl.d_thresh.ensure(g.plane * n));
         if (use_masks) CK(sl.d_masks.ensure((size_t)cc_tiles_x(g) * cc_tiles_y(g) * n * 32 * sizeof(uint2)));
         {
@@ -402,7 +411,13 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         if (const char* e = getenv("AGPU_IMG_MINB")) minb = atoi(e);
 #define LAUNCH_DT(FF, MB) k_decimate_threshold<FF, MB><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, \
                                                                                th_out, g, nstrips, nsegs, seg_tiles, n, md, vec_ok)
-        if (use_masks) {
+        if (fused_bgr) {
+#define LAUNCH_DT3(FF) k_decimate_threshold<FF, 3, false, 3><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, \
+                                                              th_out, g, nstrips, nsegs, seg_tiles, n, md, vec_ok, nullptr,                \
+                                                              sl.d_gray.as<uint8_t>(), (size_t)gfull.wp, gfull.plane)
+            if (F == 1) LAUNCH_DT3(1); else if (F == 2) LAUNCH_DT3(2); else LAUNCH_DT3(4);
+#undef LAUNCH_DT3
+        } else if (use_masks) {
             k_decimate_threshold<1, 4, true><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, nullptr, nullptr, g,
                                                                           nstrips, nsegs, seg_tiles, n, md, vec_ok,
                                                                           sl.d_masks.as<uint2>());
@@ -420,6 +435,8 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
     }
     if (F > 1) {
         *quad_im_out = quad_out; *q_pitch = g.wp; *q_frame = g.plane;
+    } else if (fused_bgr) {
+        *quad_im_out = sl.d_gray.as<uint8_t>(); *q_pitch = gfull.wp; *q_frame = gfull.plane;   // decimate 1: the gray plane
     } else {
         *quad_im_out = src; *q_pitch = s_stride; *q_frame = s_frame;
     }
@@ -744,7 +761,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     tm.mark(sl.tail);  // 7: after decode
     {
         KScope ks(h, sl, "k_reconcile", sl.tail);
-        k_reconcile<<<n, 32, 0, sl.tail>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
+        k_reconcile<<<n, REC_THREADS, 0, sl.tail>>>(sl.d_dets.as<DetRec>(), d_ndets, REC_CAP, n,
                                                           sl.d_out.as<DetRec>(), d_out_counts, c.cap_out);
     }
     LAUNCH_CHECK("k_reconcile");
@@ -867,6 +884,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     h->last_cap = c.cap;
     h->last_id_bits = c.id_bits;
     h->last_from_masks = sl.from_masks;
+    h->last_bgr = c.channels == 3;
     h->have_last = true;
     return 0;
 }
@@ -1366,6 +1384,15 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
         if (!fetch_thresh_frame(h, sl, frame, th)) return AGPU_E_CUDA;
         for (int y = 0; y < g.hd; y++) memcpy((uint8_t*)host_out + (size_t)y * g.wd, th.data() + (size_t)y * g.wp, g.wd);
         return (long long)npx;
+    }
+    if (w == "gray") {   // full-resolution gray plane converted from the BGR frames of the last call
+        const Geom gf = make_geom(g.W, g.H, 1);
+        if (!h->last_bgr || !sl.d_gray.p) { h->set_err("agpu_debug_fetch: the last call had no BGR input"); return AGPU_E_INVALID; }
+        const size_t nfull = (size_t)g.W * g.H;
+        if ((size_t)cap_bytes < nfull) return (long long)nfull;
+        if (cudaMemcpy2D(host_out, g.W, sl.d_gray.as<uint8_t>() + (size_t)frame * gf.plane, gf.wp, g.W, g.H, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return AGPU_E_CUDA;
+        return (long long)nfull;
     }
     if (w == "quad_im") {
         const uint8_t* src = sl.d_quad_im.as<uint8_t>();

@@ -476,26 +476,30 @@ __device__ int prefer_dev(const DetRec& a, const DetRec& b) {
 
 #define REC_CAP 256  // internal per-frame detection capacity before reconcile
 
-// One warp (= one CTA) per frame.  The sort keys (id, family, centre) are staged in shared memory once, so the two
-// rank sorts run out of shared memory instead of re-reading the 168-byte records n times.
-__global__ void __launch_bounds__(32)
+// One CTA of REC_THREADS threads per frame.  The sort keys (id, family, centre) are staged in shared memory once, so the
+// two rank sorts (n^2 comparisons, dealt to all threads) run out of shared memory instead of re-reading the 168-byte
+// records n times; the pairwise rule in between is sequential by definition (thread 0).
+#define REC_THREADS 128
+__global__ void __launch_bounds__(REC_THREADS)
 k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int cap_dets, int nframes,
             DetRec* __restrict__ out, int* __restrict__ out_counts, int cap_out) {
     __shared__ int s_perm[REC_CAP];
     __shared__ unsigned char s_dead[REC_CAP];
     __shared__ int s_id[REC_CAP], s_fam[REC_CAP];
     __shared__ double s_cx[REC_CAP], s_cy[REC_CAP];
-    const int lane = threadIdx.x & 31;
+    __shared__ int s_alive;
+    const int tid = threadIdx.x;
     const int frame = blockIdx.x;
     if (frame >= nframes) return;
     const int n = min(min(ndets[frame], cap_dets), REC_CAP);
     const DetRec* fd = dets + (size_t)frame * cap_dets;
     int* perm = s_perm;
     unsigned char* dead = s_dead;
-    for (int i = lane; i < n; i += 32) {
+    if (tid == 0) s_alive = 0;
+    for (int i = tid; i < n; i += REC_THREADS) {
         s_id[i] = fd[i].id; s_fam[i] = fd[i].family; s_cx[i] = fd[i].c[0]; s_cy[i] = fd[i].c[1];
     }
-    __syncwarp();
+    __syncthreads();
     // order 0: (id, family, cx, cy)   order 1: (id, cx, cy)
     auto less = [&](int a, int b, int order) {
         if (s_id[a] != s_id[b]) return s_id[a] < s_id[b];
@@ -503,15 +507,15 @@ k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int 
         if (s_cx[a] != s_cx[b]) return s_cx[a] < s_cx[b];
         return s_cy[a] < s_cy[b];
     };
-    for (int i = lane; i < n; i += 32) {
+    for (int i = tid; i < n; i += REC_THREADS) {
         int rank = 0;
         for (int j = 0; j < n; j++)
             if (less(j, i, 0) || (!less(i, j, 0) && j < i)) rank++;
         perm[rank] = i;
         dead[i] = 0;
     }
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    if (tid == 0) {
         for (int a = 0; a < n; a++) {
             const int i = perm[a];
             if (dead[i]) continue;
@@ -525,9 +529,9 @@ k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int 
             }
         }
     }
-    __syncwarp();
-    int alive_total = 0;
-    for (int i = lane; i < n; i += 32) {
+    __syncthreads();
+    int alive = 0;
+    for (int i = tid; i < n; i += REC_THREADS) {
         if (dead[i]) continue;
         int rank = 0;
         for (int j = 0; j < n; j++) {
@@ -535,9 +539,9 @@ k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int 
             if (less(j, i, 1) || (!less(i, j, 1) && j < i)) rank++;
         }
         if (rank < cap_out) out[(size_t)frame * cap_out + rank] = fd[i];
-        alive_total++;
+        alive++;
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) alive_total += __shfl_xor_sync(FULL_MASK, alive_total, off);
-    if (lane == 0) out_counts[frame] = alive_total;
+    if (alive) atomicAdd(&s_alive, alive);
+    __syncthreads();
+    if (tid == 0) out_counts[frame] = s_alive;
 }

@@ -41,18 +41,43 @@ __device__ __forceinline__ __half2 px_hi(uint32_t w) { return u2h(__byte_perm(w,
 #define H2_BIG 0x7bff7bffu   // 65504: neutral element of min
 #define H2_ZERO 0x00000000u  // 0 < 1024: neutral element of max
 
+// cv2.cvtColor(BGR2GRAY) of this OpenCV build: (B*3735 + G*19235 + R*9798 + 16384) >> 15 (SURVEY.md 8c)
+__device__ __forceinline__ uint32_t bgr2gray(uint32_t b, uint32_t g, uint32_t r) {
+    return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
+}
+
+// Four interleaved BGR pixels (12 bytes in w0 w1 w2) -> four gray bytes.  A pixel's three bytes are gathered into one
+// register with PRMT and go through two 16-bit x 8-bit dot products (DP2A): lower byte pair x (3735, 19235), upper
+// byte pair x (9798, 0) -- the fourth byte is multiplied by zero, so whatever PRMT leaves there does not matter.
+__device__ __forceinline__ uint32_t bgr4_to_gray4(uint32_t w0, uint32_t w1, uint32_t w2) {
+    const uint32_t cBG = 3735u | (19235u << 16), cR = 9798u;
+    const uint32_t p1 = __byte_perm(w0, w1, 0x6543), p2 = __byte_perm(w1, w2, 0x5432), p3 = w2 >> 8;
+    const uint32_t a0 = __dp2a_hi(cR, w0, __dp2a_lo(cBG, w0, 16384u)) << 1;   // gray in byte 2
+    const uint32_t a1 = __dp2a_hi(cR, p1, __dp2a_lo(cBG, p1, 16384u)) << 1;
+    const uint32_t a2 = __dp2a_hi(cR, p2, __dp2a_lo(cBG, p2, 16384u)) << 1;
+    const uint32_t a3 = __dp2a_hi(cR, p3, __dp2a_lo(cBG, p3, 16384u)) << 1;
+    return __byte_perm(__byte_perm(a0, a1, 0x0062), __byte_perm(a2, a3, 0x0062), 0x5410);
+}
+
 // MASKS (decimate 1 only): instead of the threshold BYTES the kernel writes what the connected-components pass
 // actually consumes -- the tile-major bit masks (2 bits per pixel: white / black, neither = 127) of k_cc.cuh.  A lane's
 // 16 pixels are half a mask row; lanes pair up (1,2), (3,4), ... (a strip of 30 lanes starts on a 32-pixel tile
 // boundary), swap two rows' worth of bits with one shuffle each, and every lane stores ONE 16-byte word (two mask
 // rows) per tile row instead of four: the threshold image never reaches HBM (N/4 bytes written instead of N, and
 // k_cc_local reads N/4 instead of N).
-template <int F, int MINB, bool MASKS = false>
+// CH == 3 (the reference's frames are BGR, tag_detector.py:25): the source is interleaved BGR; a lane
+// reads 48 bytes (three LDG.128) per source row, converts its 16 pixels with cv2's fixed-point formula, writes them to
+// the full-resolution gray plane `gray_out` (refine_edges and decode sample it; at decimate 1 it is also the quad image)
+// and carries on with the gray words exactly as in the one-channel case: gray conversion, decimation and threshold in
+// ONE pass over the frame.  With decimation the source rows between two sampled rows are converted as well.
+template <int F, int MINB, bool MASKS = false, int CH = 1>
 __global__ void __launch_bounds__(128, MINB)
 k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_stride, size_t src_frame_stride,
                      uint8_t* __restrict__ quad_im, uint8_t* __restrict__ thresh, Geom g, int nstrips, int nsegs,
-                     int seg_tiles, int nframes, int min_diff, int vec_ok, uint2* __restrict__ masks = nullptr) {
+                     int seg_tiles, int nframes, int min_diff, int vec_ok, uint2* __restrict__ masks = nullptr,
+                     uint8_t* __restrict__ gray_out = nullptr, size_t gray_pitch = 0, size_t gray_frame = 0) {
     static_assert(!MASKS || F == 1, "mask output needs 16 pixels per lane");
+    static_assert(CH == 1 || (CH == 3 && !MASKS), "BGR input writes threshold bytes");
     constexpr int TPL = 4 / F;  // tiles (4-pixel words) per lane per row
     const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -92,10 +117,44 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
                                                     __byte_perm(lo_b, hi_b, 0x5410), __byte_perm(lo_b, hi_b, 0x7632));
     };
 
-    auto load_row = [&](int gy, uint32_t(&w)[TPL]) {
+    uint8_t* fgray = CH == 3 ? gray_out + (size_t)frame * gray_frame : nullptr;
+    const bool gray_lane = lane >= 1 && lane <= 30;          // (halo lanes' columns are stored by the neighbouring strip)
+    auto load_row = [&](int gy, uint32_t(&w)[TPL], bool own = false) {   // own: this segment stores the row's gray pixels
 #pragma unroll
         for (int j = 0; j < TPL; j++) w[j] = 0;
         if (gy >= g.hd || !lane_in) return;
+        if (CH == 3) {
+            // 16 source pixels of source row sy -> 16 gray bytes (stored to the gray plane when this segment owns the row)
+            auto convert_row = [&](int sy, bool store) -> uint4 {
+                const uint8_t* row = fsrc + (size_t)sy * src_stride;
+                if (vec) {
+                    const uint4* p = reinterpret_cast<const uint4*>(row + sc0 * 3);
+                    const uint4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+                    const uint4 gq = make_uint4(bgr4_to_gray4(v0.x, v0.y, v0.z), bgr4_to_gray4(v0.w, v1.x, v1.y),
+                                                bgr4_to_gray4(v1.z, v1.w, v2.x), bgr4_to_gray4(v2.y, v2.z, v2.w));
+                    if (store) *reinterpret_cast<uint4*>(fgray + (size_t)sy * gray_pitch + sc0) = gq;
+                    return gq;
+                }
+                uint32_t gw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+                for (int k = 0; k < 16; k++) {
+                    const long sx = sc0 + k;
+                    if (sx < 0 || sx >= W) continue;
+                    const uint32_t v = bgr2gray(row[sx * 3], row[sx * 3 + 1], row[sx * 3 + 2]);
+                    gw[k >> 2] |= v << (8 * (k & 3));
+                    if (store) fgray[(size_t)sy * gray_pitch + sx] = (uint8_t)v;
+                }
+                return make_uint4(gw[0], gw[1], gw[2], gw[3]);
+            };
+            const bool store = own && gray_lane;
+            unpack16<F>(convert_row(gy * F, store), w);
+            if (F > 1 && store) {   // the source rows between two sampled rows only feed the gray plane
+#pragma unroll 1
+                for (int sub = 1; sub < F; sub++)
+                    if (gy * F + sub < H) (void)convert_row(gy * F + sub, true);
+            }
+            return;
+        }
         const uint8_t* row = fsrc + (size_t)gy * F * src_stride;
         if (vec) {
             uint4 v = __ldg(reinterpret_cast<const uint4*>(row + sc0));
@@ -107,10 +166,11 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
             }
         }
     };
+    const int own_T0 = seg * seg_tiles, own_T1 = min(own_T0 + seg_tiles, th);
     auto load_tile_row = [&](int T, uint32_t(&px)[4][TPL]) {
         if (T >= 0 && T < th) {
 #pragma unroll
-            for (int r = 0; r < 4; r++) load_row(T * 4 + r, px[r]);
+            for (int r = 0; r < 4; r++) load_row(T * 4 + r, px[r], T >= own_T0 && T < own_T1);
         } else {
 #pragma unroll
             for (int r = 0; r < 4; r++)
@@ -245,7 +305,7 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
         if (T == th - 1 && (g.hd & 3)) {  // bottom leftover rows use the last tile row
             uint32_t lr[4][TPL];
 #pragma unroll
-            for (int r = 0; r < 4; r++) load_row(th * 4 + r, lr[r]);
+            for (int r = 0; r < 4; r++) load_row(th * 4 + r, lr[r], true);
             store_rows(th * 4, g.hd - th * 4, lr, dmn, dmx, true);
         }
         if (MASKS && T == th - 1) {   // mask rows of the last tile row that lie below the image: empty
@@ -262,11 +322,6 @@ k_decimate_threshold(const uint8_t* __restrict__ src, int W, int H, size_t src_s
 #pragma unroll
             for (int j = 0; j < TPL; j++) { cur[r][j] = nxt[r][j]; nxt[r][j] = nn[r][j]; }
     }
-}
-
-// cv2.cvtColor(BGR2GRAY) of this OpenCV build: (B*3735 + G*19235 + R*9798 + 16384) >> 15 (SURVEY.md 8c)
-__device__ __forceinline__ uint32_t bgr2gray(uint32_t b, uint32_t g, uint32_t r) {
-    return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
 }
 
 // Generic front end: any integer decimation factor, 1 or 3 channels -> pitched quad_im.

@@ -131,30 +131,42 @@ __device__ bool orthogonalize(double (&R)[9]) {
     return true;
 }
 
-// 6x6 SPD solve (Cholesky); returns false when not positive definite
-__device__ bool solve6(double (&A)[36], double (&b)[6], double (&x)[6]) {
-    double L[36];
-    for (int i = 0; i < 6; i++)
+// 6x6 SPD solve (Cholesky) on the packed lower triangle S[i*(i+1)/2 + j], j <= i, with `lambda * (S_ii + 1e-12)` added
+// to the diagonal (Levenberg-Marquardt damping); every loop has constant bounds, so all of it lives in registers.
+// Returns false when the damped matrix is not positive definite.
+#define SYM(i, j) ((i) * ((i) + 1) / 2 + (j))
+__device__ __forceinline__ bool solve6_sym(const double (&S)[21], double lambda, const double (&b)[6], double (&x)[6]) {
+    double L[21];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
         for (int j = 0; j <= i; j++) {
-            double s = A[i * 6 + j];
-            for (int k = 0; k < j; k++) s -= L[i * 6 + k] * L[j * 6 + k];
+            double s = S[SYM(i, j)];
+            if (i == j) s += lambda * (s + 1e-12);
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= L[SYM(i, k)] * L[SYM(j, k)];
             if (i == j) {
                 if (!(s > 0)) return false;
-                L[i * 6 + i] = sqrt(s);
+                L[SYM(i, i)] = sqrt(s);
             } else {
-                L[i * 6 + j] = s / L[j * 6 + j];
+                L[SYM(i, j)] = s / L[SYM(j, j)];
             }
         }
+    }
     double y[6];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
         double s = b[i];
-        for (int k = 0; k < i; k++) s -= L[i * 6 + k] * y[k];
-        y[i] = s / L[i * 6 + i];
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= L[SYM(i, k)] * y[k];
+        y[i] = s / L[SYM(i, i)];
     }
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
         double s = y[i];
-        for (int k = i + 1; k < 6; k++) s -= L[k * 6 + i] * x[k];
-        x[i] = s / L[i * 6 + i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) s -= L[SYM(k, i)] * x[k];
+        x[i] = s / L[SYM(i, i)];
     }
     return true;
 }
@@ -190,46 +202,34 @@ k_pose(PoseArgs a) {
             yn = (y0 - dY) * icdist;
         }
     }
-    // ---- homography (X,Y) -> (xn,yn): 8x9 elimination, rows gathered from the 4 lanes
-    double A[72];
+    // ---- homography (X, Y) -> (xn, yn).  The object points are the corners of a square, so the 4-point homography has
+    //      a closed form (the projective square-to-quadrilateral map): ~40 flops in registers on every lane instead of
+    //      an 8x9 elimination in local memory.  (The pose oracle is cv2.solvePnP, matched through the minimiser the
+    //      iteration below converges to; the start value only has to be in its basin, as OpenCV's own is.)
+    double h[9];
+    bool ok;
     {
         const int gbase = (threadIdx.x & 31) & ~3;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            double Xi = __shfl_sync(gmask, X, gbase + i), Yi = __shfl_sync(gmask, Y, gbase + i);
-            double xi = __shfl_sync(gmask, xn, gbase + i), yi = __shfl_sync(gmask, yn, gbase + i);
-            double* r0 = &A[(2 * i) * 9];
-            double* r1 = &A[(2 * i + 1) * 9];
-            r0[0] = Xi; r0[1] = Yi; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -Xi * xi; r0[7] = -Yi * xi; r0[8] = xi;
-            r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = Xi; r1[4] = Yi; r1[5] = 1; r1[6] = -Xi * yi; r1[7] = -Yi * yi; r1[8] = yi;
-        }
-    }
-    bool ok = true;
-    for (int col = 0; col < 8; col++) {
-        double max_val = 0;
-        int max_idx = -1;
-        for (int row = col; row < 8; row++) {
-            double val = fabs(A[row * 9 + col]);
-            if (val > max_val) { max_val = val; max_idx = row; }
-        }
-        if (max_idx < 0 || max_val < 1e-14) { ok = false; break; }
-        if (max_idx != col)
-            for (int i = col; i < 9; i++) { double t = A[col * 9 + i]; A[col * 9 + i] = A[max_idx * 9 + i]; A[max_idx * 9 + i] = t; }
-        for (int i = col + 1; i < 8; i++) {
-            double f = A[i * 9 + col] / A[col * 9 + col];
-            A[i * 9 + col] = 0;
-            for (int j = col + 1; j < 9; j++) A[i * 9 + j] -= f * A[col * 9 + j];
-        }
-    }
-    double h[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    if (ok) {
-        for (int col = 7; col >= 0; col--) {
-            double sum = 0;
-            for (int i = col + 1; i < 8; i++) sum += A[col * 9 + i] * A[i * 9 + 8];
-            A[col * 9 + 8] = (A[col * 9 + 8] - sum) / A[col * 9 + col];
-        }
-        for (int i = 0; i < 8; i++) h[i] = A[i * 9 + 8];
-        h[8] = 1;
+        const double x0 = __shfl_sync(gmask, xn, gbase), y0 = __shfl_sync(gmask, yn, gbase);
+        const double x1 = __shfl_sync(gmask, xn, gbase + 1), y1 = __shfl_sync(gmask, yn, gbase + 1);
+        const double x2 = __shfl_sync(gmask, xn, gbase + 2), y2 = __shfl_sync(gmask, yn, gbase + 2);
+        const double x3 = __shfl_sync(gmask, xn, gbase + 3), y3 = __shfl_sync(gmask, yn, gbase + 3);
+        const double sx = x0 - x1 + x2 - x3, sy = y0 - y1 + y2 - y3;
+        const double dx1 = x1 - x2, dx2 = x3 - x2, dy1 = y1 - y2, dy2 = y3 - y2;
+        const double den = dx1 * dy2 - dy1 * dx2;
+        ok = fabs(den) > 1e-300;
+        const double id = ok ? 1.0 / den : 0.0;
+        const double g = (sx * dy2 - sy * dx2) * id, hh = (dx1 * sy - dy1 * sx) * id;
+        // unit square (s, t) -> image: [a b c; d e f; g hh 1], with s = X / (2 half) + 1/2, t = Y / (2 half) + 1/2
+        const double ua = x1 - x0 + g * x1, ub = x3 - x0 + hh * x3, uc = x0;
+        const double ud = y1 - y0 + g * y1, ue = y3 - y0 + hh * y3, uf = y0;
+        const double i2 = 0.5 / a.half;
+        const double w = 1.0 + 0.5 * (g + hh);
+        const double iw = (ok && fabs(w) > 1e-300) ? 1.0 / w : 1.0;
+        h[0] = ua * i2 * iw; h[1] = ub * i2 * iw; h[2] = (uc + 0.5 * (ua + ub)) * iw;
+        h[3] = ud * i2 * iw; h[4] = ue * i2 * iw; h[5] = (uf + 0.5 * (ud + ue)) * iw;
+        h[6] = g * i2 * iw;  h[7] = hh * i2 * iw; h[8] = 1.0;
+        if (!ok) { h[0] = 1; h[1] = 0; h[2] = 0; h[3] = 0; h[4] = 1; h[5] = 0; h[6] = 0; h[7] = 0; }
     }
     // ---- decomposition as in OpenCV's planar branch: normalise h1, h2; t = h3 * 2/(|h1|+|h2|)
     double R[9], t[3];
@@ -289,26 +289,19 @@ k_pose(PoseArgs a) {
         residual(R, t, ru, rv, Jr, true);
         cost = grp_sum(ru * ru + rv * rv);
         for (iters = 0; iters < 100; iters++) {
-            double JtJ[36], Jtr[6];
+            double S[21], b[6];   // packed lower triangle of J^T J, and -J^T r
 #pragma unroll
             for (int i = 0; i < 6; i++) {
-                Jtr[i] = grp_sum(Jr[i] * ru + Jr[6 + i] * rv);
+                b[i] = -grp_sum(Jr[i] * ru + Jr[6 + i] * rv);
 #pragma unroll
-                for (int j = 0; j <= i; j++) {
-                    double s = grp_sum(Jr[i] * Jr[j] + Jr[6 + i] * Jr[6 + j]);
-                    JtJ[i * 6 + j] = s;
-                    JtJ[j * 6 + i] = s;
-                }
+                for (int j = 0; j <= i; j++) S[SYM(i, j)] = grp_sum(Jr[i] * Jr[j] + Jr[6 + i] * Jr[6 + j]);
             }
             bool improved = false;
             double step_norm = 0;
+            const double cost_before = cost;
             for (int tries = 0; tries < 12 && !improved; tries++) {
-                double Ad[36], b[6], d[6];
-#pragma unroll
-                for (int k = 0; k < 36; k++) Ad[k] = JtJ[k];
-#pragma unroll
-                for (int k = 0; k < 6; k++) { Ad[k * 6 + k] += lambda * (JtJ[k * 6 + k] + 1e-12); b[k] = -Jtr[k]; }
-                bool solved = solve6(Ad, b, d);
+                double d[6];
+                const bool solved = solve6_sym(S, lambda, b, d);
                 double Rn[9], tn[3], E[9];
                 double nru = 0, nrv = 0, ncost = 1e300;
                 if (solved) {
@@ -337,6 +330,7 @@ k_pose(PoseArgs a) {
             residual(R, t, ru, rv, Jr, true);
             double tn2 = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
             if (step_norm < 1e-11 * (1 + tn2)) { iters++; break; }   // quadratic convergence: the next step would be ~1e-20
+            if (cost_before - cost <= 1e-14 * cost_before) { iters++; break; }   // at the minimum: only rounding noise is left
         }
         orthogonalize(R);
     } else {

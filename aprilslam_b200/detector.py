@@ -165,6 +165,7 @@ class Detector:
         """frames: uint8 [B,H,W] (gray) or [B,H,W,3] (bgr=True) -> per-frame DET_DTYPE record arrays (a list-like)."""
         ch = 3 if bgr else 1
         ptr, on_dev, B, W, H, stride, stream, keep = self._frames(frames, ch)
+        self._last_width = W
         out = self._result_buffer(B, cap_per_frame, DET_DTYPE)
         counts = np.zeros(B, np.int32)
         fn = self._L.agpu_detect_bgr if bgr else self._L.agpu_detect
@@ -254,7 +255,7 @@ class Detector:
     def debug_fetch(self, what: str, frame: int = 0) -> np.ndarray:
         wd, hd = C.c_int(), C.c_int()
         self._check(self._L.agpu_debug_dims(self._h, C.byref(wd), C.byref(hd)))
-        dt = {"quad_im": np.uint8, "thresh": np.uint8, "labels": np.uint32, "sizes": np.uint32,
+        dt = {"gray": np.uint8, "quad_im": np.uint8, "thresh": np.uint8, "labels": np.uint32, "sizes": np.uint32,
               "cluster_keys": np.uint64, "cluster_sizes": np.int32, "quads": np.float32, "quads_refined": np.float32,
               "quad_keys": np.uint64}[what]
         per = {"quads": 9, "quads_refined": 8}.get(what, 1)
@@ -266,6 +267,8 @@ class Detector:
         if n2 < 0:
             self._check(int(n2))
         buf = buf[:int(n2) * per]
+        if what == "gray":
+            return buf.reshape(-1, self._last_width) if getattr(self, "_last_width", 0) else buf
         if what in ("quad_im", "thresh", "labels", "sizes"):
             return buf.reshape(hd.value, wd.value)
         if per > 1:

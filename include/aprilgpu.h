@@ -102,7 +102,9 @@ int agpu_detect(agpu_handle* h, const uint8_t* frames, int on_device, int B, int
                 void* cuda_stream, agpu_detection* out, int cap_per_frame, int* counts);
 
 /* Same, on interleaved BGR frames [B][H][W][3] (stride = bytes per row, >= 3*W); gray conversion
- * is cv2.cvtColor(BGR2GRAY)'s fixed-point formula, fused into the front end. */
+ * is cv2.cvtColor(BGR2GRAY)'s fixed-point formula.  At quad_decimate 1, 2 and 4 without blur it is fused into the strip
+ * kernel: gray conversion, decimation and threshold are ONE pass over the BGR bytes (k_decimate_threshold<F,.,.,3>);
+ * other settings convert first (k_pack) and continue on the gray plane. */
 int agpu_detect_bgr(agpu_handle* h, const uint8_t* frames, int on_device, int B, int W, int H, int stride,
                     void* cuda_stream, agpu_detection* out, int cap_per_frame, int* counts);
 
@@ -153,7 +155,7 @@ int agpu_get_counters(agpu_handle* h, long long* counters /* [8] */);
 int agpu_get_tier_stats(agpu_handle* h, long long* stats /* [8] */);
 
 /* Stage dumps for parity tests (cfg.debug = 1): buffers of frame `frame` of the LAST chunk.
- * what: "quad_im" u8[hd*wd], "thresh" u8[hd*wd], "labels" u32[hd*wd] (min-index representative),
+ * what: "gray" u8[H*W] (BGR input only: the converted full-resolution plane), "quad_im" u8[hd*wd], "thresh" u8[hd*wd], "labels" u32[hd*wd] (min-index representative),
  * "sizes" u32[hd*wd] (valid at representatives), "cluster_keys" u64[n], "cluster_sizes" i32[n],
  * "quads" f32[n*9] (8 corner coords + reversed flag), "quad_keys" u64[n].
  * Returns the number of ELEMENTS available (copying at most cap_bytes), or a negative status. */

@@ -560,3 +560,40 @@ def test_reference_run_through_the_gpu_chain():
     assert d.max() <= 0.06 and np.median(d.max(axis=1)) <= 0.006, (d.max(), np.median(d.max(axis=1)))
     graph.close()
     g.close()
+
+
+# ---- BGR frames: gray conversion fused into the strip kernel ------------------------------------------
+@pytest.mark.parametrize("W,H,d", [(640, 480, 1), (640, 480, 2), (644, 484, 4), (643, 481, 1), (333, 77, 2), (1000, 600, 3),
+                                   (1920, 1080, 1)])
+def test_bgr_frames_fused_gray_conversion(ob, W, H, d):
+    """uint8 [H,W,3] BGR in (the reference's input, tag_detector.py:25): the converted gray plane equals
+    cv2.cvtColor(BGR2GRAY) byte for byte, the threshold image equals the oracle's on that gray image, and the detections
+    equal the oracle's -- for the fused kernel (decimate 1, 2, 4; aligned and ragged widths) and the k_pack fallback (3)."""
+    import cv2
+    rng = np.random.default_rng(W + H + d)
+    gray0 = synth.render(synth.grid_scene(W, H, 21, (max(1, W // 220), max(1, H // 220)), px_range=(40, 90)))
+    bgr = np.repeat(gray0[..., None], 3, axis=2).astype(np.int16)
+    bgr += rng.integers(-25, 26, bgr.shape)                      # strong colour noise: the three weights all matter
+    bgr = np.ascontiguousarray(np.clip(bgr, 0, 255).astype(np.uint8))
+    bgr[:8, :8] = rng.integers(0, 256, (8, 8, 3))                # and fully random colours in a corner
+    gray = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+    g = Detector("tag36h11", decimate=float(d), debug=True)
+    recs = g.detect_batch(bgr, cap_per_frame=128, bgr=True)[0]
+    assert np.array_equal(g.debug_fetch("gray"), gray)
+    ref, dbg = ob.OracleDetector("tag36h11", decimate=float(d)).detect_records(gray, debug=True)
+    assert np.array_equal(g.debug_fetch("thresh"), dbg["thresh"])
+    assert np.array_equal(g.debug_fetch("quad_keys"), dbg["quad_keys"])
+    assert_same_detections(recs, ref)
+    # a batch of two frames in device memory with a padded row stride
+    import torch
+    pad = torch.zeros((2, H, W + 5, 3), dtype=torch.uint8, device="cuda")
+    pad[:, :, :W] = torch.from_numpy(bgr).cuda()
+    pad[:, :, W:] = 77
+    from aprilslam_b200 import _lib
+    out = np.zeros((2, 128), _lib.DET_DTYPE)
+    counts = np.zeros(2, np.int32)
+    rc = g._L.agpu_detect_bgr(g._h, pad.data_ptr(), 1, 2, W, H, (W + 5) * 3, torch.cuda.current_stream().cuda_stream,
+                              out.ctypes.data, 128, counts.ctypes.data)
+    assert rc == 0 and counts.tolist() == [len(ref), len(ref)]
+    assert_same_detections(out[1, :counts[1]], ref)
+    g.close()
