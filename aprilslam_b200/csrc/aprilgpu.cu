@@ -103,6 +103,22 @@ struct Slot {
     HostBuf h_out, h_counts, h_poses;
     bool pending = false, from_masks = false;
     int b0 = 0, n = 0, sorted = 0;
+    // CUDA graph of the whole per-chunk pipeline for the synchronous small-batch path (a webcam loop calls detect once
+    // per frame: ~30 launches and a dozen event calls per call otherwise).  Captured the second time a call with the
+    // same key arrives; any change of geometry, capacities, pose parameters or buffer addresses re-captures.
+    struct GraphKey {
+        int W, H, stride, channels, n, cap, maxcl, maxq, cap_out, id_bits, pose;
+        double K[9], dist[8], tag_size;
+        int ndist;
+        unsigned long long buffers;   // hash of every buffer address the kernels were given
+    };
+    GraphKey graph_key, seen_key;
+    bool have_seen = false, graph_launched = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaEvent_t ev_end = nullptr;
+    long long graph_launches = 0;
+    int graph_sorted = 0;
+    bool graph_from_masks = false;
 
     void release() {
         DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_labels, &d_canon, &d_sizes, &d_roots,
@@ -120,6 +136,10 @@ struct Slot {
             if (ev_join[t]) cudaEventDestroy(ev_join[t]);
             aux[t] = nullptr; ev_join[t] = nullptr;
         }
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+        if (ev_end) cudaEventDestroy(ev_end);
+        ev_end = nullptr;
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_mid) cudaEventDestroy(ev_mid);
         if (tail) cudaStreamDestroy(tail);
@@ -155,6 +175,8 @@ struct agpu_handle {
                                                        // measured +-0 on the whole pipeline, so the simpler byte image stays the default
         int tail_threads = 32;                         // CTA size of decode / reconcile / pose: small CTAs find room on SMs
                                                        // that the streaming kernels of the next chunk keep full
+        int graph = 1;                                 // CUDA graph for single-chunk calls of up to graph_max_frames frames
+        int graph_max_frames = 8;
     } tune;
     DevBuf d_fams, d_codes, d_pose_in, d_pose_out;
     std::vector<Slot> slots;
@@ -255,6 +277,7 @@ int init_slot(agpu_handle* h, Slot& s) {
     }
     CK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_mid, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_end, cudaEventDisableTiming));
     return AGPU_OK;
 }
 
@@ -591,7 +614,7 @@ int alloc_slot(agpu_handle* h, Slot& s, const CallCtx& c) {
 }
 
 // enqueue the whole pipeline of frames [b0, b0+n) on the slot's stream (no host synchronisation)
-int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
+int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     const Geom& g = c.g;
     const int chunk = c.chunk, cap = c.cap;
     int* d_cnt = sl.d_counters.as<int>();
@@ -795,6 +818,89 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     return AGPU_OK;
 }
 
+unsigned long long slot_buffer_hash(const agpu_handle* h, const Slot& s) {
+    const DevBuf* bufs[] = {&s.d_in, &s.d_gray, &s.d_quad_im, &s.d_blur_tmp, &s.d_blur_orig, &s.d_thresh, &s.d_masks, &s.d_l16, &s.d_labels,
+                            &s.d_canon, &s.d_sizes, &s.d_roots, &s.d_dense, &s.d_dense2rep, &s.d_recs[0], &s.d_recs[1], &s.d_hist,
+                            &s.d_dtot, &s.d_qscratch, &s.d_gsort, &s.d_counters, &s.d_clusters[0], &s.d_clusters[1], &s.d_clusters[2],
+                            &s.d_clusters[3], &s.d_quads, &s.d_dets, &s.d_out, &s.d_poses, &h->d_fams, &h->d_codes};
+    unsigned long long x = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { x = (x ^ v) * 1099511628211ull; };
+    for (const DevBuf* b : bufs) mix((unsigned long long)(uintptr_t)b->p);
+    mix((unsigned long long)(uintptr_t)s.h_out.p); mix((unsigned long long)(uintptr_t)s.h_counts.p); mix((unsigned long long)(uintptr_t)s.h_poses.p);
+    return x;
+}
+
+// One chunk: either enqueue its ~30 kernels, or -- for the synchronous small-batch path -- replay them as one CUDA graph.
+int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
+    sl.graph_launched = false;
+    const bool graphable = h->tune.graph && !h->profiling && !h->cfg.debug && b0 == 0 && n == c.B &&
+                           n <= h->tune.graph_max_frames && &sl == &h->slots[0];
+    if (!graphable) return enqueue_chunk(h, sl, c, b0, n);
+    // the frames are staged in the slot's own input buffer so that every address inside the graph is fixed
+    CK(sl.d_in.ensure(c.frame_bytes * c.chunk));
+    Slot::GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.W = c.W; key.H = c.H; key.stride = c.stride; key.channels = c.channels; key.n = n; key.cap = c.cap; key.maxcl = c.maxcl;
+    key.maxq = c.maxq; key.cap_out = c.cap_out; key.id_bits = c.id_bits; key.pose = c.pose->enabled ? 1 : 0;
+    if (c.pose->enabled) {
+        memcpy(key.K, c.pose->K, sizeof(key.K)); memcpy(key.dist, c.pose->dist, sizeof(key.dist));
+        key.tag_size = c.pose->tag_size; key.ndist = c.pose->ndist;
+    }
+    key.buffers = slot_buffer_hash(h, sl);
+    const bool replay = sl.graph_exec && memcmp(&key, &sl.graph_key, sizeof(key)) == 0;
+    const bool capture = !replay && sl.have_seen && memcmp(&key, &sl.seen_key, sizeof(key)) == 0;
+    if (!replay && !capture) {   // first sighting of this key: a plain run (it also sizes every workspace)
+        sl.seen_key = key;
+        sl.have_seen = true;
+        return enqueue_chunk(h, sl, c, b0, n);
+    }
+    CK(cudaMemcpyAsync(sl.d_in.p, c.frames, c.frame_bytes * n, c.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       sl.stream));
+    if (capture) {
+        if (sl.graph_exec) { cudaGraphExecDestroy(sl.graph_exec); sl.graph_exec = nullptr; }
+        CallCtx cg = c;
+        cg.frames = sl.d_in.as<uint8_t>();
+        cg.on_device = 1;
+        const long long before = h->launches;
+        CK(cudaStreamBeginCapture(sl.stream, cudaStreamCaptureModeRelaxed));
+        int rc = enqueue_chunk(h, sl, cg, 0, n);
+        if (rc == AGPU_OK) {   // the back half ends on the tail stream: join it into the origin stream
+            if (cudaEventRecord(sl.ev_end, sl.tail) != cudaSuccess || cudaStreamWaitEvent(sl.stream, sl.ev_end, 0) != cudaSuccess)
+                rc = AGPU_E_CUDA;
+        }
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ee = cudaStreamEndCapture(sl.stream, &graph);
+        sl.pending = false;
+        if (rc != AGPU_OK || ee != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (rc == AGPU_OK) { h->set_err(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ee)); rc = AGPU_E_CUDA; }
+            return rc;
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&sl.graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            sl.graph_exec = nullptr;
+            h->set_err(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+            return AGPU_E_CUDA;
+        }
+        sl.graph_key = key;
+        sl.graph_launches = h->launches - before;
+        h->launches = before;
+        sl.graph_sorted = sl.sorted;
+        sl.graph_from_masks = sl.from_masks;
+    }
+    CK(cudaGraphLaunch(sl.graph_exec, sl.stream));
+    h->launches += sl.graph_launches;
+    sl.graph_launched = true;
+    sl.pending = true;
+    sl.b0 = b0;
+    sl.n = n;
+    sl.sorted = sl.graph_sorted;
+    sl.from_masks = sl.graph_from_masks;
+    return AGPU_OK;
+}
+
 struct Overflow {
     int max_pts = 0, max_cl_per_frame = 0, max_q_per_frame = 0, max_dense = 0;
     bool any = false;
@@ -803,7 +909,8 @@ struct Overflow {
 // wait for the slot's chunk and move its results into the caller's arrays; 1 = a work list overflowed (redo)
 int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out, agpu_pose_t* poses, int* counts,
                  Overflow& ov, int& rc_final) {
-    CK(cudaStreamSynchronize(sl.tail));   // (ordered after everything on sl.stream through ev_mid)
+    CK(cudaStreamSynchronize(sl.graph_launched ? sl.stream : sl.tail));   // (the tail is ordered after everything on sl.stream
+                                                                           // through ev_mid; a graph is launched on sl.stream)
     sl.pending = false;
     const int n = sl.n, b0 = sl.b0, chunk = c.chunk;
     if (h->profiling) {
@@ -1071,6 +1178,7 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     h->cfg.families = h->families_str.c_str();
     if (const char* e = getenv("AGPU_PRIO")) h->tune.prio = atoi(e) != 0;
     if (const char* e = getenv("AGPU_MASKS")) h->tune.masks = atoi(e) != 0;
+    if (const char* e = getenv("AGPU_GRAPH")) h->tune.graph = atoi(e) != 0;
     if (const char* e = getenv("AGPU_EDGE_WARPS")) h->tune.edge_warps = atoi(e);
     if (const char* e = getenv("AGPU_BOUNDARY_WARPS")) h->tune.boundary_warps = atoi(e);
     if (const char* e = getenv("AGPU_TAIL_THREADS")) h->tune.tail_threads = atoi(e) >= 128 ? 128 : (atoi(e) >= 64 ? 64 : 32);

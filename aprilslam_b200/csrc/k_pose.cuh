@@ -136,7 +136,9 @@ __device__ bool orthogonalize(double (&R)[9]) {
 // Returns false when the damped matrix is not positive definite.
 #define SYM(i, j) ((i) * ((i) + 1) / 2 + (j))
 __device__ __forceinline__ bool solve6_sym(const double (&S)[21], double lambda, const double (&b)[6], double (&x)[6]) {
-    double L[21];
+    // (one reciprocal square root per column instead of a square root and up to eleven divisions: the FP64 divide chain
+    // was 60 % of the kernel's stall samples.  The step only has to be a descent step; the fixed point is unchanged.)
+    double L[21], inv[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
 #pragma unroll
@@ -147,9 +149,10 @@ __device__ __forceinline__ bool solve6_sym(const double (&S)[21], double lambda,
             for (int k = 0; k < j; k++) s -= L[SYM(i, k)] * L[SYM(j, k)];
             if (i == j) {
                 if (!(s > 0)) return false;
-                L[SYM(i, i)] = sqrt(s);
+                inv[i] = rsqrt(s);
+                L[SYM(i, i)] = s * inv[i];
             } else {
-                L[SYM(i, j)] = s / L[SYM(j, j)];
+                L[SYM(i, j)] = s * inv[j];
             }
         }
     }
@@ -159,14 +162,14 @@ __device__ __forceinline__ bool solve6_sym(const double (&S)[21], double lambda,
         double s = b[i];
 #pragma unroll
         for (int k = 0; k < i; k++) s -= L[SYM(i, k)] * y[k];
-        y[i] = s / L[SYM(i, i)];
+        y[i] = s * inv[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; i--) {
         double s = y[i];
 #pragma unroll
         for (int k = i + 1; k < 6; k++) s -= L[SYM(k, i)] * x[k];
-        x[i] = s / L[SYM(i, i)];
+        x[i] = s * inv[i];
     }
     return true;
 }
