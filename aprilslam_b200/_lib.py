@@ -69,6 +69,7 @@ def load():
     L = C.CDLL(LIB_PATH)
     vp, ci, cd = C.c_void_p, C.c_int, C.c_double
     L.agpu_version.restype = ci
+    L.agpu_family_info.argtypes = [C.c_char_p, vp, vp]
     L.agpu_default_config.argtypes = [C.POINTER(AgpuConfig)]
     L.agpu_default_config.restype = None
     L.agpu_create.argtypes = [C.POINTER(AgpuConfig), C.POINTER(vp)]
@@ -102,7 +103,7 @@ def load():
     return L
 
 
-EXPORTS = ["agpu_version", "agpu_default_config", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_detect",
+EXPORTS = ["agpu_version", "agpu_family_info", "agpu_default_config", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_detect",
            "agpu_detect_bgr", "agpu_detect_pose", "agpu_pose", "agpu_set_profiling", "agpu_get_stage_ms",
            "agpu_get_kernel_ms", "agpu_get_kernel_table", "agpu_get_timeline", "agpu_get_launch_count", "agpu_get_counters", "agpu_get_tier_stats", "agpu_debug_fetch", "agpu_debug_dims",
            "agpu_stage_threshold", "agpu_stage_labels", "agpu_render", "agpu_graph_create", "agpu_graph_reset",

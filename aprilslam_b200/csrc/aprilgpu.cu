@@ -177,6 +177,7 @@ struct agpu_handle {
                                                        // that the streaming kernels of the next chunk keep full
         int graph = 1;                                 // CUDA graph for single-chunk calls of up to graph_max_frames frames
         int graph_max_frames = 8;
+        int seg_tiles = 0, img_minb = 4, slots = 0;    // AGPU_SEG_TILES / AGPU_IMG_MINB / AGPU_SLOTS (0 = default), read once
     } tune;
     DevBuf d_fams, d_codes, d_pose_in, d_pose_out;
     std::vector<Slot> slots;
@@ -418,7 +419,7 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         const int nstrips = ceil_div(g.wp, strip_px);
         const int th = g.hd >> 2;
         int seg_tiles = fused_bgr ? 16 : 8;   // (a segment re-converts its two halo tile rows: longer segments for BGR)
-        if (const char* e = getenv("AGPU_SEG_TILES")) seg_tiles = std::max(1, atoi(e));
+        if (h->tune.seg_tiles > 0) seg_tiles = h->tune.seg_tiles;
         const int nsegs = ceil_div(th, seg_tiles);
         const long long warps = (long long)n * nstrips * nsegs;
         const int blocks = ceil_div(warps * 32, 128);
@@ -430,8 +431,7 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
         {
         KScope ks(h, sl, "k_decimate_threshold", sl.stream);
         uint8_t* th_out = sl.d_thresh.as<uint8_t>();
-        int minb = 4;
-        if (const char* e = getenv("AGPU_IMG_MINB")) minb = atoi(e);
+        const int minb = h->tune.img_minb;
 #define LAUNCH_DT(FF, MB) k_decimate_threshold<FF, MB><<<blocks, 128, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, quad_out, \
                                                                                th_out, g, nstrips, nsegs, seg_tiles, n, md, vec_ok)
         if (fused_bgr) {
@@ -734,7 +734,11 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             qa.list = sl.d_clusters[t].as<ClusterRef>();
             qa.list_count = d_cnt + CNT_TIER0 + t;
             qa.cursor = d_cnt + CNT_CURSOR0 + t;
-            const int nblk = h->num_sms * h->tune.tier_ctas[t];
+            // persistent groups: a full machine's worth for big chunks, no more than the chunk can keep busy for small ones
+            // (a single 640x480 frame would otherwise launch 4000 CTAs whose only act is to find the work list empty)
+            static const int per_frame[AGPU_NTIERS] = {32, 96, 48, 12};   // per 320x240 working pixels
+            const long long area = std::max<long long>(1, (long long)g.plane / 76800);
+            const int nblk = std::max(1, (int)std::min<long long>((long long)h->num_sms * h->tune.tier_ctas[t], n * area * per_frame[t]));
             {   // this tier's slice of the per-group scratch (tiers are visited from the last to the first)
                 size_t off = 0;
                 for (int u = AGPU_NTIERS - 1; u > t; u--) off += (size_t)h->num_sms * h->tune.tier_ctas[u] * (u == 0 ? 8 : 1) * tier_cap[u];
@@ -777,7 +781,9 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         da.dbg_refined = h->cfg.debug ? sl.d_refined.as<float>() : nullptr;
         {
             KScope ks(h, sl, "k_decode_quads", sl.tail);
-            k_decode_quads<<<h->num_sms * h->tune.decode_ctas * (128 / h->tune.tail_threads), h->tune.tail_threads, 0, sl.tail>>>(da, h->prm);
+            const int dec_blocks = (int)std::min<long long>((long long)h->num_sms * h->tune.decode_ctas * (128 / h->tune.tail_threads),
+                                                            std::max(1LL, (long long)n * std::max<long long>(1, (long long)g.plane / 76800) * 256 * 32 / h->tune.tail_threads));
+            k_decode_quads<<<dec_blocks, h->tune.tail_threads, 0, sl.tail>>>(da, h->prm);
         }
         LAUNCH_CHECK("k_decode_quads");
     }
@@ -976,9 +982,9 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
         }
         h->counters[0] += h_npts[i] + h_ndups[i];   // raw edge points, as upstream counts them
         h->counters[3] += h_nd[i];
-        if (h_nd[i] > REC_CAP) {
-            h->set_err("more than 256 raw detections in one frame");
-            rc_final = AGPU_E_WORKSPACE;
+        if (h_nd[i] > REC_CAP && rc_final == AGPU_OK) {   // (upstream has no such limit; the frame keeps its first 256 candidates)
+            h->set_err("more than 256 raw detections (before reconcile) in one frame: the surplus was dropped");
+            rc_final = AGPU_E_TRUNCATED;
         }
     }
     for (int t = 0; t < AGPU_NTIERS; t++) h->counters[1] += hc[CNT_TIER0 + t];
@@ -1054,7 +1060,7 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
     chunk = std::min(chunk, B);
     c.chunk = chunk;
     int nslots = h->cfg.pipeline_slots > 0 ? h->cfg.pipeline_slots : (on_device ? 3 : 4);
-    if (const char* e = getenv("AGPU_SLOTS")) nslots = std::max(1, atoi(e));
+    if (h->tune.slots > 0) nslots = h->tune.slots;
     nslots = std::min(nslots, 8);
     nslots = std::min(nslots, ceil_div(B, chunk));
     if ((int)h->slots.size() < nslots) h->slots.resize(nslots);   // (slots are only ever appended: buffers stay put)
@@ -1179,8 +1185,18 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     if (const char* e = getenv("AGPU_PRIO")) h->tune.prio = atoi(e) != 0;
     if (const char* e = getenv("AGPU_MASKS")) h->tune.masks = atoi(e) != 0;
     if (const char* e = getenv("AGPU_GRAPH")) h->tune.graph = atoi(e) != 0;
-    if (const char* e = getenv("AGPU_EDGE_WARPS")) h->tune.edge_warps = atoi(e);
-    if (const char* e = getenv("AGPU_BOUNDARY_WARPS")) h->tune.boundary_warps = atoi(e);
+    // (experiment knobs: parsed once, clamped to what the kernels are instantiated for -- nothing here can divide by zero)
+    auto pow2_knob = [](const char* name, int dflt) {
+        const char* e = getenv(name);
+        if (!e) return dflt;
+        const int v = atoi(e);
+        return (v == 1 || v == 2 || v == 4 || v == 8) ? v : dflt;
+    };
+    h->tune.edge_warps = pow2_knob("AGPU_EDGE_WARPS", h->tune.edge_warps);
+    h->tune.boundary_warps = pow2_knob("AGPU_BOUNDARY_WARPS", h->tune.boundary_warps);
+    if (const char* e = getenv("AGPU_SEG_TILES")) h->tune.seg_tiles = std::max(0, std::min(256, atoi(e)));
+    if (const char* e = getenv("AGPU_IMG_MINB")) { const int v = atoi(e); h->tune.img_minb = (v >= 3 && v <= 6) ? v : 4; }
+    if (const char* e = getenv("AGPU_SLOTS")) h->tune.slots = std::max(0, std::min(8, atoi(e)));
     if (const char* e = getenv("AGPU_TAIL_THREADS")) h->tune.tail_threads = atoi(e) >= 128 ? 128 : (atoi(e) >= 64 ? 64 : 32);
     if (const char* e = getenv("AGPU_DECODE_CTAS")) h->tune.decode_ctas = std::max(1, std::min(16, atoi(e)));
     if (const char* e = getenv("AGPU_TIER_CAP")) {
@@ -1440,6 +1456,17 @@ int agpu_get_counters(agpu_handle* h, long long* counters) {
 int agpu_get_tier_stats(agpu_handle* h, long long* stats) {
     if (!h || !stats) return AGPU_E_INVALID;
     for (int i = 0; i < 8; i++) stats[i] = h->tier_stats[i];
+    return AGPU_OK;
+}
+
+int agpu_family_info(const char* family, int* ncodes, int* ncodes_upstream) {
+    if (!family) return AGPU_E_INVALID;
+    const FamilyDef* f = find_family(family);
+    if (!f) return AGPU_E_INVALID;
+    if (ncodes) *ncodes = f->ncodes;
+    // tagStandard41h12: upstream's table has 2115 code words; only ids 0..4 (read off the reference's own tag images) are
+    // available offline, so ids >= 5 can never be reported
+    if (ncodes_upstream) *ncodes_upstream = std::string(family) == "tagStandard41h12" ? 2115 : f->ncodes;
     return AGPU_OK;
 }
 

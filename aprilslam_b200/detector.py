@@ -55,6 +55,33 @@ class FrameLists(_SequenceABC):
         return "FrameLists(%d frames, %d records)" % (len(self), int(self._n.sum()))
 
 
+def _calibrate_pool_idle_refs():
+    """Reference count `sys.getrefcount(pool[i])` reports for an array that only a pool list refers to, measured on this
+    interpreter instead of assumed; None (no pooling: every call gets a fresh buffer) where reference counts do not exist
+    or do not move when a second reference appears."""
+    getref = getattr(sys, "getrefcount", None)
+    if getref is None:
+        return None
+    pool = [np.empty((1, 1), np.uint8)]
+    idle = getref(pool[0])
+    extra = pool[0][0, :1]          # a view, as FrameLists hands out: must raise the count
+    busy = getref(pool[0])
+    del extra
+    return idle if busy > idle and getref(pool[0]) == idle else None
+
+
+_POOL_IDLE_REFS = _calibrate_pool_idle_refs()
+
+
+def family_code_counts(family: str):
+    """(code words shipped, code words of upstream's family table) -- they differ for tagStandard41h12 (ids 0..4 only)."""
+    L = _lib.load()
+    a, b = C.c_int(), C.c_int()
+    if L.agpu_family_info(family.encode(), C.byref(a), C.byref(b)) != 0:
+        return 0, 0
+    return a.value, b.value
+
+
 def _is_torch_cuda(x) -> bool:
     return hasattr(x, "data_ptr") and hasattr(x, "is_cuda") and bool(x.is_cuda)
 
@@ -95,10 +122,22 @@ class Detector:
             raise RuntimeError((self._L.agpu_last_error(None) or b"agpu_create failed").decode())
         self._h = h
         self.device = int(device)
+        self._graphs = []     # weak references to the tag graphs that live on this handle (closed before it)
+        for f in self.families:
+            have, full = family_code_counts(f)
+            if have < full:
+                import warnings
+                warnings.warn("%s: only %d of upstream's %d code words are available offline (ids 0..%d); tags with other "
+                              "ids will not be reported" % (f, have, full, have - 1), RuntimeWarning, stacklevel=2)
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
+            for ref in getattr(self, "_graphs", []):      # a graph holds the C handle: close it first
+                g = ref()
+                if g is not None:
+                    g.close()
+            self._graphs = []
             self._L.agpu_destroy(self._h)
             self._h = None
 
@@ -152,11 +191,13 @@ class Detector:
         circulation -- results never change under a caller's feet)."""
         key = (B, cap, dtype.str if hasattr(dtype, "str") else str(dtype))
         pool = self._pool.setdefault(key, [])
-        for i in range(len(pool)):
-            if sys.getrefcount(pool[i]) == 2:          # the pool's own reference + getrefcount's argument
-                return pool[i]
+        getref = getattr(sys, "getrefcount", None)
+        if getref is not None and _POOL_IDLE_REFS is not None:
+            for i in range(len(pool)):
+                if getref(pool[i]) == _POOL_IDLE_REFS:     # nothing but the pool refers to it (count calibrated at import)
+                    return pool[i]
         buf = np.empty((B, cap), dtype)
-        if len(pool) < 4:
+        if getref is not None and _POOL_IDLE_REFS is not None and len(pool) < 4:
             pool.append(buf)
         return buf
 

@@ -38,6 +38,8 @@ class SLAMGraphBatch:
         h = C.c_void_p()
         detector._check(self._L.agpu_graph_create(detector._h, self.nstreams, self.max_tag_id, C.byref(h)))
         self._g = h
+        import weakref
+        detector._graphs.append(weakref.ref(self))     # Detector.close() closes its graphs before the handle goes away
 
     def close(self):
         if getattr(self, "_g", None):

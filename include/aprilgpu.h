@@ -38,7 +38,8 @@ typedef enum agpu_status {
     AGPU_OK = 0,
     AGPU_E_INVALID = -1,    /* bad argument (NULL, non-positive size, unknown family, ...) */
     AGPU_E_CUDA = -2,       /* CUDA runtime error or no device */
-    AGPU_E_TRUNCATED = -3,  /* more detections than cap_per_frame in at least one frame; counts[] hold the true numbers */
+    AGPU_E_TRUNCATED = -3,  /* more detections than cap_per_frame in at least one frame (counts[] hold the true numbers), or more
+                               than 256 decoded candidates in one frame before reconcile (the surplus was dropped) */
     AGPU_E_WORKSPACE = -4,  /* an internal per-frame work list overflowed (edge points / clusters / quads); raise the agpu_config limits */
     AGPU_E_UNSUPPORTED = -5
 } agpu_status;
@@ -48,7 +49,7 @@ typedef struct agpu_handle agpu_handle;
 /* Constructor arguments.  The first block mirrors upstream's Python ctor exactly (defaults in
  * parentheses are what AprilSLAM gets, because it passes only the family name). */
 typedef struct agpu_config {
-    const char* families;     /* space separated: tag36h11 tag25h9 tag16h5 tagStandard41h12 */
+    const char* families;     /* space separated: tag36h11 tag25h9 tag16h5 tagStandard41h12 (ids 0..4 only, see agpu_family_info) */
     int threads;              /* (1)  accepted for API compatibility, ignored */
     int maxhamming;           /* (1)  0..2 */
     float quad_decimate;      /* (2.0) integer factors >= 1 */
@@ -88,6 +89,12 @@ typedef struct agpu_pose_t {
 } agpu_pose_t;
 
 int agpu_version(void);
+/* Code words a built-in family ships with, and how many upstream's table has.  They differ for tagStandard41h12 (the
+ * reference's default tag_type, tag_detector.py:17): upstream has 2115 code words, only ids 0..4 -- decoded from the
+ * reference's own assets/tags/tag0..4.png -- are available offline, so a detector of that family reports ids 0..4 only
+ * (everything the reference's simulator scene contains; NOT a drop-in for tags with id >= 5).  tag36h11 (587), tag25h9
+ * (35) and tag16h5 (30) are complete. */
+int agpu_family_info(const char* family, int* ncodes, int* ncodes_upstream);
 void agpu_default_config(agpu_config* cfg);
 int agpu_create(const agpu_config* cfg, agpu_handle** out);
 int agpu_destroy(agpu_handle* h);

@@ -116,3 +116,16 @@ def test_gpu_graph_after_detection_matches_oracle():
         assert np.array_equal(st["weight"], graphs[s].weight)
     gb.close()
     det.close()
+
+
+@pytest.mark.gpu
+def test_closing_the_detector_closes_its_graphs_first_and_41h12_warns():
+    from aprilslam_b200.detector import Detector
+    from aprilslam_b200.slam_graph import SLAMGraphBatch
+    with pytest.warns(RuntimeWarning, match="only 5 of upstream's 2115 code words"):
+        det = Detector("tagStandard41h12", decimate=2.0)
+    g = SLAMGraphBatch(det, nstreams=2, max_tag_id=4)
+    det.close()                      # must not leave g with a dangling C handle
+    assert g._g is None
+    g.close()                        # idempotent
+    del g

@@ -196,3 +196,28 @@ def test_bind_to_gpu_numa_degrades_without_nvml():
     if n == 0:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+def test_family_info_reports_the_truncated_41h12_codebook():
+    """tagStandard41h12 (the reference's default tag_type) ships with ids 0..4 only; the C ABI and the Python layer say so."""
+    from aprilslam_b200.detector import family_code_counts
+    assert family_code_counts("tagStandard41h12") == (5, 2115)
+    assert family_code_counts("tag36h11") == (587, 587)
+    assert family_code_counts("tag25h9") == (35, 35) and family_code_counts("tag16h5") == (30, 30)
+    assert family_code_counts("tag99h1") == (0, 0)
+
+
+def test_result_pool_reference_count_is_calibrated():
+    """Pooled result buffers are recycled when nothing but the pool refers to them; the idle reference count is measured on
+    this interpreter (not a magic constant), and a live per-frame view keeps a buffer out of circulation."""
+    import sys
+    import numpy as np
+    from aprilslam_b200 import detector
+    assert detector._POOL_IDLE_REFS is not None
+    pool = [np.empty((4, 4), np.uint8)]
+    idle = sys.getrefcount(pool[0])          # (taken outside `assert`: pytest's rewriting would hold a reference of its own)
+    view = pool[0][1, :2]
+    busy = sys.getrefcount(pool[0])
+    del view
+    idle_again = sys.getrefcount(pool[0])
+    assert idle == idle_again == detector._POOL_IDLE_REFS and busy > idle
