@@ -97,8 +97,8 @@ struct Slot {
     std::vector<KEv> kev;              // profiling only: one event pair around EVERY kernel launch of the chunk
     size_t kev_next = 0;
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_labels, d_canon, d_sizes, d_roots, d_dense, d_dense2rep;
-    DevBuf d_recs[2], d_hist, d_dtot, d_qscratch, d_gsort;
-    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk]
+    DevBuf d_recs[2], d_hist, d_dtot, d_qscratch, d_gsort, d_pairslots, d_pairkeys;
+    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk], ncl[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
     bool pending = false, from_masks = false;
@@ -107,7 +107,7 @@ struct Slot {
     // per frame: ~30 launches and a dozen event calls per call otherwise).  Captured the second time a call with the
     // same key arrives; any change of geometry, capacities, pose parameters or buffer addresses re-captures.
     struct GraphKey {
-        int W, H, stride, channels, n, cap, maxcl, maxq, cap_out, id_bits, pose;
+        int W, H, stride, channels, n, cap, maxcl, maxq, cap_out, cid_passes, cap_keys, pose;
         double K[9], dist[8], tag_size;
         int ndist;
         unsigned long long buffers;   // hash of every buffer address the kernels were given
@@ -122,7 +122,7 @@ struct Slot {
 
     void release() {
         DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_labels, &d_canon, &d_sizes, &d_roots,
-                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_hist, &d_dtot, &d_qscratch, &d_gsort, &d_counters,
+                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_hist, &d_dtot, &d_qscratch, &d_gsort, &d_pairslots, &d_pairkeys, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
         for (DevBuf* bb : bufs) bb->release();
@@ -187,13 +187,14 @@ struct agpu_handle {
 
     // growable per-frame list capacities (0 = not chosen yet)
     int cap_points = 0, cap_clusters = 0, cap_quads = 0;
-    // most dense component ids seen in a frame so far (-1: nothing seen): decides between 11-bit ids (two radix
-    // passes) and 16-bit ids (three); a chunk whose frames do not fit is simply run again with wider ids
-    int max_dense_seen = -1;
+    // most clusters (distinct component pairs) seen in a frame so far (-1: nothing seen): decides between one radix
+    // pass over 11-bit cluster ids and two; a chunk whose frames do not fit is simply run again with two passes
+    int max_dense_seen = -1, max_clusters_seen = -1;
+    int cap_keys = 0;   // cluster-id capacity per frame (grows like the other work lists)
 
     // state of the last finished chunk (debug fetch)
     Geom geom;
-    int last_slot = 0, last_chunk = 0, last_cap = 0, last_id_bits = 16;
+    int last_slot = 0, last_chunk = 0, last_cap = 0, last_cap_keys = 0;
     bool have_last = false, last_from_masks = false, last_bgr = false;
 
     void set_err(const std::string& s) { err = s; }
@@ -565,7 +566,8 @@ struct CallCtx {   // constants of one agpu_detect* call
     size_t frame_bytes;
     Geom g;
     int chunk, cap, maxcl, maxq, cap_out, key_bits, nblk_max;
-    int id_bits;   // bits per dense component id in the pair key (11: two sort passes, 16: three)
+    int cid_passes;   // radix passes over the cluster id: 1 (ids < 2048) or 2
+    int cap_keys;     // cluster ids per frame the pair table can hand out
     size_t ncnt;
     const PoseSpec* pose;
 };
@@ -579,6 +581,8 @@ int alloc_slot(agpu_handle* h, Slot& s, const CallCtx& c) {
     CK(s.d_hist.ensure((size_t)chunk * RS_RADIX * c.nblk_max * 4));
     CK(s.d_dtot.ensure((size_t)chunk * RS_RADIX * 4));
     CK(s.d_dense2rep.ensure((size_t)chunk * AGPU_MAX_DENSE * 4));
+    CK(s.d_pairkeys.ensure((size_t)chunk * c.cap_keys * 4));
+    CK(s.d_pairslots.ensure((size_t)chunk * c.cap_keys * 4 * 8));   // open addressing at <= 25 % load
     {   // quad-fit scratch: 56 bytes per point of the largest cluster of its tier for every persistent GROUP (re-used
         // cluster after cluster, so it lives in L2), not per edge point of the chunk
         const int max_cluster = 3 * (2 * c.g.wd + 2 * c.g.hd);
@@ -625,6 +629,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int* d_ndense = d_out_counts + chunk;
     int* d_nroots = d_ndense + chunk;          // CC_SUBLISTS counters per frame
     int* d_ndups = d_nroots + CC_SUBLISTS * chunk;   // merged duplicate points per frame (raw points = npts + ndups)
+    int* d_ncl = d_ndups + chunk;                     // cluster ids handed out per frame
     StageTimer tm(h, sl);
     sl.kev_next = 0;
     tm.mark();  // 0
@@ -637,6 +642,10 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         d_src = sl.d_in.as<uint8_t>();
     }
     CK(cudaMemsetAsync(d_cnt, 0, c.ncnt * 4, sl.stream));
+    CK(cudaMemsetAsync(sl.d_pairslots.p, 0xff, (size_t)n * c.cap_keys * 4 * 8, sl.stream));
+    PairTable ptab;
+    ptab.slots = sl.d_pairslots.as<unsigned long long>(); ptab.keys = sl.d_pairkeys.as<uint32_t>(); ptab.ncl = d_ncl;
+    ptab.nslots = c.cap_keys * 4; ptab.cap_keys = c.cap_keys;
     tm.mark();  // 1: after H2D
     const uint8_t *quad_im, *gray_full;
     size_t q_pitch, q_frame, gray_pitch, gray_frame;
@@ -652,7 +661,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         const int ew = h->tune.edge_warps;
         dim3 grid(n, ceil_div(cc_tiles_x(g), ew), cc_tiles_y(g));
 #define LAUNCH_EDGES(EW) k_edges<EW><<<grid, EW * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), \
-            sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g, sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, cap, c.id_bits)
+            sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g, sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, cap, ptab)
         {
             KScope ks(h, sl, "k_edges", sl.stream);
             if (ew == 1) LAUNCH_EDGES(1); else if (ew == 2) LAUNCH_EDGES(2); else if (ew == 4) LAUNCH_EDGES(4); else LAUNCH_EDGES(8);
@@ -662,7 +671,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     }
     tm.mark();  // 4: after edges
     int cur = 0;
-    for (int shift = 32; shift < 32 + 2 * c.id_bits; shift += RS_BITS) {   // the 2*id_bits key bits: 2 or 3 passes of 11 bits
+    for (int shift = 32; shift < 32 + c.cid_passes * RS_BITS; shift += RS_BITS) {   // the cluster id: one 11-bit pass, or two
         dim3 grid(c.nblk_max, n);
         {
             KScope ks(h, sl, "k_sort_hist", sl.stream);
@@ -702,13 +711,17 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         cl.dbg_heads = h->cfg.debug ? sl.d_dbg_heads.as<ClusterRef>() : nullptr;
         cl.cap_dbg = (int)(sl.d_dbg_heads.bytes / sizeof(ClusterRef));
         dim3 grid(std::max(1, std::min(64, ceil_div(cap, 256))), n);   // grid-stride over the live points
-        {
+        if (c.cid_passes == 1) {   // the digit totals of the single pass are the cluster sizes
+            KScope ks(h, sl, "k_cluster_refs", sl.stream);
+            k_cluster_refs<<<n, 256, 0, sl.stream>>>(sl.d_dtot.as<uint32_t>(), d_ncl, g, std::max(h->prm.min_cluster_pixels, 24), cl);
+        } else {
             KScope ks(h, sl, "k_cluster_heads", sl.stream);
             k_cluster_heads<<<grid, 256, 0, sl.stream>>>(srecs, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
         }
         LAUNCH_CHECK("k_cluster_heads");
         QuadFitArgs qa;
-        qa.recs = srecs; qa.dense2rep = sl.d_dense2rep.as<uint32_t>(); qa.id_bits = c.id_bits; qa.cap = cap;
+        qa.recs = srecs; qa.dense2rep = sl.d_dense2rep.as<uint32_t>(); qa.pair_keys = sl.d_pairkeys.as<uint32_t>();
+        qa.cap_keys = c.cap_keys; qa.cap = cap;
         qa.quad_im = quad_im; qa.q_pitch = q_pitch; qa.q_frame = q_frame;
         qa.g = g;
         qa.list_cap = n * c.maxcl;
@@ -827,7 +840,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
 unsigned long long slot_buffer_hash(const agpu_handle* h, const Slot& s) {
     const DevBuf* bufs[] = {&s.d_in, &s.d_gray, &s.d_quad_im, &s.d_blur_tmp, &s.d_blur_orig, &s.d_thresh, &s.d_masks, &s.d_l16, &s.d_labels,
                             &s.d_canon, &s.d_sizes, &s.d_roots, &s.d_dense, &s.d_dense2rep, &s.d_recs[0], &s.d_recs[1], &s.d_hist,
-                            &s.d_dtot, &s.d_qscratch, &s.d_gsort, &s.d_counters, &s.d_clusters[0], &s.d_clusters[1], &s.d_clusters[2],
+                            &s.d_dtot, &s.d_qscratch, &s.d_gsort, &s.d_pairslots, &s.d_pairkeys, &s.d_counters, &s.d_clusters[0], &s.d_clusters[1], &s.d_clusters[2],
                             &s.d_clusters[3], &s.d_quads, &s.d_dets, &s.d_out, &s.d_poses, &h->d_fams, &h->d_codes};
     unsigned long long x = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { x = (x ^ v) * 1099511628211ull; };
@@ -847,7 +860,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     Slot::GraphKey key;
     memset(&key, 0, sizeof(key));
     key.W = c.W; key.H = c.H; key.stride = c.stride; key.channels = c.channels; key.n = n; key.cap = c.cap; key.maxcl = c.maxcl;
-    key.maxq = c.maxq; key.cap_out = c.cap_out; key.id_bits = c.id_bits; key.pose = c.pose->enabled ? 1 : 0;
+    key.maxq = c.maxq; key.cap_out = c.cap_out; key.cid_passes = c.cid_passes; key.cap_keys = c.cap_keys; key.pose = c.pose->enabled ? 1 : 0;
     if (c.pose->enabled) {
         memcpy(key.K, c.pose->K, sizeof(key.K)); memcpy(key.dist, c.pose->dist, sizeof(key.dist));
         key.tag_size = c.pose->tag_size; key.ndist = c.pose->ndist;
@@ -908,7 +921,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
 }
 
 struct Overflow {
-    int max_pts = 0, max_cl_per_frame = 0, max_q_per_frame = 0, max_dense = 0;
+    int max_pts = 0, max_cl_per_frame = 0, max_q_per_frame = 0, max_ncl = 0;
     bool any = false;
 };
 
@@ -948,6 +961,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     const int* h_oc = h_nd + chunk;
     const int* h_ndense = h_oc + chunk;
     const int* h_ndups = h_ndense + chunk + CC_SUBLISTS * chunk;
+    const int* h_ncl = h_ndups + chunk;
     int max_dense = 0;
     for (int i = 0; i < n; i++) max_dense = std::max(max_dense, h_ndense[i]);
     if (max_dense > AGPU_MAX_DENSE) {
@@ -958,8 +972,12 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     int max_pts = 0, max_cl = 0;
     for (int i = 0; i < n; i++) max_pts = std::max(max_pts, h_npts[i]);
     for (int t = 0; t < AGPU_NTIERS; t++) max_cl = std::max(max_cl, hc[CNT_TIER0 + t]);
+    int max_ncl = 0;
+    for (int i = 0; i < n; i++) max_ncl = std::max(max_ncl, h_ncl[i]);
+    h->max_clusters_seen = std::max(h->max_clusters_seen, max_ncl);
     bool redo = false;
-    if (max_dense > (1 << c.id_bits)) { ov.max_dense = std::max(ov.max_dense, max_dense); redo = true; }   // ids did not fit the key
+    // cluster ids did not fit the radix passes, or the pair table ran out of ids: run the chunk again
+    if (max_ncl > (1 << (RS_BITS * c.cid_passes)) || max_ncl > c.cap_keys) { ov.max_ncl = std::max(ov.max_ncl, max_ncl); redo = true; }
     if (max_pts > c.cap) { ov.max_pts = std::max(ov.max_pts, max_pts); redo = true; }
     if (max_cl > n * c.maxcl) { ov.max_cl_per_frame = std::max(ov.max_cl_per_frame, (max_cl + n - 1) / n); redo = true; }
     if (hc[CNT_NQUADS] > n * c.maxq) { ov.max_q_per_frame = std::max(ov.max_q_per_frame, (hc[CNT_NQUADS] + n - 1) / n); redo = true; }
@@ -995,7 +1013,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     h->last_slot = (int)(&sl - h->slots.data());
     h->last_chunk = n;
     h->last_cap = c.cap;
-    h->last_id_bits = c.id_bits;
+    h->last_cap_keys = c.cap_keys;
     h->last_from_masks = sl.from_masks;
     h->last_bgr = c.channels == 3;
     h->have_last = true;
@@ -1072,8 +1090,9 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
     c.cap = (c.cap + RS_TILE - 1) / RS_TILE * RS_TILE;
     c.maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
     c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
-    c.ncnt = CNT_FIXED + (size_t)(6 + CC_SUBLISTS) * chunk;
-    c.id_bits = (h->max_dense_seen >= 0 && h->max_dense_seen <= 1536) ? 11 : 16;
+    c.ncnt = CNT_FIXED + (size_t)(7 + CC_SUBLISTS) * chunk;
+    c.cid_passes = (h->max_clusters_seen >= 0 && h->max_clusters_seen <= RS_RADIX * 3 / 4) ? 1 : 2;
+    c.cap_keys = std::max(h->cap_keys, 4096);
     c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
     if (on_device) {   // order every slot stream after the producer's stream
@@ -1095,7 +1114,7 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
             if (rc) return rc;
             if (on_device) CK(cudaStreamWaitEvent(h->slots[s].stream, h->ev_user, 0));
         }
-        h->cap_points = c.cap; h->cap_clusters = c.maxcl; h->cap_quads = c.maxq;
+        h->cap_points = c.cap; h->cap_clusters = c.maxcl; h->cap_quads = c.maxq; h->cap_keys = c.cap_keys;
         Overflow ov;
         redo.clear();
         size_t next = 0;
@@ -1128,7 +1147,13 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
             if (!auto_cl) { h->set_err("cluster list overflow: raise agpu_config.max_clusters_per_frame"); return AGPU_E_WORKSPACE; }
             c.maxcl = ov.max_cl_per_frame * 2;
         }
-        if (ov.max_dense > (1 << c.id_bits)) c.id_bits = 16;
+        if (ov.max_ncl > (1 << (RS_BITS * c.cid_passes))) c.cid_passes = 2;
+        if (ov.max_ncl > c.cap_keys) {
+            int ck = c.cap_keys;
+            while (ck < ov.max_ncl + ov.max_ncl / 4) ck *= 2;
+            if (ck > (1 << 22)) { h->set_err("more than 4M edge clusters in one frame"); return AGPU_E_WORKSPACE; }
+            c.cap_keys = ck;
+        }
         if (ov.max_q_per_frame > c.maxq) {
             if (!auto_q) { h->set_err("quad list overflow: raise agpu_config.max_quads_per_frame"); return AGPU_E_WORKSPACE; }
             c.maxq = ov.max_q_per_frame * 2;
@@ -1574,11 +1599,14 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
         std::vector<uint32_t> d2r(AGPU_MAX_DENSE);
         cudaMemcpy(d2r.data(), sl.d_dense2rep.as<uint32_t>() + (size_t)frame * AGPU_MAX_DENSE, AGPU_MAX_DENSE * 4,
                    cudaMemcpyDeviceToHost);
+        std::vector<uint32_t> pk((size_t)h->last_cap_keys);
+        cudaMemcpy(pk.data(), sl.d_pairkeys.as<uint32_t>() + (size_t)frame * h->last_cap_keys, (size_t)h->last_cap_keys * 4,
+                   cudaMemcpyDeviceToHost);
         std::vector<std::pair<unsigned long long, int>> v;
         for (const ClusterRef& r : heads)
             if (r.frame == frame) {
-                const uint32_t ck = (uint32_t)(recs[r.start] >> 32);
-                const uint32_t ra = d2r[ck >> h->last_id_bits], rb = d2r[ck & ((1u << h->last_id_bits) - 1u)];
+                const uint32_t ck = pk[(uint32_t)(recs[r.start] >> 32)];   // cluster id -> pair of dense component ids
+                const uint32_t ra = d2r[ck >> 16], rb = d2r[ck & 0xffffu];
                 int raw = r.size;   // upstream's cluster size counts the duplicate points that k_edges merged
                 for (int i = 0; i < r.size; i++) raw += ((uint32_t)recs[r.start + i] >> 28) >= 8u;
                 v.push_back({unpitch_key(((unsigned long long)std::max(ra, rb) << 32) | std::min(ra, rb)), raw});

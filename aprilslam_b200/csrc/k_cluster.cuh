@@ -13,6 +13,54 @@
 #include "common.cuh"
 #include "k_cc.cuh"
 
+// Cluster ids.  A cluster is the set of edge points between one PAIR of components; its sort key used to be the pair of
+// dense component ids (2 x 11 or 2 x 16 bits: two or three radix passes).  The pairs that actually occur are few --
+// a few hundred per frame, a few thousand under sensor noise -- so k_edges renames them on the fly: a per-frame
+// open-addressing table maps the 32-bit pair key to a CLUSTER ID handed out in order of first appearance, and the record
+// carries that id.  The radix sort then needs ONE 11-bit pass for up to 2048 clusters per frame (two passes beyond), and
+// with a single pass the digit histogram IS the table of cluster sizes and the digit offsets ARE the cluster starts, so
+// no pass over the sorted records is needed to find the cluster heads (k_cluster_refs).
+struct PairTable {
+    unsigned long long* slots;   // [nframes][nslots] (pair key << 32) | cluster id; all ones = empty
+    uint32_t* keys;              // [nframes][cap_keys] cluster id -> pair key (max dense id << 16 | min dense id)
+    int* ncl;                    // [nframes] cluster ids handed out (may exceed cap_keys: the host re-runs the chunk)
+    int nslots;                  // power of two
+    int cap_keys;
+};
+#define PT_EMPTY 0xffffffffffffffffull
+
+__device__ __forceinline__ uint32_t pair_hash(uint32_t k) {
+    k ^= k >> 15; k *= 0x2c1b3c6du; k ^= k >> 12; k *= 0x297a2d39u; k ^= k >> 15;
+    return k;
+}
+
+// cluster id of pair key `key` in frame `frame` (inserted when new).  Lock-free: the 64-bit slot holds key and id, so a
+// reader never sees a key without its id; an id drawn for an insertion that loses its race is simply never used (an
+// empty cluster).  Returns 0xffffffff when the table is full (the host sees ncl > cap and re-runs the chunk).
+__device__ __forceinline__ uint32_t pair_cluster_id(const PairTable& pt, int frame, uint32_t key) {
+    unsigned long long* T = pt.slots + (size_t)frame * pt.nslots;
+    const uint32_t mask = (uint32_t)pt.nslots - 1u;
+    uint32_t slot = pair_hash(key) & mask;
+    uint32_t fresh = 0xffffffffu;
+    for (int probes = 0; probes < pt.nslots; probes++) {
+        unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(T + slot);
+        if (e == PT_EMPTY) {
+            if (fresh == 0xffffffffu) {
+                fresh = (uint32_t)atomicAdd(&pt.ncl[frame], 1);
+                if (fresh >= (uint32_t)pt.cap_keys) return 0xffffffffu;
+            }
+            e = atomicCAS(T + slot, PT_EMPTY, ((unsigned long long)key << 32) | fresh);
+            if (e == PT_EMPTY) {
+                pt.keys[(size_t)frame * pt.cap_keys + fresh] = key;
+                return fresh;
+            }
+        }
+        if ((uint32_t)(e >> 32) == key) return (uint32_t)e;
+        slot = (slot + 1) & mask;
+    }
+    return 0xffffffffu;
+}
+
 // One warp per 32x32 tile, lane = row, everything on the tile-major bit masks of k_cc_local (2 bits per pixel).
 // An edge between v0 and v1 (one white, one black) in direction d is one AND of the row's white mask with the
 // neighbour row's shifted black mask (and vice versa): a lane tests its 32 pixels x 4 directions with ~20 bit
@@ -28,9 +76,10 @@ template <int EDGE_WARPS>
 __global__ void __launch_bounds__(EDGE_WARPS * 32, EDGE_WARPS == 2 ? EDGE_MINB : 1)
 k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
         const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts,
-        int* __restrict__ ndups, int cap, int id_bits) {
+        int* __restrict__ ndups, int cap, PairTable pt) {
     __shared__ uint16_t scand[EDGE_WARPS][EDGE_CAND_PER_PASS];
     __shared__ uint16_t sdense[EDGE_WARPS][1024];   // dense component id of every run of the tile, at its start pixel
+    __shared__ unsigned long long scache[EDGE_WARPS][4];   // the warp's last pair keys and their cluster ids (a tile sees a handful)
     // grid = (frames, x blocks, tile rows): consecutive CTAs belong to DIFFERENT frames, so the per-frame append
     // counters are not hammered by every resident warp at once
     const int frame = blockIdx.x;
@@ -107,7 +156,8 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
     __syncwarp();
 
     unsigned long long* fk = recs + (size_t)frame * cap;
-    const uint32_t idmax = (1u << id_bits) - 1u;
+    if (lane < 4) scache[w][lane] = PT_EMPTY;
+    __syncwarp();
     const int npass = total_all <= EDGE_CAND_PER_PASS ? 1 : 4;
     const int rsh = npass == 1 ? 5 : 3;   // rows per pass = 1 << rsh
 #pragma unroll 1
@@ -159,21 +209,33 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
                     d1 = min(fd[fl[l1]], 0xffffu);
                 }
             }
-            bool ok = false;
+            bool ok = have && d0 != 0xffffu && d1 != 0xffffu;   // both components have >= 25 pixels
+            uint32_t okm = __ballot_sync(FULL_MASK, ok);
+            if (okm == 0) continue;
+            // pair key -> cluster id: one look-up per DISTINCT key of the batch (usually one or two), through the warp's
+            // little cache first
+            const uint32_t key = ok ? ((max(d0, d1) << 16) | min(d0, d1)) : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(FULL_MASK, key);
+            const int leader = __ffs(peers) - 1;
+            uint32_t cid = 0xffffffffu;
+            if (ok && lane == leader) {
+                const unsigned long long ce = scache[w][pair_hash(key) >> 30];
+                if ((uint32_t)(ce >> 32) == key) cid = (uint32_t)ce;
+                else {
+                    cid = pair_cluster_id(pt, frame, key);
+                    if (cid != 0xffffffffu) scache[w][pair_hash(key) >> 30] = ((unsigned long long)key << 32) | cid;
+                }
+            }
+            cid = __shfl_sync(FULL_MASK, cid, leader);
+            ok = ok && cid != 0xffffffffu;                       // (table full: the host re-runs the chunk with a larger one)
+            okm = __ballot_sync(FULL_MASK, ok);
+            if (okm == 0) continue;
             unsigned long long rec = 0;
-            if (have && d0 != 0xffffu && d1 != 0xffffu) {   // both components have >= 25 pixels
-                ok = true;
-                // 2*id_bits key bits: as few sort passes as needed.  Ids that do not fit (the host re-runs such a chunk
-                // with wider ids) are clamped so that nothing downstream indexes out of range in the meantime.
-                d0 = min(d0, idmax);
-                d1 = min(d1, idmax);
-                const uint32_t key = (max(d0, d1) << id_bits) | min(d0, d1);
+            if (ok) {
                 const int merged = (cd >> 13) & 1;
                 const int kind = merged ? (8 | pos | (((cd >> 14) & 1) << 1)) : (d | (pos << 2));
-                rec = ((unsigned long long)key << 32) | pack_point(2 * (x0 + c) + dx, 2 * (y0 + r) + dy, kind);
+                rec = ((unsigned long long)cid << 32) | pack_point(2 * (x0 + c) + dx, 2 * (y0 + r) + dy, kind);
             }
-            const uint32_t okm = __ballot_sync(FULL_MASK, ok);
-            if (okm == 0) continue;
             const uint32_t dupm = __ballot_sync(FULL_MASK, ok && ((cd >> 13) & 1u));
             int base = 0;
             if (lane == 0) {
@@ -424,5 +486,62 @@ k_cluster_heads(const unsigned long long* __restrict__ recs, const int* __restri
             }
         if (!placed) atomicAdd(&cl.counters[4], 1);
         }
+    }
+}
+
+
+// Single-pass sort (cluster ids < RS_RADIX): digit d of the pass IS cluster id d, so digit_total[d] is the cluster's size
+// and the exclusive prefix of the totals its start -- no pass over the sorted records.  One CTA per frame.
+__global__ void __launch_bounds__(256)
+k_cluster_refs(const uint32_t* __restrict__ digit_total, const int* __restrict__ ncl, Geom g, int min_size, ClusterLists cl) {
+    __shared__ int wsum[8];
+    const int frame = blockIdx.x;
+    const int n = min(ncl[frame], RS_RADIX);
+    const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);
+    const uint32_t* dt = digit_total + (size_t)frame * RS_RADIX;
+    constexpr int PER = RS_RADIX / 256;   // 8 consecutive cluster ids per thread
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int sz[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int c = threadIdx.x * PER + k;
+        sz[k] = c < n ? (int)dt[c] : 0;
+        sum += sz[k];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int start = incl - sum;
+    for (int ww = 0; ww < w; ww++) start += wsum[ww];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int size = sz[k];
+        if (size > 0) {
+            ClusterRef ref;
+            ref.frame = frame; ref.start = start; ref.size = size; ref.pad = 0;
+            if (cl.dbg_heads) {
+                const int s = atomicAdd(&cl.counters[5], 1);
+                if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
+            }
+            if (size >= min_size) {
+                if (size > max_cluster) atomicAdd(&cl.counters[4], 1);   // (see k_cluster_heads)
+                else {
+#pragma unroll
+                    for (int t = 0; t < AGPU_NTIERS; t++)
+                        if (size <= cl.cap[t]) {
+                            const int s = atomicAdd(&cl.counters[t], 1);
+                            atomicAdd(&cl.counters[12 + t], size);
+                            if (s < cl.cap_list) cl.list[t][s] = ref;
+                            break;
+                        }
+                }
+            }
+        }
+        start += size;
     }
 }

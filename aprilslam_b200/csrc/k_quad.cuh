@@ -14,9 +14,10 @@
 #include "k_cc.cuh"
 
 struct QuadFitArgs {
-    const unsigned long long* recs;   // sorted records (pair key << 32 | packed point), per-frame segments of `cap`
+    const unsigned long long* recs;   // sorted records (cluster id << 32 | packed point), per-frame segments of `cap`
     const uint32_t* dense2rep;        // [nframes][AGPU_MAX_DENSE] dense component id -> representative pixel id
-    int id_bits;                      // bits per dense id inside the pair key
+    const uint32_t* pair_keys;        // [nframes][cap_keys] cluster id (upper half of a record) -> pair of dense ids
+    int cap_keys;
     int cap;
     const uint8_t* quad_im;     // decimated gray image (may alias the source frames)
     size_t q_pitch, q_frame;    // bytes per row / per frame of quad_im
@@ -798,9 +799,9 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     q.frame = ref.frame;
     q.reversed_border = reversed;
     {
-        const uint32_t ck = (uint32_t)(a.recs[seg] >> 32);
+        const uint32_t ck = a.pair_keys[(size_t)ref.frame * a.cap_keys + (uint32_t)(a.recs[seg] >> 32)];
         const uint32_t* f2 = a.dense2rep + (size_t)ref.frame * AGPU_MAX_DENSE;
-        const uint32_t ra = f2[ck >> a.id_bits], rb = f2[ck & ((1u << a.id_bits) - 1u)];
+        const uint32_t ra = f2[ck >> 16], rb = f2[ck & 0xffffu];
         q.key = ((unsigned long long)max(ra, rb) << 32) | min(ra, rb);
     }
     return true;
