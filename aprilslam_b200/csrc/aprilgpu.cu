@@ -3,8 +3,8 @@
 //
 // Pipeline per chunk of frames (all on one stream):
 //   [H2D] -> image (k_pack / k_blur_pass / k_decimate_threshold) -> CC (k_cc_local, k_cc_boundary,
-//   k_cc_finalize) -> k_edges -> segmented radix sort (k_sort_hist/scan/scatter x passes) ->
-//   k_cluster_heads -> k_fit_quads (3 size tiers) -> k_decode_quads -> k_reconcile [-> k_pose] -> D2H
+//   k_cc_finalize) -> k_edges (records carry cluster ids) -> k_cluster_refs -> k_sort_scatter (one-sweep segmented
+//   sort by cluster id) -> k_fit_quads (4 size tiers) -> k_decode_quads -> k_reconcile [-> k_pose] -> D2H
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -97,7 +97,7 @@ struct Slot {
     std::vector<KEv> kev;              // profiling only: one event pair around EVERY kernel launch of the chunk
     size_t kev_next = 0;
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_labels, d_canon, d_sizes, d_roots, d_dense, d_dense2rep;
-    DevBuf d_recs[2], d_hist, d_dtot, d_qscratch, d_gsort, d_pairslots, d_pairkeys;
+    DevBuf d_recs[2], d_qscratch, d_gsort, d_pairslots, d_pairkeys, d_paircount, d_pairstart;
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk], ncl[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
@@ -107,7 +107,7 @@ struct Slot {
     // per frame: ~30 launches and a dozen event calls per call otherwise).  Captured the second time a call with the
     // same key arrives; any change of geometry, capacities, pose parameters or buffer addresses re-captures.
     struct GraphKey {
-        int W, H, stride, channels, n, cap, maxcl, maxq, cap_out, cid_passes, cap_keys, pose;
+        int W, H, stride, channels, n, cap, maxcl, maxq, cap_out, cap_keys, pose;
         double K[9], dist[8], tag_size;
         int ndist;
         unsigned long long buffers;   // hash of every buffer address the kernels were given
@@ -122,7 +122,7 @@ struct Slot {
 
     void release() {
         DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_labels, &d_canon, &d_sizes, &d_roots,
-                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_hist, &d_dtot, &d_qscratch, &d_gsort, &d_pairslots, &d_pairkeys, &d_counters,
+                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_qscratch, &d_gsort, &d_pairslots, &d_pairkeys, &d_paircount, &d_pairstart, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
         for (DevBuf* bb : bufs) bb->release();
@@ -187,9 +187,7 @@ struct agpu_handle {
 
     // growable per-frame list capacities (0 = not chosen yet)
     int cap_points = 0, cap_clusters = 0, cap_quads = 0;
-    // most clusters (distinct component pairs) seen in a frame so far (-1: nothing seen): decides between one radix
-    // pass over 11-bit cluster ids and two; a chunk whose frames do not fit is simply run again with two passes
-    int max_dense_seen = -1, max_clusters_seen = -1;
+    int max_dense_seen = -1, max_clusters_seen = -1;   // most components / clusters seen in one frame so far (statistics)
     int cap_keys = 0;   // cluster-id capacity per frame (grows like the other work lists)
 
     // state of the last finished chunk (debug fetch)
@@ -565,8 +563,7 @@ struct CallCtx {   // constants of one agpu_detect* call
     int on_device, channels, B, W, H, stride;
     size_t frame_bytes;
     Geom g;
-    int chunk, cap, maxcl, maxq, cap_out, key_bits, nblk_max;
-    int cid_passes;   // radix passes over the cluster id: 1 (ids < 2048) or 2
+    int chunk, cap, maxcl, maxq, cap_out, key_bits;
     int cap_keys;     // cluster ids per frame the pair table can hand out
     size_t ncnt;
     const PoseSpec* pose;
@@ -578,11 +575,11 @@ int alloc_slot(agpu_handle* h, Slot& s, const CallCtx& c) {
     const int chunk = c.chunk, cap = c.cap;
     if (!c.on_device) CK(s.d_in.ensure(c.frame_bytes * chunk));
     for (int i = 0; i < 2; i++) CK(s.d_recs[i].ensure((size_t)chunk * cap * 8));
-    CK(s.d_hist.ensure((size_t)chunk * RS_RADIX * c.nblk_max * 4));
-    CK(s.d_dtot.ensure((size_t)chunk * RS_RADIX * 4));
     CK(s.d_dense2rep.ensure((size_t)chunk * AGPU_MAX_DENSE * 4));
     CK(s.d_pairkeys.ensure((size_t)chunk * c.cap_keys * 4));
     CK(s.d_pairslots.ensure((size_t)chunk * c.cap_keys * 4 * 8));   // open addressing at <= 25 % load
+    CK(s.d_paircount.ensure((size_t)chunk * c.cap_keys * 4));
+    CK(s.d_pairstart.ensure((size_t)chunk * c.cap_keys * 4));
     {   // quad-fit scratch: 56 bytes per point of the largest cluster of its tier for every persistent GROUP (re-used
         // cluster after cluster, so it lives in L2), not per edge point of the chunk
         const int max_cluster = 3 * (2 * c.g.wd + 2 * c.g.hd);
@@ -643,8 +640,10 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     }
     CK(cudaMemsetAsync(d_cnt, 0, c.ncnt * 4, sl.stream));
     CK(cudaMemsetAsync(sl.d_pairslots.p, 0xff, (size_t)n * c.cap_keys * 4 * 8, sl.stream));
+    CK(cudaMemsetAsync(sl.d_paircount.p, 0, (size_t)n * c.cap_keys * 4, sl.stream));
     PairTable ptab;
     ptab.slots = sl.d_pairslots.as<unsigned long long>(); ptab.keys = sl.d_pairkeys.as<uint32_t>(); ptab.ncl = d_ncl;
+    ptab.count = sl.d_paircount.as<uint32_t>(); ptab.start = sl.d_pairstart.as<uint32_t>();
     ptab.nslots = c.cap_keys * 4; ptab.cap_keys = c.cap_keys;
     tm.mark();  // 1: after H2D
     const uint8_t *quad_im, *gray_full;
@@ -670,55 +669,36 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         LAUNCH_CHECK("k_edges");
     }
     tm.mark();  // 4: after edges
-    int cur = 0;
-    for (int shift = 32; shift < 32 + c.cid_passes * RS_BITS; shift += RS_BITS) {   // the cluster id: one 11-bit pass, or two
-        dim3 grid(c.nblk_max, n);
-        {
-            KScope ks(h, sl, "k_sort_hist", sl.stream);
-            k_sort_hist<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(), d_npts, cap, shift,
-                                                            sl.d_hist.as<uint32_t>(), c.nblk_max);
-        }
-        LAUNCH_CHECK("k_sort_hist");
-        {
-            KScope ks(h, sl, "k_sort_scan", sl.stream);
-            k_sort_scan<<<dim3(n, RS_SCAN_PARTS), RS_RADIX / RS_SCAN_PARTS, 0, sl.stream>>>(
-                d_npts, cap, sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
-        }
-        LAUNCH_CHECK("k_sort_scan");
-        {
-            KScope ks(h, sl, "k_sort_scatter", sl.stream);
-            k_sort_scatter<<<grid, RS_THREADS, RS_SCATTER_SMEM, sl.stream>>>(sl.d_recs[cur].as<unsigned long long>(),
-                                                               sl.d_recs[cur ^ 1].as<unsigned long long>(), d_npts, cap, shift,
-                                                               sl.d_hist.as<uint32_t>(), sl.d_dtot.as<uint32_t>(), c.nblk_max);
-        }
-        LAUNCH_CHECK("k_sort_scatter");
-        cur ^= 1;
+    // ---- cluster starts + work lists from the per-id counts, then the one-sweep scatter by cluster id
+    ClusterLists cl;
+    const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);   // upstream's cluster size limit
+    int tier_cap[AGPU_NTIERS], tier_smem[AGPU_NTIERS];    // largest cluster of a tier / capacity of its shared-memory sort buffer
+    for (int t = 0; t < AGPU_NTIERS; t++) {
+        tier_cap[t] = t == AGPU_NTIERS - 1 ? std::max(max_cluster, h->tune.tier_cap[t - 1] + 1) : h->tune.tier_cap[t];
+        tier_smem[t] = std::min(tier_cap[t], QF_SMEM_CAP);
+        cl.list[t] = sl.d_clusters[t].as<ClusterRef>();
+        cl.cap[t] = tier_cap[t];
     }
+    cl.counters = d_cnt;
+    cl.cap_list = n * c.maxcl;
+    cl.dbg_heads = h->cfg.debug ? sl.d_dbg_heads.as<ClusterRef>() : nullptr;
+    cl.cap_dbg = (int)(sl.d_dbg_heads.bytes / sizeof(ClusterRef));
+    {
+        KScope ks(h, sl, "k_cluster_refs", sl.stream);
+        k_cluster_refs<<<n, 256, 0, sl.stream>>>(ptab, g, std::max(h->prm.min_cluster_pixels, 24), cl);
+    }
+    LAUNCH_CHECK("k_cluster_refs");
+    {
+        KScope ks(h, sl, "k_sort_scatter", sl.stream);
+        dim3 grid(cap / RS_TILE, n);
+        k_sort_scatter<<<grid, RS_THREADS, 0, sl.stream>>>(sl.d_recs[0].as<unsigned long long>(), sl.d_recs[1].as<unsigned long long>(),
+                                                          d_npts, cap, ptab);
+    }
+    LAUNCH_CHECK("k_sort_scatter");
+    const int cur = 1;
     tm.mark();  // 5: after sort
     const unsigned long long* srecs = sl.d_recs[cur].as<unsigned long long>();
     {
-        ClusterLists cl;
-        const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);   // upstream's cluster size limit
-        int tier_cap[AGPU_NTIERS], tier_smem[AGPU_NTIERS];    // largest cluster of a tier / capacity of its shared-memory sort buffer
-        for (int t = 0; t < AGPU_NTIERS; t++) {
-            tier_cap[t] = t == AGPU_NTIERS - 1 ? std::max(max_cluster, h->tune.tier_cap[t - 1] + 1) : h->tune.tier_cap[t];
-            tier_smem[t] = std::min(tier_cap[t], QF_SMEM_CAP);
-            cl.list[t] = sl.d_clusters[t].as<ClusterRef>();
-            cl.cap[t] = tier_cap[t];
-        }
-        cl.counters = d_cnt;
-        cl.cap_list = n * c.maxcl;
-        cl.dbg_heads = h->cfg.debug ? sl.d_dbg_heads.as<ClusterRef>() : nullptr;
-        cl.cap_dbg = (int)(sl.d_dbg_heads.bytes / sizeof(ClusterRef));
-        dim3 grid(std::max(1, std::min(64, ceil_div(cap, 256))), n);   // grid-stride over the live points
-        if (c.cid_passes == 1) {   // the digit totals of the single pass are the cluster sizes
-            KScope ks(h, sl, "k_cluster_refs", sl.stream);
-            k_cluster_refs<<<n, 256, 0, sl.stream>>>(sl.d_dtot.as<uint32_t>(), d_ncl, g, std::max(h->prm.min_cluster_pixels, 24), cl);
-        } else {
-            KScope ks(h, sl, "k_cluster_heads", sl.stream);
-            k_cluster_heads<<<grid, 256, 0, sl.stream>>>(srecs, d_npts, cap, g, std::max(h->prm.min_cluster_pixels, 24), cl);
-        }
-        LAUNCH_CHECK("k_cluster_heads");
         QuadFitArgs qa;
         qa.recs = srecs; qa.dense2rep = sl.d_dense2rep.as<uint32_t>(); qa.pair_keys = sl.d_pairkeys.as<uint32_t>();
         qa.cap_keys = c.cap_keys; qa.cap = cap;
@@ -839,8 +819,8 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
 
 unsigned long long slot_buffer_hash(const agpu_handle* h, const Slot& s) {
     const DevBuf* bufs[] = {&s.d_in, &s.d_gray, &s.d_quad_im, &s.d_blur_tmp, &s.d_blur_orig, &s.d_thresh, &s.d_masks, &s.d_l16, &s.d_labels,
-                            &s.d_canon, &s.d_sizes, &s.d_roots, &s.d_dense, &s.d_dense2rep, &s.d_recs[0], &s.d_recs[1], &s.d_hist,
-                            &s.d_dtot, &s.d_qscratch, &s.d_gsort, &s.d_pairslots, &s.d_pairkeys, &s.d_counters, &s.d_clusters[0], &s.d_clusters[1], &s.d_clusters[2],
+                            &s.d_canon, &s.d_sizes, &s.d_roots, &s.d_dense, &s.d_dense2rep, &s.d_recs[0], &s.d_recs[1],
+                            &s.d_qscratch, &s.d_gsort, &s.d_pairslots, &s.d_pairkeys, &s.d_paircount, &s.d_pairstart, &s.d_counters, &s.d_clusters[0], &s.d_clusters[1], &s.d_clusters[2],
                             &s.d_clusters[3], &s.d_quads, &s.d_dets, &s.d_out, &s.d_poses, &h->d_fams, &h->d_codes};
     unsigned long long x = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { x = (x ^ v) * 1099511628211ull; };
@@ -860,7 +840,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     Slot::GraphKey key;
     memset(&key, 0, sizeof(key));
     key.W = c.W; key.H = c.H; key.stride = c.stride; key.channels = c.channels; key.n = n; key.cap = c.cap; key.maxcl = c.maxcl;
-    key.maxq = c.maxq; key.cap_out = c.cap_out; key.cid_passes = c.cid_passes; key.cap_keys = c.cap_keys; key.pose = c.pose->enabled ? 1 : 0;
+    key.maxq = c.maxq; key.cap_out = c.cap_out; key.cap_keys = c.cap_keys; key.pose = c.pose->enabled ? 1 : 0;
     if (c.pose->enabled) {
         memcpy(key.K, c.pose->K, sizeof(key.K)); memcpy(key.dist, c.pose->dist, sizeof(key.dist));
         key.tag_size = c.pose->tag_size; key.ndist = c.pose->ndist;
@@ -976,8 +956,8 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     for (int i = 0; i < n; i++) max_ncl = std::max(max_ncl, h_ncl[i]);
     h->max_clusters_seen = std::max(h->max_clusters_seen, max_ncl);
     bool redo = false;
-    // cluster ids did not fit the radix passes, or the pair table ran out of ids: run the chunk again
-    if (max_ncl > (1 << (RS_BITS * c.cid_passes)) || max_ncl > c.cap_keys) { ov.max_ncl = std::max(ov.max_ncl, max_ncl); redo = true; }
+    // the pair table ran out of cluster ids: run the chunk again with a larger one
+    if (max_ncl > c.cap_keys) { ov.max_ncl = std::max(ov.max_ncl, max_ncl); redo = true; }
     if (max_pts > c.cap) { ov.max_pts = std::max(ov.max_pts, max_pts); redo = true; }
     if (max_cl > n * c.maxcl) { ov.max_cl_per_frame = std::max(ov.max_cl_per_frame, (max_cl + n - 1) / n); redo = true; }
     if (hc[CNT_NQUADS] > n * c.maxq) { ov.max_q_per_frame = std::max(ov.max_q_per_frame, (hc[CNT_NQUADS] + n - 1) / n); redo = true; }
@@ -1091,7 +1071,6 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
     c.maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
     c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
     c.ncnt = CNT_FIXED + (size_t)(7 + CC_SUBLISTS) * chunk;
-    c.cid_passes = (h->max_clusters_seen >= 0 && h->max_clusters_seen <= RS_RADIX * 3 / 4) ? 1 : 2;
     c.cap_keys = std::max(h->cap_keys, 4096);
     c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
@@ -1108,7 +1087,6 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
     std::vector<std::pair<int, int>> todo, redo;
     for (int b0 = 0; b0 < B; b0 += chunk) todo.push_back({b0, std::min(chunk, B - b0)});
     while (!todo.empty()) {
-        c.nblk_max = c.cap / RS_TILE;
         for (int s = 0; s < nslots; s++) {
             int rc = alloc_slot(h, h->slots[s], c);
             if (rc) return rc;
@@ -1147,7 +1125,6 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
             if (!auto_cl) { h->set_err("cluster list overflow: raise agpu_config.max_clusters_per_frame"); return AGPU_E_WORKSPACE; }
             c.maxcl = ov.max_cl_per_frame * 2;
         }
-        if (ov.max_ncl > (1 << (RS_BITS * c.cid_passes))) c.cid_passes = 2;
         if (ov.max_ncl > c.cap_keys) {
             int ck = c.cap_keys;
             while (ck < ov.max_ncl + ov.max_ncl / 4) ck *= 2;
@@ -1332,7 +1309,7 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     ce = cudaFuncSetAttribute(k_fit_quads<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)qf_smem_per_group(QF_SMEM_CAP, 8));
     if (ce == cudaSuccess)
-        ce = cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
+        ce = cudaSuccess;
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(k_fit_quads<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(8 * qf_smem_per_group(h->tune.tier_cap[0], 1)));

@@ -5,10 +5,13 @@
 //                    64-bit record (pair key << 32) | packed point, the key being the unordered pair of the
 //                    two components' dense ids (k_cc_dense); records go to the frame's own segment of the
 //                    point list (warp-aggregated atomics).
-//   k_sort_hist / k_sort_scan / k_sort_scatter
-//                    hand-written SEGMENTED least-significant-digit radix sort (8-bit digits, stable):
-//                    every frame's segment is sorted independently, grid = (blocks, frames).
-//   k_cluster_heads  run heads of equal keys -> cluster work lists (binary search for the run end).
+//                    The pair key is renamed to a per-frame CLUSTER ID on the fly (lock-free pair table) and the
+//                    record carries that id; the number of records per id is counted as they are emitted.
+//   k_cluster_refs   exclusive prefix of the per-id counts = start of every cluster in the sorted order -> cluster
+//                    work lists by size tier (no pass over the records).
+//   k_sort_scatter   hand-written SEGMENTED one-sweep radix (counting) sort whose single digit is the cluster id:
+//                    every frame's segment is sorted independently, grid = (blocks, frames); a warp claims the
+//                    slots of all its records of one cluster with one atomic.
 #pragma once
 #include "common.cuh"
 #include "k_cc.cuh"
@@ -17,13 +20,16 @@
 // dense component ids (2 x 11 or 2 x 16 bits: two or three radix passes).  The pairs that actually occur are few --
 // a few hundred per frame, a few thousand under sensor noise -- so k_edges renames them on the fly: a per-frame
 // open-addressing table maps the 32-bit pair key to a CLUSTER ID handed out in order of first appearance, and the record
-// carries that id.  The radix sort then needs ONE 11-bit pass for up to 2048 clusters per frame (two passes beyond), and
-// with a single pass the digit histogram IS the table of cluster sizes and the digit offsets ARE the cluster starts, so
-// no pass over the sorted records is needed to find the cluster heads (k_cluster_refs).
+// carries that id.  The sort then has ONE digit -- the cluster id itself: the per-id record counts (taken while the
+// records are emitted) are the digit histogram AND the table of cluster sizes, their exclusive prefix gives the digit
+// offsets AND the cluster starts (k_cluster_refs), and one scatter sweep puts every record in place (k_sort_scatter).
+// The order of the records inside a cluster is left to the atomics: the quad fit sorts them by a total order anyway.
 struct PairTable {
     unsigned long long* slots;   // [nframes][nslots] (pair key << 32) | cluster id; all ones = empty
     uint32_t* keys;              // [nframes][cap_keys] cluster id -> pair key (max dense id << 16 | min dense id)
     int* ncl;                    // [nframes] cluster ids handed out (may exceed cap_keys: the host re-runs the chunk)
+    uint32_t* count;             // [nframes][cap_keys] records per cluster id (k_edges); then the fill cursor of the scatter
+    uint32_t* start;             // [nframes][cap_keys] first slot of the cluster in the sorted segment (k_cluster_refs)
     int nslots;                  // power of two
     int cap_keys;
 };
@@ -226,6 +232,8 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
                     if (cid != 0xffffffffu) scache[w][pair_hash(key) >> 30] = ((unsigned long long)key << 32) | cid;
                 }
             }
+            if (ok && lane == leader && cid != 0xffffffffu)      // the digit histogram of the sort, taken at the source
+                atomicAdd(&pt.count[(size_t)frame * pt.cap_keys + cid], (uint32_t)__popc(peers));
             cid = __shfl_sync(FULL_MASK, cid, leader);
             ok = ok && cid != 0xffffffffu;                       // (table full: the host re-runs the chunk with a larger one)
             okm = __ballot_sync(FULL_MASK, ok);
@@ -250,176 +258,11 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
     }
 }
 
-// ---- segmented LSD radix sort ---------------------------------------------------------------
-// Records are single 64-bit words, (pair key << 32) | point; only the 32 key bits are sorted: three passes of
-// 11-bit digits (2048 bins).
-#define RS_THREADS 512
-#define RS_ITEMS 16
-#define RS_TILE (RS_THREADS * RS_ITEMS)  // 8192 records per block: 1 byte of histogram traffic per record
-#define RS_BITS 11
-#define RS_RADIX (1 << RS_BITS)
-#define RS_SCAN_PARTS 8
-#define RS_SCATTER_SMEM ((RS_THREADS / 32) * RS_RADIX * 2 + RS_RADIX * 4)
-
-// per frame: hist[block][digit] (block-major, frame stride RS_RADIX * nblk_max)
-__global__ void __launch_bounds__(RS_THREADS)
-k_sort_hist(const unsigned long long* __restrict__ recs, const int* __restrict__ npts, int cap, int shift,
-            uint32_t* __restrict__ hist, int nblk_max) {
-    __shared__ uint32_t h[RS_RADIX];
-    const int frame = blockIdx.y, b = blockIdx.x;
-    const int n = min(npts[frame], cap);
-    const int nblk = (n + RS_TILE - 1) / RS_TILE;
-    if (b >= nblk) return;
-    for (int i = threadIdx.x; i < RS_RADIX; i += RS_THREADS) h[i] = 0;
-    __syncthreads();
-    const unsigned long long* fk = recs + (size_t)frame * cap;
-    const int base = b * RS_TILE;
-    // all loads first; then one shared-memory atomic per RUN of equal digits inside a warp: neighbouring records come
-    // from the same image tile (first pass) or the same low digit (later passes) and mostly share their digit, which
-    // would otherwise serialise 32 ways on one counter
-    const int lane = threadIdx.x & 31;
-    uint32_t dg[RS_ITEMS];
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const int i = base + r * RS_THREADS + threadIdx.x;
-        dg[r] = i < n ? ((uint32_t)(__ldg(&fk[i]) >> shift) & (RS_RADIX - 1)) : 0xffffffffu;
-    }
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const uint32_t d = dg[r];
-        const uint32_t d0 = __shfl_sync(FULL_MASK, d, 0);
-        const uint32_t same = __ballot_sync(FULL_MASK, d == d0);
-        if (d == d0) {
-            if (lane == 0 && d0 != 0xffffffffu) atomicAdd(&h[d0], (uint32_t)__popc(same));
-        } else if (d != 0xffffffffu) {
-            atomicAdd(&h[d], 1u);
-        }
-    }
-    __syncthreads();
-    uint32_t* out = hist + ((size_t)frame * nblk_max + b) * RS_RADIX;
-    for (int i = threadIdx.x; i < RS_RADIX; i += RS_THREADS) out[i] = h[i];
-}
-
-// grid (frames, RS_SCAN_PARTS): thread = one digit; exclusive prefix over the blocks (in place) and the digit's
-// total; the prefix over the digit totals is taken by every scatter block itself
-__global__ void __launch_bounds__(RS_RADIX / RS_SCAN_PARTS)
-k_sort_scan(const int* __restrict__ npts, int cap, uint32_t* __restrict__ hist, uint32_t* __restrict__ digit_total,
-            int nblk_max) {
-    const int frame = blockIdx.x;
-    const int n = min(npts[frame], cap);
-    const int nblk = (n + RS_TILE - 1) / RS_TILE;
-    const int d = blockIdx.y * blockDim.x + threadIdx.x;
-    uint32_t* fh = hist + (size_t)frame * nblk_max * RS_RADIX + d;
-    uint32_t run = 0;
-    for (int b0 = 0; b0 < nblk; b0 += 8) {   // batches of 8 independent loads, then the 8 dependent stores
-        uint32_t c[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) c[k] = b0 + k < nblk ? fh[(size_t)(b0 + k) * RS_RADIX] : 0u;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (b0 + k < nblk) {
-                fh[(size_t)(b0 + k) * RS_RADIX] = run;
-                run += c[k];
-            }
-    }
-    digit_total[(size_t)frame * RS_RADIX + d] = run;
-}
-
-__global__ void __launch_bounds__(RS_THREADS, 2)
-k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long long* __restrict__ recs_out,
-               const int* __restrict__ npts, int cap, int shift, const uint32_t* __restrict__ hist,
-               const uint32_t* __restrict__ digit_total, int nblk_max) {
-    extern __shared__ __align__(16) unsigned char rs_smem[];
-    uint16_t (*wcnt)[RS_RADIX] = reinterpret_cast<uint16_t (*)[RS_RADIX]>(rs_smem);   // per-warp digit counts (<= 512), then warp prefixes
-    uint32_t* dbase = reinterpret_cast<uint32_t*>(rs_smem + (RS_THREADS / 32) * RS_RADIX * 2);   // first output slot of digit d
-    __shared__ uint32_t wtot[RS_THREADS / 32];
-    const int frame = blockIdx.y, b = blockIdx.x;
-    const int n = min(npts[frame], cap);
-    const int nblk = (n + RS_TILE - 1) / RS_TILE;
-    if (b >= nblk) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    {
-        uint32_t* z = reinterpret_cast<uint32_t*>(&wcnt[0][0]);
-        for (int i = threadIdx.x; i < (RS_THREADS / 32) * RS_RADIX / 2; i += RS_THREADS) z[i] = 0;
-    }
-    static_assert(RS_RADIX / RS_THREADS == 4, "digit ownership below assumes 4 digits per thread");
-    const size_t seg = (size_t)frame * cap;
-    const int base = b * RS_TILE + w * (32 * RS_ITEMS);
-    unsigned long long rec[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const int i = base + r * 32 + lane;
-        rec[r] = i < n ? recs_in[seg + i] : 0xffffffffffffffffull;
-    }
-    // exclusive prefix of the frame's digit totals: thread t owns digits 4t .. 4t+3
-    {
-        constexpr int DPT = RS_RADIX / RS_THREADS;
-        const uint32_t* dt = digit_total + (size_t)frame * RS_RADIX + threadIdx.x * DPT;
-        const uint4 a = *reinterpret_cast<const uint4*>(dt);
-        const uint32_t v[DPT] = {a.x, a.y, a.z, a.w};
-        uint32_t sum = 0;
-#pragma unroll
-        for (int k = 0; k < DPT; k++) sum += v[k];
-        uint32_t incl = sum;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t t = __shfl_up_sync(FULL_MASK, incl, off);
-            if (lane >= off) incl += t;
-        }
-        if (lane == 31) wtot[w] = incl;
-        __syncthreads();
-        uint32_t run = incl - sum;
-#pragma unroll
-        for (int ww = 0; ww < RS_THREADS / 32; ww++)
-            if (ww < w) run += wtot[ww];
-#pragma unroll
-        for (int k = 0; k < DPT; k++) {
-            dbase[threadIdx.x * DPT + k] = run;
-            run += v[k];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const int i = base + r * 32 + lane;
-        const bool valid = i < n;
-        const uint32_t d = valid ? ((uint32_t)(rec[r] >> shift) & (RS_RADIX - 1)) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(FULL_MASK, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t before = 0;
-        if (valid && lane == leader) {
-            before = wcnt[w][d];
-            wcnt[w][d] = (uint16_t)(before + __popc(peers));
-        }
-        before = __shfl_sync(FULL_MASK, before, leader);
-        rank[r] = before + __popc(peers & ((1u << lane) - 1u));
-        __syncwarp();
-    }
-    __syncthreads();
-    {   // per-warp counts -> exclusive warp prefixes; add the block's offset inside each digit
-        const uint32_t* bh = hist + ((size_t)frame * nblk_max + b) * RS_RADIX;
-        for (int d = threadIdx.x; d < RS_RADIX; d += RS_THREADS) {
-            uint32_t run = 0;
-#pragma unroll
-            for (int ww = 0; ww < RS_THREADS / 32; ww++) {
-                uint32_t c = wcnt[ww][d];
-                wcnt[ww][d] = (uint16_t)run;
-                run += c;
-            }
-            dbase[d] += bh[d];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const int i = base + r * 32 + lane;
-        if (i < n) {
-            const uint32_t d = (uint32_t)(rec[r] >> shift) & (RS_RADIX - 1);
-            recs_out[seg + dbase[d] + wcnt[w][d] + rank[r]] = rec[r];
-        }
-    }
-}
+// ---- segmented one-sweep sort by cluster id ---------------------------------------------------
+// Records are single 64-bit words, (cluster id << 32) | point.
+#define RS_THREADS 256
+#define RS_ITEMS 8
+#define RS_TILE (RS_THREADS * RS_ITEMS)  // records per scatter block (and the granularity of the list capacity)
 
 // cluster work lists, by size tier (the tier decides how much shared memory the fitting warp gets)
 #define AGPU_NTIERS 4
@@ -432,116 +275,106 @@ struct ClusterLists {
     int cap_dbg;
 };
 
+// Cluster sizes -> cluster starts and work lists.  One CTA per frame: exclusive prefix of the per-id record counts (in id
+// order, 8 ids per thread and round), start[id] for the scatter, one ClusterRef per non-empty id into its size tier; the
+// counts are zeroed on the way and serve as the scatter's fill cursors afterwards.
 __global__ void __launch_bounds__(256)
-k_cluster_heads(const unsigned long long* __restrict__ recs, const int* __restrict__ npts, int cap, Geom g,
-                int min_size, ClusterLists cl) {
-    const int frame = blockIdx.y;
-    const int n = min(npts[frame], cap);
-    const unsigned long long* fk = recs + (size_t)frame * cap;
+k_cluster_refs(PairTable pt, Geom g, int min_size, ClusterLists cl) {
+    __shared__ int wsum[8];
+    __shared__ int s_carry;
+    const int frame = blockIdx.x;
+    const int n = min(pt.ncl[frame], pt.cap_keys);
     const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);
-    // four independent loads per thread and round (the kernel is a single streaming read of the sorted records: what
-    // bounds it is the number of bytes in flight); the predecessor's key comes from the neighbouring lane
-    const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 - lane < n; i0 += 4 * stride) {   // (warp-uniform bound)
-        uint32_t kk[4];
+    uint32_t* cnt = pt.count + (size_t)frame * pt.cap_keys;
+    uint32_t* st = pt.start + (size_t)frame * pt.cap_keys;
+    constexpr int PER = 8;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 256 * PER) {
+        int sz[PER], sum = 0;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int i = i0 + u * stride;
-            kk[u] = i < n ? (uint32_t)(__ldg(&fk[i]) >> 32) : 0xffffffffu;
+        for (int k = 0; k < PER; k++) {
+            const int c = base + threadIdx.x * PER + k;
+            sz[k] = c < n ? (int)cnt[c] : 0;
+            sum += sz[k];
         }
+        int incl = sum;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-        const int i = i0 + u * stride;
-        const uint32_t k = kk[u];
-        uint32_t prev = __shfl_up_sync(FULL_MASK, k, 1);
-        if (i >= n) continue;
-        if (lane == 0 && i > 0) prev = (uint32_t)(__ldg(&fk[i - 1]) >> 32);
-        if (i > 0 && prev == k) continue;
-        int lo = i + 1, hi = n;  // first index in (i, n] whose key differs
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if ((uint32_t)(fk[mid] >> 32) == k) lo = mid + 1; else hi = mid;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(FULL_MASK, incl, off);
+            if (lane >= off) incl += t;
         }
-        const int size = lo - i;
-        ClusterRef ref;
-        ref.frame = frame; ref.start = i; ref.size = size; ref.pad = 0;
-        if (cl.dbg_heads) {
-            int s = atomicAdd(&cl.counters[5], 1);
-            if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
-        }
-        if (size < min_size) continue;
-        // upstream drops clusters of more than 3(2w+2h) RAW points; a record stands for one or two raw points, so a
-        // cluster with more RECORDS than that is certainly over the limit (the exact raw count of the others is
-        // taken by the fitting group, which has to read the records anyway)
-        if (size > max_cluster) { atomicAdd(&cl.counters[4], 1); continue; }
-        bool placed = false;
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        int start = s_carry + incl - sum;
+        for (int ww = 0; ww < w; ww++) start += wsum[ww];
 #pragma unroll
-        for (int t = 0; t < AGPU_NTIERS; t++)
-            if (!placed && size <= cl.cap[t]) {
-                int s = atomicAdd(&cl.counters[t], 1);
-                atomicAdd(&cl.counters[12 + t], size);   // records handed to this tier (instrumentation)
-                if (s < cl.cap_list) cl.list[t][s] = ref;
-                placed = true;
+        for (int k = 0; k < PER; k++) {
+            const int c = base + threadIdx.x * PER + k;
+            const int size = sz[k];
+            if (c < n) { st[c] = (uint32_t)start; cnt[c] = 0u; }
+            if (size > 0) {
+                ClusterRef ref;
+                ref.frame = frame; ref.start = start; ref.size = size; ref.pad = 0;
+                if (cl.dbg_heads) {
+                    const int s = atomicAdd(&cl.counters[5], 1);
+                    if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
+                }
+                if (size >= min_size) {
+                    // upstream drops clusters of more than 3(2w+2h) RAW points; a record stands for one or two raw points,
+                    // so a cluster with more RECORDS than that is certainly over the limit (the exact raw count of the
+                    // others is taken by the fitting group, which has to read the records anyway)
+                    if (size > max_cluster) atomicAdd(&cl.counters[4], 1);
+                    else {
+#pragma unroll
+                        for (int t = 0; t < AGPU_NTIERS; t++)
+                            if (size <= cl.cap[t]) {
+                                const int s = atomicAdd(&cl.counters[t], 1);
+                                atomicAdd(&cl.counters[12 + t], size);   // records handed to this tier (instrumentation)
+                                if (s < cl.cap_list) cl.list[t][s] = ref;
+                                break;
+                            }
+                    }
+                }
             }
-        if (!placed) atomicAdd(&cl.counters[4], 1);
+            start += size;
         }
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = start;   // (the last thread's running start = end of this round)
+        __syncthreads();
     }
 }
 
-
-// Single-pass sort (cluster ids < RS_RADIX): digit d of the pass IS cluster id d, so digit_total[d] is the cluster's size
-// and the exclusive prefix of the totals its start -- no pass over the sorted records.  One CTA per frame.
-__global__ void __launch_bounds__(256)
-k_cluster_refs(const uint32_t* __restrict__ digit_total, const int* __restrict__ ncl, Geom g, int min_size, ClusterLists cl) {
-    __shared__ int wsum[8];
-    const int frame = blockIdx.x;
-    const int n = min(ncl[frame], RS_RADIX);
-    const int max_cluster = 3 * (2 * g.wd + 2 * g.hd);
-    const uint32_t* dt = digit_total + (size_t)frame * RS_RADIX;
-    constexpr int PER = RS_RADIX / 256;   // 8 consecutive cluster ids per thread
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int sz[PER], sum = 0;
+// The scatter sweep: record i of the frame's emission order goes to start[id] + (a slot of cluster id claimed with the
+// fill cursor).  The records of a warp mostly share their cluster (neighbouring image tiles), so one atomic per distinct id
+// and warp round claims the slots of all of them.
+__global__ void __launch_bounds__(RS_THREADS)
+k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long long* __restrict__ recs_out,
+               const int* __restrict__ npts, int cap, PairTable pt) {
+    const int frame = blockIdx.y;
+    const int n = min(npts[frame], cap);
+    const int base = blockIdx.x * RS_TILE;
+    if (base >= n) return;
+    const int lane = threadIdx.x & 31;
+    const size_t seg = (size_t)frame * cap;
+    uint32_t* fill = pt.count + (size_t)frame * pt.cap_keys;
+    const uint32_t* st = pt.start + (size_t)frame * pt.cap_keys;
+    unsigned long long rec[RS_ITEMS];
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int c = threadIdx.x * PER + k;
-        sz[k] = c < n ? (int)dt[c] : 0;
-        sum += sz[k];
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const int i = base + r * RS_THREADS + threadIdx.x;
+        rec[r] = i < n ? __ldg(recs_in + seg + i) : 0xffffffffffffffffull;
     }
-    int incl = sum;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(FULL_MASK, incl, off);
-        if (lane >= off) incl += t;
-    }
-    if (lane == 31) wsum[w] = incl;
-    __syncthreads();
-    int start = incl - sum;
-    for (int ww = 0; ww < w; ww++) start += wsum[ww];
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int size = sz[k];
-        if (size > 0) {
-            ClusterRef ref;
-            ref.frame = frame; ref.start = start; ref.size = size; ref.pad = 0;
-            if (cl.dbg_heads) {
-                const int s = atomicAdd(&cl.counters[5], 1);
-                if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
-            }
-            if (size >= min_size) {
-                if (size > max_cluster) atomicAdd(&cl.counters[4], 1);   // (see k_cluster_heads)
-                else {
-#pragma unroll
-                    for (int t = 0; t < AGPU_NTIERS; t++)
-                        if (size <= cl.cap[t]) {
-                            const int s = atomicAdd(&cl.counters[t], 1);
-                            atomicAdd(&cl.counters[12 + t], size);
-                            if (s < cl.cap_list) cl.list[t][s] = ref;
-                            break;
-                        }
-                }
-            }
-        }
-        start += size;
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t cid = (uint32_t)(rec[r] >> 32);
+        const bool valid = cid != 0xffffffffu;
+        const uint32_t peers = __match_any_sync(FULL_MASK, cid);
+        const int leader = __ffs(peers) - 1;
+        uint32_t slot = 0;
+        if (valid && lane == leader) slot = atomicAdd(&fill[cid], (uint32_t)__popc(peers));
+        slot = __shfl_sync(FULL_MASK, slot, leader);
+        if (valid) recs_out[seg + __ldg(&st[cid]) + slot + __popc(peers & ((1u << lane) - 1u))] = rec[r];
     }
 }
