@@ -685,7 +685,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     cl.cap_dbg = (int)(sl.d_dbg_heads.bytes / sizeof(ClusterRef));
     {
         KScope ks(h, sl, "k_cluster_refs", sl.stream);
-        k_cluster_refs<<<n, 256, 0, sl.stream>>>(ptab, g, std::max(h->prm.min_cluster_pixels, 24), cl);
+        k_cluster_refs<<<n, 256, 0, sl.stream>>>(ptab, g, std::max(h->prm.min_cluster_pixels, 24), cl, cap);
     }
     LAUNCH_CHECK("k_cluster_refs");
     {

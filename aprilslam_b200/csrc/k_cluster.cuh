@@ -278,8 +278,11 @@ struct ClusterLists {
 // Cluster sizes -> cluster starts and work lists.  One CTA per frame: exclusive prefix of the per-id record counts (in id
 // order, 8 ids per thread and round), start[id] for the scatter, one ClusterRef per non-empty id into its size tier; the
 // counts are zeroed on the way and serve as the scatter's fill cursors afterwards.
+// (`cap`: when a frame emitted more records than its segment holds the counts exceed the segment; clusters that would
+// reach past it are not listed and the scatter drops what does not fit -- the host re-runs such a chunk with a larger
+// capacity anyway.)
 __global__ void __launch_bounds__(256)
-k_cluster_refs(PairTable pt, Geom g, int min_size, ClusterLists cl) {
+k_cluster_refs(PairTable pt, Geom g, int min_size, ClusterLists cl, int cap) {
     __shared__ int wsum[8];
     __shared__ int s_carry;
     const int frame = blockIdx.x;
@@ -314,7 +317,7 @@ k_cluster_refs(PairTable pt, Geom g, int min_size, ClusterLists cl) {
             const int c = base + threadIdx.x * PER + k;
             const int size = sz[k];
             if (c < n) { st[c] = (uint32_t)start; cnt[c] = 0u; }
-            if (size > 0) {
+            if (size > 0 && start + size <= cap) {
                 ClusterRef ref;
                 ref.frame = frame; ref.start = start; ref.size = size; ref.pad = 0;
                 if (cl.dbg_heads) {
@@ -375,6 +378,7 @@ k_sort_scatter(const unsigned long long* __restrict__ recs_in, unsigned long lon
         uint32_t slot = 0;
         if (valid && lane == leader) slot = atomicAdd(&fill[cid], (uint32_t)__popc(peers));
         slot = __shfl_sync(FULL_MASK, slot, leader);
-        if (valid) recs_out[seg + __ldg(&st[cid]) + slot + __popc(peers & ((1u << lane) - 1u))] = rec[r];
+        const uint32_t pos = valid ? __ldg(&st[cid]) + slot + __popc(peers & ((1u << lane) - 1u)) : 0u;
+        if (valid && pos < (uint32_t)cap) recs_out[seg + pos] = rec[r];
     }
 }
