@@ -82,7 +82,7 @@ template <int EDGE_WARPS>
 __global__ void __launch_bounds__(EDGE_WARPS * 32, EDGE_WARPS == 2 ? EDGE_MINB : 1)
 k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
         const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts,
-        int* __restrict__ ndups, int cap, PairTable pt) {
+        int* __restrict__ ndups, int* __restrict__ nvalid, int cap, PairTable pt) {
     __shared__ uint16_t scand[EDGE_WARPS][EDGE_CAND_PER_PASS];
     __shared__ uint16_t sdense[EDGE_WARPS][1024];   // dense component id of every run of the tile, at its start pixel
     __shared__ unsigned long long scache[EDGE_WARPS][4];   // the warp's last pair keys and their cluster ids (a tile sees a handful)
@@ -136,6 +136,11 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) total_all += __shfl_xor_sync(FULL_MASK, total_all, off);
     if (total_all == 0) return;
+    // ONE reservation per tile: a slot for every candidate, claimed before the look-ups start so that the atomic's
+    // round trip hides behind them.  Candidates that turn out to touch a component of < 25 pixels leave their slot
+    // to a sentinel record (all ones) that the scatter skips; the exact record count goes to nvalid[].
+    int rbase = 0;
+    if (lane == 0) rbase = atomicAdd(&npts[frame], total_all);
 
     // ---- dense id of every run of this tile: run start -> tile-local root -> final root -> dense id.  The runs of a
     //      tile hang on a handful of roots, so one lane per distinct root does the two dependent loads.
@@ -164,6 +169,7 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
     unsigned long long* fk = recs + (size_t)frame * cap;
     if (lane < 4) scache[w][lane] = PT_EMPTY;
     __syncwarp();
+    rbase = __shfl_sync(FULL_MASK, rbase, 0);
     const int npass = total_all <= EDGE_CAND_PER_PASS ? 1 : 4;
     const int rsh = npass == 1 ? 5 : 3;   // rows per pass = 1 << rsh
 #pragma unroll 1
@@ -191,8 +197,9 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
                 }
         }
         __syncwarp();
-        for (int b = 0; b < total; b += 32) {
+        for (int b = 0; b < total; rbase += min(32, total - b), b += 32) {   // (a batch consumes as many slots as it has candidates)
             const bool have = b + lane < total;
+            const int p = rbase + lane;                          // this candidate's slot in the frame's segment
             const uint32_t cd = have ? scand[w][b + lane] : 0u;
             const int r = cd & 31, c = (cd >> 5) & 31, d = (cd >> 10) & 3, pos = (cd >> 12) & 1;
             const int dx = (d == 0 || d == 3) ? 1 : (d == 2 ? -1 : 0), dy = d == 0 ? 0 : 1;
@@ -217,7 +224,10 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
             }
             bool ok = have && d0 != 0xffffu && d1 != 0xffffu;   // both components have >= 25 pixels
             uint32_t okm = __ballot_sync(FULL_MASK, ok);
-            if (okm == 0) continue;
+            if (okm == 0) {
+                if (have && p < cap) fk[p] = PT_EMPTY;
+                continue;
+            }
             // pair key -> cluster id: one look-up per DISTINCT key of the batch (usually one or two), through the warp's
             // little cache first
             const uint32_t key = ok ? ((max(d0, d1) << 16) | min(d0, d1)) : 0xffffffffu;
@@ -237,22 +247,18 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
             cid = __shfl_sync(FULL_MASK, cid, leader);
             ok = ok && cid != 0xffffffffu;                       // (table full: the host re-runs the chunk with a larger one)
             okm = __ballot_sync(FULL_MASK, ok);
-            if (okm == 0) continue;
-            unsigned long long rec = 0;
+            unsigned long long rec = PT_EMPTY;
             if (ok) {
                 const int merged = (cd >> 13) & 1;
                 const int kind = merged ? (8 | pos | (((cd >> 14) & 1) << 1)) : (d | (pos << 2));
                 rec = ((unsigned long long)cid << 32) | pack_point(2 * (x0 + c) + dx, 2 * (y0 + r) + dy, kind);
             }
             const uint32_t dupm = __ballot_sync(FULL_MASK, ok && ((cd >> 13) & 1u));
-            int base = 0;
             if (lane == 0) {
-                base = atomicAdd(&npts[frame], __popc(okm));
-                if (dupm) atomicAdd(&ndups[frame], __popc(dupm));   // (raw point count = npts + ndups)
+                if (okm) atomicAdd(&nvalid[frame], __popc(okm));
+                if (dupm) atomicAdd(&ndups[frame], __popc(dupm));   // (raw point count = nvalid + ndups)
             }
-            base = __shfl_sync(FULL_MASK, base, 0);
-            const int p = base + __popc(okm & ((1u << lane) - 1u));
-            if (ok && p < cap) fk[p] = rec;
+            if (have && p < cap) fk[p] = rec;
         }
         __syncwarp();
     }
@@ -317,29 +323,48 @@ k_cluster_refs(PairTable pt, Geom g, int min_size, ClusterLists cl, int cap) {
             const int c = base + threadIdx.x * PER + k;
             const int size = sz[k];
             if (c < n) { st[c] = (uint32_t)start; cnt[c] = 0u; }
-            if (size > 0 && start + size <= cap) {
-                ClusterRef ref;
-                ref.frame = frame; ref.start = start; ref.size = size; ref.pad = 0;
-                if (cl.dbg_heads) {
-                    const int s = atomicAdd(&cl.counters[5], 1);
-                    if (s < cl.cap_dbg) cl.dbg_heads[s] = ref;
-                }
-                if (size >= min_size) {
-                    // upstream drops clusters of more than 3(2w+2h) RAW points; a record stands for one or two raw points,
-                    // so a cluster with more RECORDS than that is certainly over the limit (the exact raw count of the
-                    // others is taken by the fitting group, which has to read the records anyway)
-                    if (size > max_cluster) atomicAdd(&cl.counters[4], 1);
-                    else {
+            // tier of this cluster (-1: none; 4: over upstream's size limit).  The work lists are appended to by every
+            // frame's CTA at once: ONE atomic per warp and tier claims the slots of all its clusters.
+            int tier = -1;
+            const bool live = size > 0 && start + size <= cap;
+            if (live && size >= min_size) {
+                // upstream drops clusters of more than 3(2w+2h) RAW points; a record stands for one or two raw points,
+                // so a cluster with more RECORDS than that is certainly over the limit (the exact raw count of the
+                // others is taken by the fitting group, which has to read the records anyway)
+                if (size > max_cluster) tier = AGPU_NTIERS;
+                else {
 #pragma unroll
-                        for (int t = 0; t < AGPU_NTIERS; t++)
-                            if (size <= cl.cap[t]) {
-                                const int s = atomicAdd(&cl.counters[t], 1);
-                                atomicAdd(&cl.counters[12 + t], size);   // records handed to this tier (instrumentation)
-                                if (s < cl.cap_list) cl.list[t][s] = ref;
-                                break;
-                            }
-                    }
+                    for (int t = AGPU_NTIERS - 1; t >= 0; t--)
+                        if (size <= cl.cap[t]) tier = t;
                 }
+            }
+            ClusterRef ref;
+            ref.frame = frame; ref.start = start; ref.size = size; ref.pad = 0;
+            if (cl.dbg_heads) {
+                const uint32_t m = __ballot_sync(FULL_MASK, live);
+                int b0 = 0;
+                if (lane == 0 && m) b0 = atomicAdd(&cl.counters[5], __popc(m));
+                b0 = __shfl_sync(FULL_MASK, b0, 0) + __popc(m & ((1u << lane) - 1u));
+                if (live && b0 < cl.cap_dbg) cl.dbg_heads[b0] = ref;
+            }
+#pragma unroll
+            for (int t = 0; t <= AGPU_NTIERS; t++) {
+                const uint32_t m = __ballot_sync(FULL_MASK, tier == t);
+                if (m == 0) continue;
+                if (t == AGPU_NTIERS) {
+                    if (lane == 0) atomicAdd(&cl.counters[4], __popc(m));
+                    continue;
+                }
+                int recs_t = tier == t ? size : 0;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) recs_t += __shfl_xor_sync(FULL_MASK, recs_t, off);
+                int s0 = 0;
+                if (lane == 0) {
+                    s0 = atomicAdd(&cl.counters[t], __popc(m));
+                    atomicAdd(&cl.counters[12 + t], recs_t);   // records handed to this tier (instrumentation)
+                }
+                s0 = __shfl_sync(FULL_MASK, s0, 0) + __popc(m & ((1u << lane) - 1u));
+                if (tier == t && s0 < cl.cap_list) cl.list[t][s0] = ref;
             }
             start += size;
         }

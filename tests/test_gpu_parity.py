@@ -324,7 +324,7 @@ def test_instrumentation_counts_launches_and_stages():
     g = Detector("tag36h11", decimate=2.0)
     g.set_profiling(True)
     g.detect_batch(img)
-    assert g.launch_count() >= 15
+    assert g.launch_count() >= 12      # image, 4 x CC, edges, cluster refs, sort scatter, 4 quad-fit tiers, decode, reconcile
     ms = g.stage_ms()
     assert set(ms) == {"h2d", "image", "cc", "edges", "sort", "quads", "decode", "reconcile_pose", "d2h"}
     assert all(v >= 0 for v in ms.values()) and sum(ms.values()) > 0
