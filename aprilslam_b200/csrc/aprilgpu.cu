@@ -78,9 +78,10 @@ struct HostBuf {
 // eight one-warp groups into a CTA, the others use one CTA per cluster).  The last tier takes everything up to
 // upstream's own size limit, 3(2w+2h) points (set per call from the frame geometry), so no cluster upstream would
 // fit is ever skipped.
-constexpr int TIER_CAP_DEFAULT[AGPU_NTIERS] = {256, 1024, 2048, 0};
-// counter block layout (ints): [0..3] clusters per tier
-enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_CURSOR0 = 8, CNT_TIER_RECS0 = 12, CNT_FIXED = 16 };
+constexpr int TIER_CAP_DEFAULT[AGPU_NTIERS] = {256, 1024, 2048, 6144, 0};
+// (warps per cluster: 1 -- eight one-warp groups per CTA --, 2, 4, 4, 8.  The fourth tier (2049..6144 records: three CTAs
+// of four warps per SM) exists for noisy frames, whose background contours would otherwise all queue up behind the
+// one-CTA-per-SM last tier.)
 
 }  // namespace
 
@@ -90,8 +91,8 @@ enum { CNT_TIER0 = 0, CNT_OVERSIZE = 4, CNT_HEADS = 5, CNT_NQUADS = 6, CNT_CURSO
 struct Slot {
     cudaStream_t stream = nullptr;     // dense, bandwidth-bound front half: image, CC, edge points, radix sort
     cudaStream_t tail = nullptr;       // latency-bound back half (quad fit, decode, reconcile, pose, D2H): HIGH priority
-    cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};   // side streams: quad-fit tiers run concurrently
-    cudaEvent_t ev_mid = nullptr, ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr};
+    cudaStream_t aux[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr, nullptr};   // side streams: quad-fit tiers run concurrently
+    cudaEvent_t ev_mid = nullptr, ev_fork = nullptr, ev_join[AGPU_NTIERS - 1] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;   // stage timing
     struct KEv { const char* name; cudaEvent_t a, b; };
     std::vector<KEv> kev;              // profiling only: one event pair around EVERY kernel launch of the chunk
@@ -123,7 +124,7 @@ struct Slot {
     void release() {
         DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_labels, &d_canon, &d_sizes, &d_roots,
                           &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_qscratch, &d_gsort, &d_pairslots, &d_pairkeys, &d_paircount, &d_pairstart, &d_counters,
-                          &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_dbg_heads, &d_quads,
+                          &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_clusters[4], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
         for (DevBuf* bb : bufs) bb->release();
         h_out.release(); h_counts.release(); h_poses.release();
@@ -166,8 +167,9 @@ struct agpu_handle {
     // scheduling knobs (defaults below; AGPU_PRIO / AGPU_TIER_CTAS / AGPU_DECODE_CTAS override them for experiments)
     struct Tune {
         int prio = 1;                                  // back half of a chunk on high-priority streams
-        int tier_ctas[AGPU_NTIERS] = {3, 16, 8, 1};    // persistent quad-fit CTAs per SM, by size tier
-        int tier_cap[AGPU_NTIERS] = {TIER_CAP_DEFAULT[0], TIER_CAP_DEFAULT[1], TIER_CAP_DEFAULT[2], TIER_CAP_DEFAULT[3]};
+        int tier_ctas[AGPU_NTIERS] = {3, 16, 8, 3, 1};    // persistent quad-fit CTAs per SM, by size tier
+        int tier_cap[AGPU_NTIERS] = {TIER_CAP_DEFAULT[0], TIER_CAP_DEFAULT[1], TIER_CAP_DEFAULT[2], TIER_CAP_DEFAULT[3],
+                                     TIER_CAP_DEFAULT[4]};
         int decode_ctas = 4;                           // persistent decode CTAs (of 4 warps) per SM
         int edge_warps = 2, boundary_warps = 8;        // tiles (warps) per CTA of k_edges / k_cc_boundary
         int masks = 0;                                 // 1 (AGPU_MASKS=1), decimate 1: the threshold kernel writes the CC bit masks instead of
@@ -721,7 +723,8 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         // (profiling: the tiers run one after the other on the tail stream so that every kernel's event pair times
         // that kernel alone)
         const bool fork = !h->profiling;
-        static const char* const tier_name[AGPU_NTIERS] = {"k_fit_quads<1>", "k_fit_quads<2>", "k_fit_quads<4>", "k_fit_quads<8>"};
+        static const char* const tier_name[AGPU_NTIERS] = {"k_fit_quads<1>", "k_fit_quads<2>", "k_fit_quads<4>", "k_fit_quads<4>/6k",
+                                                           "k_fit_quads<8>"};
         for (int t = AGPU_NTIERS - 1; t >= 0; t--) {
             cudaStream_t st = (t == 0 || !fork) ? sl.tail : sl.aux[t - 1];
             if (t > 0 && fork) CK(cudaStreamWaitEvent(st, sl.ev_fork, 0));
@@ -730,7 +733,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             qa.cursor = d_cnt + CNT_CURSOR0 + t;
             // persistent groups: a full machine's worth for big chunks, no more than the chunk can keep busy for small ones
             // (a single 640x480 frame would otherwise launch 4000 CTAs whose only act is to find the work list empty)
-            static const int per_frame[AGPU_NTIERS] = {32, 96, 48, 12};   // per 320x240 working pixels
+            static const int per_frame[AGPU_NTIERS] = {32, 96, 48, 16, 12};   // per 320x240 working pixels
             const long long area = std::max<long long>(1, (long long)g.plane / 76800);
             const int nblk = std::max(1, (int)std::min<long long>((long long)h->num_sms * h->tune.tier_ctas[t], n * area * per_frame[t]));
             {   // this tier's slice of the per-group scratch (tiers are visited from the last to the first)
@@ -746,7 +749,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
                 k_fit_quads<1><<<nblk, 256, smem, st>>>(qa, h->prm, tier_smem[t]);
             } else if (t == 1) {
                 k_fit_quads<2><<<nblk, 64, qf_smem_per_group(tier_smem[t], 2), st>>>(qa, h->prm, tier_smem[t]);
-            } else if (t == 2) {
+            } else if (t == 2 || t == 3) {
                 k_fit_quads<4><<<nblk, 128, qf_smem_per_group(tier_smem[t], 4), st>>>(qa, h->prm, tier_smem[t]);
             } else {
                 k_fit_quads<8><<<nblk, 256, qf_smem_per_group(tier_smem[t], 8), st>>>(qa, h->prm, tier_smem[t]);
@@ -822,7 +825,7 @@ unsigned long long slot_buffer_hash(const agpu_handle* h, const Slot& s) {
     const DevBuf* bufs[] = {&s.d_in, &s.d_gray, &s.d_quad_im, &s.d_blur_tmp, &s.d_blur_orig, &s.d_thresh, &s.d_masks, &s.d_l16, &s.d_labels,
                             &s.d_canon, &s.d_sizes, &s.d_roots, &s.d_dense, &s.d_dense2rep, &s.d_recs[0], &s.d_recs[1],
                             &s.d_qscratch, &s.d_gsort, &s.d_pairslots, &s.d_pairkeys, &s.d_paircount, &s.d_pairstart, &s.d_counters, &s.d_clusters[0], &s.d_clusters[1], &s.d_clusters[2],
-                            &s.d_clusters[3], &s.d_quads, &s.d_dets, &s.d_out, &s.d_poses, &h->d_fams, &h->d_codes};
+                            &s.d_clusters[3], &s.d_clusters[4], &s.d_quads, &s.d_dets, &s.d_out, &s.d_poses, &h->d_fams, &h->d_codes};
     unsigned long long x = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { x = (x ^ v) * 1099511628211ull; };
     for (const DevBuf* b : bufs) mix((unsigned long long)(uintptr_t)b->p);
@@ -988,8 +991,13 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
         }
     }
     for (int t = 0; t < AGPU_NTIERS; t++) h->counters[1] += hc[CNT_TIER0 + t];
-    for (int t = 1; t < AGPU_NTIERS; t++) h->counters[4 + t] += hc[CNT_TIER0 + t];   // clusters per multi-warp tier
-    for (int t = 0; t < AGPU_NTIERS; t++) { h->tier_stats[t] += hc[CNT_TIER0 + t]; h->tier_stats[4 + t] += hc[CNT_TIER_RECS0 + t]; }
+    // public statistics: classes 0..3 = clusters of up to 256 / 1024 / 2048 / more records (the two large tiers together)
+    for (int t = 0; t < AGPU_NTIERS; t++) {
+        const int cls = std::min(t, 3);
+        if (cls > 0) h->counters[4 + cls] += hc[CNT_TIER0 + t];
+        h->tier_stats[cls] += hc[CNT_TIER0 + t];
+        h->tier_stats[4 + cls] += hc[CNT_TIER_RECS0 + t];
+    }
     h->counters[2] += hc[CNT_NQUADS];
     h->counters[4] += hc[CNT_OVERSIZE];
     h->last_slot = (int)(&sl - h->slots.data());
@@ -1210,7 +1218,7 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     }
     if (const char* e = getenv("AGPU_TIER_CTAS")) {
         int v[AGPU_NTIERS];
-        if (sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+        if (sscanf(e, "%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4]) == 5)
             for (int t = 0; t < AGPU_NTIERS; t++) h->tune.tier_ctas[t] = std::max(1, std::min(32, v[t]));
     }
     auto fail = [&](int rc, const std::string& msg) {
@@ -1311,10 +1319,11 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     ce = cudaFuncSetAttribute(k_fit_quads<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)qf_smem_per_group(QF_SMEM_CAP, 8));
     if (ce == cudaSuccess)
-        ce = cudaSuccess;
-    if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(k_fit_quads<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(8 * qf_smem_per_group(h->tune.tier_cap[0], 1)));
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(k_fit_quads<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)qf_smem_per_group(h->tune.tier_cap[3], 4));
     if (ce != cudaSuccess) return fail(AGPU_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
     *out = h;
     return AGPU_OK;

@@ -85,7 +85,7 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
         int* __restrict__ ndups, int* __restrict__ nvalid, int cap, PairTable pt) {
     __shared__ uint16_t scand[EDGE_WARPS][EDGE_CAND_PER_PASS];
     __shared__ uint16_t sdense[EDGE_WARPS][1024];   // dense component id of every run of the tile, at its start pixel
-    __shared__ unsigned long long scache[EDGE_WARPS][4];   // the warp's last pair keys and their cluster ids (a tile sees a handful)
+    __shared__ unsigned long long scache[EDGE_WARPS][8];   // the warp's last pair keys and their cluster ids (a tile sees a handful)
     // grid = (frames, x blocks, tile rows): consecutive CTAs belong to DIFFERENT frames, so the per-frame append
     // counters are not hammered by every resident warp at once
     const int frame = blockIdx.x;
@@ -162,7 +162,7 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
     __syncwarp();
 
     unsigned long long* fk = recs + (size_t)frame * cap;
-    if (lane < 4) scache[w][lane] = PT_EMPTY;
+    if (lane < 8) scache[w][lane] = PT_EMPTY;
     __syncwarp();
     const int npass = total_all <= EDGE_CAND_PER_PASS ? 1 : 4;
     const int rsh = npass == 1 ? 5 : 3;   // rows per pass = 1 << rsh
@@ -225,11 +225,12 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
             const int leader = __ffs(peers) - 1;
             uint32_t cid = 0xffffffffu;
             if (ok && lane == leader) {
-                const unsigned long long ce = scache[w][pair_hash(key) >> 30];
+                const uint32_t cs = pair_hash(key) >> 29;
+                const unsigned long long ce = scache[w][cs];
                 if ((uint32_t)(ce >> 32) == key) cid = (uint32_t)ce;
                 else {
                     cid = pair_cluster_id(pt, frame, key);
-                    if (cid != 0xffffffffu) scache[w][pair_hash(key) >> 30] = ((unsigned long long)key << 32) | cid;
+                    if (cid != 0xffffffffu) scache[w][cs] = ((unsigned long long)key << 32) | cid;
                 }
             }
             if (ok && lane == leader && cid != 0xffffffffu)      // the digit histogram of the sort, taken at the source
@@ -268,11 +269,14 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
 #define RS_TILE (RS_THREADS * RS_ITEMS)  // records per scatter block (and the granularity of the list capacity)
 
 // cluster work lists, by size tier (the tier decides how much shared memory the fitting warp gets)
-#define AGPU_NTIERS 4
+#define AGPU_NTIERS 5
+// counter block shared by the host and the kernels (ints): clusters per tier, clusters over upstream's size limit, all
+// heads (debug), quads, per-tier work cursors, records per tier
+enum { CNT_TIER0 = 0, CNT_OVERSIZE = 5, CNT_HEADS = 6, CNT_NQUADS = 7, CNT_CURSOR0 = 8, CNT_TIER_RECS0 = 16, CNT_FIXED = 24 };
 struct ClusterLists {
     ClusterRef* list[AGPU_NTIERS];
     int cap[AGPU_NTIERS];    // largest cluster size of the tier
-    int* counters;           // [0..3] tier counts, [4] clusters over upstream's size limit, [5] all heads (debug), [8..11] tier work cursors, [12..15] records per tier
+    int* counters;           // the CNT_* block
     int cap_list;
     ClusterRef* dbg_heads;   // all run heads (debug only, may be null)
     int cap_dbg;
@@ -340,7 +344,7 @@ k_cluster_refs(PairTable pt, Geom g, int min_size, ClusterLists cl, int cap) {
             if (cl.dbg_heads) {
                 const uint32_t m = __ballot_sync(FULL_MASK, live);
                 int b0 = 0;
-                if (lane == 0 && m) b0 = atomicAdd(&cl.counters[5], __popc(m));
+                if (lane == 0 && m) b0 = atomicAdd(&cl.counters[CNT_HEADS], __popc(m));
                 b0 = __shfl_sync(FULL_MASK, b0, 0) + __popc(m & ((1u << lane) - 1u));
                 if (live && b0 < cl.cap_dbg) cl.dbg_heads[b0] = ref;
             }
@@ -349,7 +353,7 @@ k_cluster_refs(PairTable pt, Geom g, int min_size, ClusterLists cl, int cap) {
                 const uint32_t m = __ballot_sync(FULL_MASK, tier == t);
                 if (m == 0) continue;
                 if (t == AGPU_NTIERS) {
-                    if (lane == 0) atomicAdd(&cl.counters[4], __popc(m));
+                    if (lane == 0) atomicAdd(&cl.counters[CNT_OVERSIZE], __popc(m));
                     continue;
                 }
                 int recs_t = tier == t ? size : 0;
@@ -357,8 +361,8 @@ k_cluster_refs(PairTable pt, Geom g, int min_size, ClusterLists cl, int cap) {
                 for (int off = 16; off > 0; off >>= 1) recs_t += __shfl_xor_sync(FULL_MASK, recs_t, off);
                 int s0 = 0;
                 if (lane == 0) {
-                    s0 = atomicAdd(&cl.counters[t], __popc(m));
-                    atomicAdd(&cl.counters[12 + t], recs_t);   // records handed to this tier (instrumentation)
+                    s0 = atomicAdd(&cl.counters[CNT_TIER0 + t], __popc(m));
+                    atomicAdd(&cl.counters[CNT_TIER_RECS0 + t], recs_t);   // records handed to this tier (instrumentation)
                 }
                 s0 = __shfl_sync(FULL_MASK, s0, 0) + __popc(m & ((1u << lane) - 1u));
                 if (tier == t && s0 < cl.cap_list) cl.list[t][s0] = ref;

@@ -302,6 +302,7 @@ k_pose(PoseArgs a) {
             bool improved = false;
             double step_norm = 0;
             const double cost_before = cost;
+            bool at_minimum = false;
             for (int tries = 0; tries < 12 && !improved; tries++) {
                 double d[6];
                 const bool solved = solve6_sym(S, lambda, b, d);
@@ -326,10 +327,17 @@ k_pose(PoseArgs a) {
                     lambda = fmax(lambda * 0.1, 1e-12);
                     improved = true;
                 } else {
+                    // a proposed step that is already below the resolution of the estimate and still does not lower the
+                    // cost: what is left is rounding noise -- stop instead of raising the damping eleven more times
+                    if (solved && sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3] + d[4] * d[4] + d[5] * d[5]) <
+                                      1e-9 * (1 + sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]))) {
+                        at_minimum = true;
+                        break;
+                    }
                     lambda *= 10;
                 }
             }
-            if (!improved) break;
+            if (!improved || at_minimum) break;
             residual(R, t, ru, rv, Jr, true);
             double tn2 = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
             if (step_norm < 1e-11 * (1 + tn2)) { iters++; break; }   // quadratic convergence: the next step would be ~1e-20

@@ -399,6 +399,27 @@ __device__ bool group_bucket_sort(const QGroup<NW>& G, unsigned long long* sbuf,
     return true;
 }
 
+// Tiny clusters (sensor noise produces thousands per frame): rank sort.  Every thread counts the keys below its own -- the
+// keys are distinct, so the count is the final position -- with broadcast reads of the shared buffer; no counters, no
+// scratch traffic, a few hundred instructions for the 30..60 keys such a cluster has.
+#define QF_RANK_SORT_MAX 64
+template <int NW>
+__device__ void group_rank_sort(const QGroup<NW>& G, unsigned long long* sbuf, unsigned long long* tmp, int n) {
+    constexpr int T = QGroup<NW>::T;
+#pragma unroll 1
+    for (int i = G.tid; i < n; i += T) {
+        const unsigned long long k = sbuf[i];
+        int r = 0;
+#pragma unroll 4
+        for (int j = 0; j < n; j++) r += sbuf[j] < k;
+        tmp[r] = k;
+    }
+    G.sync();
+#pragma unroll 1
+    for (int i = G.tid; i < n; i += T) sbuf[i] = tmp[i];
+    G.sync();
+}
+
 // Returns true (uniformly over the group) and fills q when the cluster yields a quad.
 template <int NW>
 __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, const DevParams& P, const ClusterRef ref,
@@ -482,8 +503,10 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         sbuf[i] = key;
     }
     G.sync();
-    // (the bucket counters borrow the prefix-moment stage: 1 KB / 2 KB of the 1.6 KB / 3+ KB it has)
-    if (sz > (NW == 1 ? 512 : 4096) ||
+    // (the bucket counters / the rank sort's second buffer borrow the prefix-moment stage: 1 KB / 2 KB of the 1.6 KB / 3+ KB
+    // it has)
+    if (sz <= QF_RANK_SORT_MAX) group_rank_sort<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(stage), sz);
+    else if (sz > (NW == 1 ? 512 : 4096) ||
         !group_bucket_sort<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(lf), sz, reinterpret_cast<uint32_t*>(stage))) {
         group_radix_sort_hi32<NW>(G, sbuf, reinterpret_cast<unsigned long long*>(lf), sz, scnt);
         group_fix_ties<NW>(G, sbuf, sz);

@@ -459,7 +459,7 @@ def run_b200(args):
         tiers_pf = [r / (B * 1.0) for r in tier["records"]]
         own = {"k_decimate_threshold": a_img, "k_cc_local": Nd + Nd // 4, "k_cc_boundary": Nd // 4,
                "k_fit_quads<1>": 8 * tiers_pf[0], "k_fit_quads<2>": 8 * tiers_pf[1], "k_fit_quads<4>": 8 * tiers_pf[2],
-               "k_fit_quads<8>": 8 * tiers_pf[3]}
+               "k_sort_scatter": 16 * sum(tiers_pf), "k_edges": Nd // 4 + 8 * sum(tiers_pf)}   # (records of clusters >= 24 points)
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:

@@ -141,7 +141,7 @@ int agpu_get_stage_ms(agpu_handle* h, float* ms /* [AGPU_NUM_STAGES] */);
  * on (and the quad-fit size tiers, normally concurrent on side streams, run one after the other), so with
  * pipeline_slots = 1 each interval is that kernel alone.  agpu_get_kernel_ms: milliseconds of one kernel summed over
  * the chunks of the last call; names: k_decimate_threshold, k_pack(bgr), k_cc_local, k_cc_boundary, k_cc_sizes,
- * k_cc_dense, k_edges, k_sort_hist, k_sort_scan, k_sort_scatter, k_cluster_heads, k_fit_quads<1|2|4|8>,
+ * k_cc_dense, k_edges, k_cluster_refs, k_sort_scatter, k_fit_quads<1>, <2>, <4>, <4>/6k, <8>,
  * k_decode_quads, k_reconcile, k_pose.  agpu_get_kernel_table: all of them as text lines "name\tms\tlaunches\n";
  * returns the bytes needed (terminator included) and copies at most cap. */
 int agpu_get_kernel_ms(agpu_handle* h, const char* kernel, float* ms);
@@ -154,11 +154,12 @@ int agpu_get_timeline(agpu_handle* h, float* out, int cap_floats);
 int agpu_get_launch_count(agpu_handle* h, long long* launches);
 /* Work counters of the last call, summed over frames: [0] edge points, [1] clusters fitted,
  * [2] quads, [3] detections before reconcile, [4] clusters over upstream's size limit of 3(2w+2h) raw points
- * (dropped before fitting, exactly as upstream drops them), [5] / [6] / [7] clusters fitted by the 2- / 4- / 8-warp
- * tiers of the quad-fit kernel (cluster size classes; [1] counts all tiers). */
+ * (dropped before fitting, exactly as upstream drops them), [5] / [6] / [7] clusters of up to 1024 / up to 2048 / more
+ * records handed to the multi-warp tiers of the quad-fit kernel ([1] counts all tiers). */
 int agpu_get_counters(agpu_handle* h, long long* counters /* [8] */);
-/* Quad-fit size tiers (1- / 2- / 4- / 8-warp groups) in the last call: [0..3] clusters, [4..7] edge-point records handed
- * to each tier (8 bytes each: the algorithmic input of k_fit_quads<1|2|4|8>). */
+/* Quad-fit size classes in the last call (clusters of up to 256 / 1024 / 2048 / more records: k_fit_quads<1>, <2>, <4>, and
+ * the two large tiers together): [0..3] clusters, [4..7] edge-point records handed to each class (8 bytes each: the
+ * algorithmic input of those kernels). */
 int agpu_get_tier_stats(agpu_handle* h, long long* stats /* [8] */);
 
 /* Stage dumps for parity tests (cfg.debug = 1): buffers of frame `frame` of the LAST chunk.
