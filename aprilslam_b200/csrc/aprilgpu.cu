@@ -99,7 +99,7 @@ struct Slot {
     size_t kev_next = 0;
     DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_labels, d_canon, d_sizes, d_roots, d_dense, d_dense2rep;
     DevBuf d_recs[2], d_qscratch, d_gsort, d_pairslots, d_pairkeys, d_paircount, d_pairstart;
-    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk], ncl[chunk], nvalid[chunk]
+    DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk], ncl[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
     HostBuf h_out, h_counts, h_poses;
     bool pending = false, from_masks = false;
@@ -629,7 +629,6 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int* d_nroots = d_ndense + chunk;          // CC_SUBLISTS counters per frame
     int* d_ndups = d_nroots + CC_SUBLISTS * chunk;   // merged duplicate points per frame (raw points = npts + ndups)
     int* d_ncl = d_ndups + chunk;                     // cluster ids handed out per frame
-    int* d_nvalid = d_ncl + chunk;                    // records emitted per frame (npts counts reserved slots, holes included)
     StageTimer tm(h, sl);
     sl.kev_next = 0;
     tm.mark();  // 0
@@ -663,7 +662,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
         const int ew = h->tune.edge_warps;
         dim3 grid(n, ceil_div(cc_tiles_x(g), ew), cc_tiles_y(g));
 #define LAUNCH_EDGES(EW) k_edges<EW><<<grid, EW * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), \
-            sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g, sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, d_nvalid, cap, ptab)
+            sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g, sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, cap, ptab)
         {
             KScope ks(h, sl, "k_edges", sl.stream);
             if (ew == 1) LAUNCH_EDGES(1); else if (ew == 2) LAUNCH_EDGES(2); else if (ew == 4) LAUNCH_EDGES(4); else LAUNCH_EDGES(8);
@@ -946,7 +945,6 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     const int* h_ndense = h_oc + chunk;
     const int* h_ndups = h_ndense + chunk + CC_SUBLISTS * chunk;
     const int* h_ncl = h_ndups + chunk;
-    const int* h_nvalid = h_ncl + chunk;
     int max_dense = 0;
     for (int i = 0; i < n; i++) max_dense = std::max(max_dense, h_ndense[i]);
     if (max_dense > AGPU_MAX_DENSE) {
@@ -983,7 +981,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
             h->set_err("more detections than cap_per_frame; counts[] hold the true numbers");
             rc_final = AGPU_E_TRUNCATED;
         }
-        h->counters[0] += h_nvalid[i] + h_ndups[i];   // raw edge points, as upstream counts them
+        h->counters[0] += h_npts[i] + h_ndups[i];   // raw edge points, as upstream counts them
         h->counters[3] += h_nd[i];
         if (h_nd[i] > REC_CAP && rc_final == AGPU_OK) {   // (upstream has no such limit; the frame keeps its first 256 candidates)
             h->set_err("more than 256 raw detections (before reconcile) in one frame: the surplus was dropped");
@@ -1080,7 +1078,7 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
     c.cap = (c.cap + RS_TILE - 1) / RS_TILE * RS_TILE;
     c.maxcl = auto_cl ? std::max(h->cap_clusters, 8192) : h->cfg.max_clusters_per_frame;
     c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
-    c.ncnt = CNT_FIXED + (size_t)(8 + CC_SUBLISTS) * chunk;
+    c.ncnt = CNT_FIXED + (size_t)(7 + CC_SUBLISTS) * chunk;
     c.cap_keys = std::max(h->cap_keys, 4096);
     c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 

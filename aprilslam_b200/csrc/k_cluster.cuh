@@ -82,7 +82,7 @@ template <int EDGE_WARPS>
 __global__ void __launch_bounds__(EDGE_WARPS * 32, EDGE_WARPS == 2 ? EDGE_MINB : 1)
 k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
         const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts,
-        int* __restrict__ ndups, int* __restrict__ nvalid, int cap, PairTable pt) {
+        int* __restrict__ ndups, int cap, PairTable pt) {
     __shared__ uint16_t scand[EDGE_WARPS][EDGE_CAND_PER_PASS];
     __shared__ uint16_t sdense[EDGE_WARPS][1024];   // dense component id of every run of the tile, at its start pixel
     __shared__ unsigned long long scache[EDGE_WARPS][8];   // the warp's last pair keys and their cluster ids (a tile sees a handful)
@@ -251,8 +251,7 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
             int base = 0;
             if (lane == 0) {
                 base = atomicAdd(&npts[frame], __popc(okm));
-                atomicAdd(&nvalid[frame], __popc(okm));
-                if (dupm) atomicAdd(&ndups[frame], __popc(dupm));   // (raw point count = nvalid + ndups)
+                if (dupm) atomicAdd(&ndups[frame], __popc(dupm));   // (raw point count = npts + ndups)
             }
             base = __shfl_sync(FULL_MASK, base, 0);
             const int p = base + __popc(okm & ((1u << lane) - 1u));
