@@ -98,6 +98,18 @@ __device__ __noinline__ void fit_line_dev(const double* lf, int sz, int i0, int 
 
 #define QF_PTAB_DOUBLES (100 * 6)
 
+// the C(9,3) = 84 triples m0 < m1 < m2 <= 8 in colexicographic order (by m2, then m1, then m0), packed m0 | m1 << 4 | m2 << 8
+struct QfTrips { unsigned short v[84]; };
+constexpr QfTrips qf_make_trips() {
+    QfTrips t{};
+    int k = 0;
+    for (int c = 2; c <= 8; c++)
+        for (int b = 1; b < c; b++)
+            for (int a = 0; a < b; a++) t.v[k++] = (unsigned short)(a | (b << 4) | (c << 8));
+    return t;
+}
+__constant__ QfTrips c_qf_trips = qf_make_trips();
+
 // A cluster is fitted by a GROUP of NW warps.  NW == 1: the group is a warp (several clusters per CTA, warp
 // synchronisation); NW > 1: the group is the whole CTA (one cluster at a time, __syncthreads), which puts
 // NW times more warps on every shared-memory sort buffer -- the buffer, not the thread count, is what limits
@@ -694,43 +706,51 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
     G.sync();
 
     // ---- exhaustive search over 4-subsets (first minimum in lexicographic order wins).  The work is dealt to the
-    //      threads; the tie-break key is the subset itself packed most-significant-first, which orders exactly
-    //      like upstream's nested loops.
+    //      threads by (m0, m1, m2) TRIPLES -- the inner loop of a triple is at most seven candidates long, so the threads
+    //      finish together -- taken from a table in colexicographic order (the triples for n maxima are a prefix of those
+    //      for n + 1), so a thread goes straight to ITS triples instead of counting through all of them.  Which pairs of
+    //      maxima are joined by an acceptable line (mse <= max) is a 100-bit mask in four registers (one ballot per 32
+    //      pairs): the inner loop tests bits and touches the table only for the subsets that survive.  The tie-break
+    //      key is the subset itself packed most-significant-first, which orders exactly like upstream's nested loops.
     double best = HUGE_VALF;
     int best_c = 0x7fffffff, best_pack = 0;
     {
         const double max_mse = P.max_line_fit_mse, max_dot = P.cos_critical_rad;
-        // dealt by (m0, m1, m2) TRIPLES: the inner loop of a triple is at most seven candidates long, so the threads
-        // finish together (dealt by pairs, the pair (0, 1) alone carried 28 of the 210 subsets)
-        int pr = 0;
-        for (int m0 = 0; m0 < nmax - 3; m0++)
-            for (int m1 = m0 + 1; m1 < nmax - 2; m1++) {
-                const double* e01 = ptab + (m0 * 10 + m1) * 6;
-                const bool ok01 = !(e01[5] > max_mse);
+        uint32_t okw[4];
+#pragma unroll
+        for (int wd = 0; wd < 4; wd++) {
+            const int i = wd * 32 + lane, ia = i / 10, ib = i - ia * 10;
+            const bool ok = i < 100 && ia < nmax && ib < nmax && ia != ib && !(ptab[i * 6 + 5] > max_mse);
+            okw[wd] = __ballot_sync(FULL_MASK, ok);
+        }
+        const unsigned long long ok_lo = okw[0] | ((unsigned long long)okw[1] << 32), ok_hi = okw[2] | ((unsigned long long)okw[3] << 32);
+        auto pair_ok = [&](int a_, int b_) -> bool {
+            const int i = a_ * 10 + b_;
+            return ((i < 64 ? ok_lo >> i : ok_hi >> (i - 64)) & 1ull) != 0ull;
+        };
+        const int n1 = nmax - 1, ntrip = n1 * (n1 - 1) * (n1 - 2) / 6;   // triples with m2 <= nmax - 2
 #pragma unroll 1
-                for (int m2 = m1 + 1; m2 < nmax - 1; m2++, pr++) {
-                    if (pr % T != tid) continue;
-                    if (!ok01) continue;
-                    const double* e12 = ptab + (m1 * 10 + m2) * 6;
-                    if (e12[5] > max_mse) continue;
-                    const double d = e01[2] * e12[2] + e01[3] * e12[3];
-                    if (fabs(d) > max_dot) continue;
+        for (int idx = tid; idx < ntrip; idx += T) {
+            const int tr = c_qf_trips.v[idx];
+            const int m0 = tr & 15, m1 = (tr >> 4) & 15, m2 = tr >> 8;
+            if (!pair_ok(m0, m1) || !pair_ok(m1, m2)) continue;
+            const double* e01 = ptab + (m0 * 10 + m1) * 6;
+            const double* e12 = ptab + (m1 * 10 + m2) * 6;
+            const double d = e01[2] * e12[2] + e01[3] * e12[3];
+            if (fabs(d) > max_dot) continue;
+            const double e012 = e01[4] + e12[4];
 #pragma unroll 1
-                    for (int m3 = m2 + 1; m3 < nmax; m3++) {
-                        const double* e23 = ptab + (m2 * 10 + m3) * 6;
-                        const double* e30 = ptab + (m3 * 10 + m0) * 6;
-                        if (e23[5] > max_mse) continue;
-                        if (e30[5] > max_mse) continue;
-                        const double err = e01[4] + e12[4] + e23[4] + e30[4];
-                        const int lex = (m0 << 12) | (m1 << 8) | (m2 << 4) | m3;
-                        if (err < best || (err == best && lex < best_c)) {
-                            best = err;
-                            best_c = lex;
-                            best_pack = m0 | (m1 << 4) | (m2 << 8) | (m3 << 12);
-                        }
-                    }
+            for (int m3 = m2 + 1; m3 < nmax; m3++) {
+                if (!pair_ok(m2, m3) || !pair_ok(m3, m0)) continue;
+                const double err = e012 + ptab[(m2 * 10 + m3) * 6 + 4] + ptab[(m3 * 10 + m0) * 6 + 4];
+                const int lex = (m0 << 12) | (m1 << 8) | (m2 << 4) | m3;
+                if (err < best || (err == best && lex < best_c)) {
+                    best = err;
+                    best_c = lex;
+                    best_pack = m0 | (m1 << 4) | (m2 << 8) | (m3 << 12);
                 }
             }
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
