@@ -97,7 +97,7 @@ struct Slot {
     struct KEv { const char* name; cudaEvent_t a, b; };
     std::vector<KEv> kev;              // profiling only: one event pair around EVERY kernel launch of the chunk
     size_t kev_next = 0;
-    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_labels, d_canon, d_sizes, d_roots, d_dense, d_dense2rep;
+    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_canon, d_canon_sizes, d_roottab, d_tilebase, d_dense2rep;
     DevBuf d_recs[2], d_qscratch, d_gsort, d_pairslots, d_pairkeys, d_paircount, d_pairstart;
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk], ncl[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
@@ -108,7 +108,7 @@ struct Slot {
     // per frame: ~30 launches and a dozen event calls per call otherwise).  Captured the second time a call with the
     // same key arrives; any change of geometry, capacities, pose parameters or buffer addresses re-captures.
     struct GraphKey {
-        int W, H, stride, channels, n, cap, maxcl, maxq, cap_out, cap_keys, pose;
+        int W, H, stride, channels, n, cap, maxcl, maxq, cap_out, cap_keys, roots_cap, pose;
         double K[9], dist[8], tag_size;
         int ndist;
         unsigned long long buffers;   // hash of every buffer address the kernels were given
@@ -122,8 +122,8 @@ struct Slot {
     bool graph_from_masks = false;
 
     void release() {
-        DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_labels, &d_canon, &d_sizes, &d_roots,
-                          &d_dense, &d_dense2rep, &d_recs[0], &d_recs[1], &d_qscratch, &d_gsort, &d_pairslots, &d_pairkeys, &d_paircount, &d_pairstart, &d_counters,
+        DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_canon, &d_canon_sizes, &d_roottab,
+                          &d_tilebase, &d_dense2rep, &d_recs[0], &d_recs[1], &d_qscratch, &d_gsort, &d_pairslots, &d_pairkeys, &d_paircount, &d_pairstart, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_clusters[4], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
         for (DevBuf* bb : bufs) bb->release();
@@ -191,6 +191,7 @@ struct agpu_handle {
     int cap_points = 0, cap_clusters = 0, cap_quads = 0;
     int max_dense_seen = -1, max_clusters_seen = -1;   // most components / clusters seen in one frame so far (statistics)
     int cap_keys = 0;   // cluster-id capacity per frame (grows like the other work lists)
+    int cap_roots = 0;  // tile-local roots per sub-list (likewise)
 
     // state of the last finished chunk (debug fetch)
     Geom geom;
@@ -467,60 +468,70 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
     return AGPU_OK;
 }
 
-int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const Geom& g, int* d_nroots, int* d_ndense,
-                 bool canonical, bool from_masks = false) {
-    CK(sl.d_labels.ensure(g.plane * n * 4));
-    CK(sl.d_sizes.ensure(g.plane * n * 4));
+// root tables of `n` frames in one allocation (five u32 arrays of CC_SUBLISTS * sub_cap entries per frame)
+int make_root_tables(agpu_handle* h, Slot& sl, int n, const Geom& g, int sub_cap, int* d_nroots, CcRoots& rt) {
+    const int tx = cc_tiles_x(g), ty = cc_tiles_y(g);
+    const size_t per = (size_t)CC_SUBLISTS * sub_cap * n;
+    CK(sl.d_roottab.ensure(per * 5 * 4));
+    CK(sl.d_tilebase.ensure((size_t)tx * ty * n * 4));
+    uint32_t* p = sl.d_roottab.as<uint32_t>();
+    rt.links = p; rt.sizes = p + per; rt.rootpix = p + 2 * per; rt.minpix = p + 3 * per; rt.dense = p + 4 * per;
+    rt.tile_base = sl.d_tilebase.as<uint32_t>();
+    rt.nroots = d_nroots;
+    rt.sub_cap = sub_cap;
+    rt.ntiles = tx * ty;
+    return AGPU_OK;
+}
+
+int default_roots_cap(const Geom& g) {   // tile-local roots per sub-list: a sixteenth of the pixels per frame in all
+    return std::max(1024, (int)(g.plane / 256));
+}
+
+int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const Geom& g, int sub_cap, int* d_nroots,
+                 int* d_ndense, bool canonical, CcRoots& rt, bool from_masks = false) {
     const int tx = cc_tiles_x(g), ty = cc_tiles_y(g);
     CK(sl.d_masks.ensure((size_t)tx * ty * n * 32 * sizeof(uint2)));
     CK(sl.d_l16.ensure((size_t)tx * ty * n * 1024 * sizeof(uint16_t)));
-    // a root sub-list (tile rows r with r % 16 == s) can never hold more than 512 roots per tile
-    const size_t sub_stride = (size_t)tx * ceil_div(ty, CC_SUBLISTS) * 512;
-    CK(sl.d_roots.ensure(sub_stride * CC_SUBLISTS * n * 4));
+    int rc = make_root_tables(h, sl, n, g, sub_cap, d_nroots, rt);
+    if (rc) return rc;
     dim3 grid(ceil_div(tx, CC_WARPS), ty, n);
     {
     KScope ks(h, sl, "k_cc_local", sl.stream);
     if (from_masks)
-        k_cc_local<true><<<grid, CC_THREADS, 0, sl.stream>>>(nullptr, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
-                                                             sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
-                                                             sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
+        k_cc_local<true><<<grid, CC_THREADS, 0, sl.stream>>>(nullptr, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), rt, g);
     else
-        k_cc_local<false><<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
-                                                              sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(),
-                                                              sl.d_roots.as<uint32_t>(), d_nroots, g, sub_stride);
+        k_cc_local<false><<<grid, CC_THREADS, 0, sl.stream>>>(d_thresh, sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), rt, g);
     }
     LAUNCH_CHECK("k_cc_local");
     {
         KScope ks(h, sl, "k_cc_boundary", sl.stream);
         const int bw = h->tune.boundary_warps;
         dim3 gridb(ceil_div(tx * ty, bw), 1, n);
-#define LAUNCH_CCB(BW) k_cc_boundary<BW><<<gridb, BW * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), sl.d_labels.as<uint32_t>(), g)
+#define LAUNCH_CCB(BW) k_cc_boundary<BW><<<gridb, BW * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), rt, g)
         if (bw == 1) LAUNCH_CCB(1); else if (bw == 2) LAUNCH_CCB(2); else if (bw == 4) LAUNCH_CCB(4); else LAUNCH_CCB(8);
 #undef LAUNCH_CCB
     }
     LAUNCH_CHECK("k_cc_boundary");
-    dim3 grids(std::max(1, std::min(8, ceil_div(g.plane / 1024, 256))), n * CC_SUBLISTS);
+    dim3 grids(std::max(1, std::min(8, ceil_div(sub_cap, 256))), n * CC_SUBLISTS);
     {
         KScope ks(h, sl, "k_cc_sizes", sl.stream);
-        k_cc_sizes<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
-                                                 d_nroots, g, sub_stride);
+        k_cc_sizes<<<grids, 256, 0, sl.stream>>>(rt);
     }
     LAUNCH_CHECK("k_cc_sizes");
     if (d_ndense) {
-        CK(sl.d_dense.ensure(g.plane * n * 4));
         CK(sl.d_dense2rep.ensure((size_t)n * AGPU_MAX_DENSE * 4));
         {
             KScope ks(h, sl, "k_cc_dense", sl.stream);
-            k_cc_dense<<<grids, 256, 0, sl.stream>>>(sl.d_labels.as<uint32_t>(), sl.d_sizes.as<uint32_t>(), sl.d_roots.as<uint32_t>(),
-                                                     d_nroots, sl.d_dense.as<uint32_t>(), sl.d_dense2rep.as<uint32_t>(), d_ndense, g, sub_stride);
+            k_cc_dense<<<grids, 256, 0, sl.stream>>>(rt, sl.d_dense2rep.as<uint32_t>(), d_ndense);
         }
         LAUNCH_CHECK("k_cc_dense");
     }
     if (canonical) {   // stage dumps only
         CK(sl.d_canon.ensure(g.plane * n * 4));
+        CK(sl.d_canon_sizes.ensure(g.plane * n * 4));
         dim3 gridf(ceil_div(g.wd, 32), ceil_div(g.hd, 8), n);
-        k_cc_canonical<<<gridf, 256, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(),
-                                                     sl.d_labels.as<uint32_t>(), sl.d_canon.as<uint32_t>(), g);
+        k_cc_canonical<<<gridf, 256, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), rt, sl.d_canon.as<uint32_t>(),
+                                                     sl.d_canon_sizes.as<uint32_t>(), g);
         LAUNCH_CHECK("k_cc_canonical");
     }
     return AGPU_OK;
@@ -567,6 +578,7 @@ struct CallCtx {   // constants of one agpu_detect* call
     Geom g;
     int chunk, cap, maxcl, maxq, cap_out, key_bits;
     int cap_keys;     // cluster ids per frame the pair table can hand out
+    int roots_cap;    // tile-local roots per sub-list of a frame (CC_SUBLISTS sub-lists)
     size_t ncnt;
     const PoseSpec* pose;
 };
@@ -655,14 +667,15 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
                              &q_frame, &gray_full, &gray_pitch, &gray_frame, &from_masks);
     if (rc) return rc;
     tm.mark();  // 2: after image
-    rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), n, g, d_nroots, d_ndense, h->cfg.debug != 0, from_masks);
+    CcRoots rt;
+    rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), n, g, c.roots_cap, d_nroots, d_ndense, h->cfg.debug != 0, rt, from_masks);
     if (rc) return rc;
     tm.mark();  // 3: after CC
     {
         const int ew = h->tune.edge_warps;
         dim3 grid(n, ceil_div(cc_tiles_x(g), ew), cc_tiles_y(g));
 #define LAUNCH_EDGES(EW) k_edges<EW><<<grid, EW * 32, 0, sl.stream>>>(sl.d_masks.as<uint2>(), sl.d_l16.as<uint16_t>(), \
-            sl.d_labels.as<uint32_t>(), sl.d_dense.as<uint32_t>(), g, sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, cap, ptab)
+            rt, g, sl.d_recs[0].as<unsigned long long>(), d_npts, d_ndups, cap, ptab)
         {
             KScope ks(h, sl, "k_edges", sl.stream);
             if (ew == 1) LAUNCH_EDGES(1); else if (ew == 2) LAUNCH_EDGES(2); else if (ew == 4) LAUNCH_EDGES(4); else LAUNCH_EDGES(8);
@@ -821,8 +834,8 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
 }
 
 unsigned long long slot_buffer_hash(const agpu_handle* h, const Slot& s) {
-    const DevBuf* bufs[] = {&s.d_in, &s.d_gray, &s.d_quad_im, &s.d_blur_tmp, &s.d_blur_orig, &s.d_thresh, &s.d_masks, &s.d_l16, &s.d_labels,
-                            &s.d_canon, &s.d_sizes, &s.d_roots, &s.d_dense, &s.d_dense2rep, &s.d_recs[0], &s.d_recs[1],
+    const DevBuf* bufs[] = {&s.d_in, &s.d_gray, &s.d_quad_im, &s.d_blur_tmp, &s.d_blur_orig, &s.d_thresh, &s.d_masks, &s.d_l16,
+                            &s.d_canon, &s.d_canon_sizes, &s.d_roottab, &s.d_tilebase, &s.d_dense2rep, &s.d_recs[0], &s.d_recs[1],
                             &s.d_qscratch, &s.d_gsort, &s.d_pairslots, &s.d_pairkeys, &s.d_paircount, &s.d_pairstart, &s.d_counters, &s.d_clusters[0], &s.d_clusters[1], &s.d_clusters[2],
                             &s.d_clusters[3], &s.d_clusters[4], &s.d_quads, &s.d_dets, &s.d_out, &s.d_poses, &h->d_fams, &h->d_codes};
     unsigned long long x = 1469598103934665603ull;
@@ -843,7 +856,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     Slot::GraphKey key;
     memset(&key, 0, sizeof(key));
     key.W = c.W; key.H = c.H; key.stride = c.stride; key.channels = c.channels; key.n = n; key.cap = c.cap; key.maxcl = c.maxcl;
-    key.maxq = c.maxq; key.cap_out = c.cap_out; key.cap_keys = c.cap_keys; key.pose = c.pose->enabled ? 1 : 0;
+    key.maxq = c.maxq; key.cap_out = c.cap_out; key.cap_keys = c.cap_keys; key.roots_cap = c.roots_cap; key.pose = c.pose->enabled ? 1 : 0;
     if (c.pose->enabled) {
         memcpy(key.K, c.pose->K, sizeof(key.K)); memcpy(key.dist, c.pose->dist, sizeof(key.dist));
         key.tag_size = c.pose->tag_size; key.ndist = c.pose->ndist;
@@ -904,7 +917,7 @@ int launch_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
 }
 
 struct Overflow {
-    int max_pts = 0, max_cl_per_frame = 0, max_q_per_frame = 0, max_ncl = 0;
+    int max_pts = 0, max_cl_per_frame = 0, max_q_per_frame = 0, max_ncl = 0, max_roots = 0;
     bool any = false;
 };
 
@@ -961,6 +974,13 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
     bool redo = false;
     // the pair table ran out of cluster ids: run the chunk again with a larger one
     if (max_ncl > c.cap_keys) { ov.max_ncl = std::max(ov.max_ncl, max_ncl); redo = true; }
+    // ... or a root sub-list was too short for the frame's tile-local roots
+    int max_roots = 0;
+    {
+        const int* h_nroots = h_ndense + chunk;
+        for (int i = 0; i < n * CC_SUBLISTS; i++) max_roots = std::max(max_roots, h_nroots[i]);
+    }
+    if (max_roots > c.roots_cap) { ov.max_roots = std::max(ov.max_roots, max_roots); redo = true; }
     if (max_pts > c.cap) { ov.max_pts = std::max(ov.max_pts, max_pts); redo = true; }
     if (max_cl > n * c.maxcl) { ov.max_cl_per_frame = std::max(ov.max_cl_per_frame, (max_cl + n - 1) / n); redo = true; }
     if (hc[CNT_NQUADS] > n * c.maxq) { ov.max_q_per_frame = std::max(ov.max_q_per_frame, (hc[CNT_NQUADS] + n - 1) / n); redo = true; }
@@ -1080,6 +1100,7 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
     c.maxq = auto_q ? std::max(h->cap_quads, 1024) : h->cfg.max_quads_per_frame;
     c.ncnt = CNT_FIXED + (size_t)(7 + CC_SUBLISTS) * chunk;
     c.cap_keys = std::max(h->cap_keys, 4096);
+    c.roots_cap = std::max(h->cap_roots, default_roots_cap(g));
     c.key_bits = [&] { int nb = 1; while (((size_t)1 << nb) < g.plane) nb++; return nb; }();
 
     if (on_device) {   // order every slot stream after the producer's stream
@@ -1100,7 +1121,7 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
             if (rc) return rc;
             if (on_device) CK(cudaStreamWaitEvent(h->slots[s].stream, h->ev_user, 0));
         }
-        h->cap_points = c.cap; h->cap_clusters = c.maxcl; h->cap_quads = c.maxq; h->cap_keys = c.cap_keys;
+        h->cap_points = c.cap; h->cap_clusters = c.maxcl; h->cap_quads = c.maxq; h->cap_keys = c.cap_keys; h->cap_roots = c.roots_cap;
         Overflow ov;
         redo.clear();
         size_t next = 0;
@@ -1133,6 +1154,7 @@ int detect_run(agpu_handle* h, const uint8_t* frames, int on_device, int channel
             if (!auto_cl) { h->set_err("cluster list overflow: raise agpu_config.max_clusters_per_frame"); return AGPU_E_WORKSPACE; }
             c.maxcl = ov.max_cl_per_frame * 2;
         }
+        if (ov.max_roots > c.roots_cap) c.roots_cap = ov.max_roots + ov.max_roots / 4;
         if (ov.max_ncl > c.cap_keys) {
             int ck = c.cap_keys;
             while (ck < ov.max_ncl + ov.max_ncl / 4) ck *= 2;
@@ -1551,7 +1573,7 @@ long long agpu_debug_fetch(agpu_handle* h, const char* what, int frame, void* ho
     if (w == "labels" || w == "sizes") {
         if ((size_t)cap_bytes < npx * 4) return (long long)npx;
         std::vector<uint32_t> tmp(g.plane), lab;
-        const uint32_t* src = (w == "labels" ? sl.d_canon.as<uint32_t>() : sl.d_sizes.as<uint32_t>()) + (size_t)frame * g.plane;
+        const uint32_t* src = (w == "labels" ? sl.d_canon.as<uint32_t>() : sl.d_canon_sizes.as<uint32_t>()) + (size_t)frame * g.plane;
         if (cudaMemcpy(tmp.data(), src, g.plane * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return AGPU_E_CUDA;
         uint32_t* o = (uint32_t*)host_out;
         if (w == "labels") {
@@ -1700,11 +1722,14 @@ int agpu_stage_labels(agpu_handle* h, const uint8_t* thresh, int W, int H, uint3
     CK(cudaMemcpy2DAsync(sl.d_thresh.p, g.wp, thresh, W, W, H, cudaMemcpyHostToDevice, sl.stream));
     CK(sl.d_counters.ensure(256));
     CK(cudaMemsetAsync(sl.d_counters.p, 0, 256, sl.stream));
-    int rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), 1, g, sl.d_counters.as<int>(), nullptr, true);
+    CcRoots rt;
+    // (worst case: every other pixel of a tile row starts a run that is a root -- 512 per tile; a stage hook has no re-run)
+    const int sub_cap = cc_tiles_x(g) * ceil_div(cc_tiles_y(g), CC_SUBLISTS) * 512;
+    int rc = run_cc_stage(h, sl, sl.d_thresh.as<uint8_t>(), 1, g, sub_cap, sl.d_counters.as<int>(), nullptr, true, rt);
     if (rc) return rc;
     std::vector<uint32_t> lab(g.plane), sz(g.plane);
     CK(cudaMemcpyAsync(lab.data(), sl.d_canon.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));
-    CK(cudaMemcpyAsync(sz.data(), sl.d_sizes.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaMemcpyAsync(sz.data(), sl.d_canon_sizes.p, g.plane * 4, cudaMemcpyDeviceToHost, sl.stream));
     CK(cudaStreamSynchronize(sl.stream));
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) {

@@ -12,10 +12,14 @@
 //                                downstream of the local pass (boundary merge, edge points) works on these
 //                                2 bits per pixel instead of the threshold bytes
 //   l16    u16   [tiles][1024]   SPARSE: defined only at the first pixel of every run; the tile-local root of the
-//                                run as a local pixel id (row * 32 + col).  A pixel finds its run start with two
+//                                run as its ORDINAL among the tile's roots.  A pixel finds its run start with two
 //                                bit operations on its row mask, so no per-pixel label image is ever written.
-//   links  u32   [plane]         SPARSE: union-find parent links between tile-local roots, indexed by raster pixel
-//                                id y * wp + x (root of a set = its smallest pixel id: canonical by construction)
+//   root tables (CcRoots)        COMPACT: the tile-local roots of a frame are numbered by their position in the
+//                                frame's root lists (16 sub-lists by tile row); a root's HANDLE = sub-list * capacity
+//                                + position, tile_base[tile] = handle of the tile's first root.  Union-find links,
+//                                pixel counts, dense ids, the root's pixel id and the smallest pixel id of its set
+//                                are arrays over handles: a few thousand entries per frame that stay in L2, instead
+//                                of sparse touches all over three plane-sized u32 arrays.
 //
 // Kernels (block-local union-find + boundary merge + sizes [+ canonical relabel]):
 //   k_cc_local    32x32-pixel tile per warp, bit-parallel row runs + union-find over runs in shared memory
@@ -129,12 +133,31 @@ __device__ __forceinline__ int cc_run_start(uint32_t M, uint32_t I, int c) {
     return 31 - __clz(S & (0xffffffffu >> (31 - c)));
 }
 
-// tile-local root (as raster pixel id) of the foreground pixel (column c, row r) of tile `tile` at (x0, y0)
-__device__ __forceinline__ uint32_t cc_pixel_root(const uint16_t* __restrict__ l16, size_t tile, int x0, int y0, int r,
-                                                  int c, uint32_t M, uint32_t I, int wp) {
+// Root tables of a chunk.  All per-frame arrays have `cap` = CC_SUBLISTS * sub_cap entries per frame; a handle is an
+// index into a frame's arrays.  When a frame has more tile-local roots than a sub-list holds the surplus tiles get no
+// handles (tile_base = CC_NO_HANDLE), every consumer treats their pixels as "no component", and the host re-runs the
+// chunk with larger lists.
+#define CC_NO_HANDLE 0xffffffffu
+struct CcRoots {
+    uint32_t* links;      // [nframes][cap] union-find parent (a handle); root of a set = its smallest handle
+    uint32_t* sizes;      // [nframes][cap] pixel count: of the tile-local root, after k_cc_sizes of the whole set at its root
+    uint32_t* rootpix;    // [nframes][cap] raster pixel id (y * wp + x) of the tile-local root
+    uint32_t* minpix;     // [nframes][cap] smallest root pixel id of the set, at its final root = the component's canonical label
+    uint32_t* dense;      // [nframes][cap] dense component id at final roots (0xffffffff: fewer than 25 pixels)
+    uint32_t* tile_base;  // [nframes][tiles] handle of the tile's first root
+    int* nroots;          // [nframes][CC_SUBLISTS] roots appended per sub-list (may exceed sub_cap)
+    int sub_cap;          // capacity of one sub-list
+    int ntiles;           // tiles per frame
+    __host__ __device__ size_t cap() const { return (size_t)CC_SUBLISTS * sub_cap; }
+};
+
+// handle of the tile-local root of the foreground pixel (column c, row r) of tile `tile` (frame-relative tile index)
+__device__ __forceinline__ uint32_t cc_pixel_root(const uint16_t* __restrict__ l16, const uint32_t* __restrict__ tile_base,
+                                                  size_t tile, int r, int c, uint32_t M, uint32_t I) {
     const int s = cc_run_start(M, I, c);
-    const uint32_t loc = l16[tile * 1024 + r * 32 + s];
-    return (uint32_t)((y0 + (int)(loc >> 5)) * wp + x0 + (int)(loc & 31u));
+    const uint32_t base = __ldg(&tile_base[tile]);
+    const uint32_t ord = l16[tile * 1024 + r * 32 + s];
+    return base == CC_NO_HANDLE ? CC_NO_HANDLE : base + ord;
 }
 
 // Local pass, bit-parallel and RUN-BALANCED.  The row masks of the 32x32 tile are built with lane = row (two bit
@@ -150,9 +173,7 @@ __device__ __forceinline__ uint32_t cc_pixel_root(const uint16_t* __restrict__ l
 #define CC_RUN_COLOUR 0x400u   // run list entry: local pixel id of the first pixel (10 bits) | colour (1 = black)
 template <bool FROM_MASKS>
 __global__ void __launch_bounds__(CC_THREADS)
-k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16_t* __restrict__ l16,
-           uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, uint32_t* __restrict__ roots,
-           int* __restrict__ nroots, Geom g, size_t sub_stride) {
+k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16_t* __restrict__ l16, CcRoots rt, Geom g) {
     __shared__ __align__(16) uint16_t sL[CC_WARPS][CC_TH * CC_PITCH + 8];   // parent links; at roots later the pixel counters
     __shared__ __align__(16) uint16_t sR[CC_WARPS][CC_TW * CC_TH];          // run list
     __shared__ uint2 sM[CC_WARPS][CC_TH];                                    // row masks {white, black}
@@ -161,8 +182,6 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
     const int x0 = (blockIdx.x * CC_WARPS + w) * CC_TW, y0 = blockIdx.y * CC_TH;
     if (x0 >= g.wd) return;   // (no block-level synchronisation anywhere below)
     const int y = y0 + lane;
-    uint32_t* fl = labels + (size_t)frame * g.plane;
-    uint32_t* fs = sizes + (size_t)frame * g.plane;
     uint16_t* L = sL[w];
     uint16_t* R = sR[w];
     uint2* Ms = sM[w];
@@ -194,7 +213,10 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
         Bm &= V;
         masks[tile * 32 + lane] = make_uint2(Wm, Bm);
     }
-    if (!__any_sync(FULL_MASK, (Wm | Bm) != 0u)) return;   // nothing but 127-pixels: no runs, no labels
+    if (!__any_sync(FULL_MASK, (Wm | Bm) != 0u)) {          // nothing but 127-pixels: no runs, no labels, no roots
+        if (lane == 0) rt.tile_base[(size_t)frame * rt.ntiles + (size_t)blockIdx.y * cc_tiles_x(g) + blockIdx.x * CC_WARPS + w] = CC_NO_HANDLE;
+        return;
+    }
     const uint32_t I = cc_initiators(x0, g.wd);   // initiator columns: 1 <= x <= w-2
 
     // ---- run list: the runs of row r occupy the entries [off(r), off(r) + popc(S_r)), white and black in column order
@@ -274,7 +296,6 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
     for (int j = lane, k = 0; j < nrun; j += 32, k++)
         if ((rootbits >> k) & 1u) L[cc_slot(R[j] & 1023u)] = 0;
     __syncwarp();
-    uint16_t* tl = l16 + tile * 1024;
     for (int j = lane, k = 0; j < nrun; j += 32, k++) {
         const uint32_t e = R[j];
         const uint32_t id = e & 1023u;
@@ -285,10 +306,10 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
         const uint32_t slot = cc_slot(root);
         atomicAdd(reinterpret_cast<uint32_t*>(L) + (slot >> 1),
                   (uint32_t)__popc(run_mask(M & (M << 1) & I, s)) << ((slot & 1) * 16));
-        tl[id] = (uint16_t)root;   // run-start label: the tile-local root of the run (sparse, 2 bytes per run)
     }
     __syncwarp();
-    // ---- append the tile's roots to the frame's root list (one atomic per tile) and publish their counts
+    // ---- the tile's roots get consecutive handles in the frame's root tables (one atomic per tile); their counter
+    //      entries then become their ORDINAL inside the tile, which is what the run-start labels store
     {
         int incl = nroot;
 #pragma unroll
@@ -299,18 +320,35 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
         const int total = __shfl_sync(FULL_MASK, incl, 31);
         const int sub = blockIdx.y & (CC_SUBLISTS - 1);
         int base = 0;
-        if (lane == 31 && total) base = atomicAdd(&nroots[frame * CC_SUBLISTS + sub], total);
+        if (lane == 31) base = atomicAdd(&rt.nroots[frame * CC_SUBLISTS + sub], total);
         base = __shfl_sync(FULL_MASK, base, 31);
-        int o = base + incl - nroot;
-        uint32_t* fr = roots + ((size_t)frame * CC_SUBLISTS + sub) * sub_stride;
+        const bool fits = base + total <= rt.sub_cap;
+        const uint32_t handle0 = (uint32_t)(sub * rt.sub_cap + base);
+        const size_t ftile = (size_t)blockIdx.y * cc_tiles_x(g) + blockIdx.x * CC_WARPS + w;
+        if (lane == 0) rt.tile_base[(size_t)frame * rt.ntiles + ftile] = fits ? handle0 : CC_NO_HANDLE;
+        int o = incl - nroot;
+        const size_t fo = (size_t)frame * rt.cap();
         for (uint32_t m = rootbits; m; m &= m - 1) {
             const int k = __ffs(m) - 1;
             const uint32_t id = R[lane + 32 * k] & 1023u;
             const uint32_t gid = (uint32_t)((y0 + (int)(id >> 5)) * g.wp + x0 + (int)(id & 31u));
-            fs[gid] = L[cc_slot(id)];
-            fl[gid] = gid;
-            fr[o++] = gid;
+            if (fits) {
+                const size_t hnd = fo + handle0 + o;
+                rt.sizes[hnd] = L[cc_slot(id)];
+                rt.links[hnd] = handle0 + o;
+                rt.rootpix[hnd] = gid;
+                rt.minpix[hnd] = gid;
+            }
+            L[cc_slot(id)] = (uint16_t)o;
+            o++;
         }
+    }
+    __syncwarp();
+    uint16_t* tl = l16 + tile * 1024;
+    for (int j = lane, k = 0; j < nrun; j += 32, k++) {
+        const uint32_t id = R[j] & 1023u;
+        const uint32_t root = ((rootbits >> k) & 1u) ? id : (uint32_t)L[cc_slot(id)];
+        tl[id] = L[cc_slot(root)];   // run-start label: the ordinal of the run's tile-local root (sparse, 2 bytes per run)
     }
 }
 
@@ -326,7 +364,7 @@ __device__ __forceinline__ uint2 cc_ld_mask(const uint2* __restrict__ fm, const 
 
 template <int CCB_WARPS>
 __global__ void __launch_bounds__(CCB_WARPS * 32)
-k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, uint32_t* __restrict__ labels, Geom g) {
+k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoots rt, Geom g) {
     const int frame = blockIdx.z;
     const int lane = threadIdx.x & 31;
     const int tiles_x = cc_tiles_x(g), tiles_y = cc_tiles_y(g);
@@ -336,7 +374,10 @@ k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16,
     const int x0 = tx * CC_TW, y0 = ty * CC_TH;
     const uint2* fm = masks + (size_t)frame * tiles_x * tiles_y * 32;
     const uint16_t* f16 = l16 + (size_t)frame * tiles_x * tiles_y * 1024;
-    uint32_t* fl = labels + (size_t)frame * g.plane;
+    uint32_t* fl = rt.links + (size_t)frame * rt.cap();
+    const uint32_t* tb = rt.tile_base + (size_t)frame * rt.ntiles;
+    // (a tile without handles -- root list overflow, the chunk is re-run -- takes no part in any union)
+    auto unite = [&](uint32_t a, uint32_t b) { if (a != CC_NO_HANDLE && b != CC_NO_HANDLE) gunion(fl, a, b); };
     const uint2 M = fm[(size_t)t * 32 + lane];
     if (!__any_sync(FULL_MASK, (M.x | M.y) != 0u)) return;
     const uint2 ML = cc_ld_mask(fm, g, tx - 1, ty, lane), MR = cc_ld_mask(fm, g, tx + 1, ty, lane);
@@ -365,16 +406,16 @@ k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16,
                 const bool do_ul = col == 0 && up_l && !up_c;
                 const bool do_ur = col == 0 && up_r && !up_c;   // (upstream: no up-right link when up is white)
                 if (!(do_left || do_up || do_ul || do_ur)) continue;
-                const uint32_t me = cc_pixel_root(f16, tl, x0, y0, 0, c, P0, I, g.wp);
-                if (do_left) gunion(fl, me, cc_pixel_root(f16, tL, x0 - 32, y0, 0, 31, PL0, IL, g.wp));
-                if (do_up) gunion(fl, me, cc_pixel_root(f16, tU, x0, y0 - 32, 31, c, PU, I, g.wp));
+                const uint32_t me = cc_pixel_root(f16, tb, tl, 0, c, P0, I);
+                if (do_left) unite(me, cc_pixel_root(f16, tb, tL, 0, 31, PL0, IL));
+                if (do_up) unite(me, cc_pixel_root(f16, tb, tU, 31, c, PU, I));
                 if (do_ul) {
-                    if (c > 0) gunion(fl, me, cc_pixel_root(f16, tU, x0, y0 - 32, 31, c - 1, PU, I, g.wp));
-                    else gunion(fl, me, cc_pixel_root(f16, tU - 1, x0 - 32, y0 - 32, 31, 31, PUL, IL, g.wp));
+                    if (c > 0) unite(me, cc_pixel_root(f16, tb, tU, 31, c - 1, PU, I));
+                    else unite(me, cc_pixel_root(f16, tb, tU - 1, 31, 31, PUL, IL));
                 }
                 if (do_ur) {
-                    if (c < 31) gunion(fl, me, cc_pixel_root(f16, tU, x0, y0 - 32, 31, c + 1, PU, I, g.wp));
-                    else gunion(fl, me, cc_pixel_root(f16, tU + 1, x0 + 32, y0 - 32, 31, 0, PUR, IR, g.wp));
+                    if (c < 31) unite(me, cc_pixel_root(f16, tb, tU, 31, c + 1, PU, I));
+                    else unite(me, cc_pixel_root(f16, tb, tU + 1, 31, 0, PUR, IR));
                 }
             }
         }
@@ -394,73 +435,69 @@ k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16,
             const bool do_left = left && !(up && upleft);
             const bool do_ul = col == 0 && upleft && !up;
             if (!(do_left || do_ul)) continue;
-            const uint32_t me = cc_pixel_root(f16, tl, x0, y0, lane, 0, P, I, g.wp);
-            if (do_left) gunion(fl, me, cc_pixel_root(f16, tL, x0 - 32, y0, lane, 31, PL, IL, g.wp));
-            if (do_ul) gunion(fl, me, cc_pixel_root(f16, tL, x0 - 32, y0, lane - 1, 31, PLu, IL, g.wp));
+            const uint32_t me = cc_pixel_root(f16, tb, tl, lane, 0, P, I);
+            if (do_left) unite(me, cc_pixel_root(f16, tb, tL, lane, 31, PL, IL));
+            if (do_ul) unite(me, cc_pixel_root(f16, tb, tL, lane - 1, 31, PLu, IL));
         }
     }
     if ((I >> 31) & 1u) {   // x = x0 + 31 is an initiator: white up-right contact into the right tile
         if ((M.x >> 31) && (MRu_w & 1u) && !(Mu.x >> 31)) {
-            const uint32_t me = cc_pixel_root(f16, tl, x0, y0, lane, 31, M.x, I, g.wp);
-            gunion(fl, me, cc_pixel_root(f16, tR, x0 + 32, y0, lane - 1, 0, MRu_w, IR, g.wp));
+            const uint32_t me = cc_pixel_root(f16, tb, tl, lane, 31, M.x, I);
+            unite(me, cc_pixel_root(f16, tb, tR, lane - 1, 0, MRu_w, IR));
         }
     }
 }
 
-// Fold the pixel counts of the tile-local roots into the final roots (after the boundary merges) and point every
-// tile-local root straight at its final root: afterwards the representative of ANY pixel is labels[labels[id]]
-// (pixel -> tile-local root -> final root), two loads instead of a chain walk.
+// Fold the pixel counts (and the smallest root pixel id) of the tile-local roots into the final roots (after the boundary
+// merges) and point every tile-local root straight at its final root: afterwards the final root of ANY pixel is
+// links[handle], one load.
 __global__ void __launch_bounds__(256)
-k_cc_sizes(uint32_t* __restrict__ labels, uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
-           const int* __restrict__ nroots, Geom g, size_t sub_stride) {
-    const int frame = blockIdx.y / CC_SUBLISTS;
-    const int n = nroots[blockIdx.y];
-    uint32_t* fl = labels + (size_t)frame * g.plane;
-    uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const uint32_t* fr = roots + (size_t)blockIdx.y * sub_stride;
+k_cc_sizes(CcRoots rt) {
+    const int frame = blockIdx.y / CC_SUBLISTS, sub = blockIdx.y % CC_SUBLISTS;
+    const int n = min(rt.nroots[blockIdx.y], rt.sub_cap);
+    const size_t fo = (size_t)frame * rt.cap();
+    uint32_t* fl = rt.links + fo;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t a = fr[i];
+        const uint32_t a = (uint32_t)(sub * rt.sub_cap + i);
         const uint32_t r = gfind(fl, a);
         if (r != a) {
-            atomicAdd(&fs[r], fs[a]);
+            atomicAdd(&rt.sizes[fo + r], rt.sizes[fo + a]);
+            atomicMin(&rt.minpix[fo + r], rt.rootpix[fo + a]);
             fl[a] = r;   // (monotone: still an ancestor for any concurrent walk)
         }
     }
 }
 
 // Dense ids for the components that can carry an edge point (final roots of >= 25 pixels): the edge-cluster key
-// becomes a pair of 16-bit ids instead of a pair of 21..23-bit pixel ids, which halves the radix-sort record
-// and its number of passes.  dense[rep] is defined at every final root (0xffffffff: component smaller than 25
-// pixels, upstream's edge-point filter); dense2rep maps back.
+// becomes a pair of 16-bit ids.  dense[] is defined at every final root (0xffffffff: component smaller than 25
+// pixels, upstream's edge-point filter); dense2rep maps back to the component's canonical pixel id.
 #define AGPU_MAX_DENSE 65535   // ids 0 .. 65534 (0xffff marks "no id" in 16-bit tables)
 __global__ void __launch_bounds__(256)
-k_cc_dense(const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sizes, const uint32_t* __restrict__ roots,
-           const int* __restrict__ nroots, uint32_t* __restrict__ dense, uint32_t* __restrict__ dense2rep,
-           int* __restrict__ ndense, Geom g, size_t sub_stride) {
-    const int frame = blockIdx.y / CC_SUBLISTS;
-    const int n = nroots[blockIdx.y];
-    const uint32_t* fl = labels + (size_t)frame * g.plane;
-    const uint32_t* fs = sizes + (size_t)frame * g.plane;
-    const uint32_t* fr = roots + (size_t)blockIdx.y * sub_stride;
-    uint32_t* fd = dense + (size_t)frame * g.plane;
+k_cc_dense(CcRoots rt, uint32_t* __restrict__ dense2rep, int* __restrict__ ndense) {
+    const int frame = blockIdx.y / CC_SUBLISTS, sub = blockIdx.y % CC_SUBLISTS;
+    const int n = min(rt.nroots[blockIdx.y], rt.sub_cap);
+    const size_t fo = (size_t)frame * rt.cap();
     uint32_t* f2 = dense2rep + (size_t)frame * AGPU_MAX_DENSE;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t a = fr[i];
-        if (__ldcg(&fl[a]) != a) continue;                             // not a final root
-        if (__ldcg(&fs[a]) < 25u) { fd[a] = 0xffffffffu; continue; }   // too small to carry edge points
+        const size_t a = fo + (size_t)(sub * rt.sub_cap + i);
+        if (__ldcg(&rt.links[a]) != (uint32_t)(sub * rt.sub_cap + i)) continue;        // not a final root
+        if (__ldcg(&rt.sizes[a]) < 25u) { rt.dense[a] = 0xffffffffu; continue; }          // too small to carry edge points
         const int d = atomicAdd(&ndense[frame], 1);
         if (d < AGPU_MAX_DENSE) {
-            fd[a] = (uint32_t)d;
-            f2[d] = a;
+            rt.dense[a] = (uint32_t)d;
+            f2[d] = __ldcg(&rt.minpix[a]);
+        } else {
+            rt.dense[a] = 0xffffffffu;
         }
     }
 }
 
-// Canonical per-pixel labels (smallest pixel id of the component; 127-pixels are singletons) for the stage dumps.
-// The pipeline itself never materialises a label image: k_edges resolves representatives on the fly.
+// Canonical per-pixel labels (smallest pixel id of the component; 127-pixels are singletons) and, at every
+// representative pixel, the component's size -- for the stage dumps.  The pipeline itself never materialises a label
+// image: k_edges resolves components on the fly.
 __global__ void __launch_bounds__(256)
-k_cc_canonical(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
-               uint32_t* __restrict__ out, Geom g) {
+k_cc_canonical(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoots rt, uint32_t* __restrict__ out,
+               uint32_t* __restrict__ out_sizes, Geom g) {
     const int frame = blockIdx.z;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= g.wd || y >= g.hd) return;
@@ -469,12 +506,18 @@ k_cc_canonical(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16
     const size_t t = (size_t)ty * tiles_x + tx;
     const uint2 M = masks[((size_t)frame * tiles_x * tiles_y + t) * 32 + r];
     const uint32_t id = (uint32_t)(y * g.wp + x);
-    uint32_t lab = id;
+    uint32_t lab = id, size = 0u;
     const uint32_t P = ((M.x >> c) & 1u) ? M.x : (((M.y >> c) & 1u) ? M.y : 0u);
     if (P) {
-        const uint32_t root = cc_pixel_root(l16 + (size_t)frame * tiles_x * tiles_y * 1024, t, tx * 32, ty * 32, r, c, P,
-                                            cc_initiators(tx * 32, g.wd), g.wp);
-        lab = gfind(labels + (size_t)frame * g.plane, root);
+        const uint32_t hnd = cc_pixel_root(l16 + (size_t)frame * tiles_x * tiles_y * 1024, rt.tile_base + (size_t)frame * rt.ntiles,
+                                           t, r, c, P, cc_initiators(tx * 32, g.wd));
+        if (hnd != CC_NO_HANDLE) {
+            const size_t fo = (size_t)frame * rt.cap();
+            const uint32_t root = gfind(rt.links + fo, hnd);
+            lab = rt.minpix[fo + root];
+            if (lab == id) size = rt.sizes[fo + root];
+        }
     }
     out[(size_t)frame * g.plane + id] = lab;
+    out_sizes[(size_t)frame * g.plane + id] = size;
 }

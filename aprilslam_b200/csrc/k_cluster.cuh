@@ -80,9 +80,8 @@ __device__ __forceinline__ uint32_t pair_cluster_id(const PairTable& pt, int fra
 #endif                 // unbounded: +6 % time; 32 registers spill and gain nothing)
 template <int EDGE_WARPS>
 __global__ void __launch_bounds__(EDGE_WARPS * 32, EDGE_WARPS == 2 ? EDGE_MINB : 1)
-k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const uint32_t* __restrict__ labels,
-        const uint32_t* __restrict__ dense, Geom g, unsigned long long* __restrict__ recs, int* __restrict__ npts,
-        int* __restrict__ ndups, int cap, PairTable pt) {
+k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoots rt, Geom g,
+        unsigned long long* __restrict__ recs, int* __restrict__ npts, int* __restrict__ ndups, int cap, PairTable pt) {
     __shared__ uint16_t scand[EDGE_WARPS][EDGE_CAND_PER_PASS];
     __shared__ uint16_t sdense[EDGE_WARPS][1024];   // dense component id of every run of the tile, at its start pixel
     __shared__ unsigned long long scache[EDGE_WARPS][8];   // the warp's last pair keys and their cluster ids (a tile sees a handful)
@@ -96,8 +95,9 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
     const size_t t = (size_t)ty * tiles_x + tx;
     const uint2* fm = masks + (size_t)frame * tiles_x * tiles_y * 32;
     const uint16_t* f16 = l16 + (size_t)frame * tiles_x * tiles_y * 1024;
-    const uint32_t* fl = labels + (size_t)frame * g.plane;
-    const uint32_t* fd = dense + (size_t)frame * g.plane;
+    const uint32_t* fl = rt.links + (size_t)frame * rt.cap();      // tile-local root -> final root (flattened by k_cc_sizes)
+    const uint32_t* fd = rt.dense + (size_t)frame * rt.cap();      // final root -> dense component id
+    const uint32_t* tb = rt.tile_base + (size_t)frame * rt.ntiles;
     const uint2 M = fm[t * 32 + lane];
     if (!__any_sync(FULL_MASK, (M.x | M.y) != 0u)) return;
     const int x0 = tx * 32, y0 = ty * 32;
@@ -143,6 +143,7 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
         const uint32_t Sw = M.x & ~(M.x & (M.x << 1) & Ix), Sb = M.y & ~(M.y & (M.y << 1) & Ix);
         uint32_t S = Sw | Sb;
         const uint16_t* tl = f16 + t * 1024 + lane * 32;
+        const uint32_t tbase = __ldg(&tb[t]);       // handle of the tile's first root (CC_NO_HANDLE: root lists overflowed)
         while (__any_sync(FULL_MASK, S != 0u)) {
             const bool have = S != 0u;
             const int c = have ? __ffs(S) - 1 : 0;
@@ -151,10 +152,7 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
             const uint32_t peers = __match_any_sync(FULL_MASK, loc);
             const int leader = __ffs(peers) - 1;
             uint32_t d = 0xffffu;
-            if (have && lane == leader) {
-                const uint32_t gid = (uint32_t)((y0 + (int)(loc >> 5)) * g.wp + x0 + (int)(loc & 31u));
-                d = min(fd[fl[gid]], 0xffffu);
-            }
+            if (have && lane == leader && tbase != CC_NO_HANDLE) d = min(fd[fl[tbase + loc]], 0xffffu);   // loc: the root's ordinal
             d = __shfl_sync(FULL_MASK, d, leader);
             if (have) sdense[w][lane * 32 + c] = (uint16_t)d;
         }
@@ -210,9 +208,9 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, const
                     d1 = sdense[w][qr * 32 + cc_run_start(pos ? Wq : Bq, Ix, qc)];
                 } else {   // neighbour tile (a tenth of the candidates): mask -> run start -> root -> dense id in global memory
                     const uint2 Q = cc_ld_mask(fm, g, qtx, qty, qr);
-                    const uint32_t l1 = cc_pixel_root(f16, (size_t)qty * tiles_x + qtx, qtx * 32, qty * 32, qr, qc,
-                                                      pos ? Q.x : Q.y, cc_initiators(qtx * 32, g.wd), g.wp);
-                    d1 = min(fd[fl[l1]], 0xffffu);
+                    const uint32_t l1 = cc_pixel_root(f16, tb, (size_t)qty * tiles_x + qtx, qr, qc, pos ? Q.x : Q.y,
+                                                      cc_initiators(qtx * 32, g.wd));
+                    d1 = l1 == CC_NO_HANDLE ? 0xffffu : min(fd[fl[l1]], 0xffffu);
                 }
             }
             bool ok = have && d0 != 0xffffu && d1 != 0xffffu;   // both components have >= 25 pixels
