@@ -244,33 +244,43 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
     }
     __syncwarp();
 
-    // ---- contacts with the row above (row 0's upper row belongs to another tile: k_cc_boundary); lane = run
-    for (int j = lane; j < nrun; j += 32) {
-        const uint32_t e = R[j];
+    // ---- contacts with the row above (row 0's upper row belongs to another tile: k_cc_boundary); lane = run.
+    //      White: 8-connected (up-left, up, up-right), black: 4-connected (up).  Upstream skips the up-right link when the
+    //      upper neighbour is white too; inside the image that link is implied (up + the upper row's own run), but at
+    //      x = wd-2 it is not (column wd-1 never continues a run), and the partition has to be upstream's.
+    //      Returns the mask of upper-row pixels the run touches (0 for row 0) and the upper row's masks.
+    auto contacts = [&](uint32_t e, uint32_t& cu, uint32_t& Su) -> uint32_t {
         const uint32_t id = e & 1023u;
         const int r = id >> 5, s = id & 31;
-        if (r == 0) continue;
+        if (r == 0) return 0u;
         const bool black = (e & CC_RUN_COLOUR) != 0u;
         const uint2 mr = Ms[r], mu = Ms[r - 1];
         const uint32_t M = black ? mr.y : mr.x, Mu = black ? mu.y : mu.x;
-        const uint32_t cu = Mu & (Mu << 1) & I, Su = Mu & ~cu;
+        cu = Mu & (Mu << 1) & I;
+        Su = Mu & ~cu;
         const uint32_t rI = run_mask(M & (M << 1) & I, s) & I;
-        // white: 8-connected (up-left, up, up-right), black: 4-connected (up).  Upstream skips the up-right link when the
-        // upper neighbour is white too; inside the image that link is implied (up + the upper row's own run), but at
-        // x = wd-2 it is not (column wd-1 never continues a run), and the partition has to be upstream's.
-        uint32_t touched = (black ? rI : (((rI & ~Mu) << 1) | rI | (rI >> 1))) & Mu;
-        while (touched) {
+        return (black ? rI : (((rI & ~Mu) << 1) | rI | (rI >> 1))) & Mu;
+    };
+    // Part 1: every run links to the FIRST upper run it touches -- a plain store into its own entry, no find, no atomic
+    // (nobody else writes that entry here).  A link climbs exactly one row, so the chains are at most 31 long.  Runs that
+    // touch further upper runs (the places where two branches of a component meet) are remembered for part 3.
+    uint32_t morebits = 0u;
+    for (int j = lane, k = 0; j < nrun; j += 32, k++) {
+        const uint32_t e = R[j];
+        uint32_t cu, Su;
+        const uint32_t touched = contacts(e, cu, Su);
+        if (touched) {
+            const uint32_t id = e & 1023u;
             const int x = __ffs(touched) - 1;
             const int su = 31 - __clz(Su & (0xffffffffu >> (31 - x)));
-            sunion(L, id, id - s - 32 + su);
-            touched &= ~run_mask(cu, su);
+            L[cc_slot(id)] = (uint16_t)(id - (id & 31u) - 32 + su);
+            if (touched & ~run_mask(cu, su)) morebits |= 1u << k;
         }
     }
     __syncwarp();
-
-    // ---- pointer jumping: runs hook to the row above concurrently, which leaves chains as deep as the tile is
-    //      tall; every round halves them (L[x] = L[L[x]] only ever moves an entry closer to its root)
-    for (int round = 0; round < 10; round++) {
+    // Part 2: pointer jumping -- every round halves the chains (L[x] = L[L[x]] only ever moves an entry closer to its
+    // root), five rounds at most
+    for (int round = 0; round < 5; round++) {
         bool changed = false;
         for (int j = lane; j < nrun; j += 32) {
             const uint32_t slot = cc_slot(R[j] & 1023u);
@@ -280,6 +290,25 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
         }
         __syncwarp();
         if (!__any_sync(FULL_MASK, changed)) break;
+    }
+    // Part 3: the remaining contacts are real unions between (now flat) trees: lock-free, larger root under the smaller
+    if (__any_sync(FULL_MASK, morebits != 0u)) {
+        for (int j = lane, k = 0; j < nrun; j += 32, k++) {
+            if (!((morebits >> k) & 1u)) continue;
+            const uint32_t e = R[j];
+            const uint32_t id = e & 1023u;
+            uint32_t cu, Su;
+            uint32_t touched = contacts(e, cu, Su);
+            bool first = true;
+            while (touched) {
+                const int x = __ffs(touched) - 1;
+                const int su = 31 - __clz(Su & (0xffffffffu >> (31 - x)));
+                if (!first) sunion(L, id, id - (id & 31u) - 32 + su);
+                first = false;
+                touched &= ~run_mask(cu, su);
+            }
+        }
+        __syncwarp();
     }
     // ---- root of every run; the entry of a ROOT then becomes its pixel counter (two 16-bit entries per word; a tile
     //      holds 1024 pixels, so a carry can never leave a counter), the entries of the other runs keep their root.
