@@ -310,8 +310,8 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
         }
         __syncwarp();
     }
-    // ---- root of every run; the entry of a ROOT then becomes its pixel counter (two 16-bit entries per word; a tile
-    //      holds 1024 pixels, so a carry can never leave a counter), the entries of the other runs keep their root.
+    // ---- root of every run; the entry of a ROOT then becomes its pixel counter (two 16-bit entries per word; id + count
+    //      <= 2047, so a carry can never leave a counter), the entries of the other runs keep their root.
     //      A lane remembers which of its runs are roots in a bit mask (run j = lane + 32 k -> bit k).
     uint32_t rootbits = 0u;
     int nroot = 0;
@@ -322,9 +322,7 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
         else L[cc_slot(id)] = (uint16_t)root;
     }
     __syncwarp();
-    for (int j = lane, k = 0; j < nrun; j += 32, k++)
-        if ((rootbits >> k) & 1u) L[cc_slot(R[j] & 1023u)] = 0;
-    __syncwarp();
+    // (a root's entry holds its own id, < 1024: the counts are added on top of it and the id is taken off again below)
     for (int j = lane, k = 0; j < nrun; j += 32, k++) {
         const uint32_t e = R[j];
         const uint32_t id = e & 1023u;
@@ -363,7 +361,7 @@ k_cc_local(const uint8_t* __restrict__ thresh, uint2* __restrict__ masks, uint16
             const uint32_t gid = (uint32_t)((y0 + (int)(id >> 5)) * g.wp + x0 + (int)(id & 31u));
             if (fits) {
                 const size_t hnd = fo + handle0 + o;
-                rt.sizes[hnd] = L[cc_slot(id)];
+                rt.sizes[hnd] = (uint32_t)L[cc_slot(id)] - id;
                 rt.links[hnd] = handle0 + o;
                 rt.rootpix[hnd] = gid;
                 rt.minpix[hnd] = gid;
@@ -391,40 +389,72 @@ __device__ __forceinline__ uint2 cc_ld_mask(const uint2* __restrict__ fm, const 
     return __ldg(&fm[((size_t)ty * cc_tiles_x(g) + tx) * 32 + r]);
 }
 
+// union of the sets of a and b whose parents pa = L[a], pb = L[b] were already loaded: both chains are walked together
+// (the two loads of a step in flight at once), larger root hooked under the smaller
+__device__ __forceinline__ void gunion_p(uint32_t* L, uint32_t a, uint32_t pa, uint32_t b, uint32_t pb) {
+    for (;;) {
+        while (pa != a || pb != b) {
+            a = pa; b = pb;
+            pa = __ldcg(&L[a]); pb = __ldcg(&L[b]);
+        }
+        if (a == b) return;
+        if (a < b) { const uint32_t t = a; a = b; b = t; }
+        const uint32_t old = atomicMin(&L[a], b);   // hook the larger root under the smaller
+        if (old == a) return;
+        a = old;                                    // a was hooked elsewhere meanwhile: keep uniting its new parent with b
+        pa = __ldcg(&L[a]); pb = __ldcg(&L[b]);
+    }
+}
+
+// A union request of the boundary merge: run-start offsets (row * 32 + first column of the run) of the two pixels inside
+// their tiles, and which neighbour tile the second one lies in.
+#define CCB_REL_LEFT 0u
+#define CCB_REL_RIGHT 1u
+#define CCB_REL_UP 2u
+#define CCB_REL_UPLEFT 3u
+#define CCB_REL_UPRIGHT 4u
+#define CCB_QUEUE 192   // 32 lanes x (3 top-row + 2 left-column + 1 right-column requests)
+
+// TWO PHASES.  Collect: the contact tests (bit operations on row masks in registers) push one 32-bit request per real,
+// non-implied contact into the warp's queue.  Execute: the requests are dealt one per lane, so all of a tile's unions run
+// side by side and every dependent step -- run-start labels + tile bases, parents, hook -- is ONE memory round trip for
+// the whole tile (the contacts used to be resolved where they were found, three divergent sections with five dependent
+// round trips each).
 template <int CCB_WARPS>
 __global__ void __launch_bounds__(CCB_WARPS * 32)
 k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoots rt, Geom g) {
+    __shared__ uint32_t sreq[CCB_WARPS][CCB_QUEUE];
+    __shared__ int scount[CCB_WARPS];
     const int frame = blockIdx.z;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int tiles_x = cc_tiles_x(g), tiles_y = cc_tiles_y(g);
-    const int t = blockIdx.x * CCB_WARPS + (threadIdx.x >> 5);
-    if (t >= tiles_x * tiles_y) return;
+    const int t = blockIdx.x * CCB_WARPS + w;
+    if (t >= tiles_x * tiles_y) return;   // (no block-level synchronisation anywhere below)
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int x0 = tx * CC_TW, y0 = ty * CC_TH;
     const uint2* fm = masks + (size_t)frame * tiles_x * tiles_y * 32;
-    const uint16_t* f16 = l16 + (size_t)frame * tiles_x * tiles_y * 1024;
-    uint32_t* fl = rt.links + (size_t)frame * rt.cap();
-    const uint32_t* tb = rt.tile_base + (size_t)frame * rt.ntiles;
-    // (a tile without handles -- root list overflow, the chunk is re-run -- takes no part in any union)
-    auto unite = [&](uint32_t a, uint32_t b) { if (a != CC_NO_HANDLE && b != CC_NO_HANDLE) gunion(fl, a, b); };
     const uint2 M = fm[(size_t)t * 32 + lane];
     if (!__any_sync(FULL_MASK, (M.x | M.y) != 0u)) return;
     const uint2 ML = cc_ld_mask(fm, g, tx - 1, ty, lane), MR = cc_ld_mask(fm, g, tx + 1, ty, lane);
+    const uint2 U = cc_ld_mask(fm, g, tx, ty - 1, 31), UL = cc_ld_mask(fm, g, tx - 1, ty - 1, 31),
+                UR = cc_ld_mask(fm, g, tx + 1, ty - 1, 31);
     const uint32_t I = cc_initiators(x0, g.wd), IL = cc_initiators(x0 - 32, g.wd), IR = cc_initiators(x0 + 32, g.wd);
-    const size_t tl = (size_t)t, tL = tl - 1, tR = tl + 1, tU = tl - tiles_x;
+    if (lane == 0) scount[w] = 0;
+    __syncwarp();
+    uint32_t* Q = sreq[w];
+    auto push = [&](uint32_t me_off, uint32_t rel, uint32_t other_off) {
+        Q[atomicAdd(&scount[w], 1)] = me_off | (other_off << 10) | (rel << 20);
+    };
 
     // ---- top row of the tile (y = y0): lane = column
     {
         const uint2 R0 = make_uint2(__shfl_sync(FULL_MASK, M.x, 0), __shfl_sync(FULL_MASK, M.y, 0));
         const uint2 L0 = make_uint2(__shfl_sync(FULL_MASK, ML.x, 0), __shfl_sync(FULL_MASK, ML.y, 0));
-        const uint2 U = cc_ld_mask(fm, g, tx, ty - 1, 31), UL = cc_ld_mask(fm, g, tx - 1, ty - 1, 31),
-                    UR = cc_ld_mask(fm, g, tx + 1, ty - 1, 31);
         const int c = lane, x = x0 + c;
         if ((I >> c) & 1u) {
-#pragma unroll
-            for (int col = 0; col < 2; col++) {   // 0: white, 1: black
-                const uint32_t P0 = col ? R0.y : R0.x;
-                if (!((P0 >> c) & 1u)) continue;
+            const int col = (R0.y >> c) & 1u;   // 0: white, 1: black
+            const uint32_t P0 = col ? R0.y : R0.x;
+            if ((P0 >> c) & 1u) {
                 const uint32_t PL0 = col ? L0.y : L0.x, PU = col ? U.y : U.x, PUL = col ? UL.y : UL.x, PUR = col ? UR.y : UR.x;
                 const bool row_l = c > 0 ? ((P0 >> (c - 1)) & 1u) : (PL0 >> 31);
                 const bool up_c = (PU >> c) & 1u;
@@ -434,46 +464,68 @@ k_cc_boundary(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16,
                 const bool do_up = up_c && !(x - 1 >= 1 && row_l && up_l);
                 const bool do_ul = col == 0 && up_l && !up_c;
                 const bool do_ur = col == 0 && up_r && !up_c;   // (upstream: no up-right link when up is white)
-                if (!(do_left || do_up || do_ul || do_ur)) continue;
-                const uint32_t me = cc_pixel_root(f16, tb, tl, 0, c, P0, I);
-                if (do_left) unite(me, cc_pixel_root(f16, tb, tL, 0, 31, PL0, IL));
-                if (do_up) unite(me, cc_pixel_root(f16, tb, tU, 31, c, PU, I));
-                if (do_ul) {
-                    if (c > 0) unite(me, cc_pixel_root(f16, tb, tU, 31, c - 1, PU, I));
-                    else unite(me, cc_pixel_root(f16, tb, tU - 1, 31, 31, PUL, IL));
-                }
-                if (do_ur) {
-                    if (c < 31) unite(me, cc_pixel_root(f16, tb, tU, 31, c + 1, PU, I));
-                    else unite(me, cc_pixel_root(f16, tb, tU + 1, 31, 0, PUR, IR));
+                if (do_left || do_up || do_ul || do_ur) {
+                    const uint32_t me = (uint32_t)cc_run_start(P0, I, c);
+                    if (do_left) push(me, CCB_REL_LEFT, (uint32_t)cc_run_start(PL0, IL, 31));
+                    if (do_up) push(me, CCB_REL_UP, 31u * 32u + (uint32_t)cc_run_start(PU, I, c));
+                    if (do_ul) {
+                        if (c > 0) push(me, CCB_REL_UP, 31u * 32u + (uint32_t)cc_run_start(PU, I, c - 1));
+                        else push(me, CCB_REL_UPLEFT, 31u * 32u + (uint32_t)cc_run_start(PUL, IL, 31));
+                    }
+                    if (do_ur) {
+                        if (c < 31) push(me, CCB_REL_UP, 31u * 32u + (uint32_t)cc_run_start(PU, I, c + 1));
+                        else push(me, CCB_REL_UPRIGHT, 31u * 32u + (uint32_t)cc_run_start(PUR, IR, 0));
+                    }
                 }
             }
         }
     }
     // ---- left and right column (rows 1..31; the corners belong to the top row): lane = row
-    const uint2 Mu = make_uint2(__shfl_up_sync(FULL_MASK, M.x, 1), __shfl_up_sync(FULL_MASK, M.y, 1));
-    const uint2 MLu = make_uint2(__shfl_up_sync(FULL_MASK, ML.x, 1), __shfl_up_sync(FULL_MASK, ML.y, 1));
-    const uint32_t MRu_w = __shfl_up_sync(FULL_MASK, MR.x, 1);
-    if (lane == 0 || y0 + lane >= g.hd) return;
-    if (I & 1u) {   // x = x0 is an initiator (x0 >= 1: there is a left tile)
-#pragma unroll
-        for (int col = 0; col < 2; col++) {
-            const uint32_t P = col ? M.y : M.x;
-            if (!(P & 1u)) continue;
-            const uint32_t PL = col ? ML.y : ML.x, Pu = col ? Mu.y : Mu.x, PLu = col ? MLu.y : MLu.x;
-            const bool left = PL >> 31, up = Pu & 1u, upleft = PLu >> 31;
-            const bool do_left = left && !(up && upleft);
-            const bool do_ul = col == 0 && upleft && !up;
-            if (!(do_left || do_ul)) continue;
-            const uint32_t me = cc_pixel_root(f16, tb, tl, lane, 0, P, I);
-            if (do_left) unite(me, cc_pixel_root(f16, tb, tL, lane, 31, PL, IL));
-            if (do_ul) unite(me, cc_pixel_root(f16, tb, tL, lane - 1, 31, PLu, IL));
+    {
+        const uint2 Mu = make_uint2(__shfl_up_sync(FULL_MASK, M.x, 1), __shfl_up_sync(FULL_MASK, M.y, 1));
+        const uint2 MLu = make_uint2(__shfl_up_sync(FULL_MASK, ML.x, 1), __shfl_up_sync(FULL_MASK, ML.y, 1));
+        const uint32_t MRu_w = __shfl_up_sync(FULL_MASK, MR.x, 1);
+        if (lane != 0 && y0 + lane < g.hd) {
+            const uint32_t r32 = (uint32_t)lane * 32u;
+            if (I & 1u) {   // x = x0 is an initiator (x0 >= 1: there is a left tile)
+                const int col = M.y & 1u;
+                const uint32_t P = col ? M.y : M.x;
+                if (P & 1u) {
+                    const uint32_t PL = col ? ML.y : ML.x, Pu = col ? Mu.y : Mu.x, PLu = col ? MLu.y : MLu.x;
+                    const bool left = PL >> 31, up = Pu & 1u, upleft = PLu >> 31;
+                    const bool do_left = left && !(up && upleft);
+                    const bool do_ul = col == 0 && upleft && !up;
+                    if (do_left) push(r32, CCB_REL_LEFT, r32 + (uint32_t)cc_run_start(PL, IL, 31));
+                    if (do_ul) push(r32, CCB_REL_LEFT, r32 - 32u + (uint32_t)cc_run_start(PLu, IL, 31));
+                }
+            }
+            if ((I >> 31) & 1u) {   // x = x0 + 31 is an initiator: white up-right contact into the right tile
+                if ((M.x >> 31) && (MRu_w & 1u) && !(Mu.x >> 31))
+                    push(r32 + (uint32_t)cc_run_start(M.x, I, 31), CCB_REL_RIGHT, r32 - 32u);   // (column 0 starts its run)
+            }
         }
     }
-    if ((I >> 31) & 1u) {   // x = x0 + 31 is an initiator: white up-right contact into the right tile
-        if ((M.x >> 31) && (MRu_w & 1u) && !(Mu.x >> 31)) {
-            const uint32_t me = cc_pixel_root(f16, tb, tl, lane, 31, M.x, I);
-            unite(me, cc_pixel_root(f16, tb, tR, lane - 1, 0, MRu_w, IR));
-        }
+    __syncwarp();
+    const int total = scount[w];
+    if (total == 0) return;
+    // ---- execute
+    const uint16_t* f16 = l16 + (size_t)frame * tiles_x * tiles_y * 1024;
+    uint32_t* fl = rt.links + (size_t)frame * rt.cap();
+    const uint32_t* tb = rt.tile_base + (size_t)frame * rt.ntiles;
+    const uint32_t base_me = __ldg(&tb[t]);
+    for (int q = lane; q < total; q += 32) {
+        const uint32_t rq = Q[q];
+        const uint32_t rel = rq >> 20;
+        const int to = t + (rel == CCB_REL_LEFT ? -1 : (rel == CCB_REL_RIGHT ? 1 : (rel == CCB_REL_UP ? -tiles_x :
+                           (rel == CCB_REL_UPLEFT ? -tiles_x - 1 : -tiles_x + 1))));
+        const uint32_t base_o = __ldg(&tb[to]);
+        const uint32_t ord_me = f16[(size_t)t * 1024 + (rq & 1023u)];
+        const uint32_t ord_o = f16[(size_t)to * 1024 + ((rq >> 10) & 1023u)];
+        // (a tile without handles -- root list overflow, the chunk is re-run -- takes no part in any union)
+        if (base_me == CC_NO_HANDLE || base_o == CC_NO_HANDLE) continue;
+        const uint32_t a = base_me + ord_me, b = base_o + ord_o;
+        const uint32_t pa = __ldcg(&fl[a]), pb = __ldcg(&fl[b]);
+        gunion_p(fl, a, pa, b, pb);
     }
 }
 

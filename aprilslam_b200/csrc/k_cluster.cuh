@@ -137,24 +137,41 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoo
     for (int off = 16; off > 0; off >>= 1) total_all += __shfl_xor_sync(FULL_MASK, total_all, off);
     if (total_all == 0) return;
 
-    // ---- dense id of every run of this tile: run start -> tile-local root -> final root -> dense id.  The runs of a
-    //      tile hang on a handful of roots, so one lane per distinct root does the two dependent loads.
+    // ---- dense id of every run of this tile: run start -> ordinal of its tile-local root -> final root -> dense id, in
+    //      three sweeps with ONE dependent memory round trip each: (1) every lane fetches the ordinals of its row's runs,
+    //      four loads in flight, and parks them in the table; (2) the tile's roots -- a handful -- are resolved side by
+    //      side, one per lane, into a little table that borrows the candidate buffer; (3) ordinals -> dense ids in place.
     {
         const uint32_t Sw = M.x & ~(M.x & (M.x << 1) & Ix), Sb = M.y & ~(M.y & (M.y << 1) & Ix);
-        uint32_t S = Sw | Sb;
+        const uint32_t Sall = Sw | Sb;
         const uint16_t* tl = f16 + t * 1024 + lane * 32;
         const uint32_t tbase = __ldg(&tb[t]);       // handle of the tile's first root (CC_NO_HANDLE: root lists overflowed)
+        uint16_t* row = &sdense[w][lane * 32];
+        uint32_t S = Sall;
+        int maxo = -1;
         while (__any_sync(FULL_MASK, S != 0u)) {
-            const bool have = S != 0u;
-            const int c = have ? __ffs(S) - 1 : 0;
-            S &= S - 1;
-            const uint32_t loc = have ? (uint32_t)tl[c] : 0xffffffffu - lane;
-            const uint32_t peers = __match_any_sync(FULL_MASK, loc);
-            const int leader = __ffs(peers) - 1;
-            uint32_t d = 0xffffu;
-            if (have && lane == leader && tbase != CC_NO_HANDLE) d = min(fd[fl[tbase + loc]], 0xffffu);   // loc: the root's ordinal
-            d = __shfl_sync(FULL_MASK, d, leader);
-            if (have) sdense[w][lane * 32 + c] = (uint16_t)d;
+            int c[4];
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                c[u] = S ? __ffs(S) - 1 : -1;
+                S &= S - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = c[u] >= 0 ? (uint32_t)tl[c[u]] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (c[u] >= 0) { row[c[u]] = (uint16_t)v[u]; maxo = max(maxo, (int)v[u]); }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) maxo = max(maxo, __shfl_xor_sync(FULL_MASK, maxo, off));
+        uint16_t* rootd = scand[w];                 // (free until the candidates are listed; a tile has at most 512 roots)
+        for (int o = lane; o <= maxo; o += 32)
+            rootd[o] = (uint16_t)(tbase != CC_NO_HANDLE ? min(fd[fl[tbase + o]], 0xffffu) : 0xffffu);
+        __syncwarp();
+        for (S = Sall; S; S &= S - 1) {
+            const int cc = __ffs(S) - 1;
+            row[cc] = rootd[row[cc]];
         }
     }
     __syncwarp();
