@@ -85,6 +85,7 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoo
     __shared__ uint16_t scand[EDGE_WARPS][EDGE_CAND_PER_PASS];
     __shared__ uint16_t sdense[EDGE_WARPS][1024];   // dense component id of every run of the tile, at its start pixel
     __shared__ unsigned long long scache[EDGE_WARPS][8];   // the warp's last pair keys and their cluster ids (a tile sees a handful)
+    __shared__ uint16_t shalo[EDGE_WARPS][100];            // dense ids of the neighbour-tile pixels the tile's candidates point at
     // grid = (frames, x blocks, tile rows): consecutive CTAs belong to DIFFERENT frames, so the per-frame append
     // counters are not hammered by every resident warp at once
     const int frame = blockIdx.x;
@@ -137,6 +138,44 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoo
     for (int off = 16; off > 0; off >>= 1) total_all += __shfl_xor_sync(FULL_MASK, total_all, off);
     if (total_all == 0) return;
 
+    // ---- halo: a candidate on the tile's right / left / bottom border has its second pixel in a neighbour tile (a tenth
+    //      of the candidates).  Their dense ids -- mask -> run start -> root -> final root -> dense id, four dependent
+    //      loads -- are fetched HERE for all of them at once (lane = row for the right and left neighbour's border column,
+    //      lane = column for the lower neighbour's first row, lanes 0 / 31 for the two corner pixels) and parked in a
+    //      98-entry table, so the candidate batches below never wait on global memory for a pixel.
+    //      Table: [0, 32) right tile (column 0, row i), [32, 64) left tile (column 31, row i), [64, 96) lower tile (row 0,
+    //      column i), 96 lower-left pixel (31, 0), 97 lower-right pixel (0, 0).
+    uint32_t hh[4];          // handles (CC_NO_HANDLE: not needed)
+    {
+        const uint32_t m3u = __shfl_up_sync(FULL_MASK, m[3], 1), m2u = __shfl_up_sync(FULL_MASK, m[2], 1);
+        const uint32_t b1 = __shfl_sync(FULL_MASK, m[1], 31), b2 = __shfl_sync(FULL_MASK, m[2], 31), b3 = __shfl_sync(FULL_MASK, m[3], 31);
+        const uint2 Nb = make_uint2(__shfl_sync(FULL_MASK, N.x, 31), __shfl_sync(FULL_MASK, N.y, 31));
+        const uint2 NLb = make_uint2(__shfl_sync(FULL_MASK, NL.x, 31), __shfl_sync(FULL_MASK, NL.y, 31));
+        const uint2 NRb = make_uint2(__shfl_sync(FULL_MASK, NR.x, 31), __shfl_sync(FULL_MASK, NR.y, 31));
+        const uint32_t IL = cc_initiators(x0 - 32, g.wd);
+        const bool needR = ((m[0] >> 31) | (lane > 0 ? m3u >> 31 : 0u)) & 1u;
+        const bool needL = lane > 0 && (m2u & 1u);
+        const bool needB = ((b1 | (b2 >> 1) | (b3 << 1)) >> lane) & 1u;
+        const bool needC = lane == 0 ? (b2 & 1u) : (lane == 31 ? (b3 >> 31) : 0u);
+        const size_t tR = t + 1, tL = t - 1, tB = t + tiles_x;
+        const size_t tC = lane == 0 ? tB - 1 : tB + 1;
+        const uint32_t PL = (ML.x >> 31) ? ML.x : ML.y, PB = ((Nb.x >> lane) & 1u) ? Nb.x : Nb.y;
+        const uint32_t PC = lane == 0 ? ((NLb.x >> 31) ? NLb.x : NLb.y) : NRb.x /* unused for column 0 */;
+        uint32_t base[4], ord[4];
+        base[0] = needR ? __ldg(&tb[tR]) : CC_NO_HANDLE;
+        base[1] = needL ? __ldg(&tb[tL]) : CC_NO_HANDLE;
+        base[2] = needB ? __ldg(&tb[tB]) : CC_NO_HANDLE;
+        base[3] = needC ? __ldg(&tb[tC]) : CC_NO_HANDLE;
+        ord[0] = needR ? (uint32_t)f16[tR * 1024 + lane * 32] : 0u;                                   // (column 0 starts its run)
+        ord[1] = needL ? (uint32_t)f16[tL * 1024 + lane * 32 + cc_run_start(PL, IL, 31)] : 0u;
+        ord[2] = needB ? (uint32_t)f16[tB * 1024 + cc_run_start(PB, Ix, lane)] : 0u;
+        ord[3] = needC ? (uint32_t)f16[tC * 1024 + (lane == 0 ? cc_run_start(PC, IL, 31) : 0)] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) hh[u] = base[u] == CC_NO_HANDLE ? CC_NO_HANDLE : base[u] + ord[u];
+#pragma unroll
+        for (int u = 0; u < 4; u++) hh[u] = hh[u] == CC_NO_HANDLE ? CC_NO_HANDLE : fl[hh[u]];   // -> final roots (loads in flight together)
+    }
+
     // ---- dense id of every run of this tile: run start -> ordinal of its tile-local root -> final root -> dense id, in
     //      three sweeps with ONE dependent memory round trip each: (1) every lane fetches the ordinals of its row's runs,
     //      four loads in flight, and parks them in the table; (2) the tile's roots -- a handful -- are resolved side by
@@ -174,11 +213,34 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoo
             row[cc] = rootd[row[cc]];
         }
     }
+    {
+        uint32_t hd[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) hd[u] = hh[u] == CC_NO_HANDLE ? 0xffffu : min(fd[hh[u]], 0xffffu);
+        shalo[w][lane] = (uint16_t)hd[0];
+        shalo[w][32 + lane] = (uint16_t)hd[1];
+        shalo[w][64 + lane] = (uint16_t)hd[2];
+        if (lane == 0) shalo[w][96] = (uint16_t)hd[3];
+        if (lane == 31) shalo[w][97] = (uint16_t)hd[3];
+    }
     __syncwarp();
 
     unsigned long long* fk = recs + (size_t)frame * cap;
     if (lane < 8) scache[w][lane] = PT_EMPTY;
     __syncwarp();
+    // The slot reservation of a batch (an atomic with a return value) is not waited for: the batch's records stay in
+    // registers and are stored when the NEXT batch has done its look-ups, by which time the reply is there.
+    bool pend = false, pend_ok = false;
+    int pend_base = 0;
+    uint32_t pend_okm = 0u;
+    unsigned long long pend_rec = 0ull;
+    auto flush = [&]() {
+        if (!pend) return;
+        const int base = __shfl_sync(FULL_MASK, pend_base, 0);
+        const int p = base + __popc(pend_okm & ((1u << lane) - 1u));
+        if (pend_ok && p < cap) fk[p] = pend_rec;
+        pend = false;
+    };
     const int npass = total_all <= EDGE_CAND_PER_PASS ? 1 : 4;
     const int rsh = npass == 1 ? 5 : 3;   // rows per pass = 1 << rsh
 #pragma unroll 1
@@ -223,11 +285,8 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoo
                 d0 = sdense[w][r * 32 + cc_run_start(pos ? Bp : Wp, Ix, c)];
                 if (qtx == tx && qty == ty) {
                     d1 = sdense[w][qr * 32 + cc_run_start(pos ? Wq : Bq, Ix, qc)];
-                } else {   // neighbour tile (a tenth of the candidates): mask -> run start -> root -> dense id in global memory
-                    const uint2 Q = cc_ld_mask(fm, g, qtx, qty, qr);
-                    const uint32_t l1 = cc_pixel_root(f16, tb, (size_t)qty * tiles_x + qtx, qr, qc, pos ? Q.x : Q.y,
-                                                      cc_initiators(qtx * 32, g.wd));
-                    d1 = l1 == CC_NO_HANDLE ? 0xffffu : min(fd[fl[l1]], 0xffffu);
+                } else {   // neighbour tile: the halo table
+                    d1 = shalo[w][qty != ty ? (qtx == tx ? 64 + qc : (qtx < tx ? 96 : 97)) : (qtx > tx ? qr : 32 + qr)];
                 }
             }
             bool ok = have && d0 != 0xffffu && d1 != 0xffffu;   // both components have >= 25 pixels
@@ -263,17 +322,16 @@ k_edges(const uint2* __restrict__ masks, const uint16_t* __restrict__ l16, CcRoo
             const uint32_t dupm = __ballot_sync(FULL_MASK, ok && ((cd >> 13) & 1u));
             // (a slot reservation per TILE instead of per batch -- sentinel records in the holes -- was measured: -3 % on
             // clean frames, +70 % under sensor noise, where most candidates touch a component of < 25 pixels)
-            int base = 0;
+            flush();
             if (lane == 0) {
-                base = atomicAdd(&npts[frame], __popc(okm));
+                pend_base = atomicAdd(&npts[frame], __popc(okm));
                 if (dupm) atomicAdd(&ndups[frame], __popc(dupm));   // (raw point count = npts + ndups)
             }
-            base = __shfl_sync(FULL_MASK, base, 0);
-            const int p = base + __popc(okm & ((1u << lane) - 1u));
-            if (ok && p < cap) fk[p] = rec;
+            pend = true; pend_ok = ok; pend_okm = okm; pend_rec = rec;
         }
         __syncwarp();
     }
+    flush();
 }
 
 // ---- segmented one-sweep sort by cluster id ---------------------------------------------------
