@@ -2,7 +2,7 @@
 // management and the per-chunk kernel pipeline.  sm_100a only; no CPU fallback of any stage.
 //
 // Pipeline per chunk of frames (all on one stream):
-//   [H2D] -> image (k_pack / k_blur_pass / k_decimate_threshold) -> CC (k_cc_local, k_cc_boundary,
+//   [H2D] -> image (k_pack / k_decimate_blur / k_decimate_threshold) -> CC (k_cc_local, k_cc_boundary,
 //   k_cc_finalize) -> k_edges (records carry cluster ids) -> k_cluster_refs -> k_sort_scatter (one-sweep segmented
 //   sort by cluster id) -> k_fit_quads (4 size tiers) -> k_decode_quads -> k_reconcile [-> k_pose] -> D2H
 #include <algorithm>
@@ -97,7 +97,7 @@ struct Slot {
     struct KEv { const char* name; cudaEvent_t a, b; };
     std::vector<KEv> kev;              // profiling only: one event pair around EVERY kernel launch of the chunk
     size_t kev_next = 0;
-    DevBuf d_in, d_gray, d_quad_im, d_blur_tmp, d_blur_orig, d_thresh, d_masks, d_l16, d_canon, d_canon_sizes, d_roottab, d_tilebase, d_dense2rep;
+    DevBuf d_in, d_gray, d_quad_im, d_thresh, d_masks, d_l16, d_canon, d_canon_sizes, d_roottab, d_tilebase, d_dense2rep;
     DevBuf d_recs[2], d_qscratch, d_gsort, d_pairslots, d_pairkeys, d_paircount, d_pairstart;
     DevBuf d_counters;  // CNT_FIXED ints + per-frame: npts[chunk], frame_quads[chunk], ndets[chunk], out_counts[chunk], ndense[chunk], nroots[16*chunk], ndups[chunk], ncl[chunk]
     DevBuf d_clusters[AGPU_NTIERS], d_dbg_heads, d_quads, d_refined, d_dets, d_out, d_poses;
@@ -122,7 +122,7 @@ struct Slot {
     bool graph_from_masks = false;
 
     void release() {
-        DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_blur_tmp, &d_blur_orig, &d_thresh, &d_masks, &d_l16, &d_canon, &d_canon_sizes, &d_roottab,
+        DevBuf* bufs[] = {&d_in, &d_gray, &d_quad_im, &d_thresh, &d_masks, &d_l16, &d_canon, &d_canon_sizes, &d_roottab,
                           &d_tilebase, &d_dense2rep, &d_recs[0], &d_recs[1], &d_qscratch, &d_gsort, &d_pairslots, &d_pairkeys, &d_paircount, &d_pairstart, &d_counters,
                           &d_clusters[0], &d_clusters[1], &d_clusters[2], &d_clusters[3], &d_clusters[4], &d_dbg_heads, &d_quads,
                           &d_refined, &d_dets, &d_out, &d_poses};
@@ -372,33 +372,26 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
     const bool fast = (f == 1 || f == 2 || f == 4) && sigma == 0.0f;
     uint8_t* quad_im = nullptr;
     if (!fast) {
-        // generic: decimate into quad_im, optional blur, then threshold the quad image with F = 1
+        // generic: decimate (+ blur) into quad_im, then threshold the quad image with F = 1
         CK(sl.d_quad_im.ensure(g.plane * n));
         quad_im = sl.d_quad_im.as<uint8_t>();
-        size_t total = (size_t)n * g.hd * (g.wp >> 2);
-        k_pack<<<ceil_div(total, 256), 256, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, 1, f, quad_im, g, n);
-        LAUNCH_CHECK("k_pack");
-        if (sigma != 0.0f) {
-            BlurKernel bk;
-            memset(&bk, 0, sizeof(bk));
-            bk.ksz = gaussian_kernel_host(std::fabs(sigma), bk.k);
-            if (bk.ksz > 1) {
-                CK(sl.d_blur_tmp.ensure(g.plane * n));
-                uint8_t* tmp = sl.d_blur_tmp.as<uint8_t>();
-                if (sigma < 0) {
-                    CK(sl.d_blur_orig.ensure(g.plane * n));
-                    CK(cudaMemcpyAsync(sl.d_blur_orig.p, quad_im, g.plane * n, cudaMemcpyDeviceToDevice, sl.stream));
-                }
-                size_t tot = (size_t)n * g.hd * g.wd;
-                k_blur_pass<<<ceil_div(tot, 256), 256, 0, sl.stream>>>(quad_im, tmp, g, n, bk, 0);
-                LAUNCH_CHECK("k_blur_pass(rows)");
-                k_blur_pass<<<ceil_div(tot, 256), 256, 0, sl.stream>>>(tmp, quad_im, g, n, bk, 1);
-                LAUNCH_CHECK("k_blur_pass(cols)");
-                if (sigma < 0) {
-                    k_unsharp<<<ceil_div(g.plane * n, 256), 256, 0, sl.stream>>>(sl.d_blur_orig.as<uint8_t>(), quad_im, g, n);
-                    LAUNCH_CHECK("k_unsharp");
-                }
-            }
+        BlurKernel bk;
+        memset(&bk, 0, sizeof(bk));
+        if (sigma != 0.0f) bk.ksz = gaussian_kernel_host(std::fabs(sigma), bk.k);
+        if (bk.ksz > 1) {
+            // U1 + U2 in one kernel: a shared-memory tile with its halo, 128-bit loads, row and column pass on chip
+            const int vec_in = (s_stride % 16 == 0) && (s_frame % 16 == 0) && (((uintptr_t)src) % 16 == 0);
+            dim3 grid(ceil_div(g.wp, BL_TW), ceil_div(g.hd, BL_TH), n);
+            const size_t smem = bl_smem_bytes(bk.ksz);
+            KScope ks(h, sl, "k_decimate_blur", sl.stream);
+            if (f == 1) k_decimate_blur<1><<<grid, 256, smem, sl.stream>>>(src, s_stride, s_frame, 1, vec_in, quad_im, g, bk, sigma < 0);
+            else if (f == 2) k_decimate_blur<2><<<grid, 256, smem, sl.stream>>>(src, s_stride, s_frame, 2, vec_in, quad_im, g, bk, sigma < 0);
+            else k_decimate_blur<0><<<grid, 256, smem, sl.stream>>>(src, s_stride, s_frame, f, 0, quad_im, g, bk, sigma < 0);
+            LAUNCH_CHECK("k_decimate_blur");
+        } else {
+            size_t total = (size_t)n * g.hd * (g.wp >> 2);
+            k_pack<<<ceil_div(total, 256), 256, 0, sl.stream>>>(src, srcW, srcH, s_stride, s_frame, 1, f, quad_im, g, n);
+            LAUNCH_CHECK("k_pack");
         }
         src = quad_im;
         s_stride = g.wp;
@@ -834,7 +827,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
 }
 
 unsigned long long slot_buffer_hash(const agpu_handle* h, const Slot& s) {
-    const DevBuf* bufs[] = {&s.d_in, &s.d_gray, &s.d_quad_im, &s.d_blur_tmp, &s.d_blur_orig, &s.d_thresh, &s.d_masks, &s.d_l16,
+    const DevBuf* bufs[] = {&s.d_in, &s.d_gray, &s.d_quad_im, &s.d_thresh, &s.d_masks, &s.d_l16,
                             &s.d_canon, &s.d_canon_sizes, &s.d_roottab, &s.d_tilebase, &s.d_dense2rep, &s.d_recs[0], &s.d_recs[1],
                             &s.d_qscratch, &s.d_gsort, &s.d_pairslots, &s.d_pairkeys, &s.d_paircount, &s.d_pairstart, &s.d_counters, &s.d_clusters[0], &s.d_clusters[1], &s.d_clusters[2],
                             &s.d_clusters[3], &s.d_clusters[4], &s.d_quads, &s.d_dets, &s.d_out, &s.d_poses, &h->d_fams, &h->d_codes};

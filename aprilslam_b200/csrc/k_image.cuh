@@ -351,45 +351,143 @@ k_pack(const uint8_t* __restrict__ src, int W, int H, size_t src_stride, size_t 
     *reinterpret_cast<uint32_t*>(quad_im + (size_t)frame * g.plane + (size_t)gy * g.wp + wx * 4) = out;
 }
 
-// Separable integer Gaussian (upstream image_u8_gaussian_blur / convolve).
-// dir 0: along rows, dir 1: along columns.  Positions outside [ksz/2, sz-ksz+ksz/2) are copied.
+// U1 + U2 fused: decimate and blur in ONE pass (upstream image_u8_decimate + image_u8_gaussian_blur, SURVEY.md A.3 / A.4;
+// `quad_sigma` of the detector, /root/reference/src/detection/tag_detector.py:18).  Separable integer Gaussian, rows then
+// columns; positions outside [ksz/2, sz - ksz + ksz/2) are copied, as upstream's convolution does; sigma < 0 sharpens,
+// v = clamp(2 * decimated - blurred).
+//
+// One CTA produces a 128 x 32 tile of the decimated image.  (1) The tile and its halo of ksz/2 pixels come in from HBM
+// once -- 128-bit loads, decimation by 2 as a byte permute of two such loads -- into a shared-memory tile; (2) the row
+// pass runs on that tile with DP4A (four taps per instruction on an unaligned four-byte window cut out of two words by
+// a funnel shift) into a second shared tile; (3) the column pass reads words of four pixels and accumulates even and
+// odd bytes as two 16-bit lanes of one register (the taps sum to at most 255, so a lane cannot overflow); (4) one
+// 32-bit store per four pixels.  HBM traffic: F*F*N_d (what the decimation touches) in, N_d out -- the three-kernel
+// version moved 7 N_d.
 struct BlurKernel {
     int ksz;
     uint8_t k[64];
 };
-__global__ void __launch_bounds__(256)
-k_blur_pass(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, Geom g, int nframes, BlurKernel bk, int dir) {
-    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    size_t total = (size_t)nframes * g.hd * g.wd;
-    if (idx >= total) return;
-    int x = (int)(idx % g.wd);
-    size_t t = idx / g.wd;
-    int y = (int)(t % g.hd);
-    int frame = (int)(t / g.hd);
-    const uint8_t* fi = in + (size_t)frame * g.plane;
-    int sz = dir == 0 ? g.wd : g.hd;
-    int p = dir == 0 ? x : y;
-    int half = bk.ksz / 2;
-    uint32_t v;
-    if (p >= half && p < sz - bk.ksz + half) {
-        uint32_t acc = 0;
-        for (int j = 0; j < bk.ksz; j++) {
-            int q = p - half + j;
-            acc += (uint32_t)bk.k[j] * (dir == 0 ? fi[(size_t)y * g.wp + q] : fi[(size_t)q * g.wp + x]);
-        }
-        v = acc >> 8;
-    } else {
-        v = fi[(size_t)y * g.wp + x];
-    }
-    out[(size_t)frame * g.plane + (size_t)y * g.wp + x] = (uint8_t)v;
+#define BL_TW 128
+#define BL_TH 32
+__host__ __device__ inline int bl_halo_cols(int half) { return (half + 15) & ~15; }            // halo rounded up to whole 16-byte chunks
+__host__ __device__ inline int bl_pitch0(int half) { return BL_TW + 2 * bl_halo_cols(half) + 16; }
+__host__ __device__ inline size_t bl_smem_bytes(int ksz) {
+    const int half = ksz / 2, rows = BL_TH + 2 * half;
+    return (size_t)rows * bl_pitch0(half) + (size_t)rows * BL_TW + 64;
 }
 
-// quad_sigma < 0: v = clamp(2*orig - blurred)
+template <int F>   // 1, 2: vector loads; 0: any factor (`Fdyn`), byte gathers
 __global__ void __launch_bounds__(256)
-k_unsharp(const uint8_t* __restrict__ orig, uint8_t* __restrict__ blurred_inout, Geom g, int nframes) {
-    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    size_t total = (size_t)nframes * g.plane;
-    if (idx >= total) return;
-    int v = 2 * (int)orig[idx] - (int)blurred_inout[idx];
-    blurred_inout[idx] = (uint8_t)min(255, max(0, v));
+k_decimate_blur(const uint8_t* __restrict__ src, size_t src_stride, size_t src_frame_stride, int Fdyn, int vec_ok,
+                uint8_t* __restrict__ quad_im, Geom g, const __grid_constant__ BlurKernel bk, int sharpen) {
+    extern __shared__ __align__(16) unsigned char bl_smem[];
+    const int ksz = bk.ksz, half = ksz / 2, hal = bl_halo_cols(half);
+    const int rows0 = BL_TH + 2 * half, pitch0 = bl_pitch0(half);
+    uint8_t* S0 = bl_smem;                                  // [rows0][pitch0] decimated input, halo included
+    uint8_t* S1 = bl_smem + (size_t)rows0 * pitch0;         // [rows0][BL_TW]  after the row pass
+    uint32_t* KW = reinterpret_cast<uint32_t*>(S1 + (size_t)rows0 * BL_TW);   // [16] taps, four per word, zero padded
+    const int frame = blockIdx.z;
+    const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
+    const int fac = F ? F : Fdyn;
+    const uint8_t* fs = src + (size_t)frame * src_frame_stride;
+    if (threadIdx.x < 16) {
+        uint32_t wv = 0;
+        for (int i = 0; i < 4; i++) {
+            const int j = threadIdx.x * 4 + i;
+            wv |= (uint32_t)(j < ksz ? bk.k[j] : 0) << (8 * i);
+        }
+        KW[threadIdx.x] = wv;
+    }
+    // ---- (1) load + decimate
+    const int chunks = (BL_TW + 2 * hal) / 16;
+    for (int i = threadIdx.x; i < rows0 * chunks; i += blockDim.x) {
+        const int r = i / chunks, ch = i - r * chunks;
+        const int gy = ty0 - half + r, gx = tx0 - hal + ch * 16;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (gy >= 0 && gy < g.hd && gx + 15 >= 0 && gx < g.wd) {
+            const uint8_t* row = fs + (size_t)gy * fac * src_stride;
+            if (F == 1 && vec_ok && gx >= 0 && gx + 16 <= g.wd) {
+                v = __ldg(reinterpret_cast<const uint4*>(row + gx));
+            } else if (F == 2 && vec_ok && gx >= 0 && gx + 16 < g.wd) {   // (< : an odd source width ends one byte early)
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(row + 2 * gx));
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(row + 2 * gx + 16));
+                v.x = __byte_perm(a.x, a.y, 0x6420); v.y = __byte_perm(a.z, a.w, 0x6420);   // the even bytes
+                v.z = __byte_perm(b.x, b.y, 0x6420); v.w = __byte_perm(b.z, b.w, 0x6420);
+            } else {
+                uint32_t wd4[4] = {0u, 0u, 0u, 0u};
+                for (int k = 0; k < 16; k++) {
+                    const int x = gx + k;
+                    if (x >= 0 && x < g.wd) wd4[k >> 2] |= (uint32_t)row[(size_t)x * fac] << (8 * (k & 3));
+                }
+                v = make_uint4(wd4[0], wd4[1], wd4[2], wd4[3]);
+            }
+        }
+        *reinterpret_cast<uint4*>(S0 + (size_t)r * pitch0 + ch * 16) = v;
+    }
+    __syncthreads();
+    // ---- (2) row pass: four pixels (one word) per thread and step
+    const int ngroups = (ksz + 3) >> 2;
+    for (int i = threadIdx.x; i < rows0 * (BL_TW / 4); i += blockDim.x) {
+        const int r = i / (BL_TW / 4), wq = i - r * (BL_TW / 4);
+        const uint8_t* row = S0 + (size_t)r * pitch0;
+        const int c0 = hal + 4 * wq;                         // column of the first of the four pixels inside S0
+        uint32_t out = *reinterpret_cast<const uint32_t*>(row + c0);   // (the copy; pixels inside the range are replaced)
+        const int gx0 = tx0 + 4 * wq;
+        if (gx0 + 3 >= half && gx0 < g.wd - ksz + half) {
+            const int a0 = c0 - half;                        // first byte of pixel 0's window
+            const uint32_t* wrow = reinterpret_cast<const uint32_t*>(row) + (a0 >> 2);
+            const int sh0 = a0 & 3;
+            uint32_t acc[4] = {0u, 0u, 0u, 0u};
+            uint32_t w0 = wrow[0], w1 = wrow[1];
+            for (int jg = 0; jg < ngroups; jg++) {
+                const uint32_t w2 = wrow[jg + 2];
+                const uint32_t kw = KW[jg];
+#pragma unroll
+                for (int px = 0; px < 4; px++) {
+                    const int sh = sh0 + px;                 // 0 .. 6
+                    const uint32_t win = sh < 4 ? __funnelshift_r(w0, w1, 8 * sh) : __funnelshift_r(w1, w2, 8 * (sh - 4));
+                    acc[px] = __dp4a(win, kw, acc[px]);
+                }
+                w0 = w1; w1 = w2;
+            }
+#pragma unroll
+            for (int px = 0; px < 4; px++) {
+                const int gx = gx0 + px;
+                if (gx >= half && gx < g.wd - ksz + half) out = (out & ~(0xffu << (8 * px))) | (((acc[px] >> 8) & 0xffu) << (8 * px));
+            }
+        }
+        *reinterpret_cast<uint32_t*>(S1 + (size_t)r * BL_TW + 4 * wq) = out;
+    }
+    __syncthreads();
+    // ---- (3) column pass + (4) store
+    uint8_t* fo = quad_im + (size_t)frame * g.plane;
+    for (int i = threadIdx.x; i < BL_TH * (BL_TW / 4); i += blockDim.x) {
+        const int r = i / (BL_TW / 4), wq = i - r * (BL_TW / 4);
+        const int gy = ty0 + r, gx0 = tx0 + 4 * wq;
+        if (gy >= g.hd || gx0 >= g.wp) continue;
+        uint32_t out = *reinterpret_cast<const uint32_t*>(S1 + (size_t)(half + r) * BL_TW + 4 * wq);
+        if (gy >= half && gy < g.hd - ksz + half) {
+            uint32_t ae = 0u, ao = 0u;
+            for (int j = 0; j < ksz; j++) {
+                const uint32_t wv = *reinterpret_cast<const uint32_t*>(S1 + (size_t)(r + j) * BL_TW + 4 * wq);
+                const uint32_t kj = (KW[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                ae += kj * (wv & 0x00ff00ffu);
+                ao += kj * ((wv >> 8) & 0x00ff00ffu);
+            }
+            out = ((ae >> 8) & 0x00ff00ffu) | (ao & 0xff00ff00u);
+        }
+        if (sharpen) {
+            const uint32_t orig = *reinterpret_cast<const uint32_t*>(S0 + (size_t)(half + r) * pitch0 + hal + 4 * wq);
+            uint32_t sw = 0u;
+#pragma unroll
+            for (int px = 0; px < 4; px++) {
+                const int v = 2 * (int)((orig >> (8 * px)) & 0xffu) - (int)((out >> (8 * px)) & 0xffu);
+                sw |= (uint32_t)min(255, max(0, v)) << (8 * px);
+            }
+            out = sw;
+        }
+        // (bytes right of the image inside the row pitch stay zero, as k_pack leaves them)
+        if (gx0 + 4 > g.wd) out &= gx0 >= g.wd ? 0u : (0xffffffffu >> (8 * (gx0 + 4 - g.wd)));
+        *reinterpret_cast<uint32_t*>(fo + (size_t)gy * g.wp + gx0) = out;
+    }
 }

@@ -115,15 +115,20 @@ def test_mask_front_end_bit_exact(ob, W, H, monkeypatch):
     det_bytes.close()
 
 
-@pytest.mark.parametrize("sigma", [0.8, 1.5, -0.8])
-def test_blur_front_end_bit_exact(ob, sigma):
+@pytest.mark.parametrize("sigma", [0.8, 1.5, -0.8, 3.1, -2.0, 9.0])
+@pytest.mark.parametrize("decimate", [1, 2, 3])
+def test_blur_front_end_bit_exact(ob, sigma, decimate):
+    """U1 + U2 fused (k_decimate_blur): kernel sizes 3 .. 37 taps, blur and sharpen, decimation by the two vector-load
+    factors and a generic one, on shapes with ragged right / bottom edges, a tile boundary inside, and images smaller
+    than the kernel (upstream copies what the window does not cover)."""
     rng = np.random.default_rng(5)
-    im = rng.integers(0, 256, (241, 323), dtype=np.uint8)
-    det = Detector("tag36h11", decimate=2.0, blur=sigma)
-    q, t = det.stage_threshold(im)
-    q_ref = ob.stage_blur(np.ascontiguousarray(im[::2, ::2]), sigma)
-    assert np.array_equal(q, q_ref)
-    assert np.array_equal(t, ob.stage_threshold(q_ref))
+    det = Detector("tag36h11", decimate=float(decimate), blur=sigma)
+    for shape in ((241, 323), (96, 512), (70, 41), (9, 13)):
+        im = rng.integers(0, 256, shape, dtype=np.uint8)
+        q, t = det.stage_threshold(im)
+        q_ref = ob.stage_blur(np.ascontiguousarray(im[::decimate, ::decimate]), sigma)
+        assert np.array_equal(q, q_ref), (shape, sigma, decimate)
+        assert np.array_equal(t, ob.stage_threshold(q_ref))
     det.close()
 
 
