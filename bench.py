@@ -375,6 +375,28 @@ def run_b200(args):
     step_host()
     e2e_steps = max(1, min(args.steps, 3))
     sec_e2e, _, _, _, _ = timed(step_host, e2e_steps)
+    # N > 1: the host-side gather SURVEY 8(e) names -- rank 0 collects every rank's per-frame lists in frame order over the
+    # process group (NCCL here), timed together with the device-resident step it follows
+    gather = None
+    if distributed:
+        from aprilslam_b200._lib import DET_DTYPE
+        from aprilslam_b200.shard import gather_lists
+
+        def step_gather():
+            dd, pp = step_dev()
+            return dd, gather_lists([np.asarray(x) for x in dd], DET_DTYPE)
+
+        step_gather()
+        sec_g, _, _, _, (own, allists) = timed(step_gather, e2e_steps)
+        ok_g = None
+        if rank == 0:
+            ok_g = len(allists) == B * world and all(
+                np.array_equal(allists[i]["id"], np.asarray(own[i])["id"]) for i in range(0, B, max(1, B // 64)))
+        gather = {"value": B * world * e2e_steps / sec_g, "unit": "frames/s", "lists_on_rank0": B * world,
+                  "rank0_lists_in_frame_order": ok_g,
+                  "bytes_gathered_per_step": int(sum(len(x) for x in own) * DET_DTYPE.itemsize * world),
+                  "note": "device-resident step + shard.gather_lists (two all_gathers: sizes, then the ragged payload) on the "
+                          "bench's process group; max over ranks"}
     # end to end from BGR frames, the reference's real input (tag_detector.py:25): 3 bytes per pixel over the host link
     e2e_bgr = None
     if not per_call and not args.no_bgr:
@@ -547,6 +569,7 @@ def run_b200(args):
                 "note": "gray uint8 host (pinned) frames through the public call; the frames cross the host link once, chunk "
                         "copies overlap the kernels of other chunks"},
         "e2e_bgr": e2e_bgr,
+        "gather": gather,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
