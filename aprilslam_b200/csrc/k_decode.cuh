@@ -33,8 +33,11 @@ __device__ __forceinline__ double bilinear_at(const uint8_t* im, size_t pitch, i
 // 4 x 16 samples: two full rounds instead of four half-empty ones); every sample runs the sequential search along the
 // edge normal on its own lane, and the per-edge moments are then accumulated in sample order (identical on every lane),
 // exactly the order of the sequential algorithm.
+// position of sample k's term in row m of the staging buffer: skewed by the row, so the nine lanes that walk the nine
+// rows side by side -- each at the same k -- hit nine different banks
+#define DEC_STAGE_AT(m, k) ((m) * 32 + (((k) + (m)) & 31))
 __device__ void refine_edges_warp(const DevParams& P, const uint8_t* im, size_t pitch, int width, int height,
-                                  float (&p)[4][2], int reversed) {
+                                  float (&p)[4][2], int reversed, double* stage) {
     const int lane = threadIdx.x & 31;
     double enx[4], eny[4];
     int ens[4], eoff[5];
@@ -58,6 +61,7 @@ __device__ void refine_edges_warp(const DevParams& P, const uint8_t* im, size_t 
     const int nsteps = (int)(2 * range * 4) + 1;
     double lines[4][4];
     double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
+    double macc = 0;      // lane m < 6: running sum of moment m of the current edge
     int cur = 0;          // edge whose moments are being accumulated (uniform over the warp)
     int cur_end = eoff[1];
     auto finish_edge = [&]() {
@@ -118,16 +122,34 @@ __device__ void refine_edges_warp(const DevParams& P, const uint8_t* im, size_t 
                 valid = 1;
             }
         }
+        // Sequential-order accumulation of the six moments (the order of the sequential algorithm -- the sums feed
+        // decisions).  Every lane parks the six terms of ITS sample in the staging buffer; lane m < 6 then runs the
+        // sequential sum of moment m over the samples (one LDS + one DADD per sample), and the six sums are handed to
+        // all lanes only where an edge ends -- instead of every lane replaying every sample through five shuffles.
         const int cnt = min(32, total - base);
-        for (int k = 0; k < cnt; k++) {  // sequential-order accumulation, identical on every lane
-            if (base + k >= cur_end) finish_edge();
-            int vk = __shfl_sync(FULL_MASK, valid, k);
-            double bx = __shfl_sync(FULL_MASK, bestx, k), by = __shfl_sync(FULL_MASK, besty, k);
-            if (vk) {
-                Mx += bx; My += by; Mxx += bx * bx; Mxy += bx * by; Myy += by * by; N += 1;
-            }
+        {
+            const double v1 = valid ? 1.0 : 0.0, bx = valid ? bestx : 0.0, by = valid ? besty : 0.0;
+            stage[DEC_STAGE_AT(0, lane)] = bx; stage[DEC_STAGE_AT(1, lane)] = by; stage[DEC_STAGE_AT(2, lane)] = bx * bx;
+            stage[DEC_STAGE_AT(3, lane)] = bx * by; stage[DEC_STAGE_AT(4, lane)] = by * by; stage[DEC_STAGE_AT(5, lane)] = v1;
         }
+        __syncwarp();
+        const int mrow = lane < 6 ? lane : 0;
+        int k = 0;
+        while (k < cnt) {
+            if (base + k >= cur_end) {   // (uniform) the edge ended with the previous sample: its sums to all lanes
+                Mx = __shfl_sync(FULL_MASK, macc, 0); My = __shfl_sync(FULL_MASK, macc, 1); Mxx = __shfl_sync(FULL_MASK, macc, 2);
+                Mxy = __shfl_sync(FULL_MASK, macc, 3); Myy = __shfl_sync(FULL_MASK, macc, 4); N = __shfl_sync(FULL_MASK, macc, 5);
+                finish_edge();
+                macc = 0;
+            }
+            const int kend = min(cnt, cur_end - base);
+#pragma unroll 4
+            for (; k < kend; k++) macc += stage[DEC_STAGE_AT(mrow, k)];
+        }
+        __syncwarp();
     }
+    Mx = __shfl_sync(FULL_MASK, macc, 0); My = __shfl_sync(FULL_MASK, macc, 1); Mxx = __shfl_sync(FULL_MASK, macc, 2);
+    Mxy = __shfl_sync(FULL_MASK, macc, 3); Myy = __shfl_sync(FULL_MASK, macc, 4); N = __shfl_sync(FULL_MASK, macc, 5);
     finish_edge();   // the fourth edge (every edge has >= 16 samples, so edges 0..2 were closed inside the loop)
     float np[4][2];
 #pragma unroll
@@ -265,6 +287,7 @@ __device__ float quad_decode_warp(const DevParams& P, const DevFamily& fam, cons
     GrayModelDev white, black;
     white.init();
     black.init();
+    double gacc = 0;      // lanes 0..8 / 9..17: running sum of one moment of the white / black model
     const int nsamp = 8 * wb;
     for (int base = 0; base < nsamp; base += 32) {
         const int t = base + lane;
@@ -295,17 +318,35 @@ __device__ float quad_decode_warp(const DevParams& P, const DevFamily& fam, cons
                 valid = 1;
             }
         }
+        // sequential-order sums of the two models' nine moments: lane k parks the nine terms of its sample, lanes 0..8 run
+        // the white model's sums and lanes 9..17 the black model's over the samples in order (a sample the model does not
+        // own adds 0.0, which leaves a sum as it is)
         const int cnt = min(32, nsamp - base);
-        for (int k = 0; k < cnt; k++) {
-            int vk = __shfl_sync(FULL_MASK, valid, k);
-            int wk = __shfl_sync(FULL_MASK, is_white, k);
-            int gk = __shfl_sync(FULL_MASK, v, k);
-            double xk = __shfl_sync(FULL_MASK, tagx, k), yk = __shfl_sync(FULL_MASK, tagy, k);
-            if (vk) {
-                if (wk) white.add(xk, yk, gk); else black.add(xk, yk, gk);
+        const uint32_t wmask = __ballot_sync(FULL_MASK, valid && is_white), bmask = __ballot_sync(FULL_MASK, valid && !is_white);
+        {
+            const double g = (double)v;
+            values[DEC_STAGE_AT(0, lane)] = tagx * tagx; values[DEC_STAGE_AT(1, lane)] = tagx * tagy; values[DEC_STAGE_AT(2, lane)] = tagx;
+            values[DEC_STAGE_AT(3, lane)] = tagy * tagy; values[DEC_STAGE_AT(4, lane)] = tagy; values[DEC_STAGE_AT(5, lane)] = 1.0;
+            values[DEC_STAGE_AT(6, lane)] = tagx * g; values[DEC_STAGE_AT(7, lane)] = tagy * g; values[DEC_STAGE_AT(8, lane)] = g;
+        }
+        __syncwarp();
+        {
+            const int mrow = lane < 9 ? lane : (lane < 18 ? lane - 9 : 0);
+            const uint32_t mine = lane < 9 ? wmask : (lane < 18 ? bmask : 0u);
+#pragma unroll 4
+            for (int k = 0; k < cnt; k++) {
+                const double t = values[DEC_STAGE_AT(mrow, k)];
+                gacc += ((mine >> k) & 1u) ? t : 0.0;
             }
         }
+        __syncwarp();
     }
+    white.A00 = __shfl_sync(FULL_MASK, gacc, 0); white.A01 = __shfl_sync(FULL_MASK, gacc, 1); white.A02 = __shfl_sync(FULL_MASK, gacc, 2);
+    white.A11 = __shfl_sync(FULL_MASK, gacc, 3); white.A12 = __shfl_sync(FULL_MASK, gacc, 4); white.A22 = __shfl_sync(FULL_MASK, gacc, 5);
+    white.B0 = __shfl_sync(FULL_MASK, gacc, 6); white.B1 = __shfl_sync(FULL_MASK, gacc, 7); white.B2 = __shfl_sync(FULL_MASK, gacc, 8);
+    black.A00 = __shfl_sync(FULL_MASK, gacc, 9); black.A01 = __shfl_sync(FULL_MASK, gacc, 10); black.A02 = __shfl_sync(FULL_MASK, gacc, 11);
+    black.A11 = __shfl_sync(FULL_MASK, gacc, 12); black.A12 = __shfl_sync(FULL_MASK, gacc, 13); black.A22 = __shfl_sync(FULL_MASK, gacc, 14);
+    black.B0 = __shfl_sync(FULL_MASK, gacc, 15); black.B1 = __shfl_sync(FULL_MASK, gacc, 16); black.B2 = __shfl_sync(FULL_MASK, gacc, 17);
     white.solve();
     black.solve();
     if ((white.interp(0, 0) - black.interp(0, 0) < 0) != (fam.reversed_border != 0)) return -1.0f;
@@ -386,8 +427,7 @@ __device__ float quad_decode_warp(const DevParams& P, const DevFamily& fam, cons
 #endif
 __global__ void __launch_bounds__(128, DEC_MINB)
 k_decode_quads(DecodeArgs a, DevParams P) {
-    __shared__ double s_values[4][DEC_GRID_MAX];
-    __shared__ double s_sharp[4][DEC_GRID_MAX];
+    __shared__ double s_buf[4][2 * DEC_GRID_MAX];   // per warp: bit grid + sharpened grid; before that the 9 x 32 staging buffer
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nq = min(*a.nquads, a.cap_quads);
     const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -397,7 +437,7 @@ k_decode_quads(DecodeArgs a, DevParams P) {
         float p[4][2];
 #pragma unroll
         for (int i = 0; i < 4; i++) { p[i][0] = q.p[i][0]; p[i][1] = q.p[i][1]; }
-        if (P.refine_edges) refine_edges_warp(P, im, a.pitch, a.W, a.H, p, q.reversed_border);
+        if (P.refine_edges) refine_edges_warp(P, im, a.pitch, a.W, a.H, p, q.reversed_border, s_buf[w]);
         if (a.dbg_refined && lane == 0) {
 #pragma unroll
             for (int i = 0; i < 4; i++) { a.dbg_refined[qi * 8 + 2 * i] = p[i][0]; a.dbg_refined[qi * 8 + 2 * i + 1] = p[i][1]; }
@@ -408,7 +448,7 @@ k_decode_quads(DecodeArgs a, DevParams P) {
             const DevFamily& fam = a.fams[fi];
             if ((fam.reversed_border != 0) != (q.reversed_border != 0)) continue;
             int id, hamming, rot;
-            float margin = quad_decode_warp(P, fam, a.codes, im, a.pitch, a.W, a.H, H, s_values[w], s_sharp[w], id,
+            float margin = quad_decode_warp(P, fam, a.codes, im, a.pitch, a.W, a.H, H, s_buf[w], s_buf[w] + DEC_GRID_MAX, id,
                                             hamming, rot);
             if (margin >= 0 && hamming < 255 && lane == 0) {
                 DetRec d;
