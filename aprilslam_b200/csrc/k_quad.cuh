@@ -436,7 +436,7 @@ __device__ void group_rank_sort(const QGroup<NW>& G, unsigned long long* sbuf, u
 template <int NW>
 __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, const DevParams& P, const ClusterRef ref,
                                   unsigned long long* sbuf, double* ptab, int* sidx, uint16_t* scnt, double* stage, double* lf,
-                                  QuadRec& q) {
+                                  long long* red, QuadRec& q) {
     constexpr int T = QGroup<NW>::T;
     const int tid = G.tid, lane = G.lane;
     const size_t seg = (size_t)ref.frame * a.cap + ref.start;
@@ -479,12 +479,39 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
         Sxgx += (long long)px * gx; Sgx += gx;
         Sygy += (long long)py * gy; Sgy += gy;
     }
-    xmin = G.reduce_min(xmin); xmax = G.reduce_max(xmax);
-    ymin = G.reduce_min(ymin); ymax = G.reduce_max(ymax);
-    Sxgx = G.reduce_sum(Sxgx); Sygy = G.reduce_sum(Sygy);
-    Sgx = G.reduce_sum(Sgx); Sgy = G.reduce_sum(Sgy);
+    // all nine group reductions at once: REDUX inside the warps (the 64-bit sums as three 20-bit slices of the biased
+    // value, so no lane sum can wrap), one shared-memory exchange and ONE barrier between the warps
+    {
+        xmin = __reduce_min_sync(FULL_MASK, xmin); xmax = __reduce_max_sync(FULL_MASK, xmax);
+        ymin = __reduce_min_sync(FULL_MASK, ymin); ymax = __reduce_max_sync(FULL_MASK, ymax);
+        nmerged = __reduce_add_sync(FULL_MASK, nmerged);
+        auto warp_sum64 = [](long long v) -> long long {   // |v| < 2^41 (98280 records x 16380 x 510 < 2^40)
+            const unsigned long long u = (unsigned long long)(v + (1ll << 41));
+            const unsigned long long c0 = __reduce_add_sync(FULL_MASK, (unsigned)(u & 0xfffffu));
+            const unsigned long long c1 = __reduce_add_sync(FULL_MASK, (unsigned)((u >> 20) & 0xfffffu));
+            const unsigned long long c2 = __reduce_add_sync(FULL_MASK, (unsigned)(u >> 40));
+            return (long long)(c0 + (c1 << 20) + (c2 << 40)) - (32ll << 41);
+        };
+        Sxgx = warp_sum64(Sxgx); Sygy = warp_sum64(Sygy); Sgx = warp_sum64(Sgx); Sgy = warp_sum64(Sgy);
+        if (NW > 1) {
+            long long* sr = red;   // [NW][10]
+            if (lane == 0) {
+                long long* o = sr + G.w * 10;
+                o[0] = xmin; o[1] = xmax; o[2] = ymin; o[3] = ymax; o[4] = nmerged; o[5] = Sxgx; o[6] = Sygy; o[7] = Sgx; o[8] = Sgy;
+            }
+            __syncthreads();
+            xmin = (int)sr[0]; xmax = (int)sr[1]; ymin = (int)sr[2]; ymax = (int)sr[3]; nmerged = (int)sr[4];
+            Sxgx = sr[5]; Sygy = sr[6]; Sgx = sr[7]; Sgy = sr[8];
+#pragma unroll
+            for (int ww = 1; ww < NW; ww++) {
+                const long long* o = sr + ww * 10;
+                xmin = min(xmin, (int)o[0]); xmax = max(xmax, (int)o[1]); ymin = min(ymin, (int)o[2]); ymax = max(ymax, (int)o[3]);
+                nmerged += (int)o[4]; Sxgx += o[5]; Sygy += o[6]; Sgx += o[7]; Sgy += o[8];
+            }
+        }
+    }
     // upstream's size limit counts the raw points (duplicates included)
-    if (sz + (int)G.reduce_sum((long long)nmerged) > 3 * (2 * a.g.wd + 2 * a.g.hd)) {
+    if (sz + nmerged > 3 * (2 * a.g.wd + 2 * a.g.hd)) {
         if (tid == 0) atomicAdd(a.oversize, 1);
         return false;
     }
@@ -874,6 +901,7 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
     __shared__ int s_i[2 * NW + 8];
     __shared__ double s_d[NW * 8];
     __shared__ int s_ok;
+    __shared__ long long s_red[NW * 10];   // the bounding-box / polarity reductions of the cluster in hand
     QGroup<NW> G;
     G.lane = threadIdx.x & 31;
     G.w = NW == 1 ? 0 : (threadIdx.x >> 5);
@@ -907,7 +935,7 @@ k_fit_quads(QuadFitArgs a, DevParams P, int wcap) {
         unsigned long long* sb = sbuf;
         if (NW == 8 && ref.size > wcap) sb = a.gsort + (size_t)blockIdx.x * a.gsort_stride;   // (the pair table stays in shared memory)
         double* lf = a.scratch + (size_t)(NW == 1 ? blockIdx.x * 8 + gi : blockIdx.x) * a.scratch_pts * 7;
-        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sb, ptab, sidx, scnt, stage, lf, q);
+        const bool ok = fit_cluster_group<NW>(G, a, P, ref, sb, ptab, sidx, scnt, stage, lf, s_red, q);
         if (ok && G.tid == 0) {
             int s = atomicAdd(a.nquads, 1);
             atomicAdd(&a.per_frame_quads[ref.frame], 1);
