@@ -42,7 +42,7 @@ torch.cuda.synchronize()
 d0.close()
 results = []
 for name, env, chunk, slots in CONFIGS:
-    for k in ("AGPU_PRIO", "AGPU_TIER_CTAS", "AGPU_DECODE_CTAS", "AGPU_TAIL_THREADS", "AGPU_EDGE_WARPS", "AGPU_BOUNDARY_WARPS", "AGPU_TIER_CAP"):
+    for k in ("AGPU_PRIO", "AGPU_TIER_CTAS", "AGPU_DECODE_CTAS", "AGPU_TAIL_THREADS", "AGPU_EDGE_WARPS", "AGPU_BOUNDARY_WARPS", "AGPU_TIER_CAP", "AGPU_MASKS", "AGPU_SLOTS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     det = Detector("tag36h11", decimate=1.0, chunk_frames=chunk, pipeline_slots=slots)
