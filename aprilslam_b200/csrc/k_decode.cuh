@@ -516,10 +516,10 @@ __device__ int prefer_dev(const DetRec& a, const DetRec& b) {
 
 #define REC_CAP 256  // internal per-frame detection capacity before reconcile
 
-// One CTA of REC_THREADS threads per frame.  The sort keys (id, family, centre) are staged in shared memory once, so the
+// One CTA of REC_THREADS threads per frame (a 4K frame carries a few hundred detections).  The sort keys (id, family, centre) are staged in shared memory once, so the
 // two rank sorts (n^2 comparisons, dealt to all threads) run out of shared memory instead of re-reading the 168-byte
-// records n times; the pairwise rule in between is sequential by definition (thread 0).
-#define REC_THREADS 128
+// records n times; the pairwise rule in between is sequential inside a run of equal ids (one thread per run).
+#define REC_THREADS 256
 __global__ void __launch_bounds__(REC_THREADS)
 k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int cap_dets, int nframes,
             DetRec* __restrict__ out, int* __restrict__ out_counts, int cap_out) {
@@ -555,8 +555,11 @@ k_reconcile(const DetRec* __restrict__ dets, const int* __restrict__ ndets, int 
         dead[i] = 0;
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int a = 0; a < n; a++) {
+    // the pairwise rule only ever compares detections of one id: the runs of equal id (consecutive in the sorted order) are
+    // independent, so every run is walked -- sequentially, as the rule is defined -- by its own thread
+    for (int a0 = tid; a0 < n; a0 += REC_THREADS) {
+        if (a0 > 0 && s_id[perm[a0 - 1]] == s_id[perm[a0]]) continue;   // not the first of its run
+        for (int a = a0; a < n && s_id[perm[a]] == s_id[perm[a0]]; a++) {
             const int i = perm[a];
             if (dead[i]) continue;
             for (int b = a + 1; b < n; b++) {
