@@ -180,6 +180,7 @@ struct agpu_handle {
         int graph = 1;                                 // CUDA graph for single-chunk calls of up to graph_max_frames frames
         int graph_max_frames = 8;
         int seg_tiles = 0, img_minb = 4, slots = 0;    // AGPU_SEG_TILES / AGPU_IMG_MINB / AGPU_SLOTS (0 = default), read once
+        int blur_strip = 1;                            // AGPU_BLUR_STRIP=0: the shared-memory blur kernel for every kernel size (tests)
     } tune;
     DevBuf d_fams, d_codes, d_pose_in, d_pose_out;
     std::vector<Slot> slots;
@@ -384,7 +385,19 @@ int run_image_stage(agpu_handle* h, Slot& sl, const uint8_t* d_src, int channels
             dim3 grid(ceil_div(g.wp, BL_TW), ceil_div(g.hd, BL_TH), n);
             const size_t smem = bl_smem_bytes(bk.ksz);
             KScope ks(h, sl, "k_decimate_blur", sl.stream);
-            if (f == 1) k_decimate_blur<1><<<grid, 256, smem, sl.stream>>>(src, s_stride, s_frame, 1, vec_in, quad_im, g, bk, sigma < 0);
+            // (7 taps at decimation 2: the ring of rows needs ~190 registers and the tile kernel is faster)
+            const bool strip = vec_in && (f == 1 || f == 2) && (bk.ksz == 3 || bk.ksz == 5 || (bk.ksz == 7 && f == 1)) && h->tune.blur_strip;
+            if (strip) {
+                // the common case: register-resident strips, no shared memory
+                const int nstrips = ceil_div(g.wp, 512), nsegs = ceil_div(g.hd, BLS_ROWS);
+                const int blocks = (int)ceil_div((long long)nstrips * nsegs * n, 4);
+#define LAUNCH_BLS(FF, KK, SS) k_decimate_blur_strip<FF, KK, SS><<<blocks, 128, 0, sl.stream>>>(src, s_stride, s_frame, quad_im, g, bk, nstrips, nsegs, n)
+#define LAUNCH_BLS_K(FF, SS) do { if (bk.ksz == 3) LAUNCH_BLS(FF, 3, SS); else if (bk.ksz == 5) LAUNCH_BLS(FF, 5, SS); else LAUNCH_BLS(FF, 7, SS); } while (0)
+                if (f == 1) { if (sigma < 0) LAUNCH_BLS_K(1, true); else LAUNCH_BLS_K(1, false); }
+                else { if (sigma < 0) LAUNCH_BLS_K(2, true); else LAUNCH_BLS_K(2, false); }
+#undef LAUNCH_BLS_K
+#undef LAUNCH_BLS
+            } else if (f == 1) k_decimate_blur<1><<<grid, 256, smem, sl.stream>>>(src, s_stride, s_frame, 1, vec_in, quad_im, g, bk, sigma < 0);
             else if (f == 2) k_decimate_blur<2><<<grid, 256, smem, sl.stream>>>(src, s_stride, s_frame, 2, vec_in, quad_im, g, bk, sigma < 0);
             else k_decimate_blur<0><<<grid, 256, smem, sl.stream>>>(src, s_stride, s_frame, f, 0, quad_im, g, bk, sigma < 0);
             LAUNCH_CHECK("k_decimate_blur");
@@ -1222,6 +1235,7 @@ int agpu_create(const agpu_config* cfg, agpu_handle** out) {
     if (const char* e = getenv("AGPU_SEG_TILES")) h->tune.seg_tiles = std::max(0, std::min(256, atoi(e)));
     if (const char* e = getenv("AGPU_IMG_MINB")) { const int v = atoi(e); h->tune.img_minb = (v >= 3 && v <= 6) ? v : 4; }
     if (const char* e = getenv("AGPU_SLOTS")) h->tune.slots = std::max(0, std::min(8, atoi(e)));
+    if (const char* e = getenv("AGPU_BLUR_STRIP")) h->tune.blur_strip = atoi(e) != 0;
     if (const char* e = getenv("AGPU_TAIL_THREADS")) h->tune.tail_threads = atoi(e) >= 128 ? 128 : (atoi(e) >= 64 ? 64 : 32);
     if (const char* e = getenv("AGPU_DECODE_CTAS")) h->tune.decode_ctas = std::max(1, std::min(16, atoi(e)));
     if (const char* e = getenv("AGPU_TIER_CAP")) {

@@ -491,3 +491,171 @@ k_decimate_blur(const uint8_t* __restrict__ src, size_t src_stride, size_t src_f
         *reinterpret_cast<uint32_t*>(fo + (size_t)gy * g.wp + gx0) = out;
     }
 }
+
+// U1 + U2, the common case (3, 5 or 7 taps -- quad_sigma up to 2 --, decimation 1 or 2, 16-byte aligned rows): NO shared
+// memory.  One warp walks down a strip of 512 decimated pixels, lane = one 16-pixel chunk per row (one LDG.128, two for
+// decimation 2 with the even bytes picked by a byte permute).  Row pass: the neighbour words come from the neighbour
+// lanes by shuffle, every output pixel is one DP4A (two for 5 / 7 taps) on a four-byte window cut out of two words by a
+// funnel shift.  Column pass: the row-pass results of the last KSZ rows stay in registers, split into even / odd bytes as
+// 16-bit lanes, so a tap is two IMADs per four pixels; the row loop is unrolled KSZ times so the ring of rows is indexed
+// statically.  One STG.128 per 16 pixels.  Borders as upstream (positions outside [ksz/2, sz - ksz + ksz/2) are copies).
+#define BLS_ROWS 32      // output rows per warp (+ KSZ - 1 halo rows it recomputes)
+template <int F, int KSZ, bool SHARPEN>
+__global__ void __launch_bounds__(128)   // (occupancy bounds were tried: 6 / 4 / 3 CTAs per SM spill and lose 1 .. 15 %)
+k_decimate_blur_strip(const uint8_t* __restrict__ src, size_t src_stride, size_t src_frame_stride,
+                      uint8_t* __restrict__ quad_im, Geom g, const __grid_constant__ BlurKernel bk, int nstrips, int nsegs, int nframes) {
+    constexpr int HALF = KSZ / 2, NG = (KSZ + 3) / 4;
+    const int lane = threadIdx.x & 31;
+    const long long unit = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (unit >= (long long)nstrips * nsegs * nframes) return;
+    const int strip = (int)(unit % nstrips), seg = (int)((unit / nstrips) % nsegs), frame = (int)(unit / ((long long)nstrips * nsegs));
+    const int x = strip * 512 + lane * 16;               // first decimated pixel of this lane's chunk
+    const int y0 = seg * BLS_ROWS;
+    const uint8_t* fs = src + (size_t)frame * src_frame_stride;
+    uint8_t* fo = quad_im + (size_t)frame * g.plane;
+    uint32_t kw[NG], kt[KSZ];
+#pragma unroll
+    for (int j = 0; j < KSZ; j++) kt[j] = bk.k[j];
+#pragma unroll
+    for (int gI = 0; gI < NG; gI++) {
+        kw[gI] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (gI * 4 + i < KSZ) kw[gI] |= kt[gI * 4 + i] << (8 * i);
+    }
+    // per word: which of its four pixels are inside the horizontal convolution range / inside the image at all
+    uint32_t cmask[4], vmask[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        cmask[j] = vmask[j] = 0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int gx = x + 4 * j + p;
+            if (gx >= HALF && gx < g.wd - KSZ + HALF) cmask[j] |= 0xffu << (8 * p);
+            if (gx < g.wd) vmask[j] |= 0xffu << (8 * p);
+        }
+    }
+    const bool in_pitch = x < g.wp;                      // (the pitch is a multiple of 16: a chunk is inside or outside)
+    const bool have_l = x >= 4, have_r = x + 16 < g.wp;  // a word left / right of the chunk exists
+    // one row of decimated pixels: the lane's four words + the word before and after them
+    auto fetch_row = [&](int gy, uint4& v, uint32_t& wl, uint32_t& wr) {
+        v = make_uint4(0u, 0u, 0u, 0u);
+        wl = 0u; wr = 0u;
+        if (gy >= 0 && gy < g.hd && in_pitch) {
+            const uint8_t* row = fs + (size_t)gy * F * src_stride;
+            if (F == 1) {
+                v = __ldg(reinterpret_cast<const uint4*>(row + x));
+                if (lane == 0 && have_l) wl = __ldg(reinterpret_cast<const uint32_t*>(row + x - 4));
+                if (lane == 31 && have_r) wr = __ldg(reinterpret_cast<const uint32_t*>(row + x + 16));
+            } else if ((size_t)(2 * x + 40) <= src_stride) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(row + 2 * x));
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(row + 2 * x + 16));
+                v.x = __byte_perm(a.x, a.y, 0x6420); v.y = __byte_perm(a.z, a.w, 0x6420);
+                v.z = __byte_perm(b.x, b.y, 0x6420); v.w = __byte_perm(b.z, b.w, 0x6420);
+                if (lane == 0 && have_l) {
+                    const uint2 c = __ldg(reinterpret_cast<const uint2*>(row + 2 * x - 8));
+                    wl = __byte_perm(c.x, c.y, 0x6420);
+                }
+                if (lane == 31 && have_r) {
+                    const uint2 c = __ldg(reinterpret_cast<const uint2*>(row + 2 * x + 32));
+                    wr = __byte_perm(c.x, c.y, 0x6420);
+                }
+            } else {   // the chunk at the end of the source row: byte by byte, inside the image only
+                uint32_t w6[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+                for (int k = -4; k < 20; k++) {
+                    const int gx = x + k;
+                    if (gx >= 0 && gx < g.wd) w6[(k + 4) >> 2] |= (uint32_t)row[(size_t)gx * 2] << (8 * ((k + 4) & 3));
+                }
+                v = make_uint4(w6[1], w6[2], w6[3], w6[4]);
+                wl = w6[0]; wr = w6[5];
+            }
+        }
+    };
+    auto assemble_row = [&](const uint4& v, uint32_t wl, uint32_t wr, uint32_t (&W)[7]) {
+        const uint32_t nl = __shfl_up_sync(FULL_MASK, v.w, 1), nr = __shfl_down_sync(FULL_MASK, v.x, 1);
+        W[0] = lane == 0 ? wl : nl;
+        W[1] = v.x; W[2] = v.y; W[3] = v.z; W[4] = v.w;
+        W[5] = lane == 31 ? wr : nr;
+        W[6] = 0u;
+    };
+    uint32_t Re[KSZ][4], Ro[KSZ][4];      // ring of row-pass results, even / odd bytes as 16-bit lanes
+    uint32_t Og[SHARPEN ? KSZ : 1][4];    // ring of the decimated pixels themselves (sharpen only)
+#pragma unroll
+    for (int s = 0; s < KSZ; s++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) Re[s][j] = Ro[s][j] = 0;
+    // rows y0 - HALF .. y0 + BLS_ROWS - 1 + HALF come in; row `gy` completes the window of output row gy - HALF
+    const int ylast = min(y0 + BLS_ROWS, g.hd) - 1 + HALF;
+#pragma unroll 1
+    for (int yb = y0 - HALF; yb <= ylast; yb += KSZ) {
+#pragma unroll
+        for (int s = 0; s < KSZ; s++) {
+            const int gy = yb + s;
+            if (gy > ylast) break;
+            uint32_t W[7];
+            {
+                uint4 cv;
+                uint32_t cwl, cwr;
+                fetch_row(gy, cv, cwl, cwr);
+                assemble_row(cv, cwl, cwr, W);
+            }
+            // ---- row pass
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t acc[4];
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    acc[p] = 0;
+#pragma unroll
+                    for (int gI = 0; gI < NG; gI++) {
+                        const int off = p - HALF + 4 * gI;                  // byte offset of the window from the word's start
+                        const int q = off >= 0 ? off / 4 : -((3 - off) / 4);  // floor(off / 4)
+                        const int sh = off - 4 * q;                          // 0 .. 3
+                        const uint32_t lo = W[1 + j + q], hi = W[2 + j + q];
+                        const uint32_t win = sh == 0 ? lo : __funnelshift_r(lo, hi, 8 * sh);
+                        acc[p] = __dp4a(win, kw[gI], acc[p]);
+                    }
+                }
+                const uint32_t conv = ((acc[0] >> 8) & 0xffu) | (acc[1] & 0xff00u) | ((acc[2] << 8) & 0xff0000u) | ((acc[3] << 16) & 0xff000000u);
+                const uint32_t r = (conv & cmask[j]) | (W[1 + j] & ~cmask[j]);
+                Re[s][j] = r & 0x00ff00ffu;
+                Ro[s][j] = (r >> 8) & 0x00ff00ffu;
+                if (SHARPEN) Og[SHARPEN ? s : 0][j] = W[1 + j];
+            }
+            // ---- column pass for output row yo = gy - HALF (its window is the ring, oldest row first: slot s + 1)
+            const int yo = gy - HALF;
+            if (yo >= y0 && yo < g.hd && in_pitch) {
+                uint4 o;
+                uint32_t ow[4];
+                const bool vconv = yo >= HALF && yo < g.hd - KSZ + HALF;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int sc = (s + KSZ - HALF) % KSZ;                   // slot of row yo itself
+                    uint32_t word = Re[sc][j] | (Ro[sc][j] << 8);
+                    if (vconv) {
+                        uint32_t ae = 0u, ao = 0u;
+#pragma unroll
+                        for (int t = 0; t < KSZ; t++) {
+                            const int st = (s + 1 + t) % KSZ;                // tap t sits on row gy - (KSZ - 1) + t
+                            ae += kt[t] * Re[st][j];
+                            ao += kt[t] * Ro[st][j];
+                        }
+                        word = ((ae >> 8) & 0x00ff00ffu) | (ao & 0xff00ff00u);
+                    }
+                    if (SHARPEN) {
+                        const uint32_t og = Og[SHARPEN ? sc : 0][j];   // the decimated pixels of row yo itself
+                        const uint32_t oe = og & 0x00ff00ffu, oo = (og >> 8) & 0x00ff00ffu;
+                        const uint32_t be = word & 0x00ff00ffu, bo = (word >> 8) & 0x00ff00ffu;
+                        // per 16-bit lane: clamp(2 * orig - blurred, 0, 255)
+                        const uint32_t de = __vminu2(__vmaxs2(__vsub2(__vadd2(oe, oe), be), 0u), 0x00ff00ffu);
+                        const uint32_t dn = __vminu2(__vmaxs2(__vsub2(__vadd2(oo, oo), bo), 0u), 0x00ff00ffu);
+                        word = de | (dn << 8);
+                    }
+                    ow[j] = word & vmask[j];
+                }
+                o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                *reinterpret_cast<uint4*>(fo + (size_t)yo * g.wp + x) = o;
+            }
+        }
+    }
+}

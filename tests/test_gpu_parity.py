@@ -115,15 +115,17 @@ def test_mask_front_end_bit_exact(ob, W, H, monkeypatch):
     det_bytes.close()
 
 
-@pytest.mark.parametrize("sigma", [0.8, 1.5, -0.8, 3.1, -2.0, 9.0])
+@pytest.mark.parametrize("sigma", [0.8, 1.3, 1.5, -0.8, -1.3, -1.7, 3.1, -2.0, 9.0])
 @pytest.mark.parametrize("decimate", [1, 2, 3])
 def test_blur_front_end_bit_exact(ob, sigma, decimate):
-    """U1 + U2 fused (k_decimate_blur): kernel sizes 3 .. 37 taps, blur and sharpen, decimation by the two vector-load
-    factors and a generic one, on shapes with ragged right / bottom edges, a tile boundary inside, and images smaller
-    than the kernel (upstream copies what the window does not cover)."""
+    """U1 + U2 fused: kernel sizes 3 .. 37 taps, blur and sharpen, decimation by the two vector-load factors and a generic
+    one.  3 / 5 / 7 taps on 16-byte aligned rows take the register-resident strip kernel (k_decimate_blur_strip), the rest
+    the shared-memory tile kernel (k_decimate_blur).  Shapes: ragged right / bottom edges, a strip / tile boundary inside
+    (the halo words of the first and last lane), a source row that ends inside the last chunk, and images smaller than
+    the kernel (upstream copies what the window does not cover)."""
     rng = np.random.default_rng(5)
     det = Detector("tag36h11", decimate=float(decimate), blur=sigma)
-    for shape in ((241, 323), (96, 512), (70, 41), (9, 13)):
+    for shape in ((241, 323), (96, 512), (70, 41), (9, 13), (241, 336), (130, 1040), (67, 1008), (150, 2096)):
         im = rng.integers(0, 256, shape, dtype=np.uint8)
         q, t = det.stage_threshold(im)
         q_ref = ob.stage_blur(np.ascontiguousarray(im[::decimate, ::decimate]), sigma)
