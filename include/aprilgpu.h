@@ -53,7 +53,7 @@ typedef struct agpu_config {
     int threads;              /* (1)  accepted for API compatibility, ignored */
     int maxhamming;           /* (1)  0..2 */
     float quad_decimate;      /* (2.0) integer factors >= 1 */
-    float quad_sigma;         /* (0.0) "blur": >0 Gaussian blur, <0 unsharp */
+    float quad_sigma;         /* (0.0) "blur": >0 Gaussian blur, <0 unsharp; fused with the decimation in one kernel */
     int refine_edges;         /* (1) */
     double decode_sharpening; /* (0.25) */
     int debug;                /* (0)  1: keep stage buffers of the last chunk for agpu_debug_fetch */
@@ -140,7 +140,7 @@ int agpu_get_stage_ms(agpu_handle* h, float* ms /* [AGPU_NUM_STAGES] */);
 /* Profiling on: EVERY kernel launch of a chunk is bracketed by its own pair of CUDA events on the stream it is launched
  * on (and the quad-fit size tiers, normally concurrent on side streams, run one after the other), so with
  * pipeline_slots = 1 each interval is that kernel alone.  agpu_get_kernel_ms: milliseconds of one kernel summed over
- * the chunks of the last call; names: k_decimate_threshold, k_pack(bgr), k_cc_local, k_cc_boundary, k_cc_sizes,
+ * the chunks of the last call; names: k_decimate_threshold, k_decimate_blur, k_pack(bgr), k_cc_local, k_cc_boundary, k_cc_sizes,
  * k_cc_dense, k_edges, k_cluster_refs, k_sort_scatter, k_fit_quads<1>, <2>, <4>, <4>/6k, <8>,
  * k_decode_quads, k_reconcile, k_pose.  agpu_get_kernel_table: all of them as text lines "name\tms\tlaunches\n";
  * returns the bytes needed (terminator included) and copies at most cap. */
