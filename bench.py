@@ -162,24 +162,25 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_run(frames: np.ndarray, K, steps: int, warmup: int, threads: int):
+def cpu_reference_run(frames: np.ndarray, K, steps: int, warmup: int, threads: int, fams: str = "tag36h11",
+                      decimate: float = 1.0, tag_size: float = TAG_SIZE, cap: int = CAP):
     """The reference's CPU path restated: detector (oracle, frames spread over `threads` host threads) +
     cv2.solvePnP per detection exactly as tag_detector.py:30-43 calls it, the per-frame pose loops spread over the same
     number of threads (cv2 releases the GIL inside solvePnP).  Returns (seconds per step, tags per frame,
     seconds of the detector alone, seconds of the pose loop alone)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle.binding import OracleDetector, reference_pose
-    det = OracleDetector("tag36h11", decimate=1.0, refine_edges=True)
+    det = OracleDetector(fams, decimate=decimate, refine_edges=True)
     dist = np.zeros((4, 1))
 
     def poses_of(recs):
-        return [reference_pose(r["p"], K, dist, TAG_SIZE) for r in recs]
+        return [reference_pose(r["p"], K, dist, tag_size) for r in recs]
 
     times, t_det, t_pose, ndet = [], [], [], 0
     with ThreadPoolExecutor(max_workers=max(1, threads)) as pool:
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            lists = det.detect_batch(frames, nthreads=threads, cap=CAP)
+            lists = det.detect_batch(frames, nthreads=threads, cap=cap)
             t1 = time.perf_counter()
             if threads > 1:
                 list(pool.map(poses_of, lists))
@@ -531,21 +532,26 @@ def run_b200(args):
                                        "algorithmic_bytes_per_frame": a_pipe,
                                        "note": "A_pipe x the PIPELINED per-GPU frame rate (`value` / n_gpus)"},
                     "kernels": kernels}
-    # CPU baseline on this box's host cores (bounded sample of the same workload; C3 only: the headline config)
+    # CPU baseline on this box's host cores: a bounded sample of the same batch (the first frames; sized from a short
+    # probe so that the sample is ~10 s of wall time whatever the shape costs on the CPU)
     cpu_baseline = None
-    if args.config == "C3":
+    if rank == 0 and world == 1:
         os.sched_setaffinity(0, cpus_before)          # the CPU baseline may use every host core again
         threads = len(os.sched_getaffinity(0)) or 1
-        nref = max(16, min(256, 16 * threads, B))     # ~10-30 core-seconds of CPU work
         t0 = time.time()
-        sec_cpu, _, sec_cpu_det, sec_cpu_pose = cpu_reference_run(frames_host[:nref], K, 1, 0, threads)
-        sec_cpu1, _, _, _ = cpu_reference_run(frames_host[:4], K, 1, 0, 1)
+        kw = dict(fams=fams if isinstance(fams, str) else " ".join(fams), decimate=d, tag_size=tag_size, cap=cap)
+        nprobe = min(B, threads)
+        sec_probe, _, _, _ = cpu_reference_run(frames_host[:nprobe], K, 1, 0, threads, **kw)
+        nref = int(max(nprobe, min(B, 256 if args.config == "C3" else 512, nprobe * 10.0 / max(sec_probe, 1e-3))))
+        sec_cpu, _, sec_cpu_det, sec_cpu_pose = cpu_reference_run(frames_host[:nref], K, 1, 0, threads, **kw)
+        n1 = min(4, B)
+        sec_cpu1, _, _, _ = cpu_reference_run(frames_host[:n1], K, 1, 0, 1, **kw)
         cpu_baseline = {"value": nref / sec_cpu, "unit": "frames/s", "cores": threads, "kind": "port",
                         "sample": "frames 0..%d of the same batch, oracle detector on %d host threads (%.2f s) + cv2.solvePnP "
                                   "per tag on the same threads (%.2f s); 1 thread (the reference's setting, "
                                   "tag_detector.py:18): %.2f frames/s" % (nref - 1, threads, sec_cpu_det, sec_cpu_pose,
-                                                                          4 / sec_cpu1),
-                        "one_thread_value": 4 / sec_cpu1, "seconds": time.time() - t0}
+                                                                          n1 / sec_cpu1),
+                        "one_thread_value": n1 / sec_cpu1, "seconds": time.time() - t0}
     line = {
         "metric": metric_of(args.config), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
