@@ -33,10 +33,12 @@
 #pragma once
 #include "common.cuh"
 
-// tile of the local pass: 32 x 32 pixels per warp (lane = ROW), 4 tiles side by side per CTA
+// tile of the local pass: 32 x 32 pixels per warp (lane = ROW), CC_WARPS tiles side by side per CTA
 #define CC_TW 32
 #define CC_TH 32
-#define CC_WARPS 4
+#ifndef CC_WARPS
+#define CC_WARPS 2   // (1: 461, 2: 450, 4: 463, 8: 510 us for the CC stage of 128 frames -- a flat tile's warp leaves at once, and a
+#endif               //  small CTA gives its slot back sooner)
 #define CC_THREADS (CC_WARPS * 32)
 #define CC_SUBLISTS 16   // root sub-lists per frame (tile row mod 16): spreads the append atomics over 16 counters
 #define CC_PITCH 33   // run-start slots of row r live at r*33 + c (16-bit entries)
