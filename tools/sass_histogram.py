@@ -17,13 +17,14 @@ for line in sass.splitlines():
         cur = demangle(m.group(1)).split("(")[0].replace("void ", "")
         kern[cur] = collections.Counter()
         continue
-    m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
     if m and cur:
         kern[cur][m.group(1)] += 1
-WATCH = ["LDG.E.128", "LDG.E.64", "LDG.E.U8", "STG.E.128", "STG.E.64", "HMNMX2", "HSET2", "IDP.2A", "PRMT", "ATOMS", "ATOMG", "RED",
+WATCH = ["LDG.E.128", "LDG.E.64", "LDG.E.U8", "STG.E.128", "STG.E.64", "HMNMX2", "HSET2", "IDP.2A", "IDP.4A", "PRMT", "SHF", "REDUX", "ATOMS", "ATOMG", "RED",
          "SHFL", "VOTE", "MATCH", "DADD", "DMUL", "DFMA", "MUFU", "BAR", "HMMA", "UTCMMA", "UTMALDG", "LDL", "STL"]
 hot = [k for k in kern if any(k.startswith(p) for p in ("k_decimate_threshold<1, 4, false, 1>", "k_decimate_threshold<1, 3, false, 3>",
-       "k_cc_local<false>", "k_cc_boundary<8>", "k_edges<2>", "k_sort_scatter", "k_sort_hist", "k_fit_quads<2>", "k_decode_quads", "k_pose"))]
+       "k_decimate_blur_strip<1, 3, false>", "k_decimate_blur<1>", "k_cc_local<false>", "k_cc_boundary<8>", "k_edges<2>", "k_sort_scatter",
+       "k_fit_quads<2>", "k_decode_quads", "k_reconcile", "k_pose"))]
 print("# cuobjdump -sass aprilslam_b200/libaprilgpu.so (sm_100a), opcode counts per kernel (static instruction count)")
 for k in hot:
     c = kern[k]
