@@ -103,17 +103,52 @@ def make_frames(distinct: int, total: int, seed0: int = 0) -> np.ndarray:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML in-process (a
+    sample every few milliseconds: the timed region of a default run is well under a second, less than nvidia-smi needs
+    to start up); `nvidia-smi -lms` as the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
+               (0x80, "hw_power_brake_slowdown"))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []      # (sm MHz, reasons bit mask)
+        self.stop_flag = False
+
+    def _nvml_sample(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        try:
+            rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.samples.append((float(sm), int(rs)))
+
+    def _nvml_loop(self):
+        while not self.stop_flag:
+            try:
+                self._nvml_sample()
+            except Exception:
+                break
+            time.sleep(0.004)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -128,6 +163,16 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            sm = [s[0] for s in self.samples]
+            mask = 0
+            for _, r in self.samples:
+                mask |= r
+            reasons = sorted(name for bit, name in self.REASONS if mask & bit)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -149,7 +194,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak_gbs():
@@ -362,7 +407,7 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         step_dev()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(phys)
     if rank == 0:
         sampler.start()
     sec, launches, _, _, res = timed(step_dev, args.steps)
