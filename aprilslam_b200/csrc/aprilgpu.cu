@@ -1009,8 +1009,8 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
         }
         h->counters[0] += h_npts[i] + h_ndups[i];   // raw edge points, as upstream counts them
         h->counters[3] += h_nd[i];
-        if (h_nd[i] > REC_CAP && rc_final == AGPU_OK) {   // (upstream has no such limit; the frame keeps its first 256 candidates)
-            h->set_err("more than 256 raw detections (before reconcile) in one frame: the surplus was dropped");
+        if (h_nd[i] > REC_CAP && rc_final == AGPU_OK) {   // (upstream has no such limit; the frame keeps its first 1024 candidates)
+            h->set_err("more than 1024 raw detections (before reconcile) in one frame: the surplus was dropped");
             rc_final = AGPU_E_TRUNCATED;
         }
     }

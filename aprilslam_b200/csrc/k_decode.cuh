@@ -514,7 +514,7 @@ __device__ int prefer_dev(const DetRec& a, const DetRec& b) {
     return -1;
 }
 
-#define REC_CAP 256  // internal per-frame detection capacity before reconcile
+#define REC_CAP 1024  // internal per-frame detection capacity before reconcile (29 KB of shared-memory sort keys)
 
 // One CTA of REC_THREADS threads per frame (a 4K frame carries a few hundred detections).  The sort keys (id, family, centre) are staged in shared memory once, so the
 // two rank sorts (n^2 comparisons, dealt to all threads) run out of shared memory instead of re-reading the 168-byte

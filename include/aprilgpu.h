@@ -39,7 +39,7 @@ typedef enum agpu_status {
     AGPU_E_INVALID = -1,    /* bad argument (NULL, non-positive size, unknown family, ...) */
     AGPU_E_CUDA = -2,       /* CUDA runtime error or no device */
     AGPU_E_TRUNCATED = -3,  /* more detections than cap_per_frame in at least one frame (counts[] hold the true numbers), or more
-                               than 256 decoded candidates in one frame before reconcile (the surplus was dropped) */
+                               than 1024 decoded candidates in one frame before reconcile (the surplus was dropped) */
     AGPU_E_WORKSPACE = -4,  /* an internal per-frame work list overflowed (edge points / clusters / quads); raise the agpu_config limits */
     AGPU_E_UNSUPPORTED = -5
 } agpu_status;

@@ -383,6 +383,20 @@ def test_4k_frame_matches_oracle(ob, d):
     g.close()
 
 
+def test_dense_board_of_more_than_256_tags(ob):
+    """A 4K frame with 416 tags (26 x 16): more decoded candidates than the 256 the per-frame reconcile stage held in
+    round 1 -- upstream has no such limit; the capacity is 1024 now."""
+    sc = synth.grid_scene(3840, 2160, 91, (26, 16), px_range=(70, 100))
+    img = synth.render(sc)
+    assert len(sc.tags) == 416
+    g = Detector("tag36h11", decimate=2.0)
+    recs = g.detect_batch(img, cap_per_frame=512)[0]
+    ref = ob.OracleDetector("tag36h11", decimate=2.0).detect_records(img, cap=1024)
+    assert len(ref) > 300
+    assert_same_detections(recs, ref)
+    g.close()
+
+
 def test_noise_frames_match_oracle(ob):
     rng = np.random.default_rng(5)
     g = Detector("tag36h11", decimate=1.0)
