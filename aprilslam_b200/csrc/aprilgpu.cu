@@ -193,6 +193,7 @@ struct agpu_handle {
     int max_dense_seen = -1, max_clusters_seen = -1;   // most components / clusters seen in one frame so far (statistics)
     int cap_keys = 0;   // cluster-id capacity per frame (grows like the other work lists)
     int cap_roots = 0;  // tile-local roots per sub-list (likewise)
+    int roots_hint = 0; // longest root sub-list of the last finished chunk (sizes the grids of k_cc_sizes / k_cc_dense)
 
     // state of the last finished chunk (debug fetch)
     Geom geom;
@@ -518,7 +519,10 @@ int run_cc_stage(agpu_handle* h, Slot& sl, const uint8_t* d_thresh, int n, const
 #undef LAUNCH_CCB
     }
     LAUNCH_CHECK("k_cc_boundary");
-    dim3 grids(std::max(1, std::min(8, ceil_div(sub_cap, 256))), n * CC_SUBLISTS);
+    // (grid-stride loops over a sub-list: any CTA count is correct; the count follows the longest sub-list the previous
+    // chunk had, so that a clean frame's ~400 roots per sub-list do not launch eight CTAs of which six find nothing)
+    const int roots_seen = h->roots_hint > 0 ? std::min(h->roots_hint, sub_cap) : sub_cap;
+    dim3 grids(std::max(1, std::min(8, ceil_div(roots_seen, 256))), n * CC_SUBLISTS);
     {
         KScope ks(h, sl, "k_cc_sizes", sl.stream);
         k_cc_sizes<<<grids, 256, 0, sl.stream>>>(rt);
@@ -987,6 +991,7 @@ int finish_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, agpu_detection* out
         for (int i = 0; i < n * CC_SUBLISTS; i++) max_roots = std::max(max_roots, h_nroots[i]);
     }
     if (max_roots > c.roots_cap) { ov.max_roots = std::max(ov.max_roots, max_roots); redo = true; }
+    h->roots_hint = std::max(1, max_roots);
     if (max_pts > c.cap) { ov.max_pts = std::max(ov.max_pts, max_pts); redo = true; }
     if (max_cl > n * c.maxcl) { ov.max_cl_per_frame = std::max(ov.max_cl_per_frame, (max_cl + n - 1) / n); redo = true; }
     if (hc[CNT_NQUADS] > n * c.maxq) { ov.max_q_per_frame = std::max(ov.max_q_per_frame, (hc[CNT_NQUADS] + n - 1) / n); redo = true; }
