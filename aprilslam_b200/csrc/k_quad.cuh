@@ -604,12 +604,14 @@ __device__ bool fit_cluster_group(const QGroup<NW>& G, const QuadFitArgs& a, con
             if (G.w == 0 && lane < 6) {
                 double* p = stage + lane * SP;
 #pragma unroll 1
-                for (int j = 0; j < T; j += 8) {   // (entries past the cluster's end hold zeros)
-                    double v[8];
+                for (int j = 0; j < T; j += 8) {   // (entries past the cluster's end hold zeros; 128-bit shared-memory accesses)
+                    double2 v[4];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) v[u] = p[j + u];
+                    for (int u = 0; u < 4; u++) v[u] = *reinterpret_cast<const double2*>(p + j + 2 * u);
 #pragma unroll
-                    for (int u = 0; u < 8; u++) { carry += v[u]; p[j + u] = carry; }
+                    for (int u = 0; u < 4; u++) { carry += v[u].x; v[u].x = carry; carry += v[u].y; v[u].y = carry; }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) *reinterpret_cast<double2*>(p + j + 2 * u) = v[u];
                 }
             }
             G.sync();
