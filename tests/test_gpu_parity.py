@@ -20,7 +20,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CORNER_TOL_PX = 0.05      # the north-star bars ...
 POSE_TOL = 1e-4
 # ... and what is asserted: a few times the largest difference ever measured between the CUDA path and the oracle
-# (tools/gpu_tolerances.py over 19 frames / 934 detections incl. augmented 1080p and 4K, profiles/r3a_tolerances.json):
+# (tools/gpu_tolerances.py over 19 frames / 934 detections incl. augmented 1080p and 4K, profiles/r4d_tolerances.json):
 # fitted quads bit-equal; corners 2.4e-4 px, centre 1.2e-4 px, margin 6.1e-5, pose 2.1e-7 units / 2.7e-6 rad.  What is
 # left comes from atan2f / cosf / sinf (CUDA's and glibc's differ by an ulp or two) inside refine_edges.
 CORNER_ACHIEVED_TOL_PX = 1e-3
