@@ -610,7 +610,7 @@ int alloc_slot(agpu_handle* h, Slot& s, const CallCtx& c) {
         size_t pts = 0;
         for (int t = 0; t < AGPU_NTIERS; t++) {
             const int cap_t = t == AGPU_NTIERS - 1 ? std::max(max_cluster, h->tune.tier_cap[t - 1] + 1) : h->tune.tier_cap[t];
-            pts += (size_t)h->num_sms * h->tune.tier_ctas[t] * (t == 0 ? 8 : 1) * cap_t;
+            pts += (size_t)h->num_sms * h->tune.tier_ctas[t] * (t == 0 ? 8 : 1) * ((cap_t + 1) & ~1);   // (even: 16-byte aligned slices)
         }
         CK(s.d_qscratch.ensure(pts * 56));
     }
@@ -700,7 +700,7 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
     int tier_cap[AGPU_NTIERS], tier_smem[AGPU_NTIERS];    // largest cluster of a tier / capacity of its shared-memory sort buffer
     for (int t = 0; t < AGPU_NTIERS; t++) {
         tier_cap[t] = t == AGPU_NTIERS - 1 ? std::max(max_cluster, h->tune.tier_cap[t - 1] + 1) : h->tune.tier_cap[t];
-        tier_smem[t] = std::min(tier_cap[t], QF_SMEM_CAP);
+        tier_smem[t] = (std::min(tier_cap[t], QF_SMEM_CAP) + 1) & ~1;   // (even: the shared-memory areas behind the sort buffer are accessed 16 bytes at a time)
         cl.list[t] = sl.d_clusters[t].as<ClusterRef>();
         cl.cap[t] = tier_cap[t];
     }
@@ -760,9 +760,9 @@ int enqueue_chunk(agpu_handle* h, Slot& sl, const CallCtx& c, int b0, int n) {
             const int nblk = std::max(1, (int)std::min<long long>((long long)h->num_sms * h->tune.tier_ctas[t], n * area * per_frame[t]));
             {   // this tier's slice of the per-group scratch (tiers are visited from the last to the first)
                 size_t off = 0;
-                for (int u = AGPU_NTIERS - 1; u > t; u--) off += (size_t)h->num_sms * h->tune.tier_ctas[u] * (u == 0 ? 8 : 1) * tier_cap[u];
+                for (int u = AGPU_NTIERS - 1; u > t; u--) off += (size_t)h->num_sms * h->tune.tier_ctas[u] * (u == 0 ? 8 : 1) * ((tier_cap[u] + 1) & ~1);
                 qa.scratch = sl.d_qscratch.as<double>() + off * 7;
-                qa.scratch_pts = tier_cap[t];
+                qa.scratch_pts = (tier_cap[t] + 1) & ~1;   // (a group's slice starts 16-byte aligned: the moments are read 16 bytes at a time)
             }
             {
             KScope ks(h, sl, tier_name[t], st);
